@@ -1,0 +1,135 @@
+/* v3s -- C ABI of the B200-native hot path of nurlicht/Volumetric-3D-Stitching.
+ *
+ * The reference has no FFI; its boundary is the Python stage API.
+ * Each entry point below names the reference function(s) it replaces (paths relative to the
+ * reference's src/python/).  Conventions:
+ *   - every pointer is a DEVICE pointer unless marked "host"; matrices are row-major;
+ *   - the caller owns every buffer (including workspaces); nothing persistent is allocated;
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on that stream and do
+ *     not synchronise the host (v3s_synth_patterns does one small pageable host-to-device copy);
+ *   - return value 0 = ok, non-zero = error, message from v3s_last_error() (thread-local);
+ *   - there is no CPU fallback: without an sm_100a device the calls fail.
+ */
+#ifndef V3S_H_
+#define V3S_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* v3s_last_error(void);
+int v3s_version(void);
+int v3s_check_device(void);
+
+/* ---- stage 1: pattern synthesis ------------------------------------------------------- */
+
+/* experiment constants of projection.py:96-107 (Projector.experiment_parameters) */
+typedef struct v3s_geometry {
+  double pixel;      /* 75e-6 m  */
+  double zd;         /* 0.5 m    */
+  double lambda;     /* 2e-9 m   */
+  int    n_p_nobin;  /* 1024     */
+  double grid_scale; /* 2e-7 m: Grid_3D = grid_scale * U, projection.py:91 */
+} v3s_geometry;
+
+void v3s_default_geometry(v3s_geometry* g /* host */);
+
+/* Projector.generate's hot loop (projection.py:35-43) = N x Projector.generate_single_image
+ * (projection.py:55-71) incl. Rotation.rotate_structure_index (rotation.py:143-162) and
+ * Projector.q_and_mask / camera_x_y / fourier_scaled_axis (projection.py:121-190).
+ *   ed    [n,n,n] FP32 object, array axes as in Projector.synsthesize_3d (projection.py:75-91)
+ *   rot9  [N,9]   FP64, row-major 3x3 per pattern = R[:,c].reshape(3,3).T of projection.py:38
+ *   out   [N, n_p*n_p] FP32 patterns, row stride out_stride elements
+ *   geom  host pointer or NULL for the reference's constants                              */
+int v3s_synth_patterns(const float* ed, int n, const double* rot9, long long N, int n_p,
+                       const v3s_geometry* geom /* host */, float* out, long long out_stride, void* stream);
+
+/* ---- stage 2: distances + k nearest neighbours ----------------------------------------- */
+
+/* DistanceMatrix.remove_offset (distance.py:70-71), first half: per-pixel sums over the local
+ * rows (FP64).  The caller divides by the global N (after an all-reduce when sharded).      */
+int v3s_column_sums(const float* img, long long n_rows, int P, long long stride, double* sums /* [P] */, void* stream);
+
+/* remove_offset + DistanceMatrix.set_norm_to_one (distance.py:66-71) and the BF16 hi/lo split
+ * of the Gram operands.  a_f32 [n_rows,P]; a_hi/a_lo [n_rows,Ppad] bf16 (NULL to skip);
+ * norms [n_rows] FP64 and zero_flag [n_rows] (1 for an all-zero centred row) are optional.   */
+int v3s_center_normalize(const float* img, long long n_rows, int P, long long stride, const double* mean /* [P] */,
+                         float* a_f32, void* a_hi, void* a_lo, int Ppad, double* norms, int* zero_flag, void* stream);
+
+/* np.matmul(A, A.T) of DistanceMatrix.convert_to_round_distance (distance.py:56) for a row
+ * panel: G[r, c] = <a_rows[r], a_all[c]>, r < n_rows, c < n_cols, tcgen05/TMEM/TMA kernel on
+ * the split BF16 operands (FP32-equivalent).  Ppad must be a multiple of 64.                */
+int v3s_gram_rows(const void* all_hi, const void* all_lo, long long n_cols, const void* rows_hi, const void* rows_lo,
+                  long long n_rows, int Ppad, float* G, long long ldg, void* stream);
+
+/* Same contraction on CUDA cores in plain FP32 -- the validation path of v3s_gram_rows.       */
+int v3s_gram_rows_simt(const float* a_all, long long n_cols, const float* a_rows, long long n_rows, int P, float* G,
+                       long long ldg, void* stream);
+
+/* DistanceMatrix.convert_to_round_distance (distance.py:51-63) as a dense FP64 matrix B [n,n]
+ * from the centred unit rows a_f32 [n,P]: d = 2 asin(|a_r - a_c| / 2), exact all-pairs form.   */
+int v3s_round_distance_dense(const float* a_f32, long long n, int P, const int* zero_flag, double* B, void* stream);
+
+/* DistanceMatrix.knn_from_round_distance (distance.py:26-48) on a caller-supplied dense FP64
+ * B [n,n]: k smallest entries per row, ascending.  key_ws float [n,n]; cand_ws int [n,min(k+margin,n)]. */
+int v3s_knn_from_dense(const double* B, long long n, int k, int margin, float* key_ws, int* cand_ws, double* S2,
+                       int* Nbr, void* stream);
+
+/* arccos epilogue + DistanceMatrix.knn_from_round_distance (distance.py:56-59, 26-48) for the
+ * panel rows [row0, row0+n_rows): S2 [n_rows,k] FP64 ascending distances, Nbr [n_rows,k] int32.
+ * cand_ws: int32 workspace [n_rows, min(k+margin, n_cols)].  Fails with the reference's message
+ * "Number of nearest neighbors to preserve is too high." when k > n_cols.                     */
+int v3s_knn_from_gram(const float* G, long long ldg, long long n_rows, long long n_cols, long long row0,
+                      const float* a_rows, const float* a_all, int P, int k, int margin, const int* zero_flag,
+                      int* cand_ws, double* S2, int* Nbr, void* stream);
+
+/* ---- stage 3: diffusion map ---------------------------------------------------------------- */
+
+/* scalar part of DiffusionMapSolver.s2_to_w_matrix (diffusion.py:297-313), bug-compatible row
+ * indexing.  scalars5 = {S2_Max, Dist_Thr, Epsilon*S2_Max, status, Index}; status 1 -> the
+ * reference's 'S2_Max = 0', 2 -> index out of range.                                          */
+int v3s_s2_scalars(const double* S2, long long N, int k, double eps, int med_row, int idx_off, double* scalars5,
+                   void* stream);
+/* in-place S2[S2 > Dist_Thr] = inf (diffusion.py:311) */
+int v3s_s2_threshold(double* S2, long long N, int k, const double* scalars5, void* stream);
+
+/* s2_to_w_matrix + anisotropic_norm + dm_cov (diffusion.py:313-325, 89-105, 244-260) fused on
+ * the kNN lists: row block [row0,row0+n_rows) of P_ep as dense FP32 [n_rows, ldp] and
+ * dinv_sqrt [N] (the diagonal of D).  ws_2N: FP64 workspace of 2N.                            */
+int v3s_build_markov(const double* S2_thresholded, const int* Nbr, long long N, int k, const double* scalars5,
+                     long long row0, long long n_rows, float* P_rows, long long ldp, double* dinv_sqrt, double* ws_2N,
+                     void* stream);
+
+/* dense FP64 forms of the same three functions, for callers of the individual reference APIs */
+int v3s_w_dense(const double* S2_thresholded, const int* Nbr, long long N, int k, double eps_eff, double* W, void* stream);
+int v3s_anisotropic_norm_dense(const double* W, long long N, double* out, double* ws_N, void* stream);
+int v3s_dm_cov_dense(const double* W, long long N, double* P_out, double* dinv_sqrt, double* ws_N, void* stream);
+
+/* dense P_ep @ X of the eigen-solver behind scipy.sparse.linalg.eigs (diffusion.py:61):
+ * Y_rows [n_rows,b] = P_rows [n_rows,N] (FP32, ld ldp) . X [N,b] (FP64), b <= 8.               */
+long long v3s_block_matvec_workspace_bytes(long long n_rows, long long N);
+int v3s_block_matvec(const float* P_rows, long long ldp, long long n_rows, long long N, const double* X, int b,
+                     double* Y_rows, void* workspace, void* stream);
+
+/* ---- stage 4: orientation retrieval ---------------------------------------------------------- */
+
+/* ComputeUtils.lsq_linear (compute.py:103-112): out162 = {X^T X (81), X^T Y (81)} partial sums
+ * over the local rows (all-reduce when sharded), X = Ps[:,1:10], Y = Rotation_R.T [n_rows,9].  */
+int v3s_fit_gram(const double* Ps, int ldx, const double* Y, long long n_rows, double* out162, void* stream);
+/* c [9,9] = pinv(X^T X) (X^T Y) */
+int v3s_fit_solve(const double* in162, double* c81, void* stream);
+/* Recon = X c, ComputeUtils.polar_decompose per row (compute.py:51-55), Rotation.rot_mat_to_quat
+ * for estimate and truth (diffusion.py:144-167, rotation.py:165-210).  Outputs (optional ones may
+ * be NULL): recon_pre [n,9], rproj [n,9], quat_est [n,4], quat_true [n,4].
+ * polar_mode 0: U.Vh^T (reference form), 1: U.Vh, 2: nearest rotation.                          */
+int v3s_fit_project(const double* Ps, int ldx, const double* Y, long long n_rows, const double* c81, int polar_mode,
+                    double* recon_pre, double* rproj, double* quat_est, double* quat_true, void* stream);
+/* Rotation.mean_geodesic_distance (rotation.py:228-244) inner sum over rows [row0,row0+n_rows)
+ * against all N columns; partials_ws: 65536 doubles; out_sum[0] = sum |acos - acos|.            */
+int v3s_sigma_pairs(const double* quat_est, const double* quat_true, long long N, long long row0, long long n_rows,
+                    double* partials_ws, double* out_sum, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* V3S_H_ */

@@ -1,0 +1,150 @@
+"""Host logic of the product on CPU: stage adapters, block Lanczos, row sharding (gloo, world 2).
+The arithmetic backend is the oracle-based stand-in `tests/cpu_ops.py`; the CUDA kernels
+themselves are covered by the `-m gpu` tests."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import v3s_oracle as orc
+from cpu_ops import OracleOps
+
+import v3s
+from v3s import _util
+from v3s.eig import block_lanczos_topk
+from v3s.pipeline import ShardPlan, eigen_stage, fit_stage, knn_stage, markov_stage, run_pipeline
+
+
+@pytest.fixture(autouse=True)
+def cpu_backend():
+    _util.set_ops(OracleOps())
+    yield
+    _util.set_ops(None)
+
+
+def test_product_fails_loudly_without_gpu():
+    _util.set_ops(None)
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        v3s.DistanceMatrix.knn(np.zeros((8, 4)), 2)
+
+
+def test_shard_plan_covers_rows():
+    for N, w in ((10, 3), (1000, 8), (7, 8), (512, 2)):
+        plans = [ShardPlan(N, r, w) for r in range(w)]
+        assert plans[0].lo == 0 and plans[-1].hi == N
+        assert all(plans[i].hi == plans[i + 1].lo for i in range(w - 1))
+        assert max(p.hi - p.lo for p in plans) - min(p.hi - p.lo for p in plans) <= 1
+
+
+def test_block_lanczos_matches_dense_eigh(golden_dir):
+    g = np.load(os.path.join(golden_dir, "connected_n15.npz"))
+    _, _, _, _, P, _ = orc.diffusion_coordinate(g["S2"].copy(), g["N"], float(g["eps"]), return_all=True)
+    Pt = torch.from_numpy(P)
+    stats = {}
+    lam, V, res = block_lanczos_topk(lambda X: Pt @ X, P.shape[0], 10, torch.device("cpu"), tol=1e-10, stats=stats)
+    w, U = np.linalg.eigh(P)
+    assert np.max(np.abs(np.sort(lam)[::-1] - w[::-1][:10])) < 1e-12
+    assert np.max(orc.principal_angles(V.numpy(), U[:, -10:])) < 1e-8
+    assert stats["converged"] and stats["matvecs"] < 60
+
+
+def test_stage_api_golden_vectors():
+    """The reference's own unit-test vectors through the product's adapters (CPU backend)."""
+    S2 = np.array([[0.0, 16.0, 9.0, 25.0], [16.0, 0.0, 25.0, 9.0], [9.0, 25.0, 0.0, 16.0], [25.0, 9.0, 16.0, 0.0]])
+    N = np.array([[1, 3, 2, 4], [2, 4, 1, 3], [3, 1, 4, 2], [4, 2, 3, 1]]) - 1
+    W1 = np.array([[1.0, 0.48675, 0.27804, 0.13534], [0.13534, 0.27804, 0.48675, 1.0],
+                   [0.13534, 0.27804, 0.48675, 1.0], [1.0, 0.48675, 0.27804, 0.13534]])
+    W = v3s.DiffusionMapSolver.s2_to_w_matrix(S2.copy(), N, 1.0, s2_median_index=3, index_offset=0)
+    assert np.all(orc.almost_equal_hybrid(W, W1, 1e-4))
+    Ps, Lam = v3s.DiffusionMapSolver.diffusion_coordinate(S2.copy(), N, 1.0, 2, False)
+    assert np.all(orc.almost_equal_hybrid(Lam, [1.0, -0.3242], 1e-4))
+    assert np.all(orc.almost_equal_hybrid(np.abs(Ps[:, 0]), np.full(4, 0.689225), 1e-4))
+    with pytest.raises(Exception, match="No spare-matrix"):
+        v3s.DiffusionMapSolver.diffusion_coordinate(S2.copy(), N, 1.0, 3, False)
+    with pytest.raises(Exception, match="Non-square"):
+        v3s.DistanceMatrix.knn_from_round_distance(np.zeros((2, 3)), 1)
+    with pytest.raises(Exception, match="too high"):
+        v3s.DistanceMatrix.knn_from_round_distance(np.zeros((3, 3)), 4)
+    assert v3s.OrientationRecoverySolver.validate_parameters(v3s.OrientationRecoverySolver.default_parameters())
+    assert not v3s.OrientationRecoverySolver.validate_parameters({})
+
+
+def test_rotation_host_helpers_match_oracle(golden_dir):
+    g = np.load(os.path.join(golden_dir, "hopf_8.npz"))
+    R, Axis, Quat = v3s.Rotation.all_rot_variables(512)
+    assert np.allclose(R, g["R"], rtol=0, atol=1e-14) and np.allclose(Axis, g["Axis"], rtol=0, atol=1e-14)
+    assert np.allclose(Quat, g["Quat"], rtol=0, atol=1e-15)
+    Rz = np.array([[0.0, -1.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 1.0]])
+    assert np.allclose(v3s.Rotation.Axis2RotMat((np.pi / 2) * np.array([0.0, 0.0, 1.0])), Rz, atol=1e-15)
+    assert np.allclose(v3s.Rotation.rot_mat_to_quat(Rz), np.sqrt(0.5) * np.array([[1.0], [0], [0], [1.0]]), atol=1e-15)
+    assert np.array_equal(v3s.Projector.synsthesize_3d(15)["ED"], orc.synthesize_3d(15)["ED"])
+    R2, _ = v3s.Rotation.random_rotations(50, seed=3)
+    assert np.array_equal(R2, orc.random_rotations(50, seed=3)[0])
+
+
+def _pipeline_inputs(N=300, n=7, seed=2):
+    R9, _ = orc.random_rotations(N, seed=seed)
+    ed = torch.from_numpy(orc.synthesize_3d(n)["ED"].astype(np.float32))
+    rot9 = torch.from_numpy(np.ascontiguousarray(R9.T.reshape(-1, 3, 3).transpose(0, 2, 1).reshape(-1, 9)))
+    rot_y = torch.from_numpy(np.ascontiguousarray(R9.T))
+    return R9, ed, rot9, rot_y
+
+
+def test_pipeline_single_process_matches_oracle():
+    N, n, k, eps = 300, 7, 60, 0.7
+    R9, ed, rot9, rot_y = _pipeline_inputs(N, n)
+    out = run_pipeline(OracleOps(), ShardPlan(N), ed, rot9, rot_y, 2 * n + 1, k, eps, check=False)
+    imgs = orc.generate_from_rotations(R9, n).astype(np.float32).astype(np.float64)
+    S2, Nn = orc.knn(imgs, k)
+    assert np.allclose(out["S2_unmutated"].numpy(), S2, atol=2e-6)
+    Ps, Lam = orc.diffusion_coordinate(S2.copy(), Nn, eps, validate=False)
+    assert np.allclose(out["Lambda"].numpy(), np.clip(Lam, 0, 1), atol=1e-6)
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        N, n, k, eps = 301, 7, 60, 0.7     # odd N: uneven row blocks
+        R9, ed, rot9, rot_y = _pipeline_inputs(N, n)
+        plan = ShardPlan.from_env(N)
+        out = run_pipeline(OracleOps(), plan, ed, rot9[plan.lo:plan.hi], rot_y, 2 * n + 1, k, eps, check=False)
+        q.put((rank, out["S2_unmutated"].numpy(), out["N"].numpy(), out["Lambda"].numpy(), out["Ps"].numpy(),
+               float(out["sigma_T"].item())))
+    except Exception as e:      # fail fast instead of letting the parent wait for the queue
+        q.put((rank, repr(e)))
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+def test_pipeline_world2_gloo_matches_single():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in range(2)], key=lambda t: t[0])
+    assert all(len(r) == 6 for r in res), res
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    N, n, k, eps = 301, 7, 60, 0.7
+    R9, ed, rot9, rot_y = _pipeline_inputs(N, n)
+    ref = run_pipeline(OracleOps(), ShardPlan(N), ed, rot9, rot_y, 2 * n + 1, k, eps, check=False)
+    for r in res:
+        # (the CPU stand-in's BLAS rounds a row block and the full matrix differently)
+        assert np.allclose(r[1], ref["S2_unmutated"].numpy(), rtol=0, atol=1e-12)
+        assert np.mean(r[2] == ref["N"].numpy()) > 0.999
+        assert np.allclose(r[3], ref["Lambda"].numpy(), atol=1e-9)
+        assert np.max(orc.principal_angles(r[4], ref["Ps"].numpy())) < 1e-5
+        assert abs(r[5] - float(ref["sigma_T"].item())) < 1e-3
+    assert np.array_equal(res[0][3], res[1][3])      # ranks agree bitwise

@@ -1,0 +1,291 @@
+// K4 -- orientation retrieval: linear fit of the 9 non-trivial diffusion coordinates to the 9
+// rotation-matrix elements, per-pattern 3x3 projection, quaternions, all-pairs geodesic error.
+//
+// Restates compute.py:103-112 (lsq_linear: M = ((b^T A) pinv(A^T A))^T), diffusion.py:144-174
+// (Recon = X c; per-row polar_decompose; rot_mat_to_quat for estimate and truth),
+// compute.py:51-55 (polar_decompose), rotation.py:165-210 (R -> axis -> quaternion) and
+// rotation.py:214-244 (Sigma_T = 2 sum |acos(clip(q1_i.q1_j,0,1)) - acos(clip(q2_i.q2_j,0,1))| / (N(N-1))).
+// Everything is FP64.  polar_mode: 0 = reference-compat U.Vh^T (compute.py:53, depends on the
+// SVD sign convention -- ours is Jacobi's, not LAPACK's), 1 = polar factor
+// U.Vh (src/octave/PolarDecompose.m), 2 = nearest rotation (det fixed to +1).
+#include "common.cuh"
+#include "v3s.h"
+
+namespace v3s {
+
+constexpr int FIT_ROWS = 128;
+
+// partial sums of X^T X (81) and X^T Y (81); X = Ps[:, 1:10] (ld = ldx), Y = R^T rows [N, 9]
+__global__ void __launch_bounds__(192)
+fit_gram_kernel(const double* __restrict__ Ps, int ldx, const double* __restrict__ Y, long long n_rows,
+                double* __restrict__ out162) {
+  __shared__ double sx[FIT_ROWS][9], sy[FIT_ROWS][9];
+  const int tid = threadIdx.x;
+  double acc = 0.0;
+  const int which = tid / 81, e = tid % 81, a = e / 9, b = e % 9;   // tid < 162 active
+  for (long long r0 = (long long)blockIdx.x * FIT_ROWS; r0 < n_rows; r0 += (long long)gridDim.x * FIT_ROWS) {
+    __syncthreads();
+    for (int i = tid; i < FIT_ROWS * 9; i += blockDim.x) {
+      const int rr = i / 9, cc = i % 9;
+      const long long r = r0 + rr;
+      sx[rr][cc] = r < n_rows ? Ps[r * ldx + 1 + cc] : 0.0;
+      sy[rr][cc] = r < n_rows ? Y[r * 9 + cc] : 0.0;
+    }
+    __syncthreads();
+    if (tid < 162) {
+      if (which == 0) for (int rr = 0; rr < FIT_ROWS; ++rr) acc += sx[rr][a] * sx[rr][b];
+      else            for (int rr = 0; rr < FIT_ROWS; ++rr) acc += sx[rr][a] * sy[rr][b];
+    }
+  }
+  if (tid < 162) atomicAdd(&out162[tid], acc);
+}
+
+// Jacobi eigen-decomposition of a symmetric n x n matrix (n <= 9), single thread.
+__device__ void jacobi_sym(double* A, double* V, int n) {
+  for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) V[i * n + j] = (i == j) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    double off = 0.0, diag = 0.0;
+    for (int i = 0; i < n; ++i) { diag += A[i * n + i] * A[i * n + i]; for (int j = i + 1; j < n; ++j) off += A[i * n + j] * A[i * n + j]; }
+    if (off <= 1e-60 || off <= 1e-34 * diag) break;
+    for (int p = 0; p < n - 1; ++p)
+      for (int q = p + 1; q < n; ++q) {
+        const double apq = A[p * n + q];
+        if (apq == 0.0) continue;
+        const double theta = (A[q * n + q] - A[p * n + p]) / (2.0 * apq);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < n; ++k) {
+          const double akp = A[k * n + p], akq = A[k * n + q];
+          A[k * n + p] = c * akp - s * akq; A[k * n + q] = s * akp + c * akq;
+        }
+        for (int k = 0; k < n; ++k) {
+          const double apk = A[p * n + k], aqk = A[q * n + k];
+          A[p * n + k] = c * apk - s * aqk; A[q * n + k] = s * apk + c * aqk;
+        }
+        for (int k = 0; k < n; ++k) {
+          const double vkp = V[k * n + p], vkq = V[k * n + q];
+          V[k * n + p] = c * vkp - s * vkq; V[k * n + q] = s * vkp + c * vkq;
+        }
+      }
+  }
+}
+
+// c = pinv(X^T X) (X^T Y); numpy's pinv cut-off: singular values <= 1e-15 * max are dropped
+__global__ void fit_solve_kernel(const double* __restrict__ in162, double* __restrict__ c81) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double A[81], V[81], pinv[81];
+  for (int i = 0; i < 81; ++i) A[i] = in162[i];
+  for (int i = 0; i < 9; ++i) for (int j = i + 1; j < 9; ++j) { const double m = 0.5 * (A[i * 9 + j] + A[j * 9 + i]); A[i * 9 + j] = A[j * 9 + i] = m; }
+  jacobi_sym(A, V, 9);
+  double wmax = 0.0;
+  for (int i = 0; i < 9; ++i) wmax = fmax(wmax, fabs(A[i * 9 + i]));
+  for (int i = 0; i < 9; ++i)
+    for (int j = 0; j < 9; ++j) {
+      double s = 0.0;
+      for (int k = 0; k < 9; ++k) {
+        const double w = A[k * 9 + k];
+        if (fabs(w) > 1e-15 * wmax) s += V[i * 9 + k] * V[j * 9 + k] / w;
+      }
+      pinv[i * 9 + j] = s;
+    }
+  const double* xty = in162 + 81;
+  for (int i = 0; i < 9; ++i)
+    for (int j = 0; j < 9; ++j) {
+      double s = 0.0;
+      for (int k = 0; k < 9; ++k) s += pinv[i * 9 + k] * xty[k * 9 + j];
+      c81[i * 9 + j] = s;
+    }
+}
+
+__device__ __forceinline__ void quat_from_rot(const double* R, double* q) {
+  // rotation.py:165-202
+  const double x = R[7] - R[5], y = R[2] - R[6], z = R[3] - R[1];
+  const double s = sqrt(x * x + y * y + z * z);
+  if (s != 0.0) {
+    const double theta = atan2(s, R[0] + R[4] + R[8] - 1.0);
+    const double f = theta / s;
+    const double ax = f * x, ay = f * y, az = f * z;
+    const double th = sqrt(ax * ax + ay * ay + az * az);
+    if (th == 0.0) { q[0] = 1; q[1] = q[2] = q[3] = 0; return; }
+    const double g = sin(th / 2) / th;
+    q[0] = cos(th / 2); q[1] = g * ax; q[2] = g * ay; q[3] = g * az;
+  } else {
+    q[0] = 1; q[1] = q[2] = q[3] = 0;
+  }
+}
+
+__global__ void __launch_bounds__(128)
+fit_project_kernel(const double* __restrict__ Ps, int ldx, const double* __restrict__ Y, long long n_rows,
+                   const double* __restrict__ c81, int polar_mode, double* __restrict__ recon_pre,
+                   double* __restrict__ rproj, double* __restrict__ quat_est, double* __restrict__ quat_true) {
+  __shared__ double sc[81];
+  if (threadIdx.x < 81) sc[threadIdx.x] = c81[threadIdx.x];
+  __syncthreads();
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < n_rows; r += (long long)gridDim.x * blockDim.x) {
+    double x[9], M[9];
+    for (int a = 0; a < 9; ++a) x[a] = Ps[r * ldx + 1 + a];
+    for (int b = 0; b < 9; ++b) {
+      double s = 0.0;
+      for (int a = 0; a < 9; ++a) s += x[a] * sc[a * 9 + b];
+      M[b] = s;
+      if (recon_pre) recon_pre[r * 9 + b] = s;
+    }
+    // SVD of M (row-major 3x3) through the eigen-decomposition of M^T M
+    double S[9], V[9];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) S[i * 3 + j] = M[0 + i] * M[0 + j] + M[3 + i] * M[3 + j] + M[6 + i] * M[6 + j];
+    jacobi_sym(S, V, 3);
+    // order singular values descending
+    int ord[3] = {0, 1, 2};
+    double w[3] = {S[0], S[4], S[8]};
+    for (int i = 0; i < 2; ++i) for (int j = 0; j < 2 - i; ++j) if (w[ord[j]] < w[ord[j + 1]]) { const int t = ord[j]; ord[j] = ord[j + 1]; ord[j + 1] = t; }
+    double Vs[9], U[9];
+    for (int k = 0; k < 3; ++k) for (int i = 0; i < 3; ++i) Vs[i * 3 + k] = V[i * 3 + ord[k]];
+    // U columns: u_k = M v_k / sigma_k; complete degenerate directions by orthogonalisation
+    double sig[3];
+    for (int k = 0; k < 3; ++k) {
+      double u[3];
+      for (int i = 0; i < 3; ++i) u[i] = M[i * 3 + 0] * Vs[0 * 3 + k] + M[i * 3 + 1] * Vs[1 * 3 + k] + M[i * 3 + 2] * Vs[2 * 3 + k];
+      sig[k] = sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+      for (int i = 0; i < 3; ++i) U[i * 3 + k] = u[i];
+    }
+    const double tiny = 1e-13 * fmax(sig[0], 1e-300);
+    if (sig[0] > tiny) for (int i = 0; i < 3; ++i) U[i * 3 + 0] /= sig[0]; else { U[0] = 1; U[3] = 0; U[6] = 0; }
+    if (sig[1] > tiny) {
+      for (int i = 0; i < 3; ++i) U[i * 3 + 1] /= sig[1];
+    } else {   // any unit vector orthogonal to u0
+      const double a0 = U[0], a1 = U[3], a2 = U[6];
+      double t[3] = {0, 0, 0};
+      if (fabs(a0) <= fabs(a1) && fabs(a0) <= fabs(a2)) t[0] = 1; else if (fabs(a1) <= fabs(a2)) t[1] = 1; else t[2] = 1;
+      const double dt = t[0] * a0 + t[1] * a1 + t[2] * a2;
+      double v0 = t[0] - dt * a0, v1 = t[1] - dt * a1, v2 = t[2] - dt * a2;
+      const double nv = sqrt(v0 * v0 + v1 * v1 + v2 * v2);
+      U[1] = v0 / nv; U[4] = v1 / nv; U[7] = v2 / nv;
+    }
+    if (sig[2] > tiny) {
+      for (int i = 0; i < 3; ++i) U[i * 3 + 2] /= sig[2];
+    } else {   // u2 = u0 x u1, sign chosen so that det(U) = det(V)
+      double c0 = U[3] * U[7] - U[6] * U[4], c1 = U[6] * U[1] - U[0] * U[7], c2 = U[0] * U[4] - U[3] * U[1];
+      const double detV = Vs[0] * (Vs[4] * Vs[8] - Vs[5] * Vs[7]) - Vs[1] * (Vs[3] * Vs[8] - Vs[5] * Vs[6]) + Vs[2] * (Vs[3] * Vs[7] - Vs[4] * Vs[6]);
+      const double sgn = detV < 0 ? -1.0 : 1.0;
+      U[2] = sgn * c0; U[5] = sgn * c1; U[8] = sgn * c2;
+    }
+    double Rp[9];
+    if (polar_mode == 0) {            // U @ Vh.T == U @ V   (compute.py:53)
+      for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Rp[i * 3 + j] = U[i * 3 + 0] * Vs[0 * 3 + j] + U[i * 3 + 1] * Vs[1 * 3 + j] + U[i * 3 + 2] * Vs[2 * 3 + j];
+    } else {                          // U @ Vh == U @ V^T
+      double d3 = 1.0;
+      if (polar_mode == 2) {
+        const double detU = U[0] * (U[4] * U[8] - U[5] * U[7]) - U[1] * (U[3] * U[8] - U[5] * U[6]) + U[2] * (U[3] * U[7] - U[4] * U[6]);
+        const double detV = Vs[0] * (Vs[4] * Vs[8] - Vs[5] * Vs[7]) - Vs[1] * (Vs[3] * Vs[8] - Vs[5] * Vs[6]) + Vs[2] * (Vs[3] * Vs[7] - Vs[4] * Vs[6]);
+        d3 = (detU * detV < 0) ? -1.0 : 1.0;
+      }
+      for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Rp[i * 3 + j] = U[i * 3 + 0] * Vs[j * 3 + 0] + U[i * 3 + 1] * Vs[j * 3 + 1] + d3 * U[i * 3 + 2] * Vs[j * 3 + 2];
+    }
+    if (rproj) for (int i = 0; i < 9; ++i) rproj[r * 9 + i] = Rp[i];
+    double q[4];
+    quat_from_rot(Rp, q);
+    for (int i = 0; i < 4; ++i) quat_est[r * 4 + i] = q[i];
+    double Rt[9];
+    for (int i = 0; i < 9; ++i) Rt[i] = Y[r * 9 + i];
+    quat_from_rot(Rt, q);
+    for (int i = 0; i < 4; ++i) quat_true[r * 4 + i] = q[i];
+  }
+}
+
+// sum over i in [row0,row0+n_rows), j in [0,N) of |acos(clip(q1_i.q1_j)) - acos(clip(q2_i.q2_j))|
+constexpr int SG_T = 256;
+__global__ void __launch_bounds__(SG_T)
+sigma_pairs_kernel(const double* __restrict__ q1, const double* __restrict__ q2, long long N, long long row0,
+                   long long n_rows, double* __restrict__ partials) {
+  __shared__ double sj1[SG_T][4], sj2[SG_T][4];
+  __shared__ double red[32];
+  const int tid = threadIdx.x;
+  const long long i = row0 + (long long)blockIdx.x * SG_T + tid;
+  const bool i_ok = i < row0 + n_rows;
+  double a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0};
+  if (i_ok) for (int t = 0; t < 4; ++t) { a1[t] = q1[i * 4 + t]; a2[t] = q2[i * 4 + t]; }
+  double acc = 0.0;
+  const long long j_per = ceil_div64(N, gridDim.y);
+  const long long j0 = (long long)blockIdx.y * j_per;
+  long long j1 = j0 + j_per;
+  if (j1 > N) j1 = N;
+  for (long long jb = j0; jb < j1; jb += SG_T) {
+    __syncthreads();
+    const long long j = jb + tid;
+    for (int t = 0; t < 4; ++t) { sj1[tid][t] = j < j1 ? q1[j * 4 + t] : 0.0; sj2[tid][t] = j < j1 ? q2[j * 4 + t] : 0.0; }
+    __syncthreads();
+    const int lim = (int)((j1 - jb) < SG_T ? (j1 - jb) : SG_T);
+    if (i_ok) {
+      for (int jj = 0; jj < lim; ++jj) {
+        double d1 = a1[0] * sj1[jj][0] + a1[1] * sj1[jj][1] + a1[2] * sj1[jj][2] + a1[3] * sj1[jj][3];
+        double d2 = a2[0] * sj2[jj][0] + a2[1] * sj2[jj][1] + a2[2] * sj2[jj][2] + a2[3] * sj2[jj][3];
+        d1 = fmin(fmax(d1, 0.0), 1.0);
+        d2 = fmin(fmax(d2, 0.0), 1.0);
+        acc += fabs(acos(d1) - acos(d2));
+      }
+    }
+  }
+  acc = block_sum(acc, red);
+  if (tid == 0) partials[(long long)blockIdx.y * gridDim.x + blockIdx.x] = acc;
+}
+
+__global__ void sum_partials_kernel(const double* __restrict__ partials, int n, double scale, double* __restrict__ out) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += partials[i];
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) out[0] = acc * scale;
+}
+
+}  // namespace v3s
+
+using namespace v3s;
+
+extern "C" int v3s_fit_gram(const double* Ps, int ldx, const double* Y, long long n_rows, double* out162, void* stream) {
+  V3S_REQUIRE(ldx >= 10 && n_rows >= 0, "v3s_fit_gram: Ps needs >= 10 columns");
+  cudaStream_t st = (cudaStream_t)stream;
+  V3S_CUDA(cudaMemsetAsync(out162, 0, sizeof(double) * 162, st));
+  if (n_rows == 0) return 0;
+  long long g = ceil_div64(n_rows, FIT_ROWS);
+  if (g > 2LL * kNumSMs) g = 2LL * kNumSMs;
+  fit_gram_kernel<<<(int)g, 192, 0, st>>>(Ps, ldx, Y, n_rows, out162);
+  V3S_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int v3s_fit_solve(const double* in162, double* c81, void* stream) {
+  fit_solve_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(in162, c81);
+  V3S_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int v3s_fit_project(const double* Ps, int ldx, const double* Y, long long n_rows, const double* c81,
+                               int polar_mode, double* recon_pre, double* rproj, double* quat_est, double* quat_true,
+                               void* stream) {
+  V3S_REQUIRE(ldx >= 10 && n_rows >= 0 && polar_mode >= 0 && polar_mode <= 2, "v3s_fit_project: bad arguments");
+  if (n_rows == 0) return 0;
+  long long g = ceil_div64(n_rows, 128);
+  if (g > 16LL * kNumSMs) g = 16LL * kNumSMs;
+  fit_project_kernel<<<(int)g, 128, 0, (cudaStream_t)stream>>>(Ps, ldx, Y, n_rows, c81, polar_mode, recon_pre, rproj,
+                                                             quat_est, quat_true);
+  V3S_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int v3s_sigma_pairs(const double* quat_est, const double* quat_true, long long N, long long row0,
+                               long long n_rows, double* partials_ws, double* out_sum, void* stream) {
+  V3S_REQUIRE(N >= 1 && row0 >= 0 && n_rows >= 0 && row0 + n_rows <= N, "v3s_sigma_pairs: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_rows == 0) { V3S_CUDA(cudaMemsetAsync(out_sum, 0, sizeof(double), st)); return 0; }
+  const int gx = (int)ceil_div64(n_rows, SG_T);
+  int gy = (int)ceil_div64(8LL * kNumSMs, gx);
+  const long long maxy = ceil_div64(N, SG_T);
+  if (gy > maxy) gy = (int)maxy;
+  if (gy < 1) gy = 1;
+  V3S_REQUIRE((long long)gx * gy <= 65536, "v3s_sigma_pairs: partials workspace (65536 doubles) too small");
+  sigma_pairs_kernel<<<dim3(gx, gy), SG_T, 0, st>>>(quat_est, quat_true, N, row0, n_rows, partials_ws);
+  V3S_CHECK_LAUNCH();
+  sum_partials_kernel<<<1, 256, 0, st>>>(partials_ws, gx * gy, 1.0, out_sum);
+  V3S_CHECK_LAUNCH();
+  return 0;
+}

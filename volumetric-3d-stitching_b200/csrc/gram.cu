@@ -1,0 +1,377 @@
+// K2b -- Gram row panel  G[r, c] = <a_r, a_c>  on tcgen05 tensor cores (sm_100a).
+//
+// Replaces np.matmul(A, A.T) in distance.py:56.  FP32-equivalent accuracy from BF16 tensor
+// cores by operand splitting a = hi + lo (prep.cu):  G = hi.hi^T + hi.lo^T + lo.hi^T  (the
+// dropped lo.lo^T term is 2^-18 relative).  All three products accumulate into the same TMEM
+// accumulator, so the split is a K-extension of one GEMM, not three GEMMs.
+//
+// Kernel shape (one CTA per SM, persistent over tiles):
+//   warp 4 lane 0 : TMA producer (cp.async.bulk.tensor, SWIZZLE_128B, 2-stage mbarrier ring)
+//   warp 5 lane 0 : tcgen05.mma issuer (cta_group::1, M=128 x N=256 x K=16, kind::f16/BF16)
+//   warps 0-3     : epilogue, tcgen05.ld TMEM -> registers -> coalesced global stores
+//   TMEM          : 2 accumulators x 256 columns (double buffered: epilogue overlaps next tile)
+// The MMA "M" side (TMEM lanes) carries the column index c of G and the "N" side (TMEM
+// columns) the panel row r, so for a fixed r the 32 lanes of a warp store 128 contiguous bytes.
+#include "common.cuh"
+#include "v3s.h"
+#include <cuda.h>
+
+namespace v3s {
+
+constexpr int BM = 128;        // TMEM lanes   <-> c (all patterns)
+constexpr int BN = 256;        // TMEM columns <-> r (panel rows)
+constexpr int BK = 64;         // bf16 elements per k-block = one 128-byte swizzle atom
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 2;
+constexpr int A_BYTES = BM * BK * 2;
+constexpr int B_BYTES = BN * BK * 2;
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // hi+lo for both operands = 96 KB
+constexpr int GRAM_THREADS = 192;
+constexpr int GRAM_SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (8-row groups 1024 B apart)
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);       // start address, bits [0,14)
+  d |= (uint64_t)0 << 16;                           // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                           // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                           // layout type: SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// instruction descriptor: D=F32, A=B=BF16, both K-major, N=256, M=128
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__global__ void __launch_bounds__(GRAM_THREADS, 1)
+gram_tc_kernel(const __grid_constant__ CUtensorMap tm_c_hi, const __grid_constant__ CUtensorMap tm_c_lo,
+               const __grid_constant__ CUtensorMap tm_r_hi, const __grid_constant__ CUtensorMap tm_r_lo,
+               float* __restrict__ G, long long ldg, int n_cols, int n_rows, int num_kb, int tiles_c, int num_tiles) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tfull = bars + 2 * STAGES;
+  uint64_t* tempty = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 4 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_c_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_c_lo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_r_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_r_lo) : "memory");
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      // ---------------- TMA producer ----------------
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int tc = tile % tiles_c, tr = tile / tiles_c;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], STAGE_BYTES);
+          const uint32_t s = smem_u32(smem + stage * STAGE_BYTES);
+          tma_load_2d(s, &tm_c_hi, kb * BK, tc * BM, &full[stage]);
+          tma_load_2d(s + A_BYTES, &tm_c_lo, kb * BK, tc * BM, &full[stage]);
+          tma_load_2d(s + 2 * A_BYTES, &tm_r_hi, kb * BK, tr * BN, &full[stage]);
+          tma_load_2d(s + 2 * A_BYTES + B_BYTES, &tm_r_lo, kb * BK, tr * BN, &full[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      // ---------------- MMA issuer ----------------
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t s = smem_u32(smem + stage * STAGE_BYTES);
+          const uint64_t a_hi = make_kmajor_sw128_desc(s);
+          const uint64_t a_lo = make_kmajor_sw128_desc(s + A_BYTES);
+          const uint64_t b_hi = make_kmajor_sw128_desc(s + 2 * A_BYTES);
+          const uint64_t b_lo = make_kmajor_sw128_desc(s + 2 * A_BYTES + B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t ko = (uint64_t)((k * UMMA_K * 2) >> 4);   // 32 B per K step, in 16-byte units
+            umma_bf16(d_tmem, a_hi + ko, b_hi + ko, kIdesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_bf16(d_tmem, a_hi + ko, b_lo + ko, kIdesc, 1u);
+            umma_bf16(d_tmem, a_lo + ko, b_hi + ko, kIdesc, 1u);
+          }
+          umma_commit(&empty[stage]);                 // frees the smem stage once these MMAs retire
+          if (kb == num_kb - 1) umma_commit(&tfull[acc]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ---------------- epilogue (warps 0..3 <-> TMEM lane quadrants) ----------------
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int tc = tile % tiles_c, tr = tile / tiles_c;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const int c = tc * BM + warp * 32 + lane;
+      const bool c_ok = c < n_cols;
+      const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(t_row + (uint32_t)(ch * 32), v);
+        tmem_ld_wait();
+        const int r0 = tr * BN + ch * 32;
+        float* dst = G + (long long)r0 * ldg + c;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (c_ok && r0 + j < n_rows) dst[(long long)j * ldg] = __uint_as_float(v[j]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ---- plain FP32 SIMT Gram: validation path for the tensor-core kernel (tests, debugging) ----
+__global__ void __launch_bounds__(256)
+gram_simt_kernel(const float* __restrict__ a_cols, const float* __restrict__ a_rows, int P, float* __restrict__ G,
+                 long long ldg, int n_cols, int n_rows) {
+  __shared__ float sc[16][65], sr[16][65];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 64;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < P; k0 += 16) {
+    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+      const int rr = i >> 4, kk = i & 15;
+      const int k = k0 + kk;
+      sc[kk][rr] = (c0 + rr < n_cols && k < P) ? a_cols[(long long)(c0 + rr) * P + k] : 0.f;
+      sr[kk][rr] = (r0 + rr < n_rows && k < P) ? a_rows[(long long)(r0 + rr) * P + k] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float cv[4], rv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { cv[i] = sc[kk][tx * 4 + i]; rv[i] = sr[kk][ty * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(rv[i], cv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      const int r = r0 + ty * 4 + i, c = c0 + tx * 4 + j;
+      if (r < n_rows && c < n_cols) G[(long long)r * ldg + c] = acc[i][j];
+    }
+}
+
+// Exact all-pairs round distance d = 2 asin(|a_r - a_c| / 2) (== arccos(<a_r,a_c>) for unit rows),
+// FP32 differences, FP64 result: the dense form of convert_to_round_distance (distance.py:51-63).
+__global__ void __launch_bounds__(256)
+round_distance_kernel(const float* __restrict__ a, int P, const int* __restrict__ zero_flag, double* __restrict__ B,
+                      long long n) {
+  __shared__ float sc[16][65], sr[16][65];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const long long c0 = (long long)blockIdx.x * 64, r0 = (long long)blockIdx.y * 64;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < P; k0 += 16) {
+    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+      const int rr = i >> 4, kk = i & 15;
+      const int k = k0 + kk;
+      sc[kk][rr] = (c0 + rr < n && k < P) ? a[(c0 + rr) * P + k] : 0.f;
+      sr[kk][rr] = (r0 + rr < n && k < P) ? a[(r0 + rr) * P + k] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float cv[4], rv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { cv[i] = sc[kk][tx * 4 + i]; rv[i] = sr[kk][ty * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float d = rv[i] - cv[j]; acc[i][j] = fmaf(d, d, acc[i][j]); }
+    }
+    __syncthreads();
+  }
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      const long long r = r0 + ty * 4 + i, c = c0 + tx * 4 + j;
+      if (r < n && c < n) {
+        double h = 0.5 * sqrt((double)acc[i][j]);
+        if (h > 1.0) h = 1.0;
+        double d = 2.0 * asin(h);
+        if (zero_flag && (zero_flag[r] || zero_flag[c])) d = 0.0;   // NaN -> 0, distance.py:58
+        B[r * n + c] = d;
+      }
+    }
+}
+
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_bf16_map(CUtensorMap* map, const void* base, long long rows, int Ppad, int box_rows) {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    V3S_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    V3S_REQUIRE(p != nullptr && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available from the driver");
+    fn = (PFN_tmapEncodeTiled)p;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)Ppad, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)Ppad * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  V3S_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
+
+}  // namespace v3s
+
+using namespace v3s;
+
+extern "C" int v3s_gram_rows(const void* all_hi, const void* all_lo, long long n_cols, const void* rows_hi,
+                             const void* rows_lo, long long n_rows, int Ppad, float* G, long long ldg, void* stream) {
+  V3S_REQUIRE(Ppad > 0 && Ppad % BK == 0, "v3s_gram_rows: Ppad=%d must be a positive multiple of %d", Ppad, BK);
+  V3S_REQUIRE(n_cols >= 0 && n_rows >= 0 && ldg >= n_cols, "v3s_gram_rows: bad shape");
+  V3S_REQUIRE(n_cols < (1LL << 31) && n_rows < (1LL << 31), "v3s_gram_rows: extents must fit int32");
+  if (n_cols == 0 || n_rows == 0) return 0;
+  CUtensorMap mc_hi, mc_lo, mr_hi, mr_lo;
+  if (make_bf16_map(&mc_hi, all_hi, n_cols, Ppad, BM)) return 1;
+  if (make_bf16_map(&mc_lo, all_lo, n_cols, Ppad, BM)) return 1;
+  if (make_bf16_map(&mr_hi, rows_hi, n_rows, Ppad, BN)) return 1;
+  if (make_bf16_map(&mr_lo, rows_lo, n_rows, Ppad, BN)) return 1;
+  const int tiles_c = (int)ceil_div64(n_cols, BM), tiles_r = (int)ceil_div64(n_rows, BN);
+  const long long nt = (long long)tiles_c * tiles_r;
+  V3S_REQUIRE(nt < (1LL << 31), "v3s_gram_rows: too many tiles");
+  static bool attr_set = false;
+  if (!attr_set) {
+    V3S_CUDA(cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM));
+    attr_set = true;
+  }
+  const int grid = (int)(nt < kNumSMs ? nt : kNumSMs);
+  gram_tc_kernel<<<grid, GRAM_THREADS, GRAM_SMEM, (cudaStream_t)stream>>>(mc_hi, mc_lo, mr_hi, mr_lo, G, ldg, (int)n_cols,
+                                                                          (int)n_rows, Ppad / BK, tiles_c, (int)nt);
+  V3S_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int v3s_gram_rows_simt(const float* a_all, long long n_cols, const float* a_rows, long long n_rows, int P,
+                                  float* G, long long ldg, void* stream) {
+  V3S_REQUIRE(P > 0 && n_cols >= 0 && n_rows >= 0 && ldg >= n_cols, "v3s_gram_rows_simt: bad shape");
+  if (n_cols == 0 || n_rows == 0) return 0;
+  dim3 grid((unsigned)ceil_div64(n_cols, 64), (unsigned)ceil_div64(n_rows, 64));
+  gram_simt_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a_all, a_rows, P, G, ldg, (int)n_cols, (int)n_rows);
+  V3S_CHECK_LAUNCH();
+  return 0;
+}
+
+
+extern "C" int v3s_round_distance_dense(const float* a_f32, long long n, int P, const int* zero_flag, double* B,
+                                        void* stream) {
+  V3S_REQUIRE(n >= 0 && P > 0, "v3s_round_distance_dense: bad shape");
+  if (n == 0) return 0;
+  dim3 grid((unsigned)ceil_div64(n, 64), (unsigned)ceil_div64(n, 64));
+  round_distance_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a_f32, P, zero_flag, B, n);
+  V3S_CHECK_LAUNCH();
+  return 0;
+}

@@ -1,0 +1,262 @@
+// K2b (second half) -- k nearest neighbours from the Gram row panel.
+//
+// Replaces distance.py:56-59 (arccos epilogue) and distance.py:26-48 (per-row full argsort).
+// arccos is monotone, so the k nearest patterns of row r are its k largest Gram entries:
+//   1. select_kernel : exact radix select (4 x 8-bit passes over the row, L2-resident) of the
+//                      kk = k + margin largest g; ties broken towards the lower index
+//   2. refine_sort_kernel : recompute the kk selected distances from the FP32 unit rows with the
+//                      well-conditioned form d = 2 asin(|a_r - a_c| / 2) (== arccos(<a_r,a_c>) for
+//                      unit vectors; arccos(g) itself amplifies FP32 error by 1/(d sin d)),
+//                      bitonic-sort by (d, index) and keep the first k.
+// Zero-norm rows (0/0 -> NaN in the reference, then NaN -> 0 at distance.py:58) get distance 0 to
+// every pattern, as in the reference.
+#include "common.cuh"
+#include "v3s.h"
+
+namespace v3s {
+
+constexpr int kSelThreads = 256;
+
+__device__ __forceinline__ float load_g(const float* __restrict__ grow, int c, bool row_zero,
+                                        const int* __restrict__ zero_flag) {
+  float g = grow[c];
+  if (zero_flag && (row_zero || zero_flag[c])) g = 1.0f;
+  return g;
+}
+
+__global__ void __launch_bounds__(kSelThreads)
+select_kernel(const float* __restrict__ G, long long ldg, int n_rows, int n_cols, long long row0, int kk,
+              const int* __restrict__ zero_flag, int* __restrict__ cand) {
+  __shared__ int hist[256];
+  __shared__ uint32_t s_prefix;
+  __shared__ int s_remaining, s_count_eq, s_slot, s_eq_taken;
+  __shared__ int s_warp_cnt[kSelThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  for (int r = blockIdx.x; r < n_rows; r += gridDim.x) {
+    const float* grow = G + (long long)r * ldg;
+    const bool row_zero = zero_flag ? (zero_flag[row0 + r] != 0) : false;
+    uint32_t prefix = 0, mask = 0;
+    int remaining = kk;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+      __syncthreads();
+      hist[tid] = 0;
+      __syncthreads();
+      for (int c = tid; c < n_cols; c += kSelThreads) {
+        const uint32_t key = float_to_key(load_g(grow, c, row_zero, zero_flag));
+        if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int cum = 0, d = 255;
+        for (; d > 0; --d) {
+          if (cum + hist[d] >= remaining) break;
+          cum += hist[d];
+        }
+        s_prefix = prefix | ((uint32_t)d << shift);
+        s_remaining = remaining - cum;
+        s_count_eq = hist[d];
+      }
+      __syncthreads();
+      prefix = s_prefix;
+      remaining = s_remaining;
+      mask |= 255u << shift;
+    }
+    // prefix == key of the kk-th largest entry; `remaining` entries equal to it are still needed
+    const uint32_t T = prefix;
+    const bool ties = (s_count_eq != remaining);
+    __syncthreads();
+    if (tid == 0) { s_slot = 0; s_eq_taken = 0; }
+    __syncthreads();
+    int* out = cand + (long long)r * kk;
+    if (!ties) {
+      for (int c = tid; c < n_cols; c += kSelThreads) {
+        const uint32_t key = float_to_key(load_g(grow, c, row_zero, zero_flag));
+        if (key >= T) out[atomicAdd(&s_slot, 1)] = c;
+      }
+    } else {
+      // ordered pass: entries > T unconditionally, entries == T lowest index first
+      for (int c0 = 0; c0 < n_cols; c0 += kSelThreads) {
+        const int c = c0 + tid;
+        uint32_t key = 0;
+        if (c < n_cols) key = float_to_key(load_g(grow, c, row_zero, zero_flag));
+        const bool gt = (c < n_cols) && key > T;
+        const bool eq = (c < n_cols) && key == T;
+        if (gt) out[atomicAdd(&s_slot, 1)] = c;
+        const unsigned bal = __ballot_sync(0xffffffffu, eq);
+        if (lane == 0) s_warp_cnt[warp] = __popc(bal);
+        __syncthreads();
+        int before = s_eq_taken;
+        for (int w = 0; w < warp; ++w) before += s_warp_cnt[w];
+        before += __popc(bal & ((1u << lane) - 1u));
+        if (eq && before < remaining) out[atomicAdd(&s_slot, 1)] = c;
+        __syncthreads();
+        if (tid == 0) {
+          int tot = 0;
+          for (int w = 0; w < kSelThreads / 32; ++w) tot += s_warp_cnt[w];
+          s_eq_taken += tot;
+        }
+        __syncthreads();
+      }
+    }
+  }
+}
+
+constexpr int kRefThreads = 256;
+
+__global__ void __launch_bounds__(kRefThreads)
+refine_sort_kernel(const float* __restrict__ a_rows, const float* __restrict__ a_all, int P, long long row0, int n_rows,
+                   const int* __restrict__ cand, int kk, int kk_pad, int k, const int* __restrict__ zero_flag,
+                   int cache_row, const double* __restrict__ Bd, long long ldb, double* __restrict__ S2,
+                   int* __restrict__ Nbr) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* sd = reinterpret_cast<double*>(smem_raw);          // kk_pad
+  int* si = reinterpret_cast<int*>(sd + kk_pad);              // kk_pad
+  float* srow = reinterpret_cast<float*>(si + kk_pad);        // P (if cache_row)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool vec4 = (P % 4 == 0);
+
+  for (int r = blockIdx.x; r < n_rows; r += gridDim.x) {
+    __syncthreads();
+    const float* arow = a_rows ? a_rows + (long long)r * P : nullptr;
+    if (Bd) {   // dense mode: exact FP64 values gathered from the caller's matrix
+      for (int s = tid; s < kk_pad; s += kRefThreads) {
+        const bool ok = s < kk;
+        const int j = ok ? cand[(long long)r * kk + s] : 0x7fffffff;
+        sd[s] = ok ? Bd[(long long)r * ldb + j] : 1e300;
+        si[s] = j;
+      }
+    }
+    if (!Bd && cache_row) {
+      for (int p = tid; p < P; p += kRefThreads) srow[p] = arow[p];
+    }
+    if (!Bd) {
+      for (int s = tid; s < kk_pad; s += kRefThreads) {
+        sd[s] = 1e300;   // padding sorts last
+        si[s] = 0x7fffffff;
+      }
+    }
+    __syncthreads();
+    const float* xr = cache_row ? srow : arow;
+    const bool rz = zero_flag ? (zero_flag[row0 + r] != 0) : false;
+    for (int s = warp; s < (Bd ? 0 : kk); s += kRefThreads / 32) {
+      const int j = cand[(long long)r * kk + s];
+      const float* aj = a_all + (long long)j * P;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      if (vec4) {
+        const float4* x4 = reinterpret_cast<const float4*>(xr);
+        const float4* y4 = reinterpret_cast<const float4*>(aj);
+        for (int p = lane; p < P / 4; p += 32) {
+          const float4 x = x4[p], y = __ldg(&y4[p]);
+          const float d0 = x.x - y.x, d1 = x.y - y.y, d2 = x.z - y.z, d3 = x.w - y.w;
+          a0 = fmaf(d0, d0, a0); a1 = fmaf(d1, d1, a1); a2 = fmaf(d2, d2, a2); a3 = fmaf(d3, d3, a3);
+        }
+      } else {
+        for (int p = lane; p < P; p += 32) {
+          const float d0 = xr[p] - __ldg(&aj[p]);
+          a0 = fmaf(d0, d0, a0);
+        }
+      }
+      double ss = ((double)a0 + (double)a1) + ((double)a2 + (double)a3);
+      ss = warp_sum(ss);
+      if (lane == 0) {
+        double half = 0.5 * sqrt(ss);
+        if (half > 1.0) half = 1.0;
+        double d = 2.0 * asin(half);
+        if (zero_flag && (rz || zero_flag[j])) d = 0.0;
+        sd[s] = d;
+        si[s] = j;
+      }
+    }
+    __syncthreads();
+    // bitonic sort of kk_pad (d, idx) pairs, ascending by d then idx
+    for (int size = 2; size <= kk_pad; size <<= 1) {
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        for (int t = tid; t < kk_pad / 2; t += kRefThreads) {
+          const int lo = 2 * t - (t & (stride - 1));
+          const int hi = lo + stride;
+          const bool up = ((lo & size) == 0);
+          const double dl = sd[lo], dh = sd[hi];
+          const int il = si[lo], ih = si[hi];
+          const bool gt = (dl > dh) || (dl == dh && il > ih);
+          if (gt == up) { sd[lo] = dh; sd[hi] = dl; si[lo] = ih; si[hi] = il; }
+        }
+        __syncthreads();
+      }
+    }
+    for (int s = tid; s < k; s += kRefThreads) {
+      S2[(long long)r * k + s] = sd[s];
+      Nbr[(long long)r * k + s] = si[s];
+    }
+  }
+}
+
+}  // namespace v3s
+
+using namespace v3s;
+
+extern "C" int v3s_knn_from_gram(const float* G, long long ldg, long long n_rows, long long n_cols, long long row0,
+                                 const float* a_rows, const float* a_all, int P, int k, int margin, const int* zero_flag,
+                                 int* cand_ws, double* S2, int* Nbr, void* stream) {
+  V3S_REQUIRE(k >= 1 && margin >= 0, "v3s_knn_from_gram: bad k/margin");
+  V3S_REQUIRE(k <= n_cols, "Number of nearest neighbors to preserve is too high.");   // distance.py:33-34
+  V3S_REQUIRE(n_rows >= 0 && n_cols < (1LL << 31) && n_rows < (1LL << 31) && ldg >= n_cols, "v3s_knn_from_gram: bad shape");
+  if (n_rows == 0) return 0;
+  long long kk = (long long)k + margin;
+  if (kk > n_cols) kk = n_cols;
+  int kk_pad = 4;
+  while (kk_pad < kk) kk_pad <<= 1;
+  V3S_REQUIRE(kk_pad <= 4096, "v3s_knn_from_gram: k + margin = %lld too large (max 4096)", kk);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = (int)(n_rows < 16LL * kNumSMs ? n_rows : 16LL * kNumSMs);
+  select_kernel<<<grid, kSelThreads, 0, st>>>(G, ldg, (int)n_rows, (int)n_cols, row0, (int)kk, zero_flag, cand_ws);
+  V3S_CHECK_LAUNCH();
+  const size_t base = (size_t)kk_pad * (sizeof(double) + sizeof(int));
+  const int cache_row = (base + (size_t)P * 4 <= 200 * 1024) ? 1 : 0;
+  const size_t smem = base + (cache_row ? (size_t)P * 4 : 0);
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    V3S_CUDA(cudaFuncSetAttribute(refine_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  const int grid2 = (int)(n_rows < 8LL * kNumSMs ? n_rows : 8LL * kNumSMs);
+  refine_sort_kernel<<<grid2, kRefThreads, smem, st>>>(a_rows, a_all, P, row0, (int)n_rows, cand_ws, (int)kk, kk_pad, k,
+                                                      zero_flag, cache_row, nullptr, 0, S2, Nbr);
+  V3S_CHECK_LAUNCH();
+  return 0;
+}
+
+
+namespace v3s {
+__global__ void neg_key_kernel(const double* __restrict__ B, long long n, float* __restrict__ key) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
+    key[e] = -(float)B[e];
+}
+}  // namespace v3s
+
+// DistanceMatrix.knn_from_round_distance (distance.py:26-48) on a caller-supplied dense FP64
+// matrix B [n,n]: per row the k smallest entries, ascending, with their column indices.
+// key_ws: float [n,n]; cand_ws: int [n, min(k+margin, n)].
+extern "C" int v3s_knn_from_dense(const double* B, long long n, int k, int margin, float* key_ws, int* cand_ws,
+                                  double* S2, int* Nbr, void* stream) {
+  V3S_REQUIRE(k >= 1 && margin >= 0 && n >= 1 && n < (1LL << 31), "v3s_knn_from_dense: bad arguments");
+  V3S_REQUIRE(k <= n, "Number of nearest neighbors to preserve is too high.");
+  cudaStream_t st = (cudaStream_t)stream;
+  long long kk = (long long)k + margin;
+  if (kk > n) kk = n;
+  int kk_pad = 4;
+  while (kk_pad < kk) kk_pad <<= 1;
+  V3S_REQUIRE(kk_pad <= 4096, "v3s_knn_from_dense: k + margin too large (max 4096)");
+  long long g = ceil_div64(n * n, 256);
+  if (g > 16LL * kNumSMs) g = 16LL * kNumSMs;
+  neg_key_kernel<<<(int)g, 256, 0, st>>>(B, n * n, key_ws);
+  V3S_CHECK_LAUNCH();
+  const int grid = (int)(n < 16LL * kNumSMs ? n : 16LL * kNumSMs);
+  select_kernel<<<grid, kSelThreads, 0, st>>>(key_ws, n, (int)n, (int)n, 0, (int)kk, nullptr, cand_ws);
+  V3S_CHECK_LAUNCH();
+  const size_t smem = (size_t)kk_pad * (sizeof(double) + sizeof(int));
+  refine_sort_kernel<<<grid, kRefThreads, smem, st>>>(nullptr, nullptr, 0, 0, (int)n, cand_ws, (int)kk, kk_pad, k, nullptr,
+                                                     0, B, n, S2, Nbr);
+  V3S_CHECK_LAUNCH();
+  return 0;
+}

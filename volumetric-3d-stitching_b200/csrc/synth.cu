@@ -1,0 +1,262 @@
+// K1 -- pattern synthesis, reference-exact mode.
+//
+// Restates projection.py:55-71 (generate_single_image) + rotation.py:143-162
+// (rotate_structure_index) per pattern, fused in one persistent CTA per SM:
+//   A. ED_rot[i,j,k] = Tri(F)(Rm (U_j, U_k, U_i))           (trilinear gather from smem)
+//      fused with the axis-2 DFT restricted to the few k_z planes the Ewald sphere touches
+//   B. 2-D DFT over axes 0,1 of those planes, magnitude, fftshift
+//   C. trilinear sampling at the (rotation-independent) detector q-grid, circular mask
+// The object F stays resident in shared memory across all patterns of the CTA.
+// Coordinates / interpolation weights are computed in FP64, values in FP32.
+#include "common.cuh"
+#include "v3s.h"
+#include <math.h>
+#include <vector>
+
+namespace v3s {
+
+struct PixelTap {   // 16 bytes
+  int   idx;        // i0 | i1<<8 | zrel<<16 | valid<<24
+  float t0, t1, t2;
+};
+
+constexpr int kSynthThreads = 512;
+constexpr int kMaxPlanes = 4;
+
+struct SynthParams {
+  int n;            // voxels per side
+  int nz;           // number of axis-2 planes needed
+  int z0;           // first (shifted) plane index
+  int P;            // pixels per pattern
+  long long N;      // patterns
+};
+
+__global__ void __launch_bounds__(kSynthThreads, 1)
+synth_kernel(const float* __restrict__ ed, const double* __restrict__ rot, const PixelTap* __restrict__ taps,
+             float* __restrict__ out, long long out_stride, SynthParams prm) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n = prm.n, n2 = n * n, n3 = n2 * n, nz = prm.nz;
+  float*  F    = reinterpret_cast<float*>(smem_raw);                         // n^3
+  float2* slab = reinterpret_cast<float2*>(F + ((n3 + 3) & ~3));             // nz*n^2
+  float2* tmp  = slab + nz * n2;                                              // nz*n^2
+  float*  gmag = reinterpret_cast<float*>(tmp + nz * n2);                     // nz*n^2
+  float2* tw   = reinterpret_cast<float2*>(gmag + ((nz * n2 + 1) & ~1));      // n
+  __shared__ double Rm[9];
+
+  const int tid = threadIdx.x;
+  for (int i = tid; i < n3; i += kSynthThreads) F[i] = ed[i];
+  for (int i = tid; i < n; i += kSynthThreads) {
+    double s, c;
+    sincospi(-2.0 * (double)i / (double)n, &s, &c);
+    tw[i] = make_float2((float)c, (float)s);
+  }
+  // frequency index (mod n) of each needed shifted plane: f = c - n/2  (np.fft.fftshift)
+  int fz[kMaxPlanes];
+#pragma unroll
+  for (int z = 0; z < kMaxPlanes; ++z) fz[z] = (((prm.z0 + z) - n / 2) % n + n) % n;
+
+  const double half_n = 0.5 * (double)n;
+  const double U0 = (1.0 - (n + 1) * 0.5) / half_n;   // U_i = (i + 1 - (n+1)/2) / (n/2), rotation.py:146
+  const double Ulast = ((double)n - (n + 1) * 0.5) / half_n;
+
+  for (long long pat = blockIdx.x; pat < prm.N; pat += gridDim.x) {
+    __syncthreads();
+    if (tid < 9) Rm[tid] = rot[pat * 9 + tid];
+    __syncthreads();
+    const double r00 = Rm[0], r01 = Rm[1], r02 = Rm[2], r10 = Rm[3], r11 = Rm[4], r12 = Rm[5], r20 = Rm[6],
+                 r21 = Rm[7], r22 = Rm[8];
+
+    // ---- phase A: rotate + DFT along axis 2 ------------------------------------------
+    for (int col = tid; col < n2; col += kSynthThreads) {
+      const int i = col / n, j = col - i * n;
+      // p = (x, y, z) = (U_j, U_k, U_i): array axes are (z, x, y), projection.py:79
+      const double px = (j + 1 - (n + 1) * 0.5) / half_n, pz = (i + 1 - (n + 1) * 0.5) / half_n;
+      const double b0 = r00 * px + r02 * pz, b1 = r10 * px + r12 * pz, b2 = r20 * px + r22 * pz;
+      float2 acc[kMaxPlanes];
+#pragma unroll
+      for (int z = 0; z < kMaxPlanes; ++z) acc[z] = make_float2(0.f, 0.f);
+      int ph[kMaxPlanes];
+#pragma unroll
+      for (int z = 0; z < kMaxPlanes; ++z) ph[z] = 0;
+      for (int k = 0; k < n; ++k) {
+        const double py = (k + 1 - (n + 1) * 0.5) / half_n;
+        const double q0 = b0 + r01 * py, q1 = b1 + r11 * py, q2 = b2 + r21 * py;
+        float v = 0.f;
+        const bool inb = !(q0 < U0 || q0 > Ulast || q1 < U0 || q1 > Ulast || q2 < U0 || q2 > Ulast);
+        if (inb) {
+          const double f0 = (q0 - U0) * half_n, f1 = (q1 - U0) * half_n, f2 = (q2 - U0) * half_n;
+          int i0 = min(max((int)f0, 0), n - 2), i1 = min(max((int)f1, 0), n - 2), i2 = min(max((int)f2, 0), n - 2);
+          const float t0 = (float)(f0 - i0), t1 = (float)(f1 - i1), t2 = (float)(f2 - i2);
+          const float* b = F + (i0 * n + i1) * n + i2;
+          const float c000 = b[0], c001 = b[1], c010 = b[n], c011 = b[n + 1];
+          const float c100 = b[n2], c101 = b[n2 + 1], c110 = b[n2 + n], c111 = b[n2 + n + 1];
+          const float c00 = c000 + t2 * (c001 - c000), c01 = c010 + t2 * (c011 - c010);
+          const float c10 = c100 + t2 * (c101 - c100), c11 = c110 + t2 * (c111 - c110);
+          const float c0 = c00 + t1 * (c01 - c00), c1 = c10 + t1 * (c11 - c10);
+          v = c0 + t0 * (c1 - c0);
+        }
+#pragma unroll
+        for (int z = 0; z < kMaxPlanes; ++z) {
+          if (z < nz) {
+            const float2 w = tw[ph[z]];
+            acc[z].x = fmaf(v, w.x, acc[z].x);
+            acc[z].y = fmaf(v, w.y, acc[z].y);
+            ph[z] += fz[z];
+            if (ph[z] >= n) ph[z] -= n;
+          }
+        }
+      }
+#pragma unroll
+      for (int z = 0; z < kMaxPlanes; ++z)
+        if (z < nz) slab[z * n2 + col] = acc[z];
+    }
+    __syncthreads();
+
+    // ---- phase B1: DFT along axis 0, output index in fftshift order ------------------
+    for (int o = tid; o < nz * n2; o += kSynthThreads) {
+      const int z = o / n2, r = o - z * n2, c0 = r / n, j = r - c0 * n;
+      const int f = ((c0 - n / 2) % n + n) % n;
+      float2 a = make_float2(0.f, 0.f);
+      int p = 0;
+      const float2* s = slab + z * n2 + j;
+      for (int i = 0; i < n; ++i) {
+        const float2 x = s[i * n], w = tw[p];
+        a.x += x.x * w.x - x.y * w.y;
+        a.y += x.x * w.y + x.y * w.x;
+        p += f; if (p >= n) p -= n;
+      }
+      tmp[o] = a;
+    }
+    __syncthreads();
+    // ---- phase B2: DFT along axis 1, magnitude ---------------------------------------
+    for (int o = tid; o < nz * n2; o += kSynthThreads) {
+      const int z = o / n2, r = o - z * n2, c0 = r / n, c1 = r - c0 * n;
+      const int f = ((c1 - n / 2) % n + n) % n;
+      float2 a = make_float2(0.f, 0.f);
+      int p = 0;
+      const float2* s = tmp + z * n2 + c0 * n;
+      for (int j = 0; j < n; ++j) {
+        const float2 x = s[j], w = tw[p];
+        a.x += x.x * w.x - x.y * w.y;
+        a.y += x.x * w.y + x.y * w.x;
+        p += f; if (p >= n) p -= n;
+      }
+      gmag[o] = sqrtf(a.x * a.x + a.y * a.y);
+    }
+    __syncthreads();
+
+    // ---- phase C: sample on the detector grid -----------------------------------------
+    float* dst = out + pat * out_stride;
+    for (int p = tid; p < prm.P; p += kSynthThreads) {
+      const PixelTap t = taps[p];
+      float v = 0.f;
+      if (t.idx >> 24) {
+        const int i0 = t.idx & 0xff, i1 = (t.idx >> 8) & 0xff, z = (t.idx >> 16) & 0xff;
+        const float* g0 = gmag + z * n2 + i0 * n + i1;
+        const float* g1 = g0 + n2;
+        const float a00 = g0[0] + t.t2 * (g1[0] - g0[0]);
+        const float a01 = g0[1] + t.t2 * (g1[1] - g0[1]);
+        const float a10 = g0[n] + t.t2 * (g1[n] - g0[n]);
+        const float a11 = g0[n + 1] + t.t2 * (g1[n + 1] - g0[n + 1]);
+        const float a0 = a00 + t.t1 * (a01 - a00), a1 = a10 + t.t1 * (a11 - a10);
+        v = a0 + t.t0 * (a1 - a0);
+      }
+      dst[p] = v;
+    }
+  }
+}
+
+// Host-side geometry (projection.py:95-117, 121-160, 164-190), FP64, once per call.
+static int build_taps(int n, int n_p, const v3s_geometry* g, std::vector<PixelTap>& taps, int* z0, int* nz) {
+  const double width = g->pixel * ((double)g->n_p_nobin / (double)n_p) * (double)n_p;  // SuperPixel * N_p
+  // k axis: projection.py:121-126 with Length = max - min of 2e-7 * U
+  std::vector<double> U(n), kax(n);
+  for (int i = 0; i < n; ++i) U[i] = ((double)(i + 1) - (n + 1) / 2.0) / (n / 2.0);
+  const double length = g->grid_scale * U[n - 1] - g->grid_scale * U[0];
+  const double d = length / (n - 1);
+  const double nyq = 0.5 / d;
+  const double N1 = (n - 1) / 2.0;
+  const double scale = 2 * nyq / n;
+  for (int c = 0; c < n; ++c) kax[c] = (-N1 + c) * scale;
+  auto locate = [&](double x, int* idx, double* t) -> bool {
+    if (x < kax[0] || x > kax[n - 1] || x != x) return false;
+    int cnt = 0;                       // searchsorted(..., side='left')
+    while (cnt < n && kax[cnt] < x) ++cnt;
+    int i = cnt - 1;
+    if (i < 0) i = 0;
+    if (i > n - 2) i = n - 2;
+    *idx = i;
+    *t = (x - kax[i]) / (kax[i + 1] - kax[i]);
+    return true;
+  };
+  const int P = n_p * n_p;
+  taps.assign(P, PixelTap{0, 0.f, 0.f, 0.f});
+  std::vector<int> iz(P, -1);
+  int zmin = 1 << 30, zmax = -1;
+  for (int u = 0; u < n_p; ++u) {
+    for (int v = 0; v < n_p; ++v) {
+      // camera_x_y: U = (Width/(N-1)) * (linspace(1,N,N) - (N+1)/2); meshgrid 'xy'
+      const double cx = (width / (n_p - 1)) * ((double)(v + 1) - (n_p + 1) / 2.0);
+      const double cy = (width / (n_p - 1)) * ((double)(u + 1) - (n_p + 1) / 2.0);
+      const double T = g->lambda * sqrt(cx * cx + cy * cy + g->zd * g->zd);
+      const double qx = cx / T, qy = cy / T, qz = g->zd / T - 1.0 / g->lambda;
+      const bool masked = (cx * cx + cy * cy) > (width / 2) * (width / 2);
+      int i0, i1, i2;
+      double t0, t1, t2;
+      if (masked) continue;
+      if (!locate(qx, &i0, &t0) || !locate(qy, &i1, &t1) || !locate(qz, &i2, &t2)) continue;
+      const int p = u * n_p + v;
+      iz[p] = i2;
+      zmin = i2 < zmin ? i2 : zmin;
+      zmax = i2 > zmax ? i2 : zmax;
+      taps[p].idx = i0 | (i1 << 8) | (1 << 24);
+      taps[p].t0 = (float)t0; taps[p].t1 = (float)t1; taps[p].t2 = (float)t2;
+    }
+  }
+  if (zmax < 0) { *z0 = 0; *nz = 2; return 0; }   // every pixel masked / out of range: all-zero patterns
+  *z0 = zmin;
+  *nz = zmax + 2 - zmin;   // planes zmin .. zmax+1
+  for (int p = 0; p < P; ++p)
+    if (iz[p] >= 0) taps[p].idx |= ((iz[p] - zmin) << 16);
+  return 0;
+}
+
+}  // namespace v3s
+
+using namespace v3s;
+
+extern "C" void v3s_default_geometry(v3s_geometry* g) {
+  // projection.py:96-107
+  g->pixel = 75e-6; g->zd = 0.5; g->lambda = 2 * 1e-9; g->n_p_nobin = 1024; g->grid_scale = 2e-7;
+}
+
+extern "C" int v3s_synth_patterns(const float* ed, int n, const double* rot9, long long N, int n_p,
+                                  const v3s_geometry* geom, float* out, long long out_stride, void* stream) {
+  V3S_REQUIRE(n >= 2 && n <= 255, "v3s_synth_patterns: n_voxel_1d=%d outside [2,255]", n);
+  V3S_REQUIRE(n_p >= 2 && N >= 0, "v3s_synth_patterns: bad n_p=%d or N=%lld", n_p, N);
+  v3s_geometry g;
+  if (geom) g = *geom; else v3s_default_geometry(&g);
+  std::vector<PixelTap> taps;
+  int z0, nz;
+  build_taps(n, n_p, &g, taps, &z0, &nz);
+  V3S_REQUIRE(nz <= kMaxPlanes, "v3s_synth_patterns: Ewald sphere spans %d k_z planes (max %d)", nz, kMaxPlanes);
+  if (N == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int P = n_p * n_p;
+  PixelTap* d_taps = nullptr;
+  V3S_CUDA(cudaMallocAsync(&d_taps, sizeof(PixelTap) * P, st));
+  V3S_CUDA(cudaMemcpyAsync(d_taps, taps.data(), sizeof(PixelTap) * P, cudaMemcpyHostToDevice, st));
+  const int n2 = n * n, n3 = n2 * n;
+  size_t smem = sizeof(float) * ((n3 + 3) & ~3) + 2 * sizeof(float2) * nz * n2 + sizeof(float) * ((nz * n2 + 1) & ~1) +
+                sizeof(float2) * n;
+  V3S_REQUIRE(smem <= 227 * 1024, "v3s_synth_patterns: object n=%d needs %zu B shared memory (max 232448)", n, smem);
+  V3S_CUDA(cudaFuncSetAttribute(synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SynthParams prm{n, nz, z0, P, N};
+  int grid = (int)(N < (long long)kNumSMs ? N : kNumSMs);
+  synth_kernel<<<grid, kSynthThreads, smem, st>>>(ed, rot9, d_taps, out, out_stride, prm);
+  V3S_CHECK_LAUNCH();
+  // the pageable source buffer must outlive the async copy: the copy above is synchronous
+  // with respect to the host for pageable memory, so `taps` may be released now.
+  V3S_CUDA(cudaFreeAsync(d_taps, st));
+  return 0;
+}

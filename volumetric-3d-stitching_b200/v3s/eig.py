@@ -1,0 +1,117 @@
+"""Block-Lanczos eigen-solver for the largest-magnitude eigenpairs of the symmetric Markov
+matrix P_ep -- the replacement for `scipy.sparse.linalg.eigs(P_ep, k)` (ARPACK, which='LM') at
+diffusion.py:61.
+
+Host-side driver.  The only O(N^2) work per step is the caller's block mat-vec (the HBM-bound
+CUDA kernel, `CudaOps.block_matvec`, FP32 matrix x FP64 block); the Lanczos basis, the two-pass
+block Gram-Schmidt re-orthogonalisation, the Cholesky-QR of the new block and the Ritz extraction
+are FP64 (an all-FP32 Lanczos misses the 1e-6 eigenvalue target).  The projected
+matrix is block tridiagonal; its few extreme eigenpairs come from LAPACK's banded solver on the
+host every `check_every` steps (a (b+1) x m band, a few kB).
+
+P_ep is exactly symmetric, so a symmetric Lanczos targeting largest |lambda| returns the same
+eigenpairs as ARPACK's non-symmetric driver, up to the sign / basis freedom the reference itself
+has (it starts ARPACK from a random vector).  Here the start block is seeded,
+so results are reproducible run to run.
+"""
+import numpy as np
+import scipy.linalg as sla
+import torch
+
+
+def _chol_qr(W):
+    """Thin QR of a tall block by two rounds of Cholesky-QR (FP64)."""
+    R_tot = None
+    for _ in range(2):
+        G = W.T @ W
+        L, info = torch.linalg.cholesky_ex(G)
+        # W <- W L^-T
+        W = torch.linalg.solve_triangular(L, W.T, upper=False).T.contiguous()
+        R = L.T
+        R_tot = R if R_tot is None else R @ R_tot
+    return W, R_tot
+
+
+def _ritz_from_band(band, m, b, nev):
+    """Largest-|lambda| eigenpairs of the m x m block-tridiagonal matrix held in lower band
+    storage band[i, j] = T[j + i, j]."""
+    Tb = band[:, :m].copy()
+    for i in range(1, b + 1):
+        Tb[i, max(m - i, 0):] = 0.0
+    want = min(nev, m)
+    if m <= 2 * want + 2:
+        w, S = sla.eig_banded(Tb, lower=True)
+    else:
+        w_hi, S_hi = sla.eig_banded(Tb, lower=True, select="i", select_range=(m - want, m - 1))
+        w_lo, S_lo = sla.eig_banded(Tb, lower=True, select="i", select_range=(0, want - 1))
+        w = np.concatenate([w_lo, w_hi])
+        S = np.concatenate([S_lo, S_hi], axis=1)
+    idx = np.argsort(-np.abs(w), kind="stable")[:want]
+    return w[idx], S[:, idx]
+
+
+def block_lanczos_topk(matvec, N, nev, device, block=8, tol=1e-8, max_dim=None, check_every=2, seed=0,
+                       min_steps=2, stats=None):
+    """Largest-magnitude `nev` eigenpairs of the symmetric operator `matvec`.
+
+    matvec: callable X [N,b] float64 tensor -> P @ X [N,b] float64 tensor (same device).
+    Returns (lambda [nev] numpy float64 sorted by decreasing |lambda|, V [N,nev] float64 tensor,
+    residual estimates [nev]).  Converged when every Ritz residual estimate
+    ||B_j S_last|| <= tol * max|theta|.
+    """
+    b = int(min(block, max(1, N // 4)))
+    if max_dim is None:
+        max_dim = min(N, 1024)
+    max_dim = max(b, (min(max_dim, N) // b) * b)
+    gen = torch.Generator(device="cpu")
+    gen.manual_seed(seed)
+    Q0 = torch.randn((N, b), generator=gen, dtype=torch.float64).to(device)
+    Q, _ = _chol_qr(Q0)
+    V = torch.zeros((max_dim, N), dtype=torch.float64, device=device)     # basis vectors as rows
+    V[:b] = Q.T
+    m = b
+    band = np.zeros((b + 1, max_dim))
+    steps = 0
+    n_matvec = 0
+    w = S = res = None
+    pending = []                         # device [2b,b] blocks not yet copied into `band`
+    while True:
+        W = matvec(Q)
+        n_matvec += 1
+        Vm = V[:m]
+        H = Vm @ W
+        W = W - Vm.T @ H
+        H2 = Vm @ W                      # second Gram-Schmidt pass (full re-orthogonalisation)
+        W = W - Vm.T @ H2
+        H = H + H2
+        A = H[m - b:m]
+        A = 0.5 * (A + A.T)
+        Qn, B = _chol_qr(W)
+        pending.append((m, torch.cat([A, B], dim=0)))      # [2b, b]: A_j over B_j
+        steps += 1
+        last = (m + b > max_dim)
+        if (steps >= min_steps and steps % check_every == 0) or last:
+            blks = torch.stack([t for _, t in pending]).cpu().numpy()   # one small D2H per check
+            for (mm, _), blk in zip(pending, blks):
+                for c in range(b):
+                    col = mm - b + c
+                    for i in range(0, b + 1):
+                        r = c + i                           # row offset inside the [A; B] stack
+                        band[i, col] = blk[r, c] if (r < b or (r - b) <= c) else 0.0
+            pending = []
+            w, S = _ritz_from_band(band, m, b, nev)
+            Bn = blk[b:]
+            res = np.linalg.norm(Bn @ S[m - b:m, :], axis=0)
+            if not np.all(np.isfinite(res)):
+                raise Exception("block Lanczos broke down (non-finite residuals)")
+            if res.max() <= tol * max(np.abs(w).max(), 1e-300) or last:
+                break
+        V[m:m + b] = Qn.T
+        m += b
+        Q = Qn
+    St = torch.from_numpy(np.ascontiguousarray(S)).to(device)
+    Y = V[:m].T @ St
+    if stats is not None:
+        stats.update({"matvecs": n_matvec, "block": b, "krylov_dim": m, "residual_max": float(res.max()),
+                      "converged": bool(res.max() <= tol * max(np.abs(w).max(), 1e-300))})
+    return w, Y, res

@@ -1,0 +1,214 @@
+"""Device operations of the hot path: thin torch-tensor wrappers over the C-ABI (include/v3s.h).
+
+Every method takes and returns CUDA tensors on the current device/stream.  This is the only
+compute backend of the product; `CudaOps()` raises without a B200 (no CPU fallback).  The host
+logic above it (pipeline.py, eig.py) is written against this small interface so that the sharding
+and solver logic can be exercised on CPU in tests with a stand-in backend.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import call, ptr, stream_ptr
+
+GRAM_KPAD = 64          # K-block of the tcgen05 Gram kernel (bf16 elements)
+KNN_MARGIN = 8          # extra candidates kept through the exact refinement
+PANEL_BYTES = 4 << 30   # Gram row panel budget (G is never materialised beyond this)
+
+
+def round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class CudaOps:
+    name = "cuda-sm100a"
+
+    def __init__(self, device=None):
+        _lib.require_device()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self._mv_ws = None
+        self._sigma_ws = None
+        self.gram_impl = "tcgen05"   # "simt" = FP32 CUDA-core validation path
+
+    # ---- allocation helpers ---------------------------------------------------------------
+    def empty(self, shape, dtype):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def zeros(self, shape, dtype):
+        return torch.zeros(shape, dtype=dtype, device=self.device)
+
+    def to_device(self, x, dtype=None):
+        t = torch.as_tensor(x)
+        if dtype is not None and t.dtype != dtype:
+            t = t.to(dtype)
+        return t.to(self.device, non_blocking=True).contiguous()
+
+    # ---- stage 1 -----------------------------------------------------------------------------
+    def synth_patterns(self, ed, rot9, n_p, geom=None):
+        """ed [n,n,n] f32, rot9 [N,9] f64 (row-major Rm) -> patterns [N, n_p^2] f32."""
+        n = ed.shape[0]
+        N = rot9.shape[0]
+        out = self.empty((N, n_p * n_p), torch.float32)
+        g = None
+        if geom is not None:
+            g = _lib.Geometry()
+            _lib.lib.v3s_default_geometry(C.byref(g))
+            for k_, v_ in geom.items():
+                setattr(g, "lambda_" if k_ == "lambda" else k_, v_)
+        call("v3s_synth_patterns", ptr(ed), n, ptr(rot9), N, n_p, C.byref(g) if g is not None else None, ptr(out),
+             n_p * n_p, stream_ptr())
+        return out
+
+    # ---- stage 2 -----------------------------------------------------------------------------
+    def column_sums(self, img):
+        sums = self.empty((img.shape[1],), torch.float64)
+        call("v3s_column_sums", ptr(img), img.shape[0], img.shape[1], img.stride(0), ptr(sums), stream_ptr())
+        return sums
+
+    def center_normalize(self, img, mean, want_split=True):
+        """-> a32 [n,P] f32, hi, lo [n,Ppad] bf16 (or None), zero_flag [n] i32."""
+        n, P = img.shape
+        Ppad = round_up(P, GRAM_KPAD)
+        a32 = self.empty((n, P), torch.float32)
+        hi = self.empty((n, Ppad), torch.bfloat16) if want_split else None
+        lo = self.empty((n, Ppad), torch.bfloat16) if want_split else None
+        zf = self.empty((n,), torch.int32)
+        call("v3s_center_normalize", ptr(img), n, P, img.stride(0), ptr(mean), ptr(a32), ptr(hi), ptr(lo), Ppad, None,
+             ptr(zf), stream_ptr())
+        return a32, hi, lo, zf
+
+    def gram_rows(self, hi_all, lo_all, a32_all, r0, r1, out=None):
+        """G[r0:r1, :] as f32 [r1-r0, ldg]."""
+        N = a32_all.shape[0]
+        nr = r1 - r0
+        ldg = round_up(N, 4)
+        G = out if out is not None else self.empty((nr, ldg), torch.float32)
+        if self.gram_impl == "simt":
+            call("v3s_gram_rows_simt", ptr(a32_all), N, ptr(a32_all[r0:r1]), nr, a32_all.shape[1], ptr(G), ldg, stream_ptr())
+        else:
+            call("v3s_gram_rows", ptr(hi_all), ptr(lo_all), N, ptr(hi_all[r0:r1]), ptr(lo_all[r0:r1]), nr,
+                 hi_all.shape[1], ptr(G), ldg, stream_ptr())
+        return G
+
+    def knn_rows(self, hi_all, lo_all, a32_all, zero_flag, r0, r1, k):
+        """k nearest neighbours (round distance) of rows [r0,r1) against all rows.
+        -> S2 [r1-r0,k] f64 ascending, Nbr [r1-r0,k] i32.  Gram panels are streamed."""
+        N, P = a32_all.shape
+        if k > N:
+            raise Exception("Number of nearest neighbors to preserve is too high.")   # distance.py:33-34
+        nr = r1 - r0
+        S2 = self.empty((nr, k), torch.float64)
+        Nbr = self.empty((nr, k), torch.int32)
+        if nr == 0:
+            return S2, Nbr
+        ldg = round_up(N, 4)
+        panel = max(256, min(nr, (PANEL_BYTES // (4 * ldg)) // 256 * 256))
+        kk = min(k + KNN_MARGIN, N)
+        G = self.empty((min(panel, nr), ldg), torch.float32)
+        cand = self.empty((min(panel, nr), kk), torch.int32)
+        zf = zero_flag if (zero_flag is not None) else None
+        for p0 in range(r0, r1, panel):
+            p1 = min(p0 + panel, r1)
+            self.gram_rows(hi_all, lo_all, a32_all, p0, p1, out=G)
+            call("v3s_knn_from_gram", ptr(G), ldg, p1 - p0, N, p0, ptr(a32_all[p0:p1]), ptr(a32_all), P, k, KNN_MARGIN,
+                 ptr(zf), ptr(cand), ptr(S2[p0 - r0:p1 - r0]), ptr(Nbr[p0 - r0:p1 - r0]), stream_ptr())
+        return S2, Nbr
+
+    def round_distance_dense(self, a32, zero_flag):
+        n, P = a32.shape
+        B = self.empty((n, n), torch.float64)
+        call("v3s_round_distance_dense", ptr(a32), n, P, ptr(zero_flag), ptr(B), stream_ptr())
+        return B
+
+    def knn_from_dense(self, B, k):
+        n = B.shape[0]
+        if k > n:
+            raise Exception("Number of nearest neighbors to preserve is too high.")
+        kk = min(k + KNN_MARGIN, n)
+        key = self.empty((n, n), torch.float32)
+        cand = self.empty((n, kk), torch.int32)
+        S2 = self.empty((n, k), torch.float64)
+        Nbr = self.empty((n, k), torch.int32)
+        call("v3s_knn_from_dense", ptr(B), n, k, KNN_MARGIN, ptr(key), ptr(cand), ptr(S2), ptr(Nbr), stream_ptr())
+        return S2, Nbr
+
+    # ---- stage 3 -----------------------------------------------------------------------------
+    def s2_scalars(self, S2, eps, med_row=4, idx_off=1):
+        sc = self.empty((5,), torch.float64)
+        call("v3s_s2_scalars", ptr(S2), S2.shape[0], S2.shape[1], float(eps), med_row, idx_off, ptr(sc), stream_ptr())
+        return sc
+
+    def s2_threshold_(self, S2, scalars):
+        call("v3s_s2_threshold", ptr(S2), S2.shape[0], S2.shape[1], ptr(scalars), stream_ptr())
+        return S2
+
+    def build_markov(self, S2t, Nbr, scalars, r0, r1):
+        N, k = S2t.shape
+        ldp = round_up(N, 4)
+        P_rows = self.empty((r1 - r0, ldp), torch.float32)
+        dis = self.empty((N,), torch.float64)
+        ws = self.empty((2 * N,), torch.float64)
+        call("v3s_build_markov", ptr(S2t), ptr(Nbr), N, k, ptr(scalars), r0, r1 - r0, ptr(P_rows), ldp, ptr(dis), ptr(ws),
+             stream_ptr())
+        return P_rows, dis
+
+    def w_dense(self, S2t, Nbr, eps_eff):
+        N, k = S2t.shape
+        W = self.empty((N, N), torch.float64)
+        call("v3s_w_dense", ptr(S2t), ptr(Nbr), N, k, float(eps_eff), ptr(W), stream_ptr())
+        return W
+
+    def anisotropic_norm_dense(self, W):
+        N = W.shape[0]
+        out = self.empty((N, N), torch.float64)
+        ws = self.empty((N,), torch.float64)
+        call("v3s_anisotropic_norm_dense", ptr(W), N, ptr(out), ptr(ws), stream_ptr())
+        return out
+
+    def dm_cov_dense(self, W):
+        N = W.shape[0]
+        P = self.empty((N, N), torch.float64)
+        dis = self.empty((N,), torch.float64)
+        ws = self.empty((N,), torch.float64)
+        call("v3s_dm_cov_dense", ptr(W), N, ptr(P), ptr(dis), ptr(ws), stream_ptr())
+        return P, dis
+
+    def block_matvec(self, P_rows, N, X):
+        """Y_rows [n_rows,b] f64 = P_rows[:, :N] (f32) @ X [N,b] (f64)."""
+        n_rows, ldp = P_rows.shape
+        b = X.shape[1]
+        need = _lib.lib.v3s_block_matvec_workspace_bytes(n_rows, N)
+        if self._mv_ws is None or self._mv_ws.numel() < need:
+            self._mv_ws = self.empty((need,), torch.uint8)
+        Y = self.empty((n_rows, b), torch.float64)
+        call("v3s_block_matvec", ptr(P_rows), ldp, n_rows, N, ptr(X), b, ptr(Y), ptr(self._mv_ws), stream_ptr())
+        return Y
+
+    # ---- stage 4 -----------------------------------------------------------------------------
+    def fit_gram(self, Ps, Y):
+        out = self.empty((162,), torch.float64)
+        call("v3s_fit_gram", ptr(Ps), Ps.stride(0), ptr(Y), Ps.shape[0], ptr(out), stream_ptr())
+        return out
+
+    def fit_solve(self, g162):
+        c = self.empty((9, 9), torch.float64)
+        call("v3s_fit_solve", ptr(g162), ptr(c), stream_ptr())
+        return c
+
+    def fit_project(self, Ps, Y, c, polar_mode):
+        n = Ps.shape[0]
+        recon = self.empty((n, 9), torch.float64)
+        rproj = self.empty((n, 9), torch.float64)
+        qe = self.empty((n, 4), torch.float64)
+        qt = self.empty((n, 4), torch.float64)
+        call("v3s_fit_project", ptr(Ps), Ps.stride(0), ptr(Y), n, ptr(c), int(polar_mode), ptr(recon), ptr(rproj), ptr(qe),
+             ptr(qt), stream_ptr())
+        return recon, rproj, qe, qt
+
+    def sigma_pairs(self, qe, qt, r0, r1):
+        if self._sigma_ws is None:
+            self._sigma_ws = self.empty((65536,), torch.float64)
+        out = self.empty((1,), torch.float64)
+        call("v3s_sigma_pairs", ptr(qe), ptr(qt), qe.shape[0], r0, r1 - r0, ptr(self._sigma_ws), ptr(out), stream_ptr())
+        return out

@@ -1,0 +1,188 @@
+"""Device-resident pipeline: patterns -> kNN round distances -> diffusion coordinates -> orientations.
+
+Host logic only; all arithmetic is done by the backend `ops` (CudaOps in the product).  The same
+functions drive one GPU or a row-sharded job (one process per GPU, torch.distributed):
+every N x N object (Gram panel, P_ep) is split by contiguous row blocks, rank g owning rows
+[lo_g, hi_g).  Exchanges:
+    all-reduce  per-pixel sums (mean image)                    P doubles
+    all-gather  centred unit rows + their BF16 split           N x P x 8 B
+    all-gather  kNN lists                                      N x k x 12 B
+    all-gather  block mat-vec result, once per Lanczos step    N x b x 8 B
+    all-reduce  Sigma_T partial sum                            1 double
+Small replicated work (Lanczos basis algebra, the 9x9 fit) is recomputed on every rank from
+identical inputs, so all ranks hold identical results without further communication.
+"""
+import math
+
+import numpy as np
+import torch
+
+from .eig import block_lanczos_topk
+
+NEV = 10   # diffusion.py:42 (k = 10 eigenpairs)
+
+
+class ShardPlan:
+    """Contiguous near-equal row blocks over the ranks of `group` (None = single process)."""
+
+    def __init__(self, N, rank=0, world=1, group=None):
+        self.N, self.rank, self.world, self.group = int(N), int(rank), int(world), group
+        base, rem = divmod(self.N, self.world)
+        self.counts = [base + (1 if r < rem else 0) for r in range(self.world)]
+        self.offsets = [sum(self.counts[:r]) for r in range(self.world)]
+        self.lo = self.offsets[self.rank]
+        self.hi = self.lo + self.counts[self.rank]
+
+    @staticmethod
+    def from_env(N):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            return ShardPlan(N, dist.get_rank(), dist.get_world_size(), dist.group.WORLD)
+        return ShardPlan(N)
+
+    # ---- collectives (no-ops for a single process) ---------------------------------------
+    def all_reduce_sum(self, t):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def all_gather_rows(self, t_local):
+        """Concatenate per-rank row blocks [count_r, ...] into [N, ...] on every rank."""
+        if self.world == 1:
+            return t_local
+        import torch.distributed as dist
+        cmax = max(self.counts)
+        tail = tuple(t_local.shape[1:])
+        if all(c == cmax for c in self.counts):
+            out = torch.empty((self.N,) + tail, dtype=t_local.dtype, device=t_local.device)
+            dist.all_gather_into_tensor(out, t_local.contiguous(), group=self.group)
+            return out
+        pad = torch.zeros((cmax,) + tail, dtype=t_local.dtype, device=t_local.device)
+        pad[: t_local.shape[0]] = t_local
+        buf = torch.empty((self.world * cmax,) + tail, dtype=t_local.dtype, device=t_local.device)
+        dist.all_gather_into_tensor(buf, pad, group=self.group)
+        return torch.cat([buf[r * cmax: r * cmax + self.counts[r]] for r in range(self.world)], dim=0)
+
+
+def _bf16_gather(plan, t):
+    # not every backend build moves bfloat16; ship the raw bytes
+    if plan.world == 1 or t is None:
+        return t
+    return plan.all_gather_rows(t.view(torch.uint8)).view(torch.bfloat16)
+
+
+def knn_stage(ops, plan, img_local, k):
+    """distance.py:17-22 (DistanceMatrix.knn) on the rank's pattern rows.
+    -> S2_all [N,k] f64, Nbr_all [N,k] i32 (replicated), a32_all."""
+    N = plan.N
+    sums = ops.column_sums(img_local)
+    plan.all_reduce_sum(sums)
+    mean = sums / N
+    a32, hi, lo, zf = ops.center_normalize(img_local, mean)
+    a32_all = plan.all_gather_rows(a32)
+    hi_all = _bf16_gather(plan, hi)
+    lo_all = _bf16_gather(plan, lo)
+    zf_all = plan.all_gather_rows(zf)
+    S2_loc, Nbr_loc = ops.knn_rows(hi_all, lo_all, a32_all, zf_all, plan.lo, plan.hi, k)
+    S2_all = plan.all_gather_rows(S2_loc)
+    Nbr_all = plan.all_gather_rows(Nbr_loc)
+    return S2_all, Nbr_all
+
+
+def check_scalars(scalars_host):
+    """Raise like diffusion.py:302 when the kernel scale is degenerate."""
+    status = int(scalars_host[3])
+    if status == 1:
+        raise Exception("S2_Max = 0")
+    if status == 2:
+        raise Exception("s2_to_w_matrix: row index out of range (S2 has fewer rows than the reference indexes)")
+
+
+def markov_stage(ops, plan, S2_all, Nbr_all, eps, med_row=4, idx_off=1, validate=True):
+    """diffusion.py:291-325, 89-105, 244-260 fused.  Mutates S2_all in place like the reference.
+    -> P_rows [hi-lo, ldp] f32, dinv_sqrt [N] f64, scalars [5]."""
+    scalars = ops.s2_scalars(S2_all, eps, med_row, idx_off)
+    if validate:
+        check_scalars(scalars.cpu().numpy())
+    ops.s2_threshold_(S2_all, scalars)
+    P_rows, dis = ops.build_markov(S2_all, Nbr_all, scalars, plan.lo, plan.hi)
+    return P_rows, dis, scalars
+
+
+def eigen_stage(ops, plan, P_rows, dis, nev=NEV, validate=True, tol=None, stats=None, seed=0, dense_below=192):
+    """diffusion.py:56-81: top-`nev` largest-magnitude eigenpairs, sort descending, scale by
+    lambda and D^-1/2.  -> Ps [N,nev] f64 tensor, Lambda [nev] f64 tensor."""
+    N = plan.N
+    if nev >= N - 1:
+        raise Exception("No spare-matrix for eigs-calculation")   # diffusion.py:59-60
+    dev = P_rows.device
+
+    def matvec(X):
+        Y = ops.block_matvec(P_rows, N, X.contiguous())
+        return plan.all_gather_rows(Y)
+
+    if N <= dense_below:
+        # tiny problems (unit-test sizes): the Krylov space is the whole space; apply the operator to I
+        eye = torch.eye(N, dtype=torch.float64, device=dev)
+        cols = [matvec(eye[:, j:j + 8].contiguous()) for j in range(0, N, 8)]
+        Pd = torch.cat(cols, dim=1)
+        Pd = 0.5 * (Pd + Pd.T)
+        w_all, V_all = torch.linalg.eigh(Pd)
+        w_np = w_all.cpu().numpy()
+        idx = np.argsort(-np.abs(w_np), kind="stable")[:nev]
+        lam = w_np[idx]
+        V = V_all[:, torch.as_tensor(idx, device=dev)]
+        if stats is not None:
+            stats.update({"matvecs": len(cols), "dense": True})
+    else:
+        lam, V, _ = block_lanczos_topk(matvec, N, nev, dev, tol=(1e-8 if tol is None else tol), stats=stats, seed=seed)
+    V = -V                                                   # diffusion.py:62 (sign is arbitrary upstream)
+    if validate:                                             # compute.py:70-72 guards, then clip
+        for w_ in lam:
+            if not (0 < w_):
+                raise Exception("negative eigen_value")
+            if not (w_ < 1 + 1e-12 + 1e-6):
+                raise Exception("too large an eigen_value " + str(w_))
+        lam = np.clip(lam, 0.0, 1.0)
+    order = np.flip(np.argsort(lam)).astype(int)             # diffusion.py:74-76
+    lam = lam[order]
+    lam_t = torch.as_tensor(lam.copy(), dtype=torch.float64, device=dev)
+    V = V[:, torch.as_tensor(order.copy(), device=dev)]
+    Ps = (V * lam_t[None, :]) * dis[:, None]                 # diffusion.py:78-81
+    return Ps.contiguous(), lam_t
+
+
+def fit_stage(ops, plan, Ps, Y, polar_mode=0, check=True):
+    """diffusion.py:109-183 (a-priori branch).  Ps [N,10], Y = Rotation_R.T [N,9] replicated.
+    -> dict(c, recon_pre, rproj, quat_est, quat_true, sigma_T)."""
+    N = plan.N
+    g = ops.fit_gram(Ps, Y)
+    c = ops.fit_solve(g)
+    recon, rproj, qe, qt = ops.fit_project(Ps, Y, c, polar_mode)
+    part = ops.sigma_pairs(qe, qt, plan.lo, plan.hi)
+    plan.all_reduce_sum(part)
+    sigma_t = (180.0 / math.pi) * 2.0 * part / (N * (N - 1))
+    out = {"c": c, "recon_pre": recon, "rproj": rproj, "quat_est": qe, "quat_true": qt, "sigma_T": sigma_t}
+    if check:
+        s = float(sigma_t.item())
+        out["sigma_T_host"] = s
+        if s > 60:
+            raise Exception("Sigma_T = " + str(s))           # diffusion.py:175-176
+    return out
+
+
+def run_pipeline(ops, plan, ed, rot9_local, rot_y_all, n_p, k, eps, polar_mode=0, check=True, stats=None,
+                 validate=True):
+    """Full path on device.  ed [n,n,n] f32; rot9_local [hi-lo,9] f64 row-major Rm of the rank's
+    patterns; rot_y_all [N,9] f64 = Rotation_R.T (the reference's column-major unfold, transposed)."""
+    img = ops.synth_patterns(ed, rot9_local, n_p)
+    S2, Nbr = knn_stage(ops, plan, img, k)
+    S2_out = S2.clone()                                      # pre-mutation copy for callers that want it
+    P_rows, dis, scalars = markov_stage(ops, plan, S2, Nbr, eps, validate=validate)
+    Ps, lam = eigen_stage(ops, plan, P_rows, dis, validate=validate, stats=stats)
+    fit = fit_stage(ops, plan, Ps, rot_y_all, polar_mode=polar_mode, check=check)
+    out = {"Images_local": img, "S2": S2, "S2_unmutated": S2_out, "N": Nbr, "Ps": Ps, "Lambda": lam, "dinv_sqrt": dis,
+           "scalars": scalars}
+    out.update(fit)
+    return out

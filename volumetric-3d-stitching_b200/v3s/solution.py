@@ -1,0 +1,73 @@
+"""OrientationRecoverySolver -- orchestration (mirror of the reference's solution.py)."""
+import numpy as np
+import torch
+
+from . import _util
+from .pipeline import ShardPlan, run_pipeline
+from .projection import Projector
+from .rotation import Rotation
+
+
+class OrientationRecoverySolver:
+
+    @staticmethod
+    def solve_and_plot(parameters):
+        """solution.py:26-30.  Plotting (plot.py) is outside the hot path; the result map is returned."""
+        return OrientationRecoverySolver.solve(parameters)
+
+    @staticmethod
+    def solve(parameters, rotations=None, N_p=None, polar_mode=0, stats=None):
+        """solution.py:34-61 -> dict of numpy float64 arrays with the reference's 11 keys.
+        Extensions that never change reference-mode results: `rotations` = explicit
+        R (9,N) instead of the Hopf grid, `N_p` = free detector size."""
+        print('OrientationRecoverySolver.solve started.')
+        if not OrientationRecoverySolver.validate_parameters(parameters):
+            parameters = OrientationRecoverySolver.default_parameters()
+        if not OrientationRecoverySolver.validate_parameters(parameters):
+            raise Exception('Default parameters are invalid.')
+        if not parameters['aPrioriFlag']:
+            raise Exception('aPrioriFlag=False is not runnable in the reference either (diffusion.py:231)')
+        ops = _util.get_ops()
+        n = parameters['n_voxel_1d']
+        if rotations is None:
+            [R, Axis, Quat] = Rotation.all_rot_variables(parameters['nRot1D'] ** 3)
+        else:
+            R = np.asarray(rotations, dtype=np.float64)
+            Axis = np.full((3, R.shape[1]), np.nan)
+            Quat = np.full((4, R.shape[1]), np.nan)
+        Nn = R.shape[1]
+        n_p = (1 + 2 * n) if N_p is None else int(N_p)
+        ed = ops.to_device(Projector.synsthesize_3d(n)['ED'].astype(np.float32), torch.float32)
+        rot9 = Projector.rot9_rowmajor(R, ops)
+        rot_y = ops.to_device(np.ascontiguousarray(R.T), torch.float64)
+        out = run_pipeline(ops, ShardPlan(Nn), ed, rot9, rot_y, n_p, parameters['k'], parameters['Epsilon'],
+                           polar_mode=polar_mode, check=True, stats=stats)
+        Images = out['Images_local'].cpu().numpy().astype(np.float64)
+        if not Images[Images != 0].size > 0:
+            raise Exception('Images is an all-zero array.')          # projection.py:47
+        print('OrientationRecoverySolver.solve ended.')
+        f64 = lambda t: t.cpu().numpy().astype(np.float64)
+        return {
+            'Ps': f64(out['Ps']), 'Lambda': f64(out['Lambda']), 'c0': f64(out['c']), 'c': f64(out['c']),
+            'S2': f64(out['S2']), 'N': f64(out['N']), 'Images': Images, 'R': R,
+            'Sigma_T': np.array([out['sigma_T_host']]), 'Axis': Axis.T, 'Quat': Quat.T,
+        }
+
+    @staticmethod
+    def validate_parameters(parameters):
+        """solution.py:65-75 (bug-compat: the exact key ORDER is required)."""
+        return (
+            isinstance(parameters, dict) and
+            list(parameters.keys()) == ['n_voxel_1d', 'nRot1D', 'k', 'Epsilon', 'plot', 'aPrioriFlag'] and
+            isinstance(parameters['n_voxel_1d'], int) and parameters['n_voxel_1d'] > 0 and
+            isinstance(parameters['k'], int) and parameters['k'] > 8 and
+            isinstance(parameters['nRot1D'], int) and parameters['nRot1D'] ** 3 - 1 > parameters['k'] and
+            isinstance(parameters['Epsilon'], float) and parameters['Epsilon'] > 0 and
+            isinstance(parameters['plot'], bool) and
+            isinstance(parameters['aPrioriFlag'], bool)
+        )
+
+    @staticmethod
+    def default_parameters():
+        """solution.py:79-87."""
+        return {'n_voxel_1d': 7, 'nRot1D': 8, 'k': 24, 'Epsilon': 0.7, 'plot': True, 'aPrioriFlag': True}
