@@ -1,0 +1,316 @@
+"""bench.py -- BASELINE.json's metric on BASELINE.json's config.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: under torch.distributed.run)
+    python bench.py --impl reference --steps K --warmup W     (the reference's CPU path, oracle port)
+
+metric: end-to-end seconds, N patterns -> orientations (synthesis -> kNN round distances ->
+diffusion-map eigenvectors -> orientation fit).  Workload at every N: BASELINE config 2,
+N = 10 000 patterns of 64 x 64 from the reference's analytic object (n = 31), k = 150,
+Epsilon = 0.7, proper random rotations (seed 0).  A "step" is one pass of the whole path.
+`value`  = seconds per pass, inputs resident in HBM (strong scaling: the same job on N GPUs).
+`e2e`    = the same pass through the reference-facing call OrientationRecoverySolver.solve with
+           host (numpy) inputs and host outputs, copies inside the timed region.
+`roofline` is for the dominant kernel of the pass (the tcgen05 Gram): algorithmic 2 N^2 P flop
+per launch set / its CUDA-event time, against the measured BF16 peak.
+"""
+import argparse
+import contextlib
+import io
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "volumetric-3d-stitching_b200"), os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+WORKLOADS = {
+    "cfg2": dict(N=10000, n=31, n_p=64, k=150, eps=0.7, desc="BASELINE config 2: N=10k patterns 64x64, full pipeline, 1 B200"),
+    "cfg3": dict(N=50000, n=31, n_p=128, k=150, eps=0.7, desc="BASELINE config 3: N=50k patterns 128x128, row-sharded"),
+    "small": dict(N=2000, n=15, n_p=31, k=150, eps=0.7, desc="debug size"),
+}
+METRIC = "end_to_end_seconds_patterns_to_orientations"
+
+
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        # under load = upper half of the samples (idle samples before/after the region are dropped)
+        load = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": (load[len(load) // 2] if load else None), "sm_max_mhz": (max(mx) if mx else None),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port of the reference's NumPy/SciPy path on a bounded sample
+# ------------------------------------------------------------------------------------------
+
+def _synth_chunk(args):
+    import v3s_oracle as orc
+    R9, n, n_p = args
+    return orc.generate_from_rotations(R9, n, n_p)
+
+
+def cpu_reference_pass(wl, sample_n, cores):
+    """One pass of the oracle port on `sample_n` patterns of the workload; every stage is timed
+    and extrapolated to the full N with the stage's own complexity (stated in `sample`)."""
+    import numpy as np
+    import scipy.sparse.linalg as spla
+    import v3s_oracle as orc
+    from multiprocessing import get_context
+    N, n, n_p, k, eps = wl["N"], wl["n"], wl["n_p"], wl["k"], wl["eps"]
+    Ns = min(sample_n, N)
+    R9, _ = orc.random_rotations(N, seed=0)
+    R9s = R9[:, :Ns]
+    t = {}
+    t0 = time.perf_counter()
+    chunks = [np.ascontiguousarray(c) for c in np.array_split(R9s, cores * 4, axis=1) if c.shape[1]]
+    with get_context("fork").Pool(cores) as pool:
+        imgs = np.concatenate(pool.map(_synth_chunk, [(c, n, n_p) for c in chunks]), axis=0)
+    t["synth"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    S2, Nn = orc.knn(imgs, min(k, Ns - 2))
+    t["knn"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    W = orc.anisotropic_norm(orc.s2_to_w_matrix(S2, Nn, eps))
+    P_ep, di = orc.dm_cov(W, dense_D=False)
+    lam, V = spla.eigs(P_ep, 10)                      # the reference's own eigen-solver call (diffusion.py:61)
+    lam, V = np.real(lam), np.real(V)
+    order = np.argsort(-lam)
+    Ps = di[:, None] * (V[:, order] * lam[order][None, :])
+    t["diffusion"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    orc.dm_fit_all(Ps, R9s, True, check=False)
+    t["fit"] = time.perf_counter() - t0
+    f = N / Ns
+    full = t["synth"] * f + (t["knn"] + t["diffusion"] + t["fit"]) * f * f
+    return full, t, Ns
+
+
+def cpu_baseline_block(wl, sample_n):
+    cores = os.cpu_count() or 1
+    full, t, Ns = cpu_reference_pass(wl, sample_n, cores)
+    return {"value": round(full, 3), "unit": "s", "cores": cores, "kind": "port",
+            "sample": ("oracle (vectorised numpy/scipy port of src/python) on the first %d of %d patterns: synth %.2fs (x N/Ns), "
+                       "knn %.2fs, W+normalise+eigs %.2fs, fit %.2fs (each x (N/Ns)^2); the as-is reference also spends ~3 us x N^2 "
+                       "in per-element Python checks, not included" % (Ns, wl["N"], t["synth"], t["knn"], t["diffusion"], t["fit"]))}
+
+
+def run_reference_arm(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals = []
+    for i in range(args.warmup + args.steps):
+        full, t, Ns = cpu_reference_pass(wl, args.cpu_sample, os.cpu_count() or 1)
+        if i >= args.warmup:
+            vals.append(full)
+    v = sum(vals) / len(vals)
+    cores = os.cpu_count() or 1
+    line = {"impl": "reference", "metric": METRIC, "value": round(v, 3), "unit": "s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(v * 1e3, 1), "higher_is_better": False, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl["desc"], "N": wl["N"], "pixels": wl["n_p"] ** 2, "k": wl["k"], "epsilon": wl["eps"]},
+            "cpu_baseline": {"value": round(v, 3), "unit": "s", "cores": cores, "kind": "port",
+                             "sample": "oracle port on the first %d of %d patterns, stage times extrapolated (synth x N/Ns, rest x (N/Ns)^2)" % (Ns, wl["N"])},
+            "e2e": {"value": round(v, 3), "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="v3s", choices=["v3s", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-sample", type=int, default=1200)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference_arm(args, wl)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    # CPU baseline first (rank 0, N=1 only): it forks worker processes, so it runs before CUDA is touched
+    cpu_base = None
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        cpu_base = cpu_baseline_block(wl, args.cpu_sample)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the v3s path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from v3s import _lib, _util
+    from v3s.pipeline import ShardPlan, run_pipeline
+    from v3s.projection import Projector
+    from v3s.rotation import Rotation
+    from v3s.solution import OrientationRecoverySolver
+    ops = _util.get_ops()
+    N, n, n_p, k, eps = wl["N"], wl["n"], wl["n_p"], wl["k"], wl["eps"]
+    plan = ShardPlan.from_env(N)
+    R9, _ = Rotation.random_rotations(N, seed=0)
+    ed = ops.to_device(Projector.synsthesize_3d(n)["ED"].astype(np.float32), torch.float32)
+    rot9_all = Projector.rot9_rowmajor(R9, ops)
+    rot9 = rot9_all[plan.lo:plan.hi].contiguous()
+    rot_y = ops.to_device(np.ascontiguousarray(R9.T), torch.float64)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_pass(stats=None):
+        return run_pipeline(ops, plan, ed, rot9, rot_y, n_p, k, eps, polar_mode=0, check=False, stats=stats, validate=False)
+
+    for _ in range(args.warmup):
+        out = one_pass()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ops.profile = True
+    ops.pop_timings()
+    launches0 = _lib.launches
+    stats = {}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        out = one_pass(stats)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = (_lib.launches - launches0) // args.steps
+    kt = ops.pop_timings()
+    ops.profile = False
+    clocks = sampler.stop() if rank == 0 else None
+    t_ms = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms = float(t_ms.item())
+    sigma_T = float(out["sigma_T"].item())
+    lam = out["Lambda"].cpu().numpy()
+
+    # ---- e2e: reference-facing call, host inputs -> host outputs (rank 0 of a 1-GPU run) ----
+    e2e = None
+    if world == 1 and not args.no_e2e:
+        params = {"n_voxel_1d": n, "nRot1D": 22, "k": k, "Epsilon": eps, "plot": False, "aPrioriFlag": True}
+        def call():
+            with contextlib.redirect_stdout(io.StringIO()):
+                return OrientationRecoverySolver.solve(params, rotations=R9, N_p=n_p, check_sigma=False)
+        for _ in range(2):
+            res = call()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        reps = max(2, min(args.steps, 3))
+        for _ in range(reps):
+            res = call()
+        torch.cuda.synchronize()
+        e2e_s = (time.perf_counter() - t0) / reps
+        h2d = R9.nbytes * 2 + ed.numel() * 4
+        d2h = sum(v.nbytes for kk_, v in res.items() if kk_ not in ("R", "Axis", "Quat"))
+        e2e = {"value": round(e2e_s, 5), "unit": "s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks, peak_src = load_peaks()
+    P = n_p * n_p
+    gram_ms = kt.get("gram", [])
+    gram_per_pass = sum(gram_ms) / args.steps if gram_ms else float("nan")
+    rows_local = plan.hi - plan.lo
+    gram_flop = 2.0 * rows_local * N * P                       # algorithmic: no split-precision multiplier
+    achieved = gram_flop / (gram_per_pass * 1e-3) / 1e12 if gram_ms else None
+    mv = kt.get("matvec", [])
+    mv_gbs = (4.0 * rows_local * N + 8.0 * N * 8 * 2) / (sum(mv) / len(mv) * 1e-3) / 1e9 if mv else None
+    stage_ms = {name: round(sum(v) / args.steps, 3) for name, v in kt.items()}
+    line = {
+        "metric": METRIC, "value": round(ms / 1e3, 5), "unit": "s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(ms, 3), "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "N": N, "pixels": P, "object_voxels_1d": n, "k": k, "epsilon": eps,
+                   "rotations": "uniform random SO(3), seed 0", "parallelism": "rows%d" % world,
+                   "l2": "inputs larger than L2 (pattern matrix %.0f MB, Markov matrix %.0f MB)" % (N * P * 4 / 1e6, rows_local * N * 4 / 1e6),
+                   "arithmetic": "BF16x3 split tcgen05 Gram (FP32 accumulate), FP32 synthesis/mat-vec, FP64 reductions + eigen-solver"},
+        "clocks": clocks,
+        "e2e": e2e,
+        "gpu_launches": int(launches),
+        "roofline": {"kernel": "gram_tc_kernel (tcgen05)", "bound": "tensor", "achieved": (round(achieved, 2) if achieved else None),
+                     "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": (round(achieved / peaks["bf16_tflops"], 4) if achieved else None),
+                     "traffic": None, "peak_source": peak_src + " bf16_tflops (burst; the step is short)",
+                     "note": "algorithmic 2*N^2*P per pass; the kernel issues 3 BF16 MMAs per product (hi.hi+hi.lo+lo.hi)",
+                     "issued_mma_frac": (round(3 * achieved / peaks["bf16_tflops"], 4) if achieved else None)},
+        "matvec": {"achieved_gbs": (round(mv_gbs, 1) if mv_gbs else None), "peak_gbs": peaks["hbm_gbs"],
+                   "frac": (round(mv_gbs / peaks["hbm_gbs"], 4) if mv_gbs else None), "launches_per_pass": len(mv) // args.steps},
+        "kernel_ms_per_pass": stage_ms,
+        "eigen": {k_: stats.get(k_) for k_ in ("matvecs", "krylov_dim", "residual_max", "converged")},
+        "result": {"sigma_T_deg": round(sigma_T, 4), "lambda_1_9": [round(float(x), 8) for x in lam[:10]]},
+        "cpu_baseline": cpu_base,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,348 @@
+"""Parity of the CUDA path (through the C-ABI / stage adapters) against the oracle and the
+fixtures generated from the unmodified reference.  Run on the B200 box: pytest -m gpu.
+
+Tolerances (BASELINE.json north_star): distances / kernel entries 1e-5 relative (the reference's
+hybrid abs/rel comparator, utils.py:76-80), eigenvalues 1e-6 relative, eigen-subspace principal
+angles < 1e-4 rad, orientations <= 0.1 deg median geodesic after one correct SO(3) projection on
+both sides; patterns are FP32: 2e-5 of the pattern maximum.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import v3s_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def v3s_mod():
+    if not torch.cuda.is_available():
+        pytest.fail("the gpu suite needs a CUDA device (there is no CPU fallback)")
+    import v3s
+    from v3s import _util
+    _util.set_ops(None)
+    return v3s
+
+
+@pytest.fixture(scope="module")
+def ops(v3s_mod):
+    from v3s import _util
+    return _util.get_ops()
+
+
+def hybrid_frac_bad(x, y, p):
+    return 1.0 - float(np.mean(orc.almost_equal_hybrid(x, y, p)))
+
+
+def rot9_rowmajor(R9):
+    return np.ascontiguousarray(R9.T.reshape(-1, 3, 3).transpose(0, 2, 1).reshape(-1, 9))
+
+
+# ------------------------------------------------------------------ stage 1
+
+@pytest.mark.parametrize("n", [7, 15, 31])
+def test_synth_vs_reference_fixture(v3s_mod, golden_dir, n):
+    g = np.load(os.path.join(golden_dir, f"images_n{n}.npz"))
+    imgs = v3s_mod.Projector.generate_from_rotations(g["R9"], n)
+    ref = g["Images"]
+    assert imgs.shape == ref.shape
+    err = np.max(np.abs(imgs - ref)) / np.max(np.abs(ref))
+    print(f"synth n={n}: max err / max = {err:.3e}")
+    assert err < 2e-5
+    assert np.array_equal(imgs == 0, ref == 0) or np.mean((imgs == 0) != (ref == 0)) < 1e-3
+
+
+def test_synth_free_detector_and_hopf(v3s_mod, golden_dir):
+    R9, _ = orc.random_rotations(6, seed=11)
+    for n, n_p in ((15, 64), (31, 64), (7, 32)):
+        ref = orc.generate_from_rotations(R9, n, n_p)
+        got = v3s_mod.Projector.generate_from_rotations(R9, n, N_p=n_p)
+        assert np.max(np.abs(got - ref)) < 2e-5 * np.max(np.abs(ref))
+    g = np.load(os.path.join(golden_dir, "default_cfg.npz"))
+    Images, R, Axis, Quat = v3s_mod.Projector.generate(8, 7)      # Hopf grid incl. the clip bug (non-orthogonal R)
+    assert Images.shape == (512, 225) and R.shape == (9, 512) and Axis.shape == (3, 512) and Quat.shape == (4, 512)
+    assert np.max(np.abs(Images - g["Images"])) < 2e-5 * np.max(np.abs(g["Images"]))
+    # generate_single_image signature (projection.py:55)
+    Exp = v3s_mod.Projector.experiment_parameters(15)["Experiment"]
+    Prot = v3s_mod.Projector.synsthesize_3d(15)
+    Q, mask = v3s_mod.Projector.q_and_mask(Exp)
+    kax = v3s_mod.Projector.fourier_scaled_axes_from_grid(Prot["Grid_3D"])[2]
+    Rm = R9[:, 0].reshape(3, 3).T
+    img = v3s_mod.Projector.generate_single_image(Prot["ED"], Rm, kax, Q, mask)[0]
+    ref = orc.generate_single_image(Prot["ED"], Rm, kax, Q, mask)[0]
+    assert np.max(np.abs(img - ref)) < 2e-5 * np.max(np.abs(ref))
+
+
+# ------------------------------------------------------------------ stage 2
+
+def test_distance_helpers_golden(v3s_mod):
+    # distance_test.py:60-79, 44-57, 11-41
+    assert np.allclose(v3s_mod.DistanceMatrix.set_norm_to_one(np.array([[3.0, 4], [-3, 4], [6, -8]])),
+                       [[0.6, 0.8], [-0.6, 0.8], [0.6, -0.8]], atol=1e-7)
+    assert np.allclose(v3s_mod.DistanceMatrix.remove_offset(np.array([[1.0, 2], [-1, -1], [3, 5]])),
+                       [[0, 0], [-2, -3], [2, 3]], atol=1e-12)
+    B = v3s_mod.DistanceMatrix.convert_to_round_distance(np.array([[3.0, 4], [-3, 4], [6, -8]]))
+    assert B.shape == (3, 3) and np.allclose(B, B.T, atol=1e-15)
+    assert np.all(np.diag(B) <= 1e-6) and np.all(B <= np.pi)
+    Bk = np.array([[0, -0.8, -0.6], [-0.8, 0, 0.6], [0.8, -0.6, 0]])
+    S2, N = v3s_mod.DistanceMatrix.knn_from_round_distance(Bk, 2)
+    assert np.array_equal(N, [[1, 2], [0, 1], [1, 2]]) and np.array_equal(S2, [[-0.8, -0.6], [-0.8, 0], [-0.6, 0]])
+    with pytest.raises(Exception, match="Non-square"):
+        v3s_mod.DistanceMatrix.knn_from_round_distance(np.zeros((2, 3)), 1)
+    with pytest.raises(Exception, match="too high"):
+        v3s_mod.DistanceMatrix.knn_from_round_distance(np.zeros((3, 3)), 4)
+    with pytest.raises(Exception, match="too high"):
+        v3s_mod.DistanceMatrix.knn(np.random.default_rng(0).random((5, 16)), 6)
+
+
+@pytest.mark.parametrize("shape", [(301, 225), (1000, 961), (2048, 4096), (77, 64)])
+def test_gram_tcgen05_vs_fp64(ops, shape):
+    N, P = shape
+    rng = np.random.default_rng(N)
+    A = rng.random((N, P)).astype(np.float32) ** 3                 # non-negative, peaked like patterns
+    img = ops.to_device(A, torch.float32)
+    mean = ops.column_sums(img) / N
+    a32, hi, lo, zf = ops.center_normalize(img, mean)
+    ref_a = orc.set_norm_to_one(orc.remove_offset(A.astype(np.float64)))
+    assert np.max(np.abs(a32.cpu().numpy() - ref_a)) < 3e-7
+    G64 = ref_a @ ref_a.T
+    G_tc = ops.gram_rows(hi, lo, a32, 0, N)[:, :N].cpu().numpy()
+    ops.gram_impl = "simt"
+    G_simt = ops.gram_rows(hi, lo, a32, 0, N)[:, :N].cpu().numpy()
+    ops.gram_impl = "tcgen05"
+    e_tc, e_simt = np.max(np.abs(G_tc - G64)), np.max(np.abs(G_simt - G64))
+    print(f"gram {shape}: max|tcgen05-f64|={e_tc:.2e} max|simt-f64|={e_simt:.2e}")
+    assert e_simt < 2e-6
+    assert e_tc < 2e-6
+    # a row panel in the middle (rows operand != all-rows operand)
+    r0, r1 = N // 3, min(N, N // 3 + 300)
+    Gp = ops.gram_rows(hi, lo, a32, r0, r1)[:, :N].cpu().numpy()
+    assert np.max(np.abs(Gp - G64[r0:r1])) < 2e-6
+
+
+def test_knn_connected_fixture(v3s_mod, golden_dir):
+    g = np.load(os.path.join(golden_dir, "connected_n15.npz"))
+    S2, N = v3s_mod.DistanceMatrix.knn(g["Images_f32"].astype(np.float64), int(g["k"]))
+    assert S2.shape == g["S2"].shape and N.shape == g["N"].shape and S2.dtype == np.float64
+    bad = hybrid_frac_bad(S2, g["S2"], 1e-5)
+    print("knn connected: frac outside 1e-5 hybrid =", bad, " max rel =",
+          np.max(np.abs(S2[:, 1:] - g["S2"][:, 1:]) / g["S2"][:, 1:]))
+    assert bad == 0.0
+    assert np.mean(N == g["N"]) > 0.9999
+    assert np.all(np.diff(S2, axis=1) >= 0) and np.array_equal(N[:, 0], np.arange(S2.shape[0]))
+
+
+def test_knn_default_cfg_fixture_with_duplicates(v3s_mod, golden_dir):
+    g = np.load(os.path.join(golden_dir, "default_cfg.npz"))
+    S2, N = v3s_mod.DistanceMatrix.knn(g["Images"], 24)
+    # duplicate images give tied ~0 distances; the reference's are ~1e-8 noise
+    assert hybrid_frac_bad(S2, g["S2"], 1e-5) < 1e-3 and np.max(np.abs(S2 - g["S2"])) < 1e-6
+    untied = np.ones_like(S2, dtype=bool)
+    d = np.abs(np.diff(g["S2"], axis=1)) > 1e-6
+    untied[:, 1:] &= d
+    untied[:, :-1] &= d
+    assert np.array_equal(N[untied], g["N"][untied])
+    # tie groups hold the same index sets
+    for r in (0, 100, 511):
+        assert set(N[r][g["S2"][r] < 1e-6]) == set(g["N"][r][g["S2"][r] < 1e-6])
+
+
+def test_knn_zero_rows_and_panels(ops):
+    """Edge cases: all-zero patterns (NaN -> 0 in the reference), ragged sizes, streamed panels."""
+    rng = np.random.default_rng(5)
+    A = rng.random((700, 100)).astype(np.float32)
+    A[13] = A.mean(0)                     # centred row == 0 -> NaN row in the reference
+    from v3s.pipeline import ShardPlan, knn_stage
+    from v3s import ops_cuda
+    S2, N = knn_stage(ops, ShardPlan(700), ops.to_device(A, torch.float32), 20)
+    oS2, oN = orc.knn(A.astype(np.float64), 20)
+    S2, N = S2.cpu().numpy(), N.cpu().numpy()
+    assert np.all(S2[13] == 0)                                       # distance 0 to everything
+    rows = np.array([r for r in range(700) if r != 13])
+    assert np.all(S2[rows, 0] == 0)
+    keep = oN[rows] != 13                                            # the NaN column is tie-ordered upstream
+    assert hybrid_frac_bad(S2[rows][:, 2:], oS2[rows][:, 2:], 1e-5) == 0.0
+    old = ops_cuda.PANEL_BYTES
+    try:
+        ops_cuda.PANEL_BYTES = 256 * 4 * 700                         # force 3 panels
+        S2p, Np = knn_stage(ops, ShardPlan(700), ops.to_device(A, torch.float32), 20)
+    finally:
+        ops_cuda.PANEL_BYTES = old
+    assert np.array_equal(S2p.cpu().numpy(), S2) and np.array_equal(Np.cpu().numpy(), N)
+
+
+# ------------------------------------------------------------------ stage 3
+
+S2_4 = np.array([[0.0, 16.0, 9.0, 25.0], [16.0, 0.0, 25.0, 9.0], [9.0, 25.0, 0.0, 16.0], [25.0, 9.0, 16.0, 0.0]])
+N_4 = np.array([[1, 3, 2, 4], [2, 4, 1, 3], [3, 1, 4, 2], [4, 2, 3, 1]]) - 1
+W1 = np.array([[1.0, 0.48675, 0.27804, 0.13534], [0.13534, 0.27804, 0.48675, 1.0],
+               [0.13534, 0.27804, 0.48675, 1.0], [1.0, 0.48675, 0.27804, 0.13534]])
+W2 = np.array([[0.27697, 0.08615, 0.057246, 0.15723], [0.08615, 0.077009, 0.10591, 0.20589],
+               [0.057246, 0.10591, 0.13482, 0.17699], [0.15723, 0.20589, 0.17699, 0.037484]])
+
+
+def test_diffusion_golden_vectors(v3s_mod):
+    D = v3s_mod.DiffusionMapSolver
+    # diffusion_test.py:27-55, 58-80, 83-113, 116-149
+    assert hybrid_frac_bad(D.s2_to_w_matrix(S2_4.copy(), N_4, 1.0, s2_median_index=3, index_offset=0), W1, 1e-4) == 0
+    assert hybrid_frac_bad(D.anisotropic_norm(W1.copy()), W2, 1e-4) == 0
+    P_exp = np.array([[0.47952, 0.16448, 0.1093, 0.27221], [0.16448, 0.16213, 0.22299, 0.3931],
+                      [0.1093, 0.22299, 0.28385, 0.33791], [0.27221, 0.3931, 0.33791, 0.064897]])
+    P, Dm = D.dm_cov(W2.copy())
+    assert hybrid_frac_bad(P, P_exp, 1e-4) == 0
+    assert hybrid_frac_bad(Dm, np.diag([1.3158, 1.4510, 1.4510, 1.3158]), 1e-4) == 0
+    Ps_exp = np.array([[-0.689225, 0.060209], [-0.689225, 0.235587], [-0.689225, 0.115495], [-0.689225, -0.348909]])
+    Ps, Lam = D.diffusion_coordinate(S2_4.copy(), N_4, 1.0, 2, False)
+    assert hybrid_frac_bad(Lam, [1.0, -0.3242], 1e-4) == 0
+    for j in range(2):      # the reference test is sign-flaky: compare up to sign
+        assert hybrid_frac_bad(Ps[:, j], Ps_exp[:, j], 2e-4) == 0 or hybrid_frac_bad(-Ps[:, j], Ps_exp[:, j], 2e-4) == 0
+    with pytest.raises(Exception, match="No spare-matrix"):
+        D.diffusion_coordinate(S2_4.copy(), N_4, 1.0, 3, False)
+    with pytest.raises(Exception, match="S2_Max = 0"):
+        D.s2_to_w_matrix(np.zeros((4, 4)), N_4, 1.0)
+    # in-place mutation of the caller's S2 (diffusion.py:311)
+    g = S2_4.copy()
+    D.s2_to_w_matrix(g, N_4, 1.0)
+    assert np.isinf(g).any()
+
+
+def test_markov_and_matvec_connected(ops, golden_dir):
+    from v3s.pipeline import ShardPlan, markov_stage
+    g = np.load(os.path.join(golden_dir, "connected_n15.npz"))
+    N = g["S2"].shape[0]
+    S2m = g["S2"].copy()
+    _, _, W1o, Wo, Po, dio = orc.diffusion_coordinate(S2m, g["N"], float(g["eps"]), return_all=True)
+    S2d = ops.to_device(g["S2"].copy(), torch.float64)
+    P_rows, dis, sc = markov_stage(ops, ShardPlan(N), S2d, ops.to_device(g["N"], torch.int32), float(g["eps"]))
+    assert np.array_equal(S2d.cpu().numpy(), S2m)                                  # same in-place thresholding
+    assert np.allclose(dis.cpu().numpy(), g["D_diag"], rtol=1e-12)
+    P = P_rows[:, :N].cpu().numpy().astype(np.float64)
+    nz = Po != 0
+    assert np.array_equal(P != 0, nz)
+    assert np.max(np.abs(P[nz] - Po[nz]) / Po[nz]) < 1e-5                          # kernel entries, FP32 storage
+    z = g["z"]
+    X = np.stack([z, np.ones(N), 1.0 / dio] + [np.random.default_rng(i).standard_normal(N) for i in range(5)], axis=1)
+    Y = ops.block_matvec(P_rows, N, ops.to_device(X, torch.float64)).cpu().numpy()
+    Yref = Po @ X
+    assert np.max(np.abs(Y - Yref)) < 2e-6 * np.max(np.abs(Yref))
+    for b in (1, 3):
+        Yb = ops.block_matvec(P_rows, N, ops.to_device(X[:, :b].copy(), torch.float64)).cpu().numpy()
+        assert np.max(np.abs(Yb - Yref[:, :b])) < 2e-6 * np.max(np.abs(Yref))
+    # row block of a sharded job
+    Pr, _ = ops.build_markov(S2d, ops.to_device(g["N"], torch.int32), sc, 300, 777)
+    assert np.array_equal(Pr[:, :N].cpu().numpy(), P_rows[300:777, :N].cpu().numpy())
+
+
+def test_eigen_connected(v3s_mod, golden_dir):
+    g = np.load(os.path.join(golden_dir, "connected_n15.npz"))
+    stats = {}
+    Ps, Lam = v3s_mod.DiffusionMapSolver.diffusion_coordinate(g["S2"].copy(), g["N"], float(g["eps"]), stats=stats)
+    print("eigen connected:", stats, "lambda rel err", np.max(np.abs(Lam - g["Lambda"]) / g["Lambda"]))
+    assert Ps.shape == (1000, 10) and Lam.shape == (10,)
+    assert np.max(np.abs(Lam - g["Lambda"]) / g["Lambda"]) < 1e-6
+    ang = orc.principal_angles(Ps, g["Ps"])
+    print("principal angles max", ang.max())
+    assert ang.max() < 1e-4
+
+
+# ------------------------------------------------------------------ stage 4
+
+def test_fit_helpers(v3s_mod, golden_dir):
+    C = v3s_mod.ComputeUtils
+    M = np.array([[1.0, -1], [2, 3]])
+    A = np.array([[0.0, -4], [-1, 1], [5, 0], [1, 2]])
+    assert hybrid_frac_bad(C.lsq_linear(A, A @ M), M, 1e-12) == 0                 # compute_test.py:10-29
+    g = np.load(os.path.join(golden_dir, "helpers.npz"))
+    assert np.allclose(C.lsq_linear(g["A"], g["b"]), g["M"], rtol=1e-9, atol=1e-12)
+    for m in g["Ms"][:6]:
+        assert np.allclose(C.polar_decompose(m, mode=1), orc.polar_decompose(m, compat=False), atol=1e-10)
+        assert np.allclose(C.polar_decompose(m, mode=2), orc.project_so3(m[None])[0], atol=1e-10)
+        Rc = C.polar_decompose(m, mode=0)
+        assert np.allclose(Rc @ Rc.T, np.eye(3), atol=1e-10)                      # orthogonal; sign convention differs
+    sig = v3s_mod.Rotation.mean_geodesic_distance_degrees(g["quats"], g["q2"])
+    assert abs(sig - float(g["sigma"])) < 1e-9
+
+
+def test_fit_connected(v3s_mod, golden_dir):
+    g = np.load(os.path.join(golden_dir, "connected_n15.npz"))
+    c, c0, sig, out = v3s_mod.DiffusionMapSolver.dm_fit_all(g["Ps"], g["R9"], True, polar_mode=2, return_all=True)
+    assert np.allclose(c, g["c"], rtol=1e-7, atol=1e-9)
+    recon = out["recon_pre"].cpu().numpy()
+    assert np.max(np.abs(recon - g["Recon_pre"])) < 1e-9
+    Ra = orc.project_so3(recon.reshape(-1, 3, 3))
+    assert np.allclose(out["rproj"].cpu().numpy().reshape(-1, 3, 3), Ra, atol=1e-9)
+    qe = out["quat_est"].cpu().numpy().T
+    assert np.allclose(qe, orc.rot_mat_to_quat_batch(Ra), atol=1e-9)
+    qt = out["quat_true"].cpu().numpy().T
+    assert abs(sig - orc.mean_geodesic_distance_degrees(qe, qt)) < 1e-8
+    with pytest.raises(Exception):
+        v3s_mod.DiffusionMapSolver.dm_fit_all(g["Ps"], g["R9"], False)
+
+
+# ------------------------------------------------------------------ whole path
+
+def test_solve_connected_end_to_end(v3s_mod, golden_dir):
+    """Synthesis -> orientations on the connected configuration, against the reference fixture:
+    orientation parity on Recon = Ps[:,1:] @ c after one correct projection on both sides."""
+    g = np.load(os.path.join(golden_dir, "connected_n15.npz"))
+    params = {"n_voxel_1d": 15, "nRot1D": 10, "k": 150, "Epsilon": 0.7, "plot": False, "aPrioriFlag": True}
+    res = v3s_mod.OrientationRecoverySolver.solve(params, rotations=g["R9"], polar_mode=2)
+    assert set(res) == {"Ps", "Lambda", "c0", "c", "S2", "N", "Images", "R", "Sigma_T", "Axis", "Quat"}
+    ref_imgs = g["Images_f32"].astype(np.float64)
+    assert np.max(np.abs(res["Images"] - ref_imgs)) < 2e-5 * ref_imgs.max()
+    assert np.max(np.abs(res["Lambda"] - g["Lambda"]) / g["Lambda"]) < 1e-5      # FP32-pattern differences included
+    recon = res["Ps"][:, 1:] @ res["c"]
+    ang = orc.geodesic_angle_deg(orc.project_so3(recon.reshape(-1, 3, 3)), orc.project_so3(g["Recon_pre"].reshape(-1, 3, 3)))
+    print("orientation parity: median", np.median(ang), "max", ang.max(), "deg")
+    assert np.median(ang) < 0.1
+    assert np.isinf(res["S2"]).any()                                               # solve() returns the mutated S2
+
+
+def test_solve_default_parameters_shapes(v3s_mod, golden_dir):
+    """solution_test.py:12-56 (shapes) + the bit-reproducible stages of the default run."""
+    g = np.load(os.path.join(golden_dir, "default_cfg.npz"))
+    p = v3s_mod.OrientationRecoverySolver.default_parameters()
+    p["plot"] = False
+    try:
+        res = v3s_mod.OrientationRecoverySolver.solve(p)
+    except Exception as e:      # Sigma_T guard: the default graph has 182 components, the
+        assert "Sigma_T" in str(e)   # reference itself lands at 53-58 deg with an arbitrary eigenbasis
+        return
+    assert res["Ps"].shape == (512, 10) and res["Lambda"].shape == (10,) and res["c"].shape == (9, 9)
+    assert res["S2"].shape == (512, 24) and res["N"].shape == (512, 24) and res["Images"].shape == (512, 225)
+    assert res["R"].shape == (9, 512) and res["Axis"].shape == (512, 3) and res["Quat"].shape == (512, 4)
+    assert np.max(np.abs(res["Images"] - g["Images"])) < 2e-5 * g["Images"].max()
+    assert np.allclose(res["Lambda"], 1.0, atol=1e-6)                              # lambda = 1 has multiplicity 182
+
+
+def test_full_size_invariants(ops):
+    """BASELINE config 2 size (N=10k, 64x64): size-independent properties of every stage."""
+    from v3s.pipeline import ShardPlan, knn_stage, markov_stage
+    N, n, n_p, k = 10000, 31, 64, 150
+    R9, _ = orc.random_rotations(N, seed=0)
+    ed = ops.to_device(orc.synthesize_3d(n)["ED"].astype(np.float32), torch.float32)
+    img = ops.synth_patterns(ed, ops.to_device(rot9_rowmajor(R9), torch.float64), n_p)
+    sub = [0, 17, 4242, 9999]
+    ref = orc.generate_from_rotations(R9[:, sub], n, n_p)
+    assert np.max(np.abs(img[sub].cpu().numpy() - ref)) < 2e-5 * ref.max()
+    S2, Nbr = knn_stage(ops, ShardPlan(N), img, k)
+    S2h, Nh = S2.cpu().numpy(), Nbr.cpu().numpy()
+    assert np.all(np.diff(S2h, axis=1) >= 0) and np.all(S2h[:, 0] == 0) and np.array_equal(Nh[:, 0], np.arange(N))
+    assert all(len(set(r)) == k for r in Nh[::97])
+    # spot-check rows against a float64 recomputation of the whole distance row
+    A = orc.set_norm_to_one(orc.remove_offset(img.cpu().numpy().astype(np.float64)))
+    for r in (3, 5000, 9998):
+        d = np.arccos(np.clip(A @ A[r], -1, 1))
+        d[r] = 0
+        idx = np.argsort(d, kind="stable")[:k]
+        assert np.array_equal(idx, Nh[r]) and hybrid_frac_bad(S2h[r], d[idx], 1e-5) == 0
+    P_rows, dis, sc = markov_stage(ops, ShardPlan(N), S2, Nbr, 0.7)
+    # P = D^-1/2 W2 D^-1/2 with d = rowsum(W2): sqrt(d) is the lambda = 1 eigenvector; P is symmetric
+    v = (1.0 / dis).reshape(-1, 1).contiguous()
+    Pv = ops.block_matvec(P_rows, N, v)
+    assert float(torch.max(torch.abs(Pv - v)) / torch.max(v)) < 1e-5
+    Pd = P_rows[:, :N]
+    assert torch.equal(Pd, Pd.T)

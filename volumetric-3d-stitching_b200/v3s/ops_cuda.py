@@ -30,6 +30,31 @@ class CudaOps:
         self._mv_ws = None
         self._sigma_ws = None
         self.gram_impl = "tcgen05"   # "simt" = FP32 CUDA-core validation path
+        self.profile = False         # when True, CUDA events bracket the named kernels (bench.py)
+        self._events = []
+
+    # ---- per-kernel device timing (CUDA events on the launching stream) ------------------------
+    def _tic(self, name):
+        if not self.profile:
+            return None
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        return (name, e0, e1)
+
+    def _toc(self, h):
+        if h is not None:
+            h[2].record()
+            self._events.append(h)
+
+    def pop_timings(self):
+        """-> {name: [ms per launch, ...]} for the launches since the last call (synchronises)."""
+        torch.cuda.synchronize()
+        out = {}
+        for name, e0, e1 in self._events:
+            out.setdefault(name, []).append(e0.elapsed_time(e1))
+        self._events = []
+        return out
 
     # ---- allocation helpers ---------------------------------------------------------------
     def empty(self, shape, dtype):
@@ -56,8 +81,10 @@ class CudaOps:
             _lib.lib.v3s_default_geometry(C.byref(g))
             for k_, v_ in geom.items():
                 setattr(g, "lambda_" if k_ == "lambda" else k_, v_)
+        h = self._tic("synth")
         call("v3s_synth_patterns", ptr(ed), n, ptr(rot9), N, n_p, C.byref(g) if g is not None else None, ptr(out),
              n_p * n_p, stream_ptr())
+        self._toc(h)
         return out
 
     # ---- stage 2 -----------------------------------------------------------------------------
@@ -74,8 +101,10 @@ class CudaOps:
         hi = self.empty((n, Ppad), torch.bfloat16) if want_split else None
         lo = self.empty((n, Ppad), torch.bfloat16) if want_split else None
         zf = self.empty((n,), torch.int32)
+        h = self._tic("center_normalize")
         call("v3s_center_normalize", ptr(img), n, P, img.stride(0), ptr(mean), ptr(a32), ptr(hi), ptr(lo), Ppad, None,
              ptr(zf), stream_ptr())
+        self._toc(h)
         return a32, hi, lo, zf
 
     def gram_rows(self, hi_all, lo_all, a32_all, r0, r1, out=None):
@@ -84,11 +113,13 @@ class CudaOps:
         nr = r1 - r0
         ldg = round_up(N, 4)
         G = out if out is not None else self.empty((nr, ldg), torch.float32)
+        h = self._tic("gram")
         if self.gram_impl == "simt":
             call("v3s_gram_rows_simt", ptr(a32_all), N, ptr(a32_all[r0:r1]), nr, a32_all.shape[1], ptr(G), ldg, stream_ptr())
         else:
             call("v3s_gram_rows", ptr(hi_all), ptr(lo_all), N, ptr(hi_all[r0:r1]), ptr(lo_all[r0:r1]), nr,
                  hi_all.shape[1], ptr(G), ldg, stream_ptr())
+        self._toc(h)
         return G
 
     def knn_rows(self, hi_all, lo_all, a32_all, zero_flag, r0, r1, k):
@@ -111,8 +142,10 @@ class CudaOps:
         for p0 in range(r0, r1, panel):
             p1 = min(p0 + panel, r1)
             self.gram_rows(hi_all, lo_all, a32_all, p0, p1, out=G)
+            h = self._tic("select_refine")
             call("v3s_knn_from_gram", ptr(G), ldg, p1 - p0, N, p0, ptr(a32_all[p0:p1]), ptr(a32_all), P, k, KNN_MARGIN,
                  ptr(zf), ptr(cand), ptr(S2[p0 - r0:p1 - r0]), ptr(Nbr[p0 - r0:p1 - r0]), stream_ptr())
+            self._toc(h)
         return S2, Nbr
 
     def round_distance_dense(self, a32, zero_flag):
@@ -149,8 +182,10 @@ class CudaOps:
         P_rows = self.empty((r1 - r0, ldp), torch.float32)
         dis = self.empty((N,), torch.float64)
         ws = self.empty((2 * N,), torch.float64)
+        h = self._tic("markov")
         call("v3s_build_markov", ptr(S2t), ptr(Nbr), N, k, ptr(scalars), r0, r1 - r0, ptr(P_rows), ldp, ptr(dis), ptr(ws),
              stream_ptr())
+        self._toc(h)
         return P_rows, dis
 
     def w_dense(self, S2t, Nbr, eps_eff):
@@ -182,7 +217,9 @@ class CudaOps:
         if self._mv_ws is None or self._mv_ws.numel() < need:
             self._mv_ws = self.empty((need,), torch.uint8)
         Y = self.empty((n_rows, b), torch.float64)
+        h = self._tic("matvec")
         call("v3s_block_matvec", ptr(P_rows), ldp, n_rows, N, ptr(X), b, ptr(Y), ptr(self._mv_ws), stream_ptr())
+        self._toc(h)
         return Y
 
     # ---- stage 4 -----------------------------------------------------------------------------
@@ -210,5 +247,7 @@ class CudaOps:
         if self._sigma_ws is None:
             self._sigma_ws = self.empty((65536,), torch.float64)
         out = self.empty((1,), torch.float64)
+        h = self._tic("sigma_pairs")
         call("v3s_sigma_pairs", ptr(qe), ptr(qt), qe.shape[0], r0, r1 - r0, ptr(self._sigma_ws), ptr(out), stream_ptr())
+        self._toc(h)
         return out

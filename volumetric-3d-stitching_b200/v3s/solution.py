@@ -16,10 +16,11 @@ class OrientationRecoverySolver:
         return OrientationRecoverySolver.solve(parameters)
 
     @staticmethod
-    def solve(parameters, rotations=None, N_p=None, polar_mode=0, stats=None):
+    def solve(parameters, rotations=None, N_p=None, polar_mode=0, stats=None, check_sigma=True):
         """solution.py:34-61 -> dict of numpy float64 arrays with the reference's 11 keys.
         Extensions that never change reference-mode results: `rotations` = explicit
-        R (9,N) instead of the Hopf grid, `N_p` = free detector size."""
+        R (9,N) instead of the Hopf grid, `N_p` = free detector size, `check_sigma=False` = report
+        Sigma_T > 60 instead of raising (diffusion.py:175-176)."""
         print('OrientationRecoverySolver.solve started.')
         if not OrientationRecoverySolver.validate_parameters(parameters):
             parameters = OrientationRecoverySolver.default_parameters()
@@ -41,7 +42,9 @@ class OrientationRecoverySolver:
         rot9 = Projector.rot9_rowmajor(R, ops)
         rot_y = ops.to_device(np.ascontiguousarray(R.T), torch.float64)
         out = run_pipeline(ops, ShardPlan(Nn), ed, rot9, rot_y, n_p, parameters['k'], parameters['Epsilon'],
-                           polar_mode=polar_mode, check=True, stats=stats)
+                           polar_mode=polar_mode, check=check_sigma, stats=stats)
+        if 'sigma_T_host' not in out:
+            out['sigma_T_host'] = float(out['sigma_T'].item())
         Images = out['Images_local'].cpu().numpy().astype(np.float64)
         if not Images[Images != 0].size > 0:
             raise Exception('Images is an all-zero array.')          # projection.py:47
