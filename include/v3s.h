@@ -34,15 +34,22 @@ typedef struct v3s_geometry {
 
 void v3s_default_geometry(v3s_geometry* g /* host */);
 
+/* Geometry of Projector.q_and_mask / camera_x_y / fourier_scaled_axis (projection.py:121-190),
+ * once per (n, n_p, geometry): writes the per-pixel interpolation taps into the caller's device
+ * workspace (v3s_synth_workspace_bytes(n_p) bytes) and the k_z plane range into meta_host[2].
+ * geom: host pointer or NULL for the reference's constants.                                   */
+long long v3s_synth_workspace_bytes(int n_p);
+int v3s_synth_prepare(int n, int n_p, const v3s_geometry* geom /* host */, void* ws_dev, int* meta_host /* host [2] */,
+                      void* stream);
+
 /* Projector.generate's hot loop (projection.py:35-43) = N x Projector.generate_single_image
- * (projection.py:55-71) incl. Rotation.rotate_structure_index (rotation.py:143-162) and
- * Projector.q_and_mask / camera_x_y / fourier_scaled_axis (projection.py:121-190).
+ * (projection.py:55-71) incl. Rotation.rotate_structure_index (rotation.py:143-162).
  *   ed    [n,n,n] FP32 object, array axes as in Projector.synsthesize_3d (projection.py:75-91)
  *   rot9  [N,9]   FP64, row-major 3x3 per pattern = R[:,c].reshape(3,3).T of projection.py:38
- *   out   [N, n_p*n_p] FP32 patterns, row stride out_stride elements
- *   geom  host pointer or NULL for the reference's constants                              */
-int v3s_synth_patterns(const float* ed, int n, const double* rot9, long long N, int n_p,
-                       const v3s_geometry* geom /* host */, float* out, long long out_stride, void* stream);
+ *   ws_dev, z0, nz  from v3s_synth_prepare
+ *   out   [N, n_p*n_p] FP32 patterns, row stride out_stride elements                        */
+int v3s_synth_patterns(const float* ed, int n, const double* rot9, long long N, int n_p, const void* ws_dev, int z0,
+                       int nz, float* out, long long out_stride, void* stream);
 
 /* ---- stage 2: distances + k nearest neighbours ----------------------------------------- */
 
@@ -110,6 +117,23 @@ int v3s_dm_cov_dense(const double* W, long long N, double* P_out, double* dinv_s
 long long v3s_block_matvec_workspace_bytes(long long n_rows, long long N);
 int v3s_block_matvec(const float* P_rows, long long ldp, long long n_rows, long long N, const double* X, int b,
                      double* Y_rows, void* workspace, void* stream);
+
+/* the same product with the block already in FP32 [N,8] (the form v3s_lanczos_step emits)      */
+int v3s_block_matvec_f32(const float* P_rows, long long ldp, long long n_rows, long long N, const float* Xf,
+                         double* Y_rows, void* workspace, void* stream);
+
+/* Device-side block-Lanczos iteration, block size 8 -- the per-iteration work ARPACK does on the
+ * host behind scipy.sparse.linalg.eigs (diffusion.py:61).  V [max_dim, ldv] FP64 basis (vectors as
+ * rows), W [N,8] FP64 block, Xf [N,8] FP32 copy for the mat-vec, ws: v3s_lanczos_workspace_doubles.
+ *   v3s_lanczos_start: orthonormalise the start block W in place; V[0..8) <- Q^T, Xf <- float(Q).
+ *   v3s_lanczos_step : W = P Q_j on entry (m = basis size, Q_j = V[m-8..m)); two-pass block
+ *       Gram-Schmidt against V[0..m), Cholesky-QR twice; on return W = Q_{j+1}, appended to V when
+ *       m + 8 <= max_dim, Xf its FP32 copy, Tblk[128] = {A_j (8x8), B_j (8x8)} of the projected
+ *       block-tridiagonal matrix; *status_out_dev != 0 after a Cholesky breakdown.                */
+long long v3s_lanczos_workspace_doubles(long long N, int max_dim);
+int v3s_lanczos_start(double* V, long long ldv, long long N, int max_dim, double* W, float* Xf, double* ws, void* stream);
+int v3s_lanczos_step(double* V, long long ldv, long long N, int m, int max_dim, double* W, float* Xf, double* Tblk,
+                     double* ws, int* status_out_dev, void* stream);
 
 /* ---- stage 4: orientation retrieval ---------------------------------------------------------- */
 

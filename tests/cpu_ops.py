@@ -137,3 +137,35 @@ class OracleOps:
         a = np.arccos(np.clip(_np(qe)[r0:r1] @ _np(qe).T, 0, 1))
         b = np.arccos(np.clip(_np(qt)[r0:r1] @ _np(qt).T, 0, 1))
         return torch.tensor([np.abs(a - b).sum()], dtype=torch.float64)
+
+    # device-driver Lanczos interface (mirrors CudaOps.lanczos_*), plain torch on CPU
+    def block_matvec_f32(self, P_rows, N, Xf):
+        return (P_rows[:, :N].to(torch.float32) @ Xf).to(torch.float64)
+
+    def lanczos_alloc(self, N, max_dim, max_steps):
+        return {"N": N, "max_dim": max_dim, "V": torch.zeros((max_dim, N), dtype=torch.float64),
+                "Xf": torch.zeros((N, 8), dtype=torch.float32), "T": torch.zeros((max_steps, 128), dtype=torch.float64),
+                "status": torch.zeros((1,), dtype=torch.int32)}
+
+    def lanczos_start(self, st, W0):
+        Q, _ = torch.linalg.qr(W0)
+        W0.copy_(Q)
+        st["V"][:8] = Q.T
+        st["Xf"].copy_(Q.to(torch.float32))
+
+    def lanczos_step(self, st, m, W, step):
+        Vm = st["V"][:m]
+        H = Vm @ W
+        W -= Vm.T @ H
+        H2 = Vm @ W
+        W -= Vm.T @ H2
+        H += H2
+        A = 0.5 * (H[m - 8:m] + H[m - 8:m].T)
+        Q, R = torch.linalg.qr(W)
+        sg = torch.sign(torch.diagonal(R))
+        Q, R = Q * sg[None, :], R * sg[:, None]          # positive diagonal, like a Cholesky factor
+        W.copy_(Q)
+        if m + 8 <= st["max_dim"]:
+            st["V"][m:m + 8] = Q.T
+        st["Xf"].copy_(Q.to(torch.float32))
+        st["T"][step] = torch.cat([A, R], dim=0).reshape(-1)

@@ -120,7 +120,7 @@ def test_gram_tcgen05_vs_fp64(ops, shape):
     # (round toward zero), so G carries a small systematic bias that grows with the number of
     # accumulation steps (3 P / 16): <= half an ulp(1) per step.  G only ranks kNN candidates -- the
     # distances themselves are recomputed exactly (select.cu) -- so what matters is the ranking below.
-    tol = 2e-6 + 3.0e-8 * (3 * P / 16)
+    tol = 1e-5 + 3.0e-8 * (3 * P / 16)      # + the dropped lo.lo^T term, 2^-18 relative
     assert e_tc < tol
     # ranking: the exact top-(k) set of every row is inside the top-(k+margin) of the tensor-core Gram
     k, margin = min(50, N // 4), 8
@@ -158,7 +158,7 @@ def test_knn_default_cfg_fixture_with_duplicates(v3s_mod, golden_dir):
     print("default cfg knn: max abs err", err.max(), "frac outside", 1 - ok.mean())
     assert ok.all()
     untied = np.ones_like(S2, dtype=bool)
-    d = np.abs(np.diff(g["S2"], axis=1)) > 1e-6
+    d = np.abs(np.diff(g["S2"], axis=1)) > 5e-6
     untied[:, 1:] &= d
     untied[:, :-1] &= d
     assert np.array_equal(N[untied], g["N"][untied])
@@ -179,6 +179,7 @@ def test_knn_zero_rows_and_panels(ops):
     S2, N = knn_stage(ops, ShardPlan(700), ops.to_device(A, torch.float32), 20)
     oS2, oN = orc.knn(A.astype(np.float64), 20)
     S2, N = S2.cpu().numpy(), N.cpu().numpy()
+    print("row 1:", S2[1, :5], N[1, :5], "oracle:", oS2[1, :5], oN[1, :5])
     assert np.all(S2[13] == 0) and np.all(S2[363] == 0)              # distance 0 to everything
     rows = np.array([r for r in range(700) if r not in (13, 363)])
     assert np.all(S2[rows, :3] == 0)                                 # self + the two NaN columns

@@ -52,6 +52,20 @@ def test_block_lanczos_matches_dense_eigh(golden_dir):
     assert stats["converged"] and stats["matvecs"] < 60
 
 
+def test_device_driver_lanczos_host_logic(golden_dir):
+    """block_lanczos_device (the host side of csrc/lanczos.cu) against dense eigh, CPU stand-in steps."""
+    from v3s.eig import block_lanczos_device
+    g = np.load(os.path.join(golden_dir, "connected_n15.npz"))
+    _, _, _, _, P, _ = orc.diffusion_coordinate(g["S2"].copy(), g["N"], float(g["eps"]), return_all=True)
+    Pt = torch.from_numpy(P)
+    stats = {}
+    lam, V, res = block_lanczos_device(OracleOps(), lambda Xf: Pt @ Xf.to(torch.float64), P.shape[0], 10, tol=1e-7, stats=stats)
+    w, U = np.linalg.eigh(P)
+    assert np.max(np.abs(np.sort(lam)[::-1] - w[::-1][:10])) < 1e-7     # the operand block is FP32 (Xf)
+    assert np.max(orc.principal_angles(V.numpy(), U[:, -10:])) < 1e-5
+    assert stats["converged"] and stats["driver"] == "device"
+
+
 def test_stage_api_golden_vectors():
     """The reference's own unit-test vectors through the product's adapters (CPU backend)."""
     S2 = np.array([[0.0, 16.0, 9.0, 25.0], [16.0, 0.0, 25.0, 9.0], [9.0, 25.0, 0.0, 16.0], [25.0, 9.0, 16.0, 0.0]])

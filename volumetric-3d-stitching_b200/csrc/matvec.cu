@@ -155,6 +155,9 @@ extern "C" long long v3s_block_matvec_workspace_bytes(long long n_rows, long lon
   return (long long)sizeof(float) * N * MV_B + (long long)sizeof(double) * nchunks * n_rows * MV_B + 256;
 }
 
+static int mv_run(const float* P_rows, long long ldp, long long n_rows, long long N, const float* Xf, int b,
+                  double* Y_rows, double* Ypart, cudaStream_t st);
+
 extern "C" int v3s_block_matvec(const float* P_rows, long long ldp, long long n_rows, long long N, const double* X, int b,
                                 double* Y_rows, void* workspace, void* stream) {
   V3S_REQUIRE(b >= 1 && b <= MV_B, "v3s_block_matvec: block size b=%d outside [1,%d]", b, MV_B);
@@ -162,14 +165,29 @@ extern "C" int v3s_block_matvec(const float* P_rows, long long ldp, long long n_
   V3S_REQUIRE(((uintptr_t)P_rows & 15) == 0, "v3s_block_matvec: P_rows must be 16-byte aligned");
   if (n_rows == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  int nchunks; long long cc;
-  mv_plan(n_rows, N, &nchunks, &cc);
   float* Xf = reinterpret_cast<float*>(workspace);
   double* Ypart = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(workspace) + (((size_t)sizeof(float) * N * MV_B + 255) & ~(size_t)255));
   long long g = ceil_div64(N * MV_B, 256);
   if (g > 8LL * kNumSMs) g = 8LL * kNumSMs;
   x_to_f32_kernel<<<(int)g, 256, 0, st>>>(X, N, b, Xf);
   V3S_CHECK_LAUNCH();
+  return mv_run(P_rows, ldp, n_rows, N, Xf, b, Y_rows, Ypart, st);
+}
+
+// Same product with the block already in FP32 [N,8] (the form the Lanczos step emits).
+extern "C" int v3s_block_matvec_f32(const float* P_rows, long long ldp, long long n_rows, long long N, const float* Xf,
+                                    double* Y_rows, void* workspace, void* stream) {
+  V3S_REQUIRE(n_rows >= 0 && N >= 1 && ldp >= N && ldp % 4 == 0, "v3s_block_matvec_f32: bad shape (ldp must be a multiple of 4)");
+  V3S_REQUIRE(((uintptr_t)P_rows & 15) == 0 && ((uintptr_t)Xf & 15) == 0, "v3s_block_matvec_f32: pointers must be 16-byte aligned");
+  if (n_rows == 0) return 0;
+  double* Ypart = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(workspace) + (((size_t)sizeof(float) * N * MV_B + 255) & ~(size_t)255));
+  return mv_run(P_rows, ldp, n_rows, N, Xf, MV_B, Y_rows, Ypart, (cudaStream_t)stream);
+}
+
+static int mv_run(const float* P_rows, long long ldp, long long n_rows, long long N, const float* Xf, int b,
+                  double* Y_rows, double* Ypart, cudaStream_t st) {
+  int nchunks; long long cc;
+  mv_plan(n_rows, N, &nchunks, &cc);
   dim3 grid((unsigned)ceil_div64(n_rows, MV_WARPS * MV_ROWS), (unsigned)nchunks);
   block_matvec_kernel<<<grid, MV_THREADS, 0, st>>>(P_rows, ldp, n_rows, N, Xf, cc, Ypart);
   V3S_CHECK_LAUNCH();

@@ -230,33 +230,44 @@ extern "C" void v3s_default_geometry(v3s_geometry* g) {
   g->pixel = 75e-6; g->zd = 0.5; g->lambda = 2 * 1e-9; g->n_p_nobin = 1024; g->grid_scale = 2e-7;
 }
 
-extern "C" int v3s_synth_patterns(const float* ed, int n, const double* rot9, long long N, int n_p,
-                                  const v3s_geometry* geom, float* out, long long out_stride, void* stream) {
-  V3S_REQUIRE(n >= 2 && n <= 255, "v3s_synth_patterns: n_voxel_1d=%d outside [2,255]", n);
-  V3S_REQUIRE(n_p >= 2 && N >= 0, "v3s_synth_patterns: bad n_p=%d or N=%lld", n_p, N);
+extern "C" long long v3s_synth_workspace_bytes(int n_p) { return (long long)sizeof(PixelTap) * n_p * n_p; }
+
+// Geometry set-up, once per (n, n_p, geometry): fills the caller's device workspace with the
+// per-pixel interpolation taps and returns the k_z plane range in meta_host = {z0, nz}.
+extern "C" int v3s_synth_prepare(int n, int n_p, const v3s_geometry* geom, void* ws_dev, int* meta_host, void* stream) {
+  V3S_REQUIRE(n >= 2 && n <= 255, "v3s_synth_prepare: n_voxel_1d=%d outside [2,255]", n);
+  V3S_REQUIRE(n_p >= 2, "v3s_synth_prepare: bad n_p=%d", n_p);
   v3s_geometry g;
   if (geom) g = *geom; else v3s_default_geometry(&g);
   std::vector<PixelTap> taps;
   int z0, nz;
   build_taps(n, n_p, &g, taps, &z0, &nz);
-  V3S_REQUIRE(nz <= kMaxPlanes, "v3s_synth_patterns: Ewald sphere spans %d k_z planes (max %d)", nz, kMaxPlanes);
+  V3S_REQUIRE(nz <= kMaxPlanes, "v3s_synth_prepare: Ewald sphere spans %d k_z planes (max %d)", nz, kMaxPlanes);
+  // pageable source: the copy is staged before the call returns, so `taps` may be released
+  V3S_CUDA(cudaMemcpyAsync(ws_dev, taps.data(), sizeof(PixelTap) * n_p * n_p, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  meta_host[0] = z0;
+  meta_host[1] = nz;
+  return 0;
+}
+
+extern "C" int v3s_synth_patterns(const float* ed, int n, const double* rot9, long long N, int n_p, const void* ws_dev,
+                                  int z0, int nz, float* out, long long out_stride, void* stream) {
+  V3S_REQUIRE(n >= 2 && n <= 255 && n_p >= 2 && N >= 0, "v3s_synth_patterns: bad n=%d n_p=%d N=%lld", n, n_p, N);
+  V3S_REQUIRE(nz >= 1 && nz <= kMaxPlanes && ws_dev != nullptr, "v3s_synth_patterns: call v3s_synth_prepare first");
   if (N == 0) return 0;
-  cudaStream_t st = (cudaStream_t)stream;
   const int P = n_p * n_p;
-  PixelTap* d_taps = nullptr;
-  V3S_CUDA(cudaMallocAsync(&d_taps, sizeof(PixelTap) * P, st));
-  V3S_CUDA(cudaMemcpyAsync(d_taps, taps.data(), sizeof(PixelTap) * P, cudaMemcpyHostToDevice, st));
   const int n2 = n * n, n3 = n2 * n;
   size_t smem = sizeof(float) * ((n3 + 3) & ~3) + 2 * sizeof(float2) * nz * n2 + sizeof(float) * ((nz * n2 + 1) & ~1) +
                 sizeof(float2) * n;
   V3S_REQUIRE(smem <= 227 * 1024, "v3s_synth_patterns: object n=%d needs %zu B shared memory (max 232448)", n, smem);
-  V3S_CUDA(cudaFuncSetAttribute(synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    V3S_CUDA(cudaFuncSetAttribute(synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
   SynthParams prm{n, nz, z0, P, N};
   int grid = (int)(N < (long long)kNumSMs ? N : kNumSMs);
-  synth_kernel<<<grid, kSynthThreads, smem, st>>>(ed, rot9, d_taps, out, out_stride, prm);
+  synth_kernel<<<grid, kSynthThreads, smem, (cudaStream_t)stream>>>(ed, rot9, (const PixelTap*)ws_dev, out, out_stride, prm);
   V3S_CHECK_LAUNCH();
-  // the pageable source buffer must outlive the async copy: the copy above is synchronous
-  // with respect to the host for pageable memory, so `taps` may be released now.
-  V3S_CUDA(cudaFreeAsync(d_taps, st));
   return 0;
 }

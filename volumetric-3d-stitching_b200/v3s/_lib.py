@@ -29,7 +29,9 @@ SIGNATURES = {
     "v3s_version": (i32, []),
     "v3s_check_device": (i32, []),
     "v3s_default_geometry": (None, [C.POINTER(Geometry)]),
-    "v3s_synth_patterns": (i32, [p, i32, p, i64, i32, C.POINTER(Geometry), p, i64, p]),
+    "v3s_synth_workspace_bytes": (i64, [i32]),
+    "v3s_synth_prepare": (i32, [i32, i32, C.POINTER(Geometry), p, C.POINTER(i32), p]),
+    "v3s_synth_patterns": (i32, [p, i32, p, i64, i32, p, i32, i32, p, i64, p]),
     "v3s_column_sums": (i32, [p, i64, i32, i64, p, p]),
     "v3s_center_normalize": (i32, [p, i64, i32, i64, p, p, p, p, i32, p, p, p]),
     "v3s_gram_rows": (i32, [p, p, i64, p, p, i64, i32, p, i64, p]),
@@ -45,6 +47,10 @@ SIGNATURES = {
     "v3s_dm_cov_dense": (i32, [p, i64, p, p, p, p]),
     "v3s_block_matvec_workspace_bytes": (i64, [i64, i64]),
     "v3s_block_matvec": (i32, [p, i64, i64, i64, p, i32, p, p, p]),
+    "v3s_block_matvec_f32": (i32, [p, i64, i64, i64, p, p, p, p]),
+    "v3s_lanczos_workspace_doubles": (i64, [i64, i32]),
+    "v3s_lanczos_start": (i32, [p, i64, i64, i32, p, p, p, p]),
+    "v3s_lanczos_step": (i32, [p, i64, i64, i32, i32, p, p, p, p, p, p]),
     "v3s_fit_gram": (i32, [p, i32, p, i64, p, p]),
     "v3s_fit_solve": (i32, [p, p, p]),
     "v3s_fit_project": (i32, [p, i32, p, i64, p, i32, p, p, p, p, p]),

@@ -82,6 +82,76 @@ def _ritz_from_band(band, m, b, nev):
     return wz[idx], Q @ Z[:, idx]
 
 
+def _fill_band(band, b, m_of_block, blk):
+    for c in range(b):
+        col = m_of_block - b + c
+        for i in range(0, b + 1):
+            r = c + i                           # row offset inside the [A; B] stack
+            band[i, col] = blk[r, c] if (r < b or (r - b) <= c) else 0.0
+
+
+def _next_check(steps, res_max, target, prev, max_gap):
+    """Schedule the next Ritz extraction from the observed convergence rate (it is host work)."""
+    gap = 4
+    if prev is not None and res_max < prev[1]:
+        rate = np.log(prev[1] / res_max) / (steps - prev[0])
+        gap = int(np.ceil(0.85 * np.log(res_max / target) / rate))
+    return steps + max(1, min(max_gap, gap))
+
+
+def block_lanczos_device(ops, matvec_f32, N, nev, tol=1e-8, max_dim=None, first_check=6, seed=0, max_gap=16,
+                         stats=None):
+    """Same algorithm as `block_lanczos_topk`, with every per-step operation enqueued on the GPU by
+    the C-ABI (`v3s_lanczos_start` / `v3s_lanczos_step`, csrc/lanczos.cu): the host only launches,
+    and reads back the small (A_j, B_j) blocks when it extracts Ritz pairs.
+
+    matvec_f32: Xf [N,8] float32 tensor -> P @ Xf as [N,8] float64 tensor (all-gathered when sharded).
+    """
+    b = 8
+    if max_dim is None:
+        max_dim = min(N, 1024)
+    max_dim = max(b, (min(max_dim, N) // b) * b)
+    max_steps = max_dim // b
+    st = ops.lanczos_alloc(N, max_dim, max_steps)
+    gen = torch.Generator(device="cpu")
+    gen.manual_seed(seed)
+    W0 = torch.randn((N, b), generator=gen, dtype=torch.float64).to(ops.device)
+    ops.lanczos_start(st, W0)
+    m, steps, copied = b, 0, 0
+    band = np.zeros((b + 1, max_dim))
+    next_check, prev, n_checks = min(first_check, max_steps), None, 0
+    w = S = res = None
+    while True:
+        W = matvec_f32(st["Xf"])
+        ops.lanczos_step(st, m, W, steps)
+        steps += 1
+        last = (m + b > max_dim)
+        if steps >= next_check or last:
+            blks = st["T"][copied:steps].cpu().numpy().reshape(-1, 2 * b, b)     # one small D2H per check
+            if int(st["status"].item()) != 0:
+                raise Exception("block Lanczos broke down (Cholesky-QR of a rank-deficient block)")
+            for i_, blk in enumerate(blks):
+                _fill_band(band, b, (copied + i_ + 1) * b, blk)
+            copied = steps
+            w, S = _ritz_from_band(band, m, b, nev)
+            res = np.linalg.norm(blks[-1][b:] @ S[m - b:m, :], axis=0)
+            if not np.all(np.isfinite(res)):
+                raise Exception("block Lanczos broke down (non-finite residuals)")
+            target = tol * max(np.abs(w).max(), 1e-300)
+            n_checks += 1
+            if res.max() <= target or last:
+                break
+            next_check = _next_check(steps, res.max(), target, prev, max_gap)
+            prev = (steps, res.max())
+        m += b
+    St = torch.from_numpy(np.ascontiguousarray(S)).to(ops.device)
+    Y = st["V"][:m].T @ St
+    if stats is not None:
+        stats.update({"matvecs": steps, "block": b, "krylov_dim": m, "ritz_checks": n_checks, "residual_max": float(res.max()),
+                      "converged": bool(res.max() <= tol * max(np.abs(w).max(), 1e-300)), "driver": "device"})
+    return w, Y, res
+
+
 def block_lanczos_topk(matvec, N, nev, device, block=8, tol=1e-8, max_dim=None, first_check=6, seed=0,
                        max_gap=16, stats=None):
     """Largest-magnitude `nev` eigenpairs of the symmetric operator `matvec`.
@@ -126,11 +196,7 @@ def block_lanczos_topk(matvec, N, nev, device, block=8, tol=1e-8, max_dim=None, 
         if steps >= next_check or last:
             blks = torch.stack([t for _, t in pending]).cpu().numpy()   # one small D2H per check
             for (mm, _), blk in zip(pending, blks):
-                for c in range(b):
-                    col = mm - b + c
-                    for i in range(0, b + 1):
-                        r = c + i                           # row offset inside the [A; B] stack
-                        band[i, col] = blk[r, c] if (r < b or (r - b) <= c) else 0.0
+                _fill_band(band, b, mm, blk)
             pending = []
             w, S = _ritz_from_band(band, m, b, nev)
             Bn = blk[b:]
@@ -141,13 +207,8 @@ def block_lanczos_topk(matvec, N, nev, device, block=8, tol=1e-8, max_dim=None, 
             n_checks += 1
             if res.max() <= target or last:
                 break
-            # schedule the next check from the observed convergence rate (Ritz extraction is host work)
-            gap = 4
-            if prev is not None and res.max() < prev[1]:
-                rate = np.log(prev[1] / res.max()) / (steps - prev[0])
-                gap = int(np.ceil(0.85 * np.log(res.max() / target) / rate))
+            next_check = _next_check(steps, res.max(), target, prev, max_gap)
             prev = (steps, res.max())
-            next_check = steps + max(1, min(max_gap, gap))
         V[m:m + b] = Qn.T
         m += b
         Q = Qn

@@ -32,6 +32,7 @@ class CudaOps:
         self.gram_impl = "tcgen05"   # "simt" = FP32 CUDA-core validation path
         self.profile = False         # when True, CUDA events bracket the named kernels (bench.py)
         self._events = []
+        self._synth_prep = {}
 
     # ---- per-kernel device timing (CUDA events on the launching stream) ------------------------
     def _tic(self, name):
@@ -75,15 +76,23 @@ class CudaOps:
         n = ed.shape[0]
         N = rot9.shape[0]
         out = self.empty((N, n_p * n_p), torch.float32)
-        g = None
-        if geom is not None:
-            g = _lib.Geometry()
-            _lib.lib.v3s_default_geometry(C.byref(g))
-            for k_, v_ in geom.items():
-                setattr(g, "lambda_" if k_ == "lambda" else k_, v_)
+        key = (n, n_p, tuple(sorted(geom.items())) if geom else None)
+        prep = self._synth_prep.get(key)
+        if prep is None:                       # geometry set-up once per (n, n_p, geometry)
+            g = None
+            if geom is not None:
+                g = _lib.Geometry()
+                _lib.lib.v3s_default_geometry(C.byref(g))
+                for k_, v_ in geom.items():
+                    setattr(g, "lambda_" if k_ == "lambda" else k_, v_)
+            ws = self.empty((int(_lib.lib.v3s_synth_workspace_bytes(n_p)),), torch.uint8)
+            meta = (C.c_int * 2)()
+            call("v3s_synth_prepare", n, n_p, C.byref(g) if g is not None else None, ptr(ws), meta, stream_ptr())
+            prep = (ws, int(meta[0]), int(meta[1]))
+            self._synth_prep[key] = prep
         h = self._tic("synth")
-        call("v3s_synth_patterns", ptr(ed), n, ptr(rot9), N, n_p, C.byref(g) if g is not None else None, ptr(out),
-             n_p * n_p, stream_ptr())
+        call("v3s_synth_patterns", ptr(ed), n, ptr(rot9), N, n_p, ptr(prep[0]), prep[1], prep[2], ptr(out), n_p * n_p,
+             stream_ptr())
         self._toc(h)
         return out
 
@@ -213,14 +222,46 @@ class CudaOps:
         """Y_rows [n_rows,b] f64 = P_rows[:, :N] (f32) @ X [N,b] (f64)."""
         n_rows, ldp = P_rows.shape
         b = X.shape[1]
+        ws = self._mv_workspace(n_rows, N)
+        Y = self.empty((n_rows, b), torch.float64)
+        h = self._tic("matvec")
+        call("v3s_block_matvec", ptr(P_rows), ldp, n_rows, N, ptr(X), b, ptr(Y), ptr(ws), stream_ptr())
+        self._toc(h)
+        return Y
+
+    def _mv_workspace(self, n_rows, N):
         need = _lib.lib.v3s_block_matvec_workspace_bytes(n_rows, N)
         if self._mv_ws is None or self._mv_ws.numel() < need:
             self._mv_ws = self.empty((need,), torch.uint8)
-        Y = self.empty((n_rows, b), torch.float64)
+        return self._mv_ws
+
+    def block_matvec_f32(self, P_rows, N, Xf):
+        """Y_rows [n_rows,8] f64 = P_rows[:, :N] (f32) @ Xf [N,8] (f32)."""
+        n_rows, ldp = P_rows.shape
+        Y = self.empty((n_rows, 8), torch.float64)
+        ws = self._mv_workspace(n_rows, N)
         h = self._tic("matvec")
-        call("v3s_block_matvec", ptr(P_rows), ldp, n_rows, N, ptr(X), b, ptr(Y), ptr(self._mv_ws), stream_ptr())
+        call("v3s_block_matvec_f32", ptr(P_rows), ldp, n_rows, N, ptr(Xf), ptr(Y), ptr(ws), stream_ptr())
         self._toc(h)
         return Y
+
+    # device-side block-Lanczos state and steps (lanczos.cu)
+    def lanczos_alloc(self, N, max_dim, max_steps):
+        st = {"N": N, "max_dim": max_dim,
+              "V": self.empty((max_dim, N), torch.float64), "Xf": self.empty((N, 8), torch.float32),
+              "T": self.zeros((max_steps, 128), torch.float64), "status": self.zeros((1,), torch.int32),
+              "ws": self.empty((int(_lib.lib.v3s_lanczos_workspace_doubles(N, max_dim)),), torch.float64)}
+        return st
+
+    def lanczos_start(self, st, W0):
+        call("v3s_lanczos_start", ptr(st["V"]), st["N"], st["N"], st["max_dim"], ptr(W0), ptr(st["Xf"]), ptr(st["ws"]),
+             stream_ptr())
+
+    def lanczos_step(self, st, m, W, step):
+        h = self._tic("lanczos_orth")
+        call("v3s_lanczos_step", ptr(st["V"]), st["N"], st["N"], m, st["max_dim"], ptr(W), ptr(st["Xf"]),
+             ptr(st["T"][step]), ptr(st["ws"]), ptr(st["status"]), stream_ptr())
+        self._toc(h)
 
     # ---- stage 4 -----------------------------------------------------------------------------
     def fit_gram(self, Ps, Y):

@@ -17,7 +17,7 @@ import math
 import numpy as np
 import torch
 
-from .eig import block_lanczos_topk
+from .eig import block_lanczos_device, block_lanczos_topk
 
 NEV = 10   # diffusion.py:42 (k = 10 eigenpairs)
 
@@ -135,6 +135,10 @@ def eigen_stage(ops, plan, P_rows, dis, nev=NEV, validate=True, tol=None, stats=
         V = V_all[:, torch.as_tensor(idx, device=dev)]
         if stats is not None:
             stats.update({"matvecs": len(cols), "dense": True})
+    elif hasattr(ops, "lanczos_step") and N >= 64:
+        def matvec_f32(Xf):
+            return plan.all_gather_rows(ops.block_matvec_f32(P_rows, N, Xf))
+        lam, V, _ = block_lanczos_device(ops, matvec_f32, N, nev, tol=(1e-8 if tol is None else tol), stats=stats, seed=seed)
     else:
         lam, V, _ = block_lanczos_topk(matvec, N, nev, dev, tol=(1e-8 if tol is None else tol), stats=stats, seed=seed)
     V = -V                                                   # diffusion.py:62 (sign is arbitrary upstream)

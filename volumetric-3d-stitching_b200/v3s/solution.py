@@ -45,14 +45,14 @@ class OrientationRecoverySolver:
                            polar_mode=polar_mode, check=check_sigma, stats=stats)
         if 'sigma_T_host' not in out:
             out['sigma_T_host'] = float(out['sigma_T'].item())
-        Images = out['Images_local'].cpu().numpy().astype(np.float64)
-        if not Images[Images != 0].size > 0:
+        if not bool(torch.any(out['Images_local'] != 0)):
             raise Exception('Images is an all-zero array.')          # projection.py:47
         print('OrientationRecoverySolver.solve ended.')
-        f64 = lambda t: t.cpu().numpy().astype(np.float64)
+        # the reference returns float64 everywhere: widen on the device, then one copy per array
+        f64 = lambda t: t.to(torch.float64).cpu().numpy()
         return {
             'Ps': f64(out['Ps']), 'Lambda': f64(out['Lambda']), 'c0': f64(out['c']), 'c': f64(out['c']),
-            'S2': f64(out['S2']), 'N': f64(out['N']), 'Images': Images, 'R': R,
+            'S2': f64(out['S2']), 'N': f64(out['N']), 'Images': f64(out['Images_local']), 'R': R,
             'Sigma_T': np.array([out['sigma_T_host']]), 'Axis': Axis.T, 'Quat': Quat.T,
         }
 
