@@ -303,7 +303,8 @@ def main():
         "matvec": {"achieved_gbs": (round(mv_gbs, 1) if mv_gbs else None), "peak_gbs": peaks["hbm_gbs"],
                    "frac": (round(mv_gbs / peaks["hbm_gbs"], 4) if mv_gbs else None), "launches_per_pass": len(mv) // args.steps},
         "kernel_ms_per_pass": stage_ms,
-        "eigen": {k_: stats.get(k_) for k_ in ("matvecs", "krylov_dim", "residual_max", "converged")},
+        "eigen": {k_: stats.get(k_) for k_ in ("driver", "matvecs", "probe_steps", "cheb_steps", "degree", "krylov_dim",
+                                               "ritz_checks", "residual_max", "converged")},
         "result": {"sigma_T_deg": round(sigma_T, 4), "lambda_1_9": [round(float(x), 8) for x in lam[:10]]},
         "cpu_baseline": cpu_base,
     }

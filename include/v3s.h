@@ -135,6 +135,12 @@ int v3s_lanczos_start(double* V, long long ldv, long long N, int max_dim, double
 int v3s_lanczos_step(double* V, long long ldv, long long N, int m, int max_dim, double* W, float* Xf, double* Tblk,
                      double* ws, int* status_out_dev, void* stream);
 
+/* Chebyshev three-term recurrence on a block (polynomial acceleration of the Lanczos operator):
+ * Y_out = alpha * PY + beta * Yk + gamma * Ykm1 (Ykm1 may be NULL; Y_out may alias it), FP64 [count],
+ * and Xf_out = float(Y_out) for the next mat-vec (may be NULL).                                   */
+int v3s_cheb_combine(const double* PY, const double* Yk, const double* Ykm1, double alpha, double beta, double gamma,
+                     double* Y_out, float* Xf_out, long long count, void* stream);
+
 /* ---- stage 4: orientation retrieval ---------------------------------------------------------- */
 
 /* ComputeUtils.lsq_linear (compute.py:103-112): out162 = {X^T X (81), X^T Y (81)} partial sums

@@ -169,3 +169,11 @@ class OracleOps:
             st["V"][m:m + 8] = Q.T
         st["Xf"].copy_(Q.to(torch.float32))
         st["T"][step] = torch.cat([A, R], dim=0).reshape(-1)
+
+    def cheb_combine(self, PY, Yk, Ykm1, alpha, beta, gamma, Y_out, Xf_out):
+        v = alpha * PY + beta * Yk
+        if Ykm1 is not None:
+            v = v + gamma * Ykm1
+        Y_out.copy_(v)
+        if Xf_out is not None:
+            Xf_out.copy_(v.to(torch.float32))

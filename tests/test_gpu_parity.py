@@ -157,11 +157,13 @@ def test_knn_default_cfg_fixture_with_duplicates(v3s_mod, golden_dir):
     ok = orc.almost_equal_hybrid(S2, g["S2"], 1e-5) | (err < 5e-7)
     print("default cfg knn: max abs err", err.max(), "frac outside", 1 - ok.mean())
     assert ok.all()
-    untied = np.ones_like(S2, dtype=bool)
-    d = np.abs(np.diff(g["S2"], axis=1)) > 5e-6
-    untied[:, 1:] &= d
-    untied[:, :-1] &= d
-    assert np.array_equal(N[untied], g["N"][untied])
+    # indices: wherever ours differs from the reference's, the two patterns are tied (duplicate or
+    # near-duplicate images): the reference's own distance to our pick equals its listed distance
+    B = orc.convert_to_round_distance(np.asfortranarray(g["Images"]))
+    diff = N != g["N"]
+    rr, cc = np.nonzero(diff)
+    assert np.all(np.abs(B[rr, N[rr, cc].astype(int)] - g["S2"][rr, cc]) < 1e-6)
+    print("default cfg knn: index mismatches (all tied):", diff.sum(), "of", diff.size)
     # tie groups hold the same index sets
     for r in (0, 100, 511):
         assert set(N[r][g["S2"][r] < 1e-6]) == set(g["N"][r][g["S2"][r] < 1e-6])
@@ -183,7 +185,7 @@ def test_knn_zero_rows_and_panels(ops):
     assert np.all(S2[13] == 0) and np.all(S2[363] == 0)              # distance 0 to everything
     rows = np.array([r for r in range(700) if r not in (13, 363)])
     assert np.all(S2[rows, :3] == 0)                                 # self + the two NaN columns
-    assert np.all(oS2[rows, :3] == 0)
+    assert np.all(oS2[rows, :3] < 1e-7)                              # (the reference's self distance is ~1e-8 noise)
     assert hybrid_frac_bad(S2[rows][:, 3:], oS2[rows][:, 3:], 1e-5) == 0.0
     old = ops_cuda.PANEL_BYTES
     try:

@@ -66,6 +66,22 @@ def test_device_driver_lanczos_host_logic(golden_dir):
     assert stats["converged"] and stats["driver"] == "device"
 
 
+def test_chebyshev_lanczos_host_logic(golden_dir):
+    """Probe -> Chebyshev-filtered Lanczos -> Rayleigh-Ritz with P, on the CPU stand-in."""
+    from v3s.eig import chebyshev_lanczos_device
+    g = np.load(os.path.join(golden_dir, "connected_n15.npz"))
+    _, _, _, _, P, _ = orc.diffusion_coordinate(g["S2"].copy(), g["N"], float(g["eps"]), return_all=True)
+    Pt = torch.from_numpy(P)
+    stats = {}
+    lam, V, res = chebyshev_lanczos_device(OracleOps(), lambda Xf: Pt @ Xf.to(torch.float64), lambda X: Pt @ X,
+                                           P.shape[0], 10, tol=1e-8, probe_steps=4, stats=stats)
+    w, U = np.linalg.eigh(P)
+    assert stats["driver"] == "device-chebyshev" and stats["cheb_steps"] > 0 and stats["converged"]
+    assert np.max(np.abs(lam - w[::-1][:10])) < 1e-9
+    assert np.max(orc.principal_angles(V.numpy(), U[:, -10:])) < 1e-5
+    assert res.max() < 1e-6
+
+
 def test_stage_api_golden_vectors():
     """The reference's own unit-test vectors through the product's adapters (CPU backend)."""
     S2 = np.array([[0.0, 16.0, 9.0, 25.0], [16.0, 0.0, 25.0, 9.0], [9.0, 25.0, 0.0, 16.0], [25.0, 9.0, 16.0, 0.0]])

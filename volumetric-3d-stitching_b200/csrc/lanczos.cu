@@ -252,6 +252,19 @@ __global__ void lz_store_blocks_kernel(const double* __restrict__ Hsum, int m, c
   }
 }
 
+// Chebyshev three-term recurrence on a block: Y_out = alpha * PY + beta * Yk + gamma * Ykm1 (FP64),
+// plus the FP32 copy the next mat-vec reads.  Y_out may alias Ykm1.
+__global__ void lz_cheb_combine_kernel(const double* __restrict__ PY, const double* __restrict__ Yk,
+                                       const double* Ykm1, double alpha, double beta, double gamma, double* Y_out,
+                                       float* __restrict__ Xf_out, long long count) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < count; e += (long long)gridDim.x * blockDim.x) {
+    double v = fma(alpha, PY[e], beta * Yk[e]);
+    if (Ykm1) v = fma(gamma, Ykm1[e], v);
+    Y_out[e] = v;
+    if (Xf_out) Xf_out[e] = (float)v;
+  }
+}
+
 struct LzWs {
   double *Hpart, *Hcur, *Hsum, *Gpart, *small;
   int* status;
@@ -344,5 +357,16 @@ extern "C" int v3s_lanczos_step(double* V, long long ldv, long long N, int m, in
   lz_store_blocks_kernel<<<1, 64, 0, st>>>(Hsum, m, small, Tblk);
   V3S_CHECK_LAUNCH();
   if (status_out_dev) V3S_CUDA(cudaMemcpyAsync(status_out_dev, status, sizeof(int), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+extern "C" int v3s_cheb_combine(const double* PY, const double* Yk, const double* Ykm1, double alpha, double beta,
+                                double gamma, double* Y_out, float* Xf_out, long long count, void* stream) {
+  V3S_REQUIRE(count >= 0, "v3s_cheb_combine: bad count");
+  if (count == 0) return 0;
+  long long g = ceil_div64(count, 256);
+  if (g > 8LL * kNumSMs) g = 8LL * kNumSMs;
+  lz_cheb_combine_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(PY, Yk, Ykm1, alpha, beta, gamma, Y_out, Xf_out, count);
+  V3S_CHECK_LAUNCH();
   return 0;
 }

@@ -51,6 +51,7 @@ SIGNATURES = {
     "v3s_lanczos_workspace_doubles": (i64, [i64, i32]),
     "v3s_lanczos_start": (i32, [p, i64, i64, i32, p, p, p, p]),
     "v3s_lanczos_step": (i32, [p, i64, i64, i32, i32, p, p, p, p, p, p]),
+    "v3s_cheb_combine": (i32, [p, p, p, f64, f64, f64, p, p, i64, p]),
     "v3s_fit_gram": (i32, [p, i32, p, i64, p, p]),
     "v3s_fit_solve": (i32, [p, p, p]),
     "v3s_fit_project": (i32, [p, i32, p, i64, p, i32, p, p, p, p, p]),

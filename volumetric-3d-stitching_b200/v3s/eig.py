@@ -32,7 +32,7 @@ def _chol_qr(W):
     return W, R_tot
 
 
-def _ritz_from_band(band, m, b, nev):
+def _ritz_from_band(band, m, b, nev, both_ends=True):
     """Largest-|lambda| eigenpairs of the m x m block-tridiagonal matrix held in lower band
     storage band[i, j] = T[j + i, j].
 
@@ -49,9 +49,9 @@ def _ritz_from_band(band, m, b, nev):
         w, S = sla.eig_banded(Tb, lower=True)
         idx = np.argsort(-np.abs(w), kind="stable")[:want]
         return w[idx], S[:, idx]
-    w_hi = sla.eig_banded(Tb, lower=True, eigvals_only=True, select="i", select_range=(m - want, m - 1))
-    w_lo = sla.eig_banded(Tb, lower=True, eigvals_only=True, select="i", select_range=(0, want - 1))
-    w = np.concatenate([w_lo, w_hi])
+    w = sla.eig_banded(Tb, lower=True, eigvals_only=True, select="i", select_range=(m - want, m - 1))
+    if both_ends:      # largest |lambda| may sit at the negative end ('LM' semantics of eigs)
+        w = np.concatenate([sla.eig_banded(Tb, lower=True, eigvals_only=True, select="i", select_range=(0, want - 1)), w])
     theta = w[np.argsort(-np.abs(w), kind="stable")[:want]]
     # general band storage for solve_banded: ab[b + i - j, j] = T[i, j]
     ab = np.zeros((2 * b + 1, m))
@@ -100,7 +100,7 @@ def _next_check(steps, res_max, target, prev, max_gap):
 
 
 def block_lanczos_device(ops, matvec_f32, N, nev, tol=1e-8, max_dim=None, first_check=6, seed=0, max_gap=16,
-                         stats=None):
+                         stats=None, start_block=None, both_ends=True):
     """Same algorithm as `block_lanczos_topk`, with every per-step operation enqueued on the GPU by
     the C-ABI (`v3s_lanczos_start` / `v3s_lanczos_step`, csrc/lanczos.cu): the host only launches,
     and reads back the small (A_j, B_j) blocks when it extracts Ritz pairs.
@@ -113,9 +113,12 @@ def block_lanczos_device(ops, matvec_f32, N, nev, tol=1e-8, max_dim=None, first_
     max_dim = max(b, (min(max_dim, N) // b) * b)
     max_steps = max_dim // b
     st = ops.lanczos_alloc(N, max_dim, max_steps)
-    gen = torch.Generator(device="cpu")
-    gen.manual_seed(seed)
-    W0 = torch.randn((N, b), generator=gen, dtype=torch.float64).to(ops.device)
+    if start_block is None:
+        gen = torch.Generator(device="cpu")
+        gen.manual_seed(seed)
+        W0 = torch.randn((N, b), generator=gen, dtype=torch.float64).to(ops.device)
+    else:
+        W0 = start_block.clone()
     ops.lanczos_start(st, W0)
     m, steps, copied = b, 0, 0
     band = np.zeros((b + 1, max_dim))
@@ -133,7 +136,7 @@ def block_lanczos_device(ops, matvec_f32, N, nev, tol=1e-8, max_dim=None, first_
             for i_, blk in enumerate(blks):
                 _fill_band(band, b, (copied + i_ + 1) * b, blk)
             copied = steps
-            w, S = _ritz_from_band(band, m, b, nev)
+            w, S = _ritz_from_band(band, m, b, nev, both_ends)
             res = np.linalg.norm(blks[-1][b:] @ S[m - b:m, :], axis=0)
             if not np.all(np.isfinite(res)):
                 raise Exception("block Lanczos broke down (non-finite residuals)")
@@ -150,6 +153,88 @@ def block_lanczos_device(ops, matvec_f32, N, nev, tol=1e-8, max_dim=None, first_
         stats.update({"matvecs": steps, "block": b, "krylov_dim": m, "ritz_checks": n_checks, "residual_max": float(res.max()),
                       "converged": bool(res.max() <= tol * max(np.abs(w).max(), 1e-300)), "driver": "device"})
     return w, Y, res
+
+
+def chebyshev_lanczos_device(ops, matvec_f32, matvec_f64, N, nev, tol=1e-8, degree=8, probe_steps=10, seed=0,
+                             stats=None):
+    """Largest eigenpairs of the symmetric operator P by block Lanczos on a Chebyshev polynomial
+    of P (device driver).  Clustered top eigenvalues (gaps ~1e-4 at N = 10^4) make plain Lanczos
+    need a Krylov space of ~600 vectors, whose Ritz extraction is O(m^2 b) host work per check;
+    Lanczos on T_d((P - c)/e), with [c-e, c+e] = [-1, cut] the unwanted part of the spectrum,
+    converges in ~4x fewer steps for ~1.8x more (HBM-bound, host-free) mat-vecs.
+
+      1. probe: `probe_steps` plain block-Lanczos steps.  Ritz values are lower bounds of the
+         eigenvalues (Cauchy interlacing), so cut = theta_nev(probe) <= lambda_nev: the wanted
+         eigenvalues are never inside the damped interval.
+      2. Lanczos on p(P), started from the probe's best Ritz block.
+      3. Rayleigh-Ritz of P itself on the converged subspace (eigenvalues of P, not of p(P)).
+
+    matvec_f32: Xf [N,8] f32 -> P Xf [N,8] f64;  matvec_f64: X [N,b<=8] f64 -> P X.
+    Falls back to plain largest-magnitude Lanczos when the probe shows a negative eigenvalue whose
+    magnitude competes with the wanted ones (the filter targets the algebraically largest).
+    """
+    b = 8
+    st1 = {}
+    w0, Y0, res0 = block_lanczos_device(ops, matvec_f32, N, nev, tol=tol, max_dim=probe_steps * b, seed=seed,
+                                        first_check=probe_steps, stats=st1, both_ends=True)
+    n_mv = st1["matvecs"]
+    info = {"probe_steps": st1["matvecs"], "degree": degree}
+    if st1["converged"]:
+        lam, Y, res = w0, Y0, res0
+        info.update({"cheb_steps": 0, "krylov_dim": st1["krylov_dim"]})
+    elif np.any(w0 < 0) or len(w0) < nev:
+        st2 = {}
+        lam, Y, res = block_lanczos_device(ops, matvec_f32, N, nev, tol=tol, seed=seed, stats=st2)
+        if stats is not None:
+            stats.update(st2)
+            stats["matvecs"] += n_mv
+            stats["driver"] = "device-plain(LM)"
+        return lam, Y, res
+    else:
+        cut, lo = float(np.min(w0)), -1.0
+        c, e = 0.5 * (cut + lo), 0.5 * (cut - lo)
+        bufs = [ops.empty((N, b), torch.float64) for _ in range(3)]
+        Xf = ops.empty((N, b), torch.float32)
+        count = [0]
+
+        def cheb_op(Xf0):
+            # Y0 = the block as the mat-vec sees it (FP32-rounded), Y1 = (P Y0 - c Y0)/e, then the recurrence
+            Ykm1, Yk, spare = bufs
+            Ykm1.copy_(Xf0)
+            ops.cheb_combine(matvec_f32(Xf0), Ykm1, None, 1.0 / e, -c / e, 0.0, Yk, Xf)
+            count[0] += 1
+            for _ in range(degree - 1):
+                ops.cheb_combine(matvec_f32(Xf), Yk, Ykm1, 2.0 / e, -2.0 * c / e, -1.0, spare, Xf)
+                Ykm1, Yk, spare = Yk, spare, Ykm1
+                count[0] += 1
+            return Yk          # scratch: the Lanczos step overwrites it with Q_{j+1}
+
+        order = np.argsort(-w0, kind="stable")[:b]
+        start = Y0[:, torch.as_tensor(order.copy(), device=Y0.device)].contiguous()
+        st2 = {}
+        _, Y, res = block_lanczos_device(ops, cheb_op, N, nev, tol=tol, seed=seed, first_check=4, max_gap=8, stats=st2,
+                                         start_block=start, both_ends=False)
+        n_mv += count[0]
+        info.update({"cheb_steps": st2["matvecs"], "krylov_dim": st2["krylov_dim"], "cut": cut,
+                     "ritz_checks": st2["ritz_checks"], "converged": st2["converged"]})
+        # Rayleigh-Ritz with P itself
+        PY = torch.cat([matvec_f64(Y[:, j:j + b].contiguous()) for j in range(0, Y.shape[1], b)], dim=1)
+        n_mv += (Y.shape[1] + b - 1) // b
+        H = Y.T @ PY
+        lam_t, Z = torch.linalg.eigh(0.5 * (H + H.T))
+        Y = Y @ Z
+        R = PY @ Z - Y * lam_t[None, :]
+        lam = lam_t.cpu().numpy()
+        res = torch.linalg.norm(R, dim=0).cpu().numpy()
+        idx = np.argsort(-np.abs(lam), kind="stable")
+        lam, res = lam[idx], res[idx]
+        Y = Y[:, torch.as_tensor(idx.copy(), device=Y.device)]
+        info["true_residual_max"] = float(res.max())
+    if stats is not None:
+        stats.update(info)
+        stats.update({"matvecs": n_mv, "block": b, "residual_max": float(np.max(res)), "driver": "device-chebyshev",
+                      "converged": bool(info.get("converged", st1["converged"]))})
+    return lam, Y, res
 
 
 def block_lanczos_topk(matvec, N, nev, device, block=8, tol=1e-8, max_dim=None, first_check=6, seed=0,

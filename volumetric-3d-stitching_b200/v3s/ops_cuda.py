@@ -254,6 +254,7 @@ class CudaOps:
         return st
 
     def lanczos_start(self, st, W0):
+        """Orthonormalise W0 [N,8] (FP64, overwritten) into the first basis block."""
         call("v3s_lanczos_start", ptr(st["V"]), st["N"], st["N"], st["max_dim"], ptr(W0), ptr(st["Xf"]), ptr(st["ws"]),
              stream_ptr())
 
@@ -262,6 +263,10 @@ class CudaOps:
         call("v3s_lanczos_step", ptr(st["V"]), st["N"], st["N"], m, st["max_dim"], ptr(W), ptr(st["Xf"]),
              ptr(st["T"][step]), ptr(st["ws"]), ptr(st["status"]), stream_ptr())
         self._toc(h)
+
+    def cheb_combine(self, PY, Yk, Ykm1, alpha, beta, gamma, Y_out, Xf_out):
+        call("v3s_cheb_combine", ptr(PY), ptr(Yk), ptr(Ykm1), float(alpha), float(beta), float(gamma), ptr(Y_out),
+             ptr(Xf_out), PY.numel(), stream_ptr())
 
     # ---- stage 4 -----------------------------------------------------------------------------
     def fit_gram(self, Ps, Y):

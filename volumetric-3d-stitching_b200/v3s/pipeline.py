@@ -17,7 +17,7 @@ import math
 import numpy as np
 import torch
 
-from .eig import block_lanczos_device, block_lanczos_topk
+from .eig import block_lanczos_device, block_lanczos_topk, chebyshev_lanczos_device
 
 NEV = 10   # diffusion.py:42 (k = 10 eigenpairs)
 
@@ -110,7 +110,7 @@ def markov_stage(ops, plan, S2_all, Nbr_all, eps, med_row=4, idx_off=1, validate
     return P_rows, dis, scalars
 
 
-def eigen_stage(ops, plan, P_rows, dis, nev=NEV, validate=True, tol=None, stats=None, seed=0, dense_below=192):
+def eigen_stage(ops, plan, P_rows, dis, nev=NEV, validate=True, tol=None, stats=None, seed=0, dense_below=600):
     """diffusion.py:56-81: top-`nev` largest-magnitude eigenpairs, sort descending, scale by
     lambda and D^-1/2.  -> Ps [N,nev] f64 tensor, Lambda [nev] f64 tensor."""
     N = plan.N
@@ -138,7 +138,12 @@ def eigen_stage(ops, plan, P_rows, dis, nev=NEV, validate=True, tol=None, stats=
     elif hasattr(ops, "lanczos_step") and N >= 64:
         def matvec_f32(Xf):
             return plan.all_gather_rows(ops.block_matvec_f32(P_rows, N, Xf))
-        lam, V, _ = block_lanczos_device(ops, matvec_f32, N, nev, tol=(1e-8 if tol is None else tol), stats=stats, seed=seed)
+        if N >= 2048 and nev <= 16:
+            lam, V, _ = chebyshev_lanczos_device(ops, matvec_f32, matvec, N, nev, tol=(1e-8 if tol is None else tol),
+                                                 stats=stats, seed=seed)
+        else:
+            lam, V, _ = block_lanczos_device(ops, matvec_f32, N, nev, tol=(1e-8 if tol is None else tol), stats=stats,
+                                             seed=seed)
     else:
         lam, V, _ = block_lanczos_topk(matvec, N, nev, dev, tol=(1e-8 if tol is None else tol), stats=stats, seed=seed)
     V = -V                                                   # diffusion.py:62 (sign is arbitrary upstream)
