@@ -118,13 +118,17 @@ long long v3s_block_matvec_workspace_bytes(long long n_rows, long long N);
 int v3s_block_matvec(const float* P_rows, long long ldp, long long n_rows, long long N, const double* X, int b,
                      double* Y_rows, void* workspace, void* stream);
 
-/* the same product with the block already in FP32 [N,8] (the form v3s_lanczos_step emits)      */
-int v3s_block_matvec_f32(const float* P_rows, long long ldp, long long n_rows, long long N, const float* Xf,
+/* the same product with the block already in FP32 "strip layout" (the form v3s_lanczos_step and
+ * v3s_cheb_combine emit): v3s_xf_floats(N) floats, columns in strips of 128, each strip stored as
+ * float4 [j/4][col%4][(col%128)/4]; padding columns of the last strip must be zero.            */
+long long v3s_xf_floats(long long N);
+int v3s_block_matvec_f32(const float* P_rows, long long ldp, long long n_rows, long long N, const float* Xf_strips,
                          double* Y_rows, void* workspace, void* stream);
 
 /* Device-side block-Lanczos iteration, block size 8 -- the per-iteration work ARPACK does on the
  * host behind scipy.sparse.linalg.eigs (diffusion.py:61).  V [max_dim, ldv] FP64 basis (vectors as
- * rows), W [N,8] FP64 block, Xf [N,8] FP32 copy for the mat-vec, ws: v3s_lanczos_workspace_doubles.
+ * rows), W [N,8] FP64 block, Xf FP32 strip-layout copy for the mat-vec (v3s_xf_floats(N) floats,
+ * zero-initialised by the caller), ws: v3s_lanczos_workspace_doubles(N, max_dim) doubles.
  *   v3s_lanczos_start: orthonormalise the start block W in place; V[0..8) <- Q^T, Xf <- float(Q).
  *   v3s_lanczos_step : W = P Q_j on entry (m = basis size, Q_j = V[m-8..m)); two-pass block
  *       Gram-Schmidt against V[0..m), Cholesky-QR twice; on return W = Q_{j+1}, appended to V when
@@ -137,7 +141,7 @@ int v3s_lanczos_step(double* V, long long ldv, long long N, int m, int max_dim, 
 
 /* Chebyshev three-term recurrence on a block (polynomial acceleration of the Lanczos operator):
  * Y_out = alpha * PY + beta * Yk + gamma * Ykm1 (Ykm1 may be NULL; Y_out may alias it), FP64 [count],
- * and Xf_out = float(Y_out) for the next mat-vec (may be NULL).                                   */
+ * count = 8 N, and Xf_out = float(Y_out) in strip layout for the next mat-vec (may be NULL).      */
 int v3s_cheb_combine(const double* PY, const double* Yk, const double* Ykm1, double alpha, double beta, double gamma,
                      double* Y_out, float* Xf_out, long long count, void* stream);
 

@@ -139,6 +139,9 @@ class OracleOps:
         return torch.tensor([np.abs(a - b).sum()], dtype=torch.float64)
 
     # device-driver Lanczos interface (mirrors CudaOps.lanczos_*), plain torch on CPU
+    def alloc_xf(self, N):
+        return torch.zeros((N, 8), dtype=torch.float32)
+
     def block_matvec_f32(self, P_rows, N, Xf):
         return (P_rows[:, :N].to(torch.float32) @ Xf).to(torch.float64)
 

@@ -59,7 +59,7 @@ def test_device_driver_lanczos_host_logic(golden_dir):
     _, _, _, _, P, _ = orc.diffusion_coordinate(g["S2"].copy(), g["N"], float(g["eps"]), return_all=True)
     Pt = torch.from_numpy(P)
     stats = {}
-    lam, V, res = block_lanczos_device(OracleOps(), lambda Xf: Pt @ Xf.to(torch.float64), P.shape[0], 10, tol=1e-7, stats=stats)
+    lam, V, res = block_lanczos_device(OracleOps(), lambda Xf, Q: Pt @ Xf.to(torch.float64), P.shape[0], 10, tol=1e-7, stats=stats)
     w, U = np.linalg.eigh(P)
     assert np.max(np.abs(np.sort(lam)[::-1] - w[::-1][:10])) < 1e-7     # the operand block is FP32 (Xf)
     assert np.max(orc.principal_angles(V.numpy(), U[:, -10:])) < 1e-5

@@ -66,6 +66,17 @@ __device__ __forceinline__ T block_sum(T v, T* scratch) {
   return r;
 }
 
+// FP32 operand block X [N, 8] of the block mat-vec, stored in "strip layout": columns of P in
+// strips of 128, each strip = 1024 floats laid out as float4 [half = j/4][cc = col%4][lane = (col%128)/4],
+// so that one 4 KB bulk copy per strip lands in shared memory ready for conflict-free 128-bit reads
+// by the lane that owns columns lane*4 .. lane*4+3.  Buffer length: xf_strip_floats(N).
+__host__ __device__ inline long long xf_strip_index(long long col, int j) {
+  const long long strip = col >> 7;
+  const int cl = (int)(col & 127);
+  return strip * 1024 + (long long)(((((j >> 2) << 2) + (cl & 3)) * 32 + (cl >> 2)) * 4 + (j & 3));
+}
+__host__ __device__ inline long long xf_strip_floats(long long N) { return ((N + 127) >> 7) * 1024; }
+
 // order-preserving float <-> uint key (larger float => larger key)
 __device__ __forceinline__ uint32_t float_to_key(float f) {
   uint32_t u = __float_as_uint(f);

@@ -235,9 +235,8 @@ __global__ void lz_scale_kernel(double* __restrict__ W, long long N, const doubl
 #pragma unroll
       for (int j = 0; j < LB; ++j) Vnext[(long long)j * ldv + n] = q[j];
     }
-    float4* x4 = reinterpret_cast<float4*>(Xf + n * LB);
-    x4[0] = make_float4((float)q[0], (float)q[1], (float)q[2], (float)q[3]);
-    x4[1] = make_float4((float)q[4], (float)q[5], (float)q[6], (float)q[7]);
+    *reinterpret_cast<float4*>(Xf + xf_strip_index(n, 0)) = make_float4((float)q[0], (float)q[1], (float)q[2], (float)q[3]);
+    *reinterpret_cast<float4*>(Xf + xf_strip_index(n, 4)) = make_float4((float)q[4], (float)q[5], (float)q[6], (float)q[7]);
   }
 }
 
@@ -252,8 +251,8 @@ __global__ void lz_store_blocks_kernel(const double* __restrict__ Hsum, int m, c
   }
 }
 
-// Chebyshev three-term recurrence on a block: Y_out = alpha * PY + beta * Yk + gamma * Ykm1 (FP64),
-// plus the FP32 copy the next mat-vec reads.  Y_out may alias Ykm1.
+// Chebyshev three-term recurrence on a block [N,8]: Y_out = alpha * PY + beta * Yk + gamma * Ykm1
+// (FP64), plus the FP32 strip-layout copy the next mat-vec reads.  Y_out may alias Ykm1.
 __global__ void lz_cheb_combine_kernel(const double* __restrict__ PY, const double* __restrict__ Yk,
                                        const double* Ykm1, double alpha, double beta, double gamma, double* Y_out,
                                        float* __restrict__ Xf_out, long long count) {
@@ -261,7 +260,7 @@ __global__ void lz_cheb_combine_kernel(const double* __restrict__ PY, const doub
     double v = fma(alpha, PY[e], beta * Yk[e]);
     if (Ykm1) v = fma(gamma, Ykm1[e], v);
     Y_out[e] = v;
-    if (Xf_out) Xf_out[e] = (float)v;
+    if (Xf_out) Xf_out[xf_strip_index(e >> 3, (int)(e & 7))] = (float)v;
   }
 }
 

@@ -47,6 +47,7 @@ SIGNATURES = {
     "v3s_dm_cov_dense": (i32, [p, i64, p, p, p, p]),
     "v3s_block_matvec_workspace_bytes": (i64, [i64, i64]),
     "v3s_block_matvec": (i32, [p, i64, i64, i64, p, i32, p, p, p]),
+    "v3s_xf_floats": (i64, [i64]),
     "v3s_block_matvec_f32": (i32, [p, i64, i64, i64, p, p, p, p]),
     "v3s_lanczos_workspace_doubles": (i64, [i64, i32]),
     "v3s_lanczos_start": (i32, [p, i64, i64, i32, p, p, p, p]),

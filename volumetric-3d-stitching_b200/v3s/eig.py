@@ -99,13 +99,15 @@ def _next_check(steps, res_max, target, prev, max_gap):
     return steps + max(1, min(max_gap, gap))
 
 
-def block_lanczos_device(ops, matvec_f32, N, nev, tol=1e-8, max_dim=None, first_check=6, seed=0, max_gap=16,
+def block_lanczos_device(ops, op, N, nev, tol=1e-8, max_dim=None, first_check=6, seed=0, max_gap=16,
                          stats=None, start_block=None, both_ends=True):
     """Same algorithm as `block_lanczos_topk`, with every per-step operation enqueued on the GPU by
     the C-ABI (`v3s_lanczos_start` / `v3s_lanczos_step`, csrc/lanczos.cu): the host only launches,
     and reads back the small (A_j, B_j) blocks when it extracts Ritz pairs.
 
-    matvec_f32: Xf [N,8] float32 tensor -> P @ Xf as [N,8] float64 tensor (all-gathered when sharded).
+    op(Xf, Q): the operator applied to the current block -- Xf is the backend's FP32 copy of the
+    block (opaque layout, what `ops.block_matvec_f32` consumes), Q the same block in FP64 [N,8];
+    returns [N,8] float64 (all-gathered when sharded), which the step overwrites with the next block.
     """
     b = 8
     if max_dim is None:
@@ -120,13 +122,15 @@ def block_lanczos_device(ops, matvec_f32, N, nev, tol=1e-8, max_dim=None, first_
     else:
         W0 = start_block.clone()
     ops.lanczos_start(st, W0)
+    Q = W0                               # FP64 copy of the current block
     m, steps, copied = b, 0, 0
     band = np.zeros((b + 1, max_dim))
     next_check, prev, n_checks = min(first_check, max_steps), None, 0
     w = S = res = None
     while True:
-        W = matvec_f32(st["Xf"])
+        W = op(st["Xf"], Q)
         ops.lanczos_step(st, m, W, steps)
+        Q = W
         steps += 1
         last = (m + b > max_dim)
         if steps >= next_check or last:
@@ -175,7 +179,8 @@ def chebyshev_lanczos_device(ops, matvec_f32, matvec_f64, N, nev, tol=1e-8, degr
     """
     b = 8
     st1 = {}
-    w0, Y0, res0 = block_lanczos_device(ops, matvec_f32, N, nev, tol=tol, max_dim=probe_steps * b, seed=seed,
+    plain_op = lambda Xf, Q: matvec_f32(Xf)
+    w0, Y0, res0 = block_lanczos_device(ops, plain_op, N, nev, tol=tol, max_dim=probe_steps * b, seed=seed,
                                         first_check=probe_steps, stats=st1, both_ends=True)
     n_mv = st1["matvecs"]
     info = {"probe_steps": st1["matvecs"], "degree": degree}
@@ -184,7 +189,7 @@ def chebyshev_lanczos_device(ops, matvec_f32, matvec_f64, N, nev, tol=1e-8, degr
         info.update({"cheb_steps": 0, "krylov_dim": st1["krylov_dim"]})
     elif np.any(w0 < 0) or len(w0) < nev:
         st2 = {}
-        lam, Y, res = block_lanczos_device(ops, matvec_f32, N, nev, tol=tol, seed=seed, stats=st2)
+        lam, Y, res = block_lanczos_device(ops, plain_op, N, nev, tol=tol, seed=seed, stats=st2)
         if stats is not None:
             stats.update(st2)
             stats["matvecs"] += n_mv
@@ -194,18 +199,18 @@ def chebyshev_lanczos_device(ops, matvec_f32, matvec_f64, N, nev, tol=1e-8, degr
         cut, lo = float(np.min(w0)), -1.0
         c, e = 0.5 * (cut + lo), 0.5 * (cut - lo)
         bufs = [ops.empty((N, b), torch.float64) for _ in range(3)]
-        Xf = ops.empty((N, b), torch.float32)
+        Xf = ops.alloc_xf(N)
         count = [0]
 
-        def cheb_op(Xf0):
-            # Y0 = the block as the mat-vec sees it (FP32-rounded), Y1 = (P Y0 - c Y0)/e, then the recurrence
-            Ykm1, Yk, spare = bufs
-            Ykm1.copy_(Xf0)
+        def cheb_op(Xf0, Q):
+            # Y0 = Q, Y1 = (P Y0 - c Y0)/e, Y_{k+1} = 2 (P Y_k - c Y_k)/e - Y_{k-1}
+            Yk, spare = [t for t in bufs if t.data_ptr() != Q.data_ptr()][:2]
+            Ykm1 = Q
             ops.cheb_combine(matvec_f32(Xf0), Ykm1, None, 1.0 / e, -c / e, 0.0, Yk, Xf)
             count[0] += 1
-            for _ in range(degree - 1):
+            for i in range(degree - 1):
                 ops.cheb_combine(matvec_f32(Xf), Yk, Ykm1, 2.0 / e, -2.0 * c / e, -1.0, spare, Xf)
-                Ykm1, Yk, spare = Yk, spare, Ykm1
+                Ykm1, Yk, spare = Yk, spare, (Ykm1 if i > 0 else [t for t in bufs if t.data_ptr() not in (Yk.data_ptr(), spare.data_ptr())][0])
                 count[0] += 1
             return Yk          # scratch: the Lanczos step overwrites it with Q_{j+1}
 

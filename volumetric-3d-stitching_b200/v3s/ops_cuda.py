@@ -235,8 +235,12 @@ class CudaOps:
             self._mv_ws = self.empty((need,), torch.uint8)
         return self._mv_ws
 
+    def alloc_xf(self, N):
+        """FP32 operand block of the mat-vec in strip layout (opaque to the host logic), zeroed."""
+        return self.zeros((int(_lib.lib.v3s_xf_floats(N)),), torch.float32)
+
     def block_matvec_f32(self, P_rows, N, Xf):
-        """Y_rows [n_rows,8] f64 = P_rows[:, :N] (f32) @ Xf [N,8] (f32)."""
+        """Y_rows [n_rows,8] f64 = P_rows[:, :N] (f32) @ X, X given as the FP32 strip-layout block."""
         n_rows, ldp = P_rows.shape
         Y = self.empty((n_rows, 8), torch.float64)
         ws = self._mv_workspace(n_rows, N)
@@ -248,7 +252,7 @@ class CudaOps:
     # device-side block-Lanczos state and steps (lanczos.cu)
     def lanczos_alloc(self, N, max_dim, max_steps):
         st = {"N": N, "max_dim": max_dim,
-              "V": self.empty((max_dim, N), torch.float64), "Xf": self.empty((N, 8), torch.float32),
+              "V": self.empty((max_dim, N), torch.float64), "Xf": self.alloc_xf(N),
               "T": self.zeros((max_steps, 128), torch.float64), "status": self.zeros((1,), torch.int32),
               "ws": self.empty((int(_lib.lib.v3s_lanczos_workspace_doubles(N, max_dim)),), torch.float64)}
         return st

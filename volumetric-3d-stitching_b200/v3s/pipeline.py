@@ -142,8 +142,8 @@ def eigen_stage(ops, plan, P_rows, dis, nev=NEV, validate=True, tol=None, stats=
             lam, V, _ = chebyshev_lanczos_device(ops, matvec_f32, matvec, N, nev, tol=(1e-8 if tol is None else tol),
                                                  stats=stats, seed=seed)
         else:
-            lam, V, _ = block_lanczos_device(ops, matvec_f32, N, nev, tol=(1e-8 if tol is None else tol), stats=stats,
-                                             seed=seed)
+            lam, V, _ = block_lanczos_device(ops, lambda Xf, Q: matvec_f32(Xf), N, nev,
+                                             tol=(1e-8 if tol is None else tol), stats=stats, seed=seed)
     else:
         lam, V, _ = block_lanczos_topk(matvec, N, nev, dev, tol=(1e-8 if tol is None else tol), stats=stats, seed=seed)
     V = -V                                                   # diffusion.py:62 (sign is arbitrary upstream)
