@@ -42,14 +42,18 @@ __global__ void x_to_f32_kernel(const double* __restrict__ X, long long N, int b
 // grid.x = row groups of 32 rows, grid.y = column chunks (multiples of 128 columns)
 __global__ void __launch_bounds__(MV_THREADS, 2)
 block_matvec_kernel(const __grid_constant__ CUtensorMap tmP, const float* __restrict__ XfS, long long n_rows, long long N,
-                    long long chunk_cols, double* __restrict__ Ypart) {
+                    long long chunk_cols, double* __restrict__ Ypart, int reverse) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + MV_STAGES * MV_STAGE_BYTES);
   uint64_t* empty = full + MV_STAGES;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const long long row0 = (long long)blockIdx.x * MV_TILE_ROWS;
-  const long long c_begin = (long long)blockIdx.y * chunk_cols;
+  // serpentine order: consecutive launches walk P in opposite directions, so the tail of the previous
+  // pass (still in the 126 MB L2) is what the next pass reads first
+  const unsigned bx = reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
+  const unsigned by = reverse ? gridDim.y - 1 - blockIdx.y : blockIdx.y;
+  const long long row0 = (long long)bx * MV_TILE_ROWS;
+  const long long c_begin = (long long)by * chunk_cols;
   long long c_end = c_begin + chunk_cols;
   if (c_end > N) c_end = N;
   const int nstrips = (int)((c_end - c_begin + MV_STRIP - 1) / MV_STRIP);
@@ -112,7 +116,7 @@ block_matvec_kernel(const __grid_constant__ CUtensorMap tmP, const float* __rest
   }
   // warp-shuffle reduction in FP64; lane (r*8+j) % 32 keeps value (r, j)
   const long long rbase = row0 + warp * MV_ROWS;
-  double* yp = Ypart + (long long)blockIdx.y * n_rows * MV_B;
+  double* yp = Ypart + (long long)by * n_rows * MV_B;
 #pragma unroll
   for (int r = 0; r < MV_ROWS; ++r) {
 #pragma unroll
@@ -163,7 +167,8 @@ static int mv_run(const float* P_rows, long long ldp, long long n_rows, long lon
     attr_set = true;
   }
   dim3 grid((unsigned)ceil_div64(n_rows, MV_TILE_ROWS), (unsigned)nchunks);
-  block_matvec_kernel<<<grid, MV_THREADS, MV_SMEM, st>>>(tm, XfS, n_rows, N, cc, Ypart);
+  static unsigned launch_parity = 0;
+  block_matvec_kernel<<<grid, MV_THREADS, MV_SMEM, st>>>(tm, XfS, n_rows, N, cc, Ypart, (int)(launch_parity++ & 1));
   V3S_CHECK_LAUNCH();
   long long g2 = ceil_div64(n_rows * MV_B, 256);
   if (g2 > 8LL * kNumSMs) g2 = 8LL * kNumSMs;
