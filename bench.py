@@ -135,7 +135,16 @@ def cpu_reference_pass(wl, sample_n, cores):
     return full, t, Ns
 
 
+def _use_all_host_threads():
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core (numpy is
+    # imported lazily, after this)
+    n = str(os.cpu_count() or 1)
+    for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[k] = n
+
+
 def cpu_baseline_block(wl, sample_n):
+    _use_all_host_threads()
     cores = os.cpu_count() or 1
     full, t, Ns = cpu_reference_pass(wl, sample_n, cores)
     return {"value": round(full, 3), "unit": "s", "cores": cores, "kind": "port",
@@ -148,6 +157,7 @@ def run_reference_arm(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    _use_all_host_threads()
     vals = []
     for i in range(args.warmup + args.steps):
         full, t, Ns = cpu_reference_pass(wl, args.cpu_sample, os.cpu_count() or 1)
