@@ -264,6 +264,34 @@ def test_markov_and_matvec_connected(ops, golden_dir):
     assert np.array_equal(Pr[:, :N].cpu().numpy(), P_rows[300:777, :N].cpu().numpy())
 
 
+@pytest.mark.parametrize("shape", [(1000, 1000), (477, 1003), (33, 130), (1, 128), (3000, 20000), (20000, 2500)])
+def test_block_matvec_shapes(ops, shape):
+    """Ragged row / column counts, row blocks of a sharded matrix, both operand forms."""
+    n_rows, N = shape
+    g = torch.Generator(device="cpu").manual_seed(n_rows + N)
+    ld = (N + 3) // 4 * 4
+    Pm = torch.zeros((n_rows, ld), dtype=torch.float32)
+    Pm[:, :N] = torch.rand((n_rows, N), generator=g) * (torch.rand((n_rows, N), generator=g) < 0.05)
+    X = torch.randn((N, 8), generator=g, dtype=torch.float64)
+    Pd, Xd = Pm.cuda(), X.cuda()
+    ref = Pm[:, :N].double() @ X
+    scale = ref.abs().max().item() + 1e-30
+    for rep in range(2):                                   # both serpentine directions
+        Y = ops.block_matvec(Pd, N, Xd).cpu()
+        assert (Y - ref).abs().max().item() < 3e-6 * scale
+    Y5 = ops.block_matvec(Pd, N, Xd[:, :5].contiguous()).cpu()
+    assert (Y5 - ref[:, :5]).abs().max().item() < 3e-6 * scale
+    # strip-layout FP32 operand, as emitted by the Lanczos step kernels
+    st = ops.lanczos_alloc(max(N, 8), 8, 1) if N >= 8 else None
+    if st is not None:
+        W0 = X.clone().cuda()
+        ops.lanczos_start(st, W0)                          # W0 <- orthonormal Q, st["Xf"] <- float(Q) in strip layout
+        Yq = ops.block_matvec_f32(Pd, N, st["Xf"]).cpu()
+        refq = Pm[:, :N].double() @ W0.cpu()
+        assert (Yq - refq).abs().max().item() < 3e-6 * (refq.abs().max().item() + 1e-30)
+        assert (W0.T @ W0 - torch.eye(8, dtype=torch.float64, device="cuda")).abs().max().item() < 1e-12
+
+
 def test_eigen_connected(v3s_mod, golden_dir):
     g = np.load(os.path.join(golden_dir, "connected_n15.npz"))
     stats = {}

@@ -4,15 +4,16 @@
 // (diffusion.py:61).  P_rows is the FP32 row block [n_rows, N] of the Markov matrix, X the Lanczos
 // block [N, 8].  Algorithmic traffic per call: 4 n_rows N bytes of P, read exactly once.
 //
-// Kernel: work item = (32-row group, column chunk).  A producer thread streams the item's
+// Kernel: 2 persistent CTAs per SM, each owning an equal contiguous range of (32-row group,
+// 128-column strip) units (no tail wave).  A producer thread streams the range's
 // 32 x 128 FP32 tiles of P (TMA 2-D tensor copy, 16 KB) and the matching 4 KB strip of X (TMA bulk
 // copy, strip layout, common.cuh) through a 4-stage mbarrier ring -- up to 8 tiles in flight per SM
 // with two resident CTAs, independent of register pressure.  Four consumer warps own 8 rows each:
 // lane l reads columns 4l..4l+3 of its rows and the 8 X values of those columns with 128-bit
 // shared loads, accumulates 8 rows x 8 vectors in FP32 registers, and the per-lane partial sums
-// are combined with warp shuffles in FP64 ("warp-shuffle-reduced").  Column chunks give enough
-// CTAs to fill 148 SMs at small N; per-chunk partials are reduced in a fixed order by a second
-// tiny kernel, so results are run-to-run deterministic.
+// are combined with warp shuffles in FP64 ("warp-shuffle-reduced") at the end of each row-group
+// segment.  Segment partials are added in a fixed order by a second tiny kernel, so results are
+// run-to-run deterministic.
 #include "common.cuh"
 #include "v3s.h"
 #include "tma.cuh"
@@ -39,10 +40,15 @@ __global__ void x_to_f32_kernel(const double* __restrict__ X, long long N, int b
   }
 }
 
-// grid.x = row groups of 32 rows, grid.y = column chunks (multiples of 128 columns)
+// Work unit = (32-row group, 128-column strip); units are numbered row-group-major and split into
+// equal contiguous ranges, one per CTA (grid = 2 x SM count, all CTAs co-resident: no tail wave).
+// A CTA's range may cross row-group boundaries; every (CTA, row-group) segment writes its partial
+// sums to its own slot and `reduce_segments_kernel` adds the slots of a row group in a fixed order.
+
 __global__ void __launch_bounds__(MV_THREADS, 2)
 block_matvec_kernel(const __grid_constant__ CUtensorMap tmP, const float* __restrict__ XfS, long long n_rows, long long N,
-                    long long chunk_cols, double* __restrict__ Ypart, int reverse) {
+                    int nstrips_row, long long units_per_cta, long long total_units, int maxseg,
+                    double* __restrict__ Ypart, int reverse) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + MV_STAGES * MV_STAGE_BYTES);
@@ -50,13 +56,10 @@ block_matvec_kernel(const __grid_constant__ CUtensorMap tmP, const float* __rest
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // serpentine order: consecutive launches walk P in opposite directions, so the tail of the previous
   // pass (still in the 126 MB L2) is what the next pass reads first
-  const unsigned bx = reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
-  const unsigned by = reverse ? gridDim.y - 1 - blockIdx.y : blockIdx.y;
-  const long long row0 = (long long)bx * MV_TILE_ROWS;
-  const long long c_begin = (long long)by * chunk_cols;
-  long long c_end = c_begin + chunk_cols;
-  if (c_end > N) c_end = N;
-  const int nstrips = (int)((c_end - c_begin + MV_STRIP - 1) / MV_STRIP);
+  const long long cta = reverse ? (long long)gridDim.x - 1 - blockIdx.x : blockIdx.x;
+  const long long u0 = cta * units_per_cta;
+  long long u1 = u0 + units_per_cta;
+  if (u1 > total_units) u1 = total_units;
 
   if (tid == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmP) : "memory");
@@ -64,19 +67,22 @@ block_matvec_kernel(const __grid_constant__ CUtensorMap tmP, const float* __rest
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  if (u0 >= u1) return;
 
   if (warp == MV_WARPS) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int s = 0; s < nstrips; ++s) {
+      long long rg = u0 / nstrips_row;
+      int s = (int)(u0 - rg * nstrips_row);
+      for (long long u = u0; u < u1; ++u) {
         mbar_wait(&empty[stage], phase ^ 1);
         mbar_expect_tx(&full[stage], MV_STAGE_BYTES);
         const uint32_t dst = smem_u32(smem + stage * MV_STAGE_BYTES);
-        const long long col0 = c_begin + (long long)s * MV_STRIP;
-        tma_load_2d(dst, &tmP, (int)col0, (int)row0, &full[stage]);
-        tma_load_1d(dst + MV_P_BYTES, XfS + (col0 >> 7) * 1024, MV_X_BYTES, &full[stage]);
+        tma_load_2d(dst, &tmP, s * MV_STRIP, (int)(rg * MV_TILE_ROWS), &full[stage]);
+        tma_load_1d(dst + MV_P_BYTES, XfS + (long long)s * 1024, MV_X_BYTES, &full[stage]);
         if (++stage == MV_STAGES) { stage = 0; phase ^= 1; }
+        if (++s == nstrips_row) { s = 0; ++rg; }
       }
     }
     return;
@@ -90,7 +96,10 @@ block_matvec_kernel(const __grid_constant__ CUtensorMap tmP, const float* __rest
 
   int stage = 0;
   uint32_t phase = 0;
-  for (int s = 0; s < nstrips; ++s) {
+  const long long rg_first = u0 / nstrips_row;
+  long long rg = rg_first;
+  int s = (int)(u0 - rg * nstrips_row);
+  for (long long u = u0; u < u1; ++u) {
     mbar_wait(&full[stage], phase);
     const float4* pt = reinterpret_cast<const float4*>(smem + stage * MV_STAGE_BYTES) + (warp * MV_ROWS) * (MV_STRIP / 4) + lane;
     const float4* xt = reinterpret_cast<const float4*>(smem + stage * MV_STAGE_BYTES + MV_P_BYTES) + lane;
@@ -113,51 +122,68 @@ block_matvec_kernel(const __grid_constant__ CUtensorMap tmP, const float* __rest
         acc[r][6] = fmaf(pv, x1[cc].z, acc[r][6]); acc[r][7] = fmaf(pv, x1[cc].w, acc[r][7]);
       }
     }
-  }
-  // warp-shuffle reduction in FP64; lane (r*8+j) % 32 keeps value (r, j)
-  const long long rbase = row0 + warp * MV_ROWS;
-  double* yp = Ypart + (long long)by * n_rows * MV_B;
+    ++s;
+    if (s == nstrips_row || u + 1 == u1) {
+      // end of this row group's segment: warp-shuffle reduction in FP64 into the segment's slot;
+      // lane (r*8+j) % 32 keeps value (r, j)
+      double* slot = Ypart + ((cta * maxseg + (rg - rg_first)) * MV_TILE_ROWS + warp * MV_ROWS) * MV_B;
 #pragma unroll
-  for (int r = 0; r < MV_ROWS; ++r) {
+      for (int r = 0; r < MV_ROWS; ++r) {
 #pragma unroll
-    for (int j = 0; j < MV_B; ++j) {
-      const double v = warp_sum((double)acc[r][j]);
-      if (lane == ((r * MV_B + j) & 31) && rbase + r < n_rows) yp[(rbase + r) * MV_B + j] = v;
+        for (int j = 0; j < MV_B; ++j) {
+          const double v = warp_sum((double)acc[r][j]);
+          if (lane == ((r * MV_B + j) & 31)) slot[r * MV_B + j] = v;
+          acc[r][j] = 0.f;
+        }
+      }
+      s = 0;
+      ++rg;
     }
   }
 }
 
-__global__ void reduce_parts_kernel(const double* __restrict__ Ypart, long long n_rows, int nchunks, int b,
-                                    double* __restrict__ Y) {
+// Y[row][j] = sum over the CTAs whose unit range intersects the row's group, in CTA order
+__global__ void reduce_segments_kernel(const double* __restrict__ Ypart, long long n_rows, int nstrips_row,
+                                       long long units_per_cta, int maxseg, int b, double* __restrict__ Y) {
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n_rows * MV_B; e += (long long)gridDim.x * blockDim.x) {
     const long long i = e / MV_B;
     const int j = (int)(e - i * MV_B);
     if (j >= b) continue;
-    double s = 0.0;
-    for (int c = 0; c < nchunks; ++c) s += Ypart[(long long)c * n_rows * MV_B + e];
-    Y[i * b + j] = s;
+    const long long rg = i / MV_TILE_ROWS;
+    const int rr = (int)(i - rg * MV_TILE_ROWS);
+    const long long c_first = (rg * nstrips_row) / units_per_cta;
+    const long long c_last = ((rg + 1) * nstrips_row - 1) / units_per_cta;
+    double sum = 0.0;
+    for (long long c = c_first; c <= c_last; ++c) {
+      const long long first_rg = (c * units_per_cta) / nstrips_row;
+      sum += Ypart[((c * maxseg + (rg - first_rg)) * MV_TILE_ROWS + rr) * MV_B + j];
+    }
+    Y[i * b + j] = sum;
   }
 }
 
-static inline void mv_plan(long long n_rows, long long N, int* nchunks, long long* chunk_cols) {
+struct MvPlan { int grid; int nstrips_row; int maxseg; long long units_per_cta, total_units; };
+static inline MvPlan mv_plan(long long n_rows, long long N) {
+  MvPlan p;
+  p.nstrips_row = (int)ceil_div64(N, MV_STRIP);
   const long long row_groups = ceil_div64(n_rows, MV_TILE_ROWS);
-  long long want = ceil_div64(4LL * kNumSMs, row_groups);     // aim for >= 2 waves of 2 CTAs per SM
-  long long max_chunks = N / 2048;                            // keep >= 2048 columns (16 strips) per chunk
-  if (max_chunks < 1) max_chunks = 1;
-  if (want > max_chunks) want = max_chunks;
-  if (want < 1) want = 1;
-  if (want > 64) want = 64;
-  long long cc = ceil_div64(ceil_div64(N, want), MV_STRIP) * MV_STRIP;
-  *chunk_cols = cc;
-  *nchunks = (int)ceil_div64(N, cc);
+  p.total_units = row_groups * p.nstrips_row;
+  long long ctas = 2LL * kNumSMs;
+  long long upc = ceil_div64(p.total_units, ctas);
+  const long long min_upc = ceil_div64(p.nstrips_row, 4);      // keep segments long enough to amortise the reduction
+  if (upc < min_upc) upc = min_upc;
+  if (upc < 1) upc = 1;
+  p.units_per_cta = upc;
+  p.grid = (int)ceil_div64(p.total_units, upc);
+  p.maxseg = (int)ceil_div64(upc, p.nstrips_row) + 1;          // row groups a contiguous range can touch
+  return p;
 }
 
 static inline size_t mv_xf_bytes(long long N) { return ((size_t)xf_strip_floats(N) * sizeof(float) + 255) & ~(size_t)255; }
 
 static int mv_run(const float* P_rows, long long ldp, long long n_rows, long long N, const float* XfS, int b,
                   double* Y_rows, double* Ypart, cudaStream_t st) {
-  int nchunks; long long cc;
-  mv_plan(n_rows, N, &nchunks, &cc);
+  const MvPlan pl = mv_plan(n_rows, N);
   CUtensorMap tm;
   if (make_tmap_2d(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, P_rows, n_rows, N, ldp * 4, MV_STRIP, MV_TILE_ROWS,
                    CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
@@ -166,13 +192,13 @@ static int mv_run(const float* P_rows, long long ldp, long long n_rows, long lon
     V3S_CUDA(cudaFuncSetAttribute(block_matvec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MV_SMEM));
     attr_set = true;
   }
-  dim3 grid((unsigned)ceil_div64(n_rows, MV_TILE_ROWS), (unsigned)nchunks);
   static unsigned launch_parity = 0;
-  block_matvec_kernel<<<grid, MV_THREADS, MV_SMEM, st>>>(tm, XfS, n_rows, N, cc, Ypart, (int)(launch_parity++ & 1));
+  block_matvec_kernel<<<pl.grid, MV_THREADS, MV_SMEM, st>>>(tm, XfS, n_rows, N, pl.nstrips_row, pl.units_per_cta,
+                                                           pl.total_units, pl.maxseg, Ypart, (int)(launch_parity++ & 1));
   V3S_CHECK_LAUNCH();
   long long g2 = ceil_div64(n_rows * MV_B, 256);
   if (g2 > 8LL * kNumSMs) g2 = 8LL * kNumSMs;
-  reduce_parts_kernel<<<(int)g2, 256, 0, st>>>(Ypart, n_rows, nchunks, b, Y_rows);
+  reduce_segments_kernel<<<(int)g2, 256, 0, st>>>(Ypart, n_rows, pl.nstrips_row, pl.units_per_cta, pl.maxseg, b, Y_rows);
   V3S_CHECK_LAUNCH();
   return 0;
 }
@@ -184,9 +210,8 @@ using namespace v3s;
 extern "C" long long v3s_xf_floats(long long N) { return xf_strip_floats(N); }
 
 extern "C" long long v3s_block_matvec_workspace_bytes(long long n_rows, long long N) {
-  int nchunks; long long cc;
-  mv_plan(n_rows, N, &nchunks, &cc);
-  return (long long)mv_xf_bytes(N) + (long long)sizeof(double) * nchunks * n_rows * MV_B + 256;
+  const MvPlan pl = mv_plan(n_rows, N);
+  return (long long)mv_xf_bytes(N) + (long long)sizeof(double) * pl.grid * pl.maxseg * MV_TILE_ROWS * MV_B + 256;
 }
 
 extern "C" int v3s_block_matvec(const float* P_rows, long long ldp, long long n_rows, long long N, const double* X, int b,
