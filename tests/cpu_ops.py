@@ -150,6 +150,12 @@ class OracleOps:
                 "Xf": torch.zeros((N, 8), dtype=torch.float32), "T": torch.zeros((max_steps, 128), dtype=torch.float64),
                 "status": torch.zeros((1,), dtype=torch.int32)}
 
+    def lanczos_snapshot(self, st, s0, s1):
+        return (st["T"][s0:s1].reshape(-1).clone().numpy(), int(st["status"].item()))
+
+    def lanczos_snapshot_wait(self, snap):
+        return snap
+
     def lanczos_start(self, st, W0):
         Q, _ = torch.linalg.qr(W0)
         W0.copy_(Q)

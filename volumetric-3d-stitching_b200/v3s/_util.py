@@ -36,3 +36,47 @@ def back(t, like, dtype=np.float64):
     if is_torch(like):
         return t
     return t.detach().cpu().numpy().astype(dtype, copy=False)
+
+
+# ---- bulk device -> host transfer of a result set -------------------------------------------
+_pinned = {"buf": None}
+_pool = None
+
+
+def fetch_many(tensors):
+    """{name: CUDA tensor} -> {name: fresh numpy array}.  All copies go through one cached pinned
+    staging buffer (async D2H on the current stream, one synchronisation), then are copied out to
+    freshly allocated numpy arrays by a few threads (numpy releases the GIL while copying), so the
+    caller owns the results and the next call may reuse the staging buffer."""
+    global _pool
+    import concurrent.futures as cf
+    items = [(k, t.contiguous()) for k, t in tensors.items()]
+    offs, total = [], 0
+    for _, t in items:
+        offs.append(total)
+        total += (t.numel() * t.element_size() + 255) // 256 * 256
+    if _pinned["buf"] is None or _pinned["buf"].numel() < total:
+        _pinned["buf"] = torch.empty((max(total, 1),), dtype=torch.uint8, pin_memory=True)
+    stage = _pinned["buf"]
+    views = []
+    for (k, t), o in zip(items, offs):
+        nbytes = t.numel() * t.element_size()
+        v = stage[o:o + nbytes].view(t.dtype).view(t.shape)
+        v.copy_(t, non_blocking=True)
+        views.append(v)
+    torch.cuda.current_stream().synchronize()
+    if _pool is None:
+        _pool = cf.ThreadPoolExecutor(max_workers=8)
+    out, jobs = {}, []
+    for (k, t), v in zip(items, views):
+        src = v.numpy()
+        dst = np.empty(src.shape, dtype=src.dtype)
+        out[k] = dst
+        flat_s, flat_d = src.reshape(-1), dst.reshape(-1)
+        n = flat_s.size
+        step = max(1 << 20, (n + 7) // 8)
+        for a in range(0, n, step):
+            jobs.append(_pool.submit(np.copyto, flat_d[a:a + step], flat_s[a:a + step]))
+    for j in jobs:
+        j.result()
+    return out

@@ -14,9 +14,20 @@ eigenpairs as ARPACK's non-symmetric driver, up to the sign / basis freedom the 
 has (it starts ARPACK from a random vector).  Here the start block is seeded,
 so results are reproducible run to run.
 """
+import contextlib
+
 import numpy as np
 import scipy.linalg as sla
 import torch
+
+try:                                     # small LAPACK calls are faster and far more predictable on one thread
+    from threadpoolctl import threadpool_limits as _tp_limits
+except Exception:                        # pragma: no cover
+    _tp_limits = None
+
+
+def _one_thread():
+    return _tp_limits(limits=1) if _tp_limits is not None else contextlib.nullcontext()
 
 
 def _chol_qr(W):
@@ -33,6 +44,11 @@ def _chol_qr(W):
 
 
 def _ritz_from_band(band, m, b, nev, both_ends=True):
+    with _one_thread():
+        return _ritz_from_band_impl(band, m, b, nev, both_ends)
+
+
+def _ritz_from_band_impl(band, m, b, nev, both_ends=True):
     """Largest-|lambda| eigenpairs of the m x m block-tridiagonal matrix held in lower band
     storage band[i, j] = T[j + i, j].
 
@@ -45,7 +61,7 @@ def _ritz_from_band(band, m, b, nev, both_ends=True):
     for i in range(1, b + 1):
         Tb[i, max(m - i, 0):] = 0.0
     want = min(nev, m)
-    if m <= 96:
+    if m <= 200:
         w, S = sla.eig_banded(Tb, lower=True)
         idx = np.argsort(-np.abs(w), kind="stable")[:want]
         return w[idx], S[:, idx]
@@ -127,34 +143,50 @@ def block_lanczos_device(ops, op, N, nev, tol=1e-8, max_dim=None, first_check=6,
     band = np.zeros((b + 1, max_dim))
     next_check, prev, n_checks = min(first_check, max_steps), None, 0
     w = S = res = None
-    while True:
+    def do_step():
+        nonlocal Q, steps
         W = op(st["Xf"], Q)
         ops.lanczos_step(st, m, W, steps)
         Q = W
         steps += 1
+
+    n_spec = 0
+    while True:
+        do_step()
         last = (m + b > max_dim)
         if steps >= next_check or last:
-            blks = st["T"][copied:steps].cpu().numpy().reshape(-1, 2 * b, b)     # one small D2H per check
-            if int(st["status"].item()) != 0:
+            # snapshot the new (A_j, B_j) blocks asynchronously, keep the GPU busy with one speculative
+            # step while the host extracts Ritz pairs, then wait for the snapshot only
+            s_chk, m_chk = steps, m
+            snap = ops.lanczos_snapshot(st, copied, s_chk)
+            if not last and m + 2 * b <= max_dim:
+                m += b
+                do_step()
+                n_spec += 1
+            blks, status = ops.lanczos_snapshot_wait(snap)
+            blks = blks.reshape(-1, 2 * b, b)
+            if status != 0:
                 raise Exception("block Lanczos broke down (Cholesky-QR of a rank-deficient block)")
             for i_, blk in enumerate(blks):
                 _fill_band(band, b, (copied + i_ + 1) * b, blk)
-            copied = steps
-            w, S = _ritz_from_band(band, m, b, nev, both_ends)
-            res = np.linalg.norm(blks[-1][b:] @ S[m - b:m, :], axis=0)
+            copied = s_chk
+            w, S = _ritz_from_band(band, m_chk, b, nev, both_ends)
+            res = np.linalg.norm(blks[-1][b:] @ S[m_chk - b:m_chk, :], axis=0)
             if not np.all(np.isfinite(res)):
                 raise Exception("block Lanczos broke down (non-finite residuals)")
             target = tol * max(np.abs(w).max(), 1e-300)
             n_checks += 1
-            if res.max() <= target or last:
+            if res.max() <= target or last or m + b > max_dim:
+                m = m_chk
                 break
-            next_check = _next_check(steps, res.max(), target, prev, max_gap)
-            prev = (steps, res.max())
+            next_check = max(steps + 1, _next_check(s_chk, res.max(), target, prev, max_gap))
+            prev = (s_chk, res.max())
         m += b
     St = torch.from_numpy(np.ascontiguousarray(S)).to(ops.device)
     Y = st["V"][:m].T @ St
     if stats is not None:
-        stats.update({"matvecs": steps, "block": b, "krylov_dim": m, "ritz_checks": n_checks, "residual_max": float(res.max()),
+        stats.update({"matvecs": steps, "block": b, "krylov_dim": m, "ritz_checks": n_checks, "speculative_steps": n_spec,
+                      "residual_max": float(res.max()),
                       "converged": bool(res.max() <= tol * max(np.abs(w).max(), 1e-300)), "driver": "device"})
     return w, Y, res
 
@@ -229,8 +261,8 @@ def chebyshev_lanczos_device(ops, matvec_f32, matvec_f64, N, nev, tol=1e-8, degr
         lam_t, Z = torch.linalg.eigh(0.5 * (H + H.T))
         Y = Y @ Z
         R = PY @ Z - Y * lam_t[None, :]
-        lam = lam_t.cpu().numpy()
-        res = torch.linalg.norm(R, dim=0).cpu().numpy()
+        both = torch.stack([lam_t, torch.linalg.norm(R, dim=0)]).cpu().numpy()      # one D2H
+        lam, res = both[0], both[1]
         idx = np.argsort(-np.abs(lam), kind="stable")
         lam, res = lam[idx], res[idx]
         Y = Y[:, torch.as_tensor(idx.copy(), device=Y.device)]

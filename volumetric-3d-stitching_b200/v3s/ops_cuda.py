@@ -33,6 +33,7 @@ class CudaOps:
         self.profile = False         # when True, CUDA events bracket the named kernels (bench.py)
         self._events = []
         self._synth_prep = {}
+        self._pin = None
 
     # ---- per-kernel device timing (CUDA events on the launching stream) ------------------------
     def _tic(self, name):
@@ -256,6 +257,24 @@ class CudaOps:
               "T": self.zeros((max_steps, 128), torch.float64), "status": self.zeros((1,), torch.int32),
               "ws": self.empty((int(_lib.lib.v3s_lanczos_workspace_doubles(N, max_dim)),), torch.float64)}
         return st
+
+    def lanczos_snapshot(self, st, s0, s1):
+        """Async D2H of the (A_j, B_j) blocks of steps [s0, s1) and the breakdown flag into pinned
+        host memory; returns a handle for `lanczos_snapshot_wait`."""
+        if self._pin is None or self._pin.numel() < st["T"].numel() + 1:
+            self._pin = torch.empty((st["T"].numel() + 1,), dtype=torch.float64, pin_memory=True)
+        n = (s1 - s0) * 128
+        self._pin[:n].copy_(st["T"][s0:s1].reshape(-1), non_blocking=True)
+        self._pin[n:n + 1].copy_(st["status"].to(torch.float64), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return (ev, n)
+
+    def lanczos_snapshot_wait(self, snap):
+        ev, n = snap
+        ev.synchronize()
+        host = self._pin[:n + 1].numpy()
+        return host[:n].copy(), int(host[n])
 
     def lanczos_start(self, st, W0):
         """Orthonormalise W0 [N,8] (FP64, overwritten) into the first basis block."""

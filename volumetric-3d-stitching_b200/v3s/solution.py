@@ -43,17 +43,20 @@ class OrientationRecoverySolver:
         rot_y = ops.to_device(np.ascontiguousarray(R.T), torch.float64)
         out = run_pipeline(ops, ShardPlan(Nn), ed, rot9, rot_y, n_p, parameters['k'], parameters['Epsilon'],
                            polar_mode=polar_mode, check=check_sigma, stats=stats)
-        if 'sigma_T_host' not in out:
-            out['sigma_T_host'] = float(out['sigma_T'].item())
-        if not bool(torch.any(out['Images_local'] != 0)):
+        # the reference returns float64 everywhere: widen on the device, one staged transfer for all arrays
+        f64 = lambda t: t.to(torch.float64)
+        host = _util.fetch_many({
+            'Ps': f64(out['Ps']), 'Lambda': f64(out['Lambda']), 'c': f64(out['c']), 'S2': f64(out['S2']),
+            'N': f64(out['N']), 'Images': f64(out['Images_local']),
+            'nonzero': torch.any(out['Images_local'] != 0).reshape(1).to(torch.uint8),
+            'Sigma_T': out['sigma_T'].reshape(1).to(torch.float64)})
+        if not host['nonzero'][0]:
             raise Exception('Images is an all-zero array.')          # projection.py:47
         print('OrientationRecoverySolver.solve ended.')
-        # the reference returns float64 everywhere: widen on the device, then one copy per array
-        f64 = lambda t: t.to(torch.float64).cpu().numpy()
         return {
-            'Ps': f64(out['Ps']), 'Lambda': f64(out['Lambda']), 'c0': f64(out['c']), 'c': f64(out['c']),
-            'S2': f64(out['S2']), 'N': f64(out['N']), 'Images': f64(out['Images_local']), 'R': R,
-            'Sigma_T': np.array([out['sigma_T_host']]), 'Axis': Axis.T, 'Quat': Quat.T,
+            'Ps': host['Ps'], 'Lambda': host['Lambda'], 'c0': host['c'].copy(), 'c': host['c'],
+            'S2': host['S2'], 'N': host['N'], 'Images': host['Images'], 'R': R,
+            'Sigma_T': np.array([out.get('sigma_T_host', float(host['Sigma_T'][0]))]), 'Axis': Axis.T, 'Quat': Quat.T,
         }
 
     @staticmethod
