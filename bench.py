@@ -229,6 +229,8 @@ def main():
         torch.cuda.synchronize()
 
     def one_pass(stats=None):
+        if stats is not None:
+            stats.clear()
         return run_pipeline(ops, plan, ed, rot9, rot_y, n_p, k, eps, polar_mode=0, check=False, stats=stats, validate=False)
 
     for _ in range(args.warmup):
@@ -308,7 +310,7 @@ def main():
         "roofline": None, "roofline_other": None,
         "kernel_ms_per_pass": stage_ms,
         "eigen": {k_: stats.get(k_) for k_ in ("driver", "matvecs", "probe_steps", "cheb_steps", "degree", "krylov_dim",
-                                               "ritz_checks", "residual_max", "converged")},
+                                               "ritz_checks", "locking_rounds", "residual_max", "converged")},
         "result": {"sigma_T_deg": round(sigma_T, 4), "lambda_1_9": [round(float(x), 8) for x in lam[:10]]},
         "cpu_baseline": cpu_base,
     }

@@ -156,10 +156,10 @@ class OracleOps:
     def lanczos_snapshot_wait(self, snap):
         return snap
 
-    def lanczos_start(self, st, W0):
+    def lanczos_start(self, st, W0, row0=0):
         Q, _ = torch.linalg.qr(W0)
         W0.copy_(Q)
-        st["V"][:8] = Q.T
+        st["V"][row0:row0 + 8] = Q.T
         st["Xf"].copy_(Q.to(torch.float32))
 
     def lanczos_step(self, st, m, W, step):

@@ -304,6 +304,28 @@ def test_eigen_connected(v3s_mod, golden_dir):
     assert ang.max() < 1e-4
 
 
+def test_reference_mode_hopf_grid_2744(v3s_mod):
+    """The reference's own larger configuration (solution.py:81-83: n=15, nRot1D=14, k=100): Hopf
+    grid with the axis-clip bug -> many duplicate patterns and a kNN graph with ~1700 components,
+    i.e. lambda = 1 with multiplicity far beyond the Lanczos block size."""
+    Images, R, Axis, Quat = v3s_mod.Projector.generate(14, 15)
+    assert Images.shape == (2744, 961)
+    S2, N = v3s_mod.DistanceMatrix.knn(Images, 100)
+    oS2, oN = orc.knn(Images, 100)
+    err = np.abs(S2 - oS2)
+    assert (orc.almost_equal_hybrid(S2, oS2, 1e-5) | (err < 5e-7)).all()
+    stats = {}
+    Ps, Lam = v3s_mod.DiffusionMapSolver.diffusion_coordinate(oS2.copy(), oN, 0.7, stats=stats)
+    oPs, oLam = orc.diffusion_coordinate(oS2.copy(), oN, 0.7)
+    print("hopf 2744:", stats, Lam)
+    assert np.allclose(Lam, oLam, atol=1e-6) and np.allclose(oLam, 1.0)
+    # every returned vector is an eigenvector for lambda = 1 (the basis inside the eigenspace is arbitrary upstream too)
+    _, _, _, _, P, di = orc.diffusion_coordinate(oS2.copy(), oN, 0.7, return_all=True)
+    Vn = Ps / di[:, None]
+    assert np.max(np.abs(P @ Vn - Vn)) < 1e-5 * np.max(np.abs(Vn))
+    assert np.linalg.matrix_rank(Vn, tol=1e-6) == 10
+
+
 # ------------------------------------------------------------------ stage 4
 
 def test_fit_helpers(v3s_mod, golden_dir):

@@ -67,13 +67,28 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// Tile order: groups of GRAM_GROUP column blocks, row blocks innermost-but-one, so that the ~148
+// tiles in flight at any time form a compact (rows x cols) patch whose operands are shared through
+// L2 instead of being re-read from HBM for every tile.
+constexpr int GRAM_GROUP = 16;
+__device__ __forceinline__ void gram_decode_tile(int tile, int tiles_c, int tiles_r, int& tc, int& tr) {
+  const int per_group = GRAM_GROUP * tiles_r;
+  const int g = tile / per_group;
+  const int first_c = g * GRAM_GROUP;
+  const int gw = min(GRAM_GROUP, tiles_c - first_c);
+  const int rem = tile - g * per_group;
+  tc = first_c + rem % gw;
+  tr = rem / gw;
+}
+
 // instruction descriptor: D=F32, A=B=BF16, both K-major, N=256, M=128
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
 __global__ void __launch_bounds__(GRAM_THREADS, 1)
 gram_tc_kernel(const __grid_constant__ CUtensorMap tm_c_hi, const __grid_constant__ CUtensorMap tm_c_lo,
                const __grid_constant__ CUtensorMap tm_r_hi, const __grid_constant__ CUtensorMap tm_r_lo,
-               float* __restrict__ G, long long ldg, int n_cols, int n_rows, int num_kb, int tiles_c, int num_tiles) {
+               float* __restrict__ G, long long ldg, int n_cols, int n_rows, int num_kb, int tiles_c, int tiles_r,
+               int num_tiles) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -110,7 +125,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tm_c_hi, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int tc = tile % tiles_c, tr = tile / tiles_c;
+        int tc, tr;
+        gram_decode_tile(tile, tiles_c, tiles_r, tc, tr);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_expect_tx(&full[stage], STAGE_BYTES);
@@ -162,7 +178,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tm_c_hi, const __grid_constan
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int tc = tile % tiles_c, tr = tile / tiles_c;
+      int tc, tr;
+      gram_decode_tile(tile, tiles_c, tiles_r, tc, tr);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const int c = tc * BM + warp * 32 + lane;
@@ -322,7 +339,7 @@ extern "C" int v3s_gram_rows(const void* all_hi, const void* all_lo, long long n
   }
   const int grid = (int)(nt < kNumSMs ? nt : kNumSMs);
   gram_tc_kernel<<<grid, GRAM_THREADS, GRAM_SMEM, (cudaStream_t)stream>>>(mc_hi, mc_lo, mr_hi, mr_lo, G, ldg, (int)n_cols,
-                                                                          (int)n_rows, Ppad / BK, tiles_c, (int)nt);
+                                                                          (int)n_rows, Ppad / BK, tiles_c, tiles_r, (int)nt);
   V3S_CHECK_LAUNCH();
   return 0;
 }

@@ -116,7 +116,7 @@ def _next_check(steps, res_max, target, prev, max_gap):
 
 
 def block_lanczos_device(ops, op, N, nev, tol=1e-8, max_dim=None, first_check=6, seed=0, max_gap=16,
-                         stats=None, start_block=None, both_ends=True):
+                         stats=None, start_block=None, both_ends=True, lock=None):
     """Same algorithm as `block_lanczos_topk`, with every per-step operation enqueued on the GPU by
     the C-ABI (`v3s_lanczos_start` / `v3s_lanczos_step`, csrc/lanczos.cu): the host only launches,
     and reads back the small (A_j, B_j) blocks when it extracts Ritz pairs.
@@ -124,29 +124,37 @@ def block_lanczos_device(ops, op, N, nev, tol=1e-8, max_dim=None, first_check=6,
     op(Xf, Q): the operator applied to the current block -- Xf is the backend's FP32 copy of the
     block (opaque layout, what `ops.block_matvec_f32` consumes), Q the same block in FP64 [N,8];
     returns [N,8] float64 (all-gathered when sharded), which the step overwrites with the next block.
+    lock: optional [L,N] orthonormal rows (L a multiple of 8, zero rows allowed) that every block is
+    kept orthogonal to -- converged eigenvectors of earlier runs (see `topk_with_locking`).
     """
     b = 8
     if max_dim is None:
         max_dim = min(N, 1024)
     max_dim = max(b, (min(max_dim, N) // b) * b)
     max_steps = max_dim // b
-    st = ops.lanczos_alloc(N, max_dim, max_steps)
+    L = 0 if lock is None else int(lock.shape[0])
+    st = ops.lanczos_alloc(N, max_dim + L, max_steps)
+    if L:
+        st["V"][:L] = lock
     if start_block is None:
         gen = torch.Generator(device="cpu")
         gen.manual_seed(seed)
         W0 = torch.randn((N, b), generator=gen, dtype=torch.float64).to(ops.device)
     else:
         W0 = start_block.clone()
-    ops.lanczos_start(st, W0)
+    if L:
+        W0 -= lock.T @ (lock @ W0)
+        W0 -= lock.T @ (lock @ W0)
+    ops.lanczos_start(st, W0, L)
     Q = W0                               # FP64 copy of the current block
-    m, steps, copied = b, 0, 0
+    m, steps, copied = b, 0, 0           # m counts the Krylov basis only (rows L .. L+m of V)
     band = np.zeros((b + 1, max_dim))
     next_check, prev, n_checks = min(first_check, max_steps), None, 0
     w = S = res = None
     def do_step():
         nonlocal Q, steps
         W = op(st["Xf"], Q)
-        ops.lanczos_step(st, m, W, steps)
+        ops.lanczos_step(st, L + m, W, steps)
         Q = W
         steps += 1
 
@@ -183,7 +191,7 @@ def block_lanczos_device(ops, op, N, nev, tol=1e-8, max_dim=None, first_check=6,
             prev = (s_chk, res.max())
         m += b
     St = torch.from_numpy(np.ascontiguousarray(S)).to(ops.device)
-    Y = st["V"][:m].T @ St
+    Y = st["V"][L:L + m].T @ St
     if stats is not None:
         stats.update({"matvecs": steps, "block": b, "krylov_dim": m, "ritz_checks": n_checks, "speculative_steps": n_spec,
                       "residual_max": float(res.max()),
@@ -192,7 +200,7 @@ def block_lanczos_device(ops, op, N, nev, tol=1e-8, max_dim=None, first_check=6,
 
 
 def chebyshev_lanczos_device(ops, matvec_f32, matvec_f64, N, nev, tol=1e-8, degree=8, probe_steps=10, seed=0,
-                             stats=None):
+                             stats=None, lock=None):
     """Largest eigenpairs of the symmetric operator P by block Lanczos on a Chebyshev polynomial
     of P (device driver).  Clustered top eigenvalues (gaps ~1e-4 at N = 10^4) make plain Lanczos
     need a Krylov space of ~600 vectors, whose Ritz extraction is O(m^2 b) host work per check;
@@ -213,7 +221,7 @@ def chebyshev_lanczos_device(ops, matvec_f32, matvec_f64, N, nev, tol=1e-8, degr
     st1 = {}
     plain_op = lambda Xf, Q: matvec_f32(Xf)
     w0, Y0, res0 = block_lanczos_device(ops, plain_op, N, nev, tol=tol, max_dim=probe_steps * b, seed=seed,
-                                        first_check=probe_steps, stats=st1, both_ends=True)
+                                        first_check=probe_steps, stats=st1, both_ends=True, lock=lock)
     n_mv = st1["matvecs"]
     info = {"probe_steps": st1["matvecs"], "degree": degree}
     if st1["converged"]:
@@ -221,7 +229,7 @@ def chebyshev_lanczos_device(ops, matvec_f32, matvec_f64, N, nev, tol=1e-8, degr
         info.update({"cheb_steps": 0, "krylov_dim": st1["krylov_dim"]})
     elif np.any(w0 < 0) or len(w0) < nev:
         st2 = {}
-        lam, Y, res = block_lanczos_device(ops, plain_op, N, nev, tol=tol, seed=seed, stats=st2)
+        lam, Y, res = block_lanczos_device(ops, plain_op, N, nev, tol=tol, seed=seed, stats=st2, lock=lock)
         if stats is not None:
             stats.update(st2)
             stats["matvecs"] += n_mv
@@ -250,7 +258,7 @@ def chebyshev_lanczos_device(ops, matvec_f32, matvec_f64, N, nev, tol=1e-8, degr
         start = Y0[:, torch.as_tensor(order.copy(), device=Y0.device)].contiguous()
         st2 = {}
         _, Y, res = block_lanczos_device(ops, cheb_op, N, nev, tol=tol, seed=seed, first_check=4, max_gap=8, stats=st2,
-                                         start_block=start, both_ends=False)
+                                         start_block=start, both_ends=False, lock=lock)
         n_mv += count[0]
         info.update({"cheb_steps": st2["matvecs"], "krylov_dim": st2["krylov_dim"], "cut": cut,
                      "ritz_checks": st2["ritz_checks"], "converged": st2["converged"]})
@@ -271,6 +279,46 @@ def chebyshev_lanczos_device(ops, matvec_f32, matvec_f64, N, nev, tol=1e-8, degr
         stats.update(info)
         stats.update({"matvecs": n_mv, "block": b, "residual_max": float(np.max(res)), "driver": "device-chebyshev",
                       "converged": bool(info.get("converged", st1["converged"]))})
+    return lam, Y, res
+
+
+def topk_with_locking(run, nev, block=8, rel_tol=1e-6, max_rounds=8, stats=None):
+    """A block Krylov space holds at most `block` independent vectors of one eigenspace, so an
+    eigenvalue of multiplicity >= block (disconnected kNN graphs: lambda = 1 once per component) can
+    hide further copies.  When the converged set contains such a saturated cluster, rerun with the
+    found eigenvectors locked (deflated) until a run contributes nothing new to the top `nev`.
+
+    run(lock) -> (lam [nev] numpy, Y [N,nev] tensor, res); lock is None or [L,N] rows."""
+    lam, Y, res = run(None)
+    rounds = 1
+    found_lam, found_Y = lam.copy(), Y
+    while rounds < max_rounds:
+        a = np.abs(lam)
+        saturated = any(int(np.sum(np.abs(a - x) <= rel_tol * max(x, 1e-300))) >= block for x in a)
+        if not saturated:
+            break
+        Lrows = found_Y.T.contiguous()
+        pad = (-Lrows.shape[0]) % 8
+        if pad:
+            Lrows = torch.cat([Lrows, torch.zeros((pad, Lrows.shape[1]), dtype=Lrows.dtype, device=Lrows.device)], dim=0)
+        lam2, Y2, res2 = run(Lrows)
+        rounds += 1
+        floor = np.min(np.abs(lam))
+        new = np.abs(lam2) > floor * (1 + rel_tol) + 1e-300
+        found_lam = np.concatenate([found_lam, lam2])
+        found_Y = torch.cat([found_Y, Y2], dim=1)
+        all_lam = np.concatenate([lam, lam2])
+        all_res = np.concatenate([res, res2])
+        all_Y = torch.cat([Y, Y2], dim=1)
+        # prefer the already-held vectors on ties (stable sort on -|lambda|)
+        idx = np.argsort(-np.abs(all_lam), kind="stable")[:nev]
+        contributed = bool(np.any(idx >= len(lam)) and np.any(new))
+        lam, res = all_lam[idx], all_res[idx]
+        Y = all_Y[:, torch.as_tensor(idx.copy(), device=all_Y.device)]
+        if not contributed:
+            break
+    if stats is not None:
+        stats["locking_rounds"] = rounds
     return lam, Y, res
 
 

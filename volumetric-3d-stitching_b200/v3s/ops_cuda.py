@@ -276,10 +276,10 @@ class CudaOps:
         host = self._pin[:n + 1].numpy()
         return host[:n].copy(), int(host[n])
 
-    def lanczos_start(self, st, W0):
-        """Orthonormalise W0 [N,8] (FP64, overwritten) into the first basis block."""
-        call("v3s_lanczos_start", ptr(st["V"]), st["N"], st["N"], st["max_dim"], ptr(W0), ptr(st["Xf"]), ptr(st["ws"]),
-             stream_ptr())
+    def lanczos_start(self, st, W0, row0=0):
+        """Orthonormalise W0 [N,8] (FP64, overwritten) into the basis block at rows [row0, row0+8)."""
+        call("v3s_lanczos_start", ptr(st["V"][row0:]), st["N"], st["N"], st["max_dim"], ptr(W0), ptr(st["Xf"]),
+             ptr(st["ws"]), stream_ptr())
 
     def lanczos_step(self, st, m, W, step):
         h = self._tic("lanczos_orth")

@@ -17,7 +17,7 @@ import math
 import numpy as np
 import torch
 
-from .eig import block_lanczos_device, block_lanczos_topk, chebyshev_lanczos_device
+from .eig import block_lanczos_device, block_lanczos_topk, chebyshev_lanczos_device, topk_with_locking
 
 NEV = 10   # diffusion.py:42 (k = 10 eigenpairs)
 
@@ -138,12 +138,22 @@ def eigen_stage(ops, plan, P_rows, dis, nev=NEV, validate=True, tol=None, stats=
     elif hasattr(ops, "lanczos_step") and N >= 64:
         def matvec_f32(Xf):
             return plan.all_gather_rows(ops.block_matvec_f32(P_rows, N, Xf))
-        if N >= 2048 and nev <= 16:
-            lam, V, _ = chebyshev_lanczos_device(ops, matvec_f32, matvec, N, nev, tol=(1e-8 if tol is None else tol),
-                                                 stats=stats, seed=seed)
-        else:
-            lam, V, _ = block_lanczos_device(ops, lambda Xf, Q: matvec_f32(Xf), N, nev,
-                                             tol=(1e-8 if tol is None else tol), stats=stats, seed=seed)
+        tol_ = 1e-8 if tol is None else tol
+
+        def run(lock):
+            st_ = {}
+            if N >= 2048 and nev <= 16:
+                r = chebyshev_lanczos_device(ops, matvec_f32, matvec, N, nev, tol=tol_, stats=st_, seed=seed, lock=lock)
+            else:
+                r = block_lanczos_device(ops, lambda Xf, Q: matvec_f32(Xf), N, nev, tol=tol_, stats=st_, seed=seed,
+                                         lock=lock)
+            if stats is not None:
+                prev_mv = stats.get("matvecs", 0)
+                stats.update(st_)
+                stats["matvecs"] = prev_mv + st_.get("matvecs", 0)
+            return r
+
+        lam, V, _ = topk_with_locking(run, nev, stats=stats)
     else:
         lam, V, _ = block_lanczos_topk(matvec, N, nev, dev, tol=(1e-8 if tol is None else tol), stats=stats, seed=seed)
     V = -V                                                   # diffusion.py:62 (sign is arbitrary upstream)
