@@ -78,17 +78,24 @@ int v3s_gram_rows_simt(const float* a_all, long long n_cols, const float* a_rows
 int v3s_round_distance_dense(const float* a_f32, long long n, int P, const int* zero_flag, double* B, void* stream);
 
 /* DistanceMatrix.knn_from_round_distance (distance.py:26-48) on a caller-supplied dense FP64
- * B [n,n]: k smallest entries per row, ascending.  key_ws float [n,n]; cand_ws int [n,min(k+margin,n)]. */
-int v3s_knn_from_dense(const double* B, long long n, int k, int margin, float* key_ws, int* cand_ws, double* S2,
-                       int* Nbr, void* stream);
+ * B [n,n]: k smallest entries per row, ascending.  key_ws float [n,n]; cand_ws int [n,min(k+margin,n)];
+ * count_ws int [n].                                                                            */
+int v3s_knn_from_dense(const double* B, long long n, int k, int margin, float* key_ws, int* cand_ws, int* count_ws,
+                       double* S2, int* Nbr, void* stream);
 
 /* arccos epilogue + DistanceMatrix.knn_from_round_distance (distance.py:56-59, 26-48) for the
  * panel rows [row0, row0+n_rows): S2 [n_rows,k] FP64 ascending distances, Nbr [n_rows,k] int32.
- * cand_ws: int32 workspace [n_rows, min(k+margin, n_cols)].  Fails with the reference's message
- * "Number of nearest neighbors to preserve is too high." when k > n_cols.                     */
+ * Candidates = every entry of the row within eps_g of its (k+margin)-th largest Gram value (a
+ * value margin: with |G - G_exact| <= eps_g/2 the exact k nearest are provably among them), at
+ * most `cap` per row (cand_ws int [n_rows,cap], count_ws int [n_rows]); *overflow_flag (device,
+ * may be NULL) counts rows whose band exceeded cap and fell back to exactly k+margin candidates.
+ * Their distances are recomputed from the FP32 rows as 2 asin(|a_r - a_c|/2) and sorted.
+ * Fails with the reference's message "Number of nearest neighbors to preserve is too high."
+ * when k > n_cols.                                                                              */
 int v3s_knn_from_gram(const float* G, long long ldg, long long n_rows, long long n_cols, long long row0,
-                      const float* a_rows, const float* a_all, int P, int k, int margin, const int* zero_flag,
-                      int* cand_ws, double* S2, int* Nbr, void* stream);
+                      const float* a_rows, const float* a_all, int P, int k, int margin, float eps_g, int cap,
+                      const int* zero_flag, int* cand_ws, int* count_ws, int* overflow_flag, double* S2, int* Nbr,
+                      void* stream);
 
 /* ---- stage 3: diffusion map ---------------------------------------------------------------- */
 

@@ -26,7 +26,8 @@ __device__ __forceinline__ float load_g(const float* __restrict__ grow, int c, b
 
 __global__ void __launch_bounds__(kSelThreads)
 select_kernel(const float* __restrict__ G, long long ldg, int n_rows, int n_cols, long long row0, int kk,
-              const int* __restrict__ zero_flag, int* __restrict__ cand) {
+              float eps_g, int cap, const int* __restrict__ zero_flag, int* __restrict__ cand,
+              int* __restrict__ cand_count, int* __restrict__ overflow) {
   __shared__ int hist[256];
   __shared__ uint32_t s_prefix;
   __shared__ int s_remaining, s_count_eq, s_slot, s_eq_taken;
@@ -64,11 +65,36 @@ select_kernel(const float* __restrict__ G, long long ldg, int n_rows, int n_cols
     }
     // prefix == key of the kk-th largest entry; `remaining` entries equal to it are still needed
     const uint32_t T = prefix;
-    const bool ties = (s_count_eq != remaining);
+    bool ties = (s_count_eq != remaining);
     __syncthreads();
     if (tid == 0) { s_slot = 0; s_eq_taken = 0; }
     __syncthreads();
-    int* out = cand + (long long)r * kk;
+    int* out = cand + (long long)r * cap;
+    bool done = false;
+    if (eps_g > 0.f && cap > kk) {
+      // value margin: keep EVERY entry within eps_g of the kk-th largest.  With |G - G_exact| <= eps_g/2
+      // this provably contains the exact top-kk set, whatever the tie / near-tie structure of the row.
+      const float g_lo = key_to_float(T) - eps_g;
+      for (int c = tid; c < n_cols; c += kSelThreads) {
+        if (load_g(grow, c, row_zero, zero_flag) >= g_lo) {
+          const int slot = atomicAdd(&s_slot, 1);
+          if (slot < cap) out[slot] = c;
+        }
+      }
+      __syncthreads();
+      if (s_slot <= cap) {
+        done = true;
+        if (tid == 0) cand_count[r] = s_slot;
+      } else {
+        if (tid == 0 && overflow) atomicAdd(overflow, 1);   // band larger than the buffer: fall back to exactly kk
+        ties = true;
+      }
+      __syncthreads();
+      if (tid == 0) { s_slot = 0; s_eq_taken = 0; }
+      __syncthreads();
+    }
+    if (done) continue;
+    if (tid == 0) cand_count[r] = kk;
     if (!ties) {
       for (int c = tid; c < n_cols; c += kSelThreads) {
         const uint32_t key = float_to_key(load_g(grow, c, row_zero, zero_flag));
@@ -106,7 +132,8 @@ constexpr int kRefThreads = 256;
 
 __global__ void __launch_bounds__(kRefThreads)
 refine_sort_kernel(const float* __restrict__ a_rows, const float* __restrict__ a_all, int P, long long row0, int n_rows,
-                   const int* __restrict__ cand, int kk, int kk_pad, int k, const int* __restrict__ zero_flag,
+                   const int* __restrict__ cand, const int* __restrict__ cand_count, int cap, int kk_pad, int k,
+                   const int* __restrict__ zero_flag,
                    int cache_row, const double* __restrict__ Bd, long long ldb, double* __restrict__ S2,
                    int* __restrict__ Nbr) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -118,11 +145,12 @@ refine_sort_kernel(const float* __restrict__ a_rows, const float* __restrict__ a
 
   for (int r = blockIdx.x; r < n_rows; r += gridDim.x) {
     __syncthreads();
+    const int kk = cand_count[r];
     const float* arow = a_rows ? a_rows + (long long)r * P : nullptr;
     if (Bd) {   // dense mode: exact FP64 values gathered from the caller's matrix
       for (int s = tid; s < kk_pad; s += kRefThreads) {
         const bool ok = s < kk;
-        const int j = ok ? cand[(long long)r * kk + s] : 0x7fffffff;
+        const int j = ok ? cand[(long long)r * cap + s] : 0x7fffffff;
         sd[s] = ok ? Bd[(long long)r * ldb + j] : 1e300;
         si[s] = j;
       }
@@ -140,7 +168,7 @@ refine_sort_kernel(const float* __restrict__ a_rows, const float* __restrict__ a
     const float* xr = cache_row ? srow : arow;
     const bool rz = zero_flag ? (zero_flag[row0 + r] != 0) : false;
     for (int s = warp; s < (Bd ? 0 : kk); s += kRefThreads / 32) {
-      const int j = cand[(long long)r * kk + s];
+      const int j = cand[(long long)r * cap + s];
       const float* aj = a_all + (long long)j * P;
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
       if (vec4) {
@@ -196,20 +224,24 @@ refine_sort_kernel(const float* __restrict__ a_rows, const float* __restrict__ a
 using namespace v3s;
 
 extern "C" int v3s_knn_from_gram(const float* G, long long ldg, long long n_rows, long long n_cols, long long row0,
-                                 const float* a_rows, const float* a_all, int P, int k, int margin, const int* zero_flag,
-                                 int* cand_ws, double* S2, int* Nbr, void* stream) {
+                                 const float* a_rows, const float* a_all, int P, int k, int margin, float eps_g, int cap,
+                                 const int* zero_flag, int* cand_ws, int* count_ws, int* overflow_flag, double* S2,
+                                 int* Nbr, void* stream) {
   V3S_REQUIRE(k >= 1 && margin >= 0, "v3s_knn_from_gram: bad k/margin");
   V3S_REQUIRE(k <= n_cols, "Number of nearest neighbors to preserve is too high.");   // distance.py:33-34
   V3S_REQUIRE(n_rows >= 0 && n_cols < (1LL << 31) && n_rows < (1LL << 31) && ldg >= n_cols, "v3s_knn_from_gram: bad shape");
   if (n_rows == 0) return 0;
   long long kk = (long long)k + margin;
   if (kk > n_cols) kk = n_cols;
+  if (cap < kk) cap = (int)kk;
+  if (cap > n_cols) cap = (int)n_cols;
   int kk_pad = 4;
-  while (kk_pad < kk) kk_pad <<= 1;
-  V3S_REQUIRE(kk_pad <= 4096, "v3s_knn_from_gram: k + margin = %lld too large (max 4096)", kk);
+  while (kk_pad < cap) kk_pad <<= 1;
+  V3S_REQUIRE(kk_pad <= 4096, "v3s_knn_from_gram: candidate capacity %d too large (max 4096)", cap);
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = (int)(n_rows < 16LL * kNumSMs ? n_rows : 16LL * kNumSMs);
-  select_kernel<<<grid, kSelThreads, 0, st>>>(G, ldg, (int)n_rows, (int)n_cols, row0, (int)kk, zero_flag, cand_ws);
+  select_kernel<<<grid, kSelThreads, 0, st>>>(G, ldg, (int)n_rows, (int)n_cols, row0, (int)kk, eps_g, cap, zero_flag,
+                                              cand_ws, count_ws, overflow_flag);
   V3S_CHECK_LAUNCH();
   const size_t base = (size_t)kk_pad * (sizeof(double) + sizeof(int));
   const int cache_row = (base + (size_t)P * 4 <= 200 * 1024) ? 1 : 0;
@@ -220,12 +252,11 @@ extern "C" int v3s_knn_from_gram(const float* G, long long ldg, long long n_rows
     smem_set = smem;
   }
   const int grid2 = (int)(n_rows < 8LL * kNumSMs ? n_rows : 8LL * kNumSMs);
-  refine_sort_kernel<<<grid2, kRefThreads, smem, st>>>(a_rows, a_all, P, row0, (int)n_rows, cand_ws, (int)kk, kk_pad, k,
-                                                      zero_flag, cache_row, nullptr, 0, S2, Nbr);
+  refine_sort_kernel<<<grid2, kRefThreads, smem, st>>>(a_rows, a_all, P, row0, (int)n_rows, cand_ws, count_ws, cap, kk_pad,
+                                                      k, zero_flag, cache_row, nullptr, 0, S2, Nbr);
   V3S_CHECK_LAUNCH();
   return 0;
 }
-
 
 namespace v3s {
 __global__ void neg_key_kernel(const double* __restrict__ B, long long n, float* __restrict__ key) {
@@ -236,9 +267,9 @@ __global__ void neg_key_kernel(const double* __restrict__ B, long long n, float*
 
 // DistanceMatrix.knn_from_round_distance (distance.py:26-48) on a caller-supplied dense FP64
 // matrix B [n,n]: per row the k smallest entries, ascending, with their column indices.
-// key_ws: float [n,n]; cand_ws: int [n, min(k+margin, n)].
+// key_ws: float [n,n]; cand_ws: int [n, min(k+margin, n)]; count_ws: int [n].
 extern "C" int v3s_knn_from_dense(const double* B, long long n, int k, int margin, float* key_ws, int* cand_ws,
-                                  double* S2, int* Nbr, void* stream) {
+                                  int* count_ws, double* S2, int* Nbr, void* stream) {
   V3S_REQUIRE(k >= 1 && margin >= 0 && n >= 1 && n < (1LL << 31), "v3s_knn_from_dense: bad arguments");
   V3S_REQUIRE(k <= n, "Number of nearest neighbors to preserve is too high.");
   cudaStream_t st = (cudaStream_t)stream;
@@ -252,11 +283,12 @@ extern "C" int v3s_knn_from_dense(const double* B, long long n, int k, int margi
   neg_key_kernel<<<(int)g, 256, 0, st>>>(B, n * n, key_ws);
   V3S_CHECK_LAUNCH();
   const int grid = (int)(n < 16LL * kNumSMs ? n : 16LL * kNumSMs);
-  select_kernel<<<grid, kSelThreads, 0, st>>>(key_ws, n, (int)n, (int)n, 0, (int)kk, nullptr, cand_ws);
+  select_kernel<<<grid, kSelThreads, 0, st>>>(key_ws, n, (int)n, (int)n, 0, (int)kk, 0.f, (int)kk, nullptr, cand_ws,
+                                              count_ws, nullptr);
   V3S_CHECK_LAUNCH();
   const size_t smem = (size_t)kk_pad * (sizeof(double) + sizeof(int));
-  refine_sort_kernel<<<grid, kRefThreads, smem, st>>>(nullptr, nullptr, 0, 0, (int)n, cand_ws, (int)kk, kk_pad, k, nullptr,
-                                                     0, B, n, S2, Nbr);
+  refine_sort_kernel<<<grid, kRefThreads, smem, st>>>(nullptr, nullptr, 0, 0, (int)n, cand_ws, count_ws, (int)kk, kk_pad, k,
+                                                     nullptr, 0, B, n, S2, Nbr);
   V3S_CHECK_LAUNCH();
   return 0;
 }

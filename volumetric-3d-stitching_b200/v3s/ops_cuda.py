@@ -13,7 +13,14 @@ from . import _lib
 from ._lib import call, ptr, stream_ptr
 
 GRAM_KPAD = 64          # K-block of the tcgen05 Gram kernel (bf16 elements)
-KNN_MARGIN = 8          # extra candidates kept through the exact refinement
+KNN_MARGIN = 8          # extra candidates (by count) kept through the exact refinement
+KNN_EXTRA_CAP = 160     # room per row for the value margin (entries within eps_g of the (k+margin)-th)
+
+
+def gram_error_bound(P):
+    """|G_tcgen05 - G_exact| for unit rows of length P: dropped lo.lo^T term (2^-18) + the tensor
+    core's truncating FP32 accumulate over 3P/16 steps (validated in test_gram_tcgen05_vs_fp64)."""
+    return 1e-5 + 3.0e-8 * (3.0 * P / 16.0)
 PANEL_BYTES = 4 << 30   # Gram row panel budget (G is never materialised beyond this)
 
 
@@ -145,16 +152,20 @@ class CudaOps:
             return S2, Nbr
         ldg = round_up(N, 4)
         panel = max(256, min(nr, (PANEL_BYTES // (4 * ldg)) // 256 * 256))
-        kk = min(k + KNN_MARGIN, N)
+        cap = min(k + KNN_MARGIN + KNN_EXTRA_CAP, N)
+        eps_g = 2.0 * gram_error_bound(P) if self.gram_impl == "tcgen05" else 2e-5
         G = self.empty((min(panel, nr), ldg), torch.float32)
-        cand = self.empty((min(panel, nr), kk), torch.int32)
+        cand = self.empty((min(panel, nr), cap), torch.int32)
+        cnt = self.empty((min(panel, nr),), torch.int32)
+        self.knn_overflow = self.zeros((1,), torch.int32)
         zf = zero_flag if (zero_flag is not None) else None
         for p0 in range(r0, r1, panel):
             p1 = min(p0 + panel, r1)
             self.gram_rows(hi_all, lo_all, a32_all, p0, p1, out=G)
             h = self._tic("select_refine")
             call("v3s_knn_from_gram", ptr(G), ldg, p1 - p0, N, p0, ptr(a32_all[p0:p1]), ptr(a32_all), P, k, KNN_MARGIN,
-                 ptr(zf), ptr(cand), ptr(S2[p0 - r0:p1 - r0]), ptr(Nbr[p0 - r0:p1 - r0]), stream_ptr())
+                 eps_g, cap, ptr(zf), ptr(cand), ptr(cnt), ptr(self.knn_overflow), ptr(S2[p0 - r0:p1 - r0]),
+                 ptr(Nbr[p0 - r0:p1 - r0]), stream_ptr())
             self._toc(h)
         return S2, Nbr
 
@@ -171,9 +182,10 @@ class CudaOps:
         kk = min(k + KNN_MARGIN, n)
         key = self.empty((n, n), torch.float32)
         cand = self.empty((n, kk), torch.int32)
+        cnt = self.empty((n,), torch.int32)
         S2 = self.empty((n, k), torch.float64)
         Nbr = self.empty((n, k), torch.int32)
-        call("v3s_knn_from_dense", ptr(B), n, k, KNN_MARGIN, ptr(key), ptr(cand), ptr(S2), ptr(Nbr), stream_ptr())
+        call("v3s_knn_from_dense", ptr(B), n, k, KNN_MARGIN, ptr(key), ptr(cand), ptr(cnt), ptr(S2), ptr(Nbr), stream_ptr())
         return S2, Nbr
 
     # ---- stage 3 -----------------------------------------------------------------------------
