@@ -323,6 +323,14 @@ def main():
                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": (round(mv_gbs / peaks["hbm_gbs"], 4) if mv_gbs else None),
                "traffic": None, "ms_per_pass": round(sum(mv) / args.steps, 3) if mv else None, "launches_per_pass": len(mv) // args.steps,
                "peak_source": peak_src + " hbm_gbs", "note": "algorithmic 4*rows*N + 8*N*8*2 bytes per launch"}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(args.workload, {})
+    except Exception:
+        traffic = {}
+    if world == 1:
+        mv_roof["traffic"] = traffic.get("block_matvec_kernel")
+        gram_roof["traffic"] = traffic.get("gram_tc_kernel")
+        mv_roof["traffic_source"] = gram_roof["traffic_source"] = "profiles/r01_traffic.json (ncu --set full, bytes per launch)"
     dominant_is_mv = bool(mv) and (not gram_ms or sum(mv) >= sum(gram_ms))
     line["roofline"], line["roofline_other"] = (mv_roof, gram_roof) if dominant_is_mv else (gram_roof, mv_roof)
     line.pop("matvec", None)
