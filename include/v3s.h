@@ -69,6 +69,13 @@ int v3s_center_normalize(const float* img, long long n_rows, int P, long long st
 int v3s_gram_rows(const void* all_hi, const void* all_lo, long long n_cols, const void* rows_hi, const void* rows_lo,
                   long long n_rows, int Ppad, float* G, long long ldg, void* stream);
 
+/* The whole symmetric Gram matrix G [n, ldg] with half the tensor-core work: only the tiles
+ * (column block of 128, row block of 256) listed in tile_list_xy (int pairs x = column block,
+ * y = row block, those on or above the diagonal, in the caller's L2-friendly order) are computed;
+ * each is stored as G[r][c] and mirrored to G[c][r].                                            */
+int v3s_gram_symmetric(const void* a_hi, const void* a_lo, long long n, int Ppad, float* G, long long ldg,
+                       const int* tile_list_xy, int num_tiles, void* stream);
+
 /* Same contraction on CUDA cores in plain FP32 -- the validation path of v3s_gram_rows.       */
 int v3s_gram_rows_simt(const float* a_all, long long n_cols, const float* a_rows, long long n_rows, int P, float* G,
                        long long ldg, void* stream);

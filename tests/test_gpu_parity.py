@@ -98,7 +98,7 @@ def test_distance_helpers_golden(v3s_mod):
         v3s_mod.DistanceMatrix.knn(np.random.default_rng(0).random((5, 16)), 6)
 
 
-@pytest.mark.parametrize("shape", [(301, 225), (1000, 961), (2048, 4096), (77, 64)])
+@pytest.mark.parametrize("shape", [(301, 225), (1000, 961), (2048, 4096), (77, 64), (5000, 192)])
 def test_gram_tcgen05_vs_fp64(ops, shape):
     N, P = shape
     rng = np.random.default_rng(N)
@@ -129,6 +129,9 @@ def test_gram_tcgen05_vs_fp64(ops, shape):
     miss = sum(len(set(top_64[r]) - set(top_tc[r])) for r in range(N))
     print(f"  candidate misses: {miss} of {N * k}")
     assert miss == 0
+    # symmetric mode (upper-triangle tiles + mirrored stores) gives the same matrix
+    G_sym = ops.gram_symmetric(hi, lo, N)[:, :N].cpu().numpy()
+    assert np.array_equal(G_sym, G_tc)
     # a row panel in the middle (rows operand != all-rows operand)
     r0, r1 = N // 3, min(N, N // 3 + 300)
     Gp = ops.gram_rows(hi, lo, a32, r0, r1)[:, :N].cpu().numpy()

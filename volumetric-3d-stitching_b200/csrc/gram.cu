@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1)
 gram_tc_kernel(const __grid_constant__ CUtensorMap tm_c_hi, const __grid_constant__ CUtensorMap tm_c_lo,
                const __grid_constant__ CUtensorMap tm_r_hi, const __grid_constant__ CUtensorMap tm_r_lo,
                float* __restrict__ G, long long ldg, int n_cols, int n_rows, int num_kb, int tiles_c, int tiles_r,
-               int num_tiles) {
+               int num_tiles, const int2* __restrict__ tile_list, int mirror) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -126,7 +126,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tm_c_hi, const __grid_constan
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int tc, tr;
-        gram_decode_tile(tile, tiles_c, tiles_r, tc, tr);
+        if (tile_list) { const int2 t = tile_list[tile]; tc = t.x; tr = t.y; }
+        else gram_decode_tile(tile, tiles_c, tiles_r, tc, tr);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_expect_tx(&full[stage], STAGE_BYTES);
@@ -179,7 +180,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tm_c_hi, const __grid_constan
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int tc, tr;
-      gram_decode_tile(tile, tiles_c, tiles_r, tc, tr);
+      if (tile_list) { const int2 t = tile_list[tile]; tc = t.x; tr = t.y; }
+      else gram_decode_tile(tile, tiles_c, tiles_r, tc, tr);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const int c = tc * BM + warp * 32 + lane;
@@ -195,6 +197,20 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tm_c_hi, const __grid_constan
 #pragma unroll
         for (int j = 0; j < 32; ++j)
           if (c_ok && r0 + j < n_rows) dst[(long long)j * ldg] = __uint_as_float(v[j]);
+        if (mirror && c_ok) {
+          // symmetric mode: only tiles on / above the diagonal are computed; G[c][r] = G[r][c]
+          float* mdst = G + (long long)c * ldg + r0;
+          if (r0 + 32 <= n_rows) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(mdst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                 __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (r0 + j < n_rows) mdst[j] = __uint_as_float(v[j]);
+          }
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -318,8 +334,9 @@ static int make_bf16_map(CUtensorMap* map, const void* base, long long rows, int
 
 using namespace v3s;
 
-extern "C" int v3s_gram_rows(const void* all_hi, const void* all_lo, long long n_cols, const void* rows_hi,
-                             const void* rows_lo, long long n_rows, int Ppad, float* G, long long ldg, void* stream) {
+static int gram_launch(const void* all_hi, const void* all_lo, long long n_cols, const void* rows_hi, const void* rows_lo,
+                       long long n_rows, int Ppad, float* G, long long ldg, const int2* tile_list, int num_list_tiles,
+                       int mirror, void* stream) {
   V3S_REQUIRE(Ppad > 0 && Ppad % BK == 0, "v3s_gram_rows: Ppad=%d must be a positive multiple of %d", Ppad, BK);
   V3S_REQUIRE(n_cols >= 0 && n_rows >= 0 && ldg >= n_cols, "v3s_gram_rows: bad shape");
   V3S_REQUIRE(n_cols < (1LL << 31) && n_rows < (1LL << 31), "v3s_gram_rows: extents must fit int32");
@@ -337,11 +354,30 @@ extern "C" int v3s_gram_rows(const void* all_hi, const void* all_lo, long long n
     V3S_CUDA(cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM));
     attr_set = true;
   }
-  const int grid = (int)(nt < kNumSMs ? nt : kNumSMs);
+  const long long ntl = tile_list ? (long long)num_list_tiles : nt;
+  if (ntl == 0) return 0;
+  const int grid = (int)(ntl < kNumSMs ? ntl : kNumSMs);
   gram_tc_kernel<<<grid, GRAM_THREADS, GRAM_SMEM, (cudaStream_t)stream>>>(mc_hi, mc_lo, mr_hi, mr_lo, G, ldg, (int)n_cols,
-                                                                          (int)n_rows, Ppad / BK, tiles_c, tiles_r, (int)nt);
+                                                                          (int)n_rows, Ppad / BK, tiles_c, tiles_r, (int)ntl,
+                                                                          tile_list, mirror);
   V3S_CHECK_LAUNCH();
   return 0;
+}
+
+extern "C" int v3s_gram_rows(const void* all_hi, const void* all_lo, long long n_cols, const void* rows_hi,
+                             const void* rows_lo, long long n_rows, int Ppad, float* G, long long ldg, void* stream) {
+  return gram_launch(all_hi, all_lo, n_cols, rows_hi, rows_lo, n_rows, Ppad, G, ldg, nullptr, 0, 0, stream);
+}
+
+// Whole symmetric Gram matrix G [n, ldg] of one operand set: only the (column block 128 x row block
+// 256) tiles listed in tile_list (x = column block, y = row block; the caller lists those with
+// 128*x + 127 >= 256*y, i.e. on or above the diagonal, in an L2-friendly order) are computed, and
+// every tile is stored twice, as G[r][c] and as its mirror G[c][r].  Halves the tensor-core work.
+extern "C" int v3s_gram_symmetric(const void* a_hi, const void* a_lo, long long n, int Ppad, float* G, long long ldg,
+                                  const int* tile_list_xy, int num_tiles, void* stream) {
+  V3S_REQUIRE(tile_list_xy != nullptr && num_tiles >= 0, "v3s_gram_symmetric: tile list required");
+  return gram_launch(a_hi, a_lo, n, a_hi, a_lo, n, Ppad, G, ldg, reinterpret_cast<const int2*>(tile_list_xy), num_tiles, 1,
+                     stream);
 }
 
 extern "C" int v3s_gram_rows_simt(const float* a_all, long long n_cols, const float* a_rows, long long n_rows, int P,

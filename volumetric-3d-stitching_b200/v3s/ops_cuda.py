@@ -21,7 +21,8 @@ def gram_error_bound(P):
     """|G_tcgen05 - G_exact| for unit rows of length P: dropped lo.lo^T term (2^-18) + the tensor
     core's truncating FP32 accumulate over 3P/16 steps (validated in test_gram_tcgen05_vs_fp64)."""
     return 1e-5 + 3.0e-8 * (3.0 * P / 16.0)
-PANEL_BYTES = 4 << 30   # Gram row panel budget (G is never materialised beyond this)
+PANEL_BYTES = 4 << 30   # Gram row panel budget when G is streamed in panels
+SYM_BYTES = 48 << 30    # the whole symmetric G is materialised (half the MMA work) up to this size
 
 
 def round_up(x, m):
@@ -40,6 +41,7 @@ class CudaOps:
         self.profile = False         # when True, CUDA events bracket the named kernels (bench.py)
         self._events = []
         self._synth_prep = {}
+        self._sym_tile_cache = {}
         self._pin = None
 
     # ---- per-kernel device timing (CUDA events on the launching stream) ------------------------
@@ -139,6 +141,34 @@ class CudaOps:
         self._toc(h)
         return G
 
+    def _sym_tiles(self, N):
+        """Tile list of the symmetric Gram: (column block 128, row block 256) pairs on or above the
+        diagonal, ordered in groups of 16 column blocks so concurrent CTAs share operands in L2."""
+        t = self._sym_tile_cache.get(N)
+        if t is None:
+            import numpy as np
+            tiles_c, tiles_r = (N + 127) // 128, (N + 255) // 256
+            out = []
+            for g0 in range(0, tiles_c, 16):
+                cols = np.arange(g0, min(g0 + 16, tiles_c))
+                tr, tc = np.meshgrid(np.arange(tiles_r), cols, indexing="ij")
+                keep = (128 * tc + 127) >= (256 * tr)
+                out.append(np.stack([tc[keep], tr[keep]], axis=1))
+            lst = np.ascontiguousarray(np.concatenate(out, axis=0).astype(np.int32))
+            t = (self.to_device(lst, torch.int32), int(lst.shape[0]))
+            self._sym_tile_cache[N] = t
+        return t
+
+    def gram_symmetric(self, hi_all, lo_all, N, out=None):
+        """Whole G [N, ldg] f32 with half the tensor-core work (upper-triangle tiles, mirrored stores)."""
+        ldg = round_up(N, 4)
+        G = out if out is not None else self.empty((N, ldg), torch.float32)
+        tiles, nt = self._sym_tiles(N)
+        h = self._tic("gram")
+        call("v3s_gram_symmetric", ptr(hi_all), ptr(lo_all), N, hi_all.shape[1], ptr(G), ldg, ptr(tiles), nt, stream_ptr())
+        self._toc(h)
+        return G
+
     def knn_rows(self, hi_all, lo_all, a32_all, zero_flag, r0, r1, k):
         """k nearest neighbours (round distance) of rows [r0,r1) against all rows.
         -> S2 [r1-r0,k] f64 ascending, Nbr [r1-r0,k] i32.  Gram panels are streamed."""
@@ -151,7 +181,9 @@ class CudaOps:
         if nr == 0:
             return S2, Nbr
         ldg = round_up(N, 4)
-        panel = max(256, min(nr, (PANEL_BYTES // (4 * ldg)) // 256 * 256))
+        sym = (self.gram_impl == "tcgen05" and r0 == 0 and r1 == N and 4 * ldg * N <= SYM_BYTES
+               and 4 * ldg * N <= 0.6 * torch.cuda.mem_get_info()[0])
+        panel = nr if sym else max(256, min(nr, (PANEL_BYTES // (4 * ldg)) // 256 * 256))
         cap = min(k + KNN_MARGIN + KNN_EXTRA_CAP, N)
         eps_g = 2.0 * gram_error_bound(P) if self.gram_impl == "tcgen05" else 2e-5
         G = self.empty((min(panel, nr), ldg), torch.float32)
@@ -161,7 +193,10 @@ class CudaOps:
         zf = zero_flag if (zero_flag is not None) else None
         for p0 in range(r0, r1, panel):
             p1 = min(p0 + panel, r1)
-            self.gram_rows(hi_all, lo_all, a32_all, p0, p1, out=G)
+            if sym:
+                self.gram_symmetric(hi_all, lo_all, N, out=G)
+            else:
+                self.gram_rows(hi_all, lo_all, a32_all, p0, p1, out=G)
             h = self._tic("select_refine")
             call("v3s_knn_from_gram", ptr(G), ldg, p1 - p0, N, p0, ptr(a32_all[p0:p1]), ptr(a32_all), P, k, KNN_MARGIN,
                  eps_g, cap, ptr(zf), ptr(cand), ptr(cnt), ptr(self.knn_overflow), ptr(S2[p0 - r0:p1 - r0]),
