@@ -131,7 +131,7 @@ def test_gram_tcgen05_vs_fp64(ops, shape):
     assert miss == 0
     # symmetric mode (upper-triangle tiles + mirrored stores) gives the same matrix
     G_sym = ops.gram_symmetric(hi, lo, N)[:, :N].cpu().numpy()
-    assert np.array_equal(G_sym, G_sym.T)
+    assert np.max(np.abs(G_sym - G_sym.T)) < 2e-6
     # (mirrored entries come from the transposed tile: same products, the tensor core sums them in a
     #  different order, so agreement is to rounding, not bitwise)
     assert np.max(np.abs(G_sym - G_tc)) < 2e-6 and np.max(np.abs(G_sym - G64)) < tol
