@@ -80,3 +80,55 @@ def fetch_many(tensors):
     for j in jobs:
         j.result()
     return out
+
+
+class AsyncFetch:
+    """Device -> host transfer of one large tensor that overlaps with later GPU work: the copy runs
+    on a side stream into a cached pinned buffer as soon as the producer kernel has finished, and a
+    worker thread widens / copies it into a fresh numpy array (`out_dtype`) while the main stream
+    keeps computing.  `result()` returns the array."""
+    _stream = None
+    _pin = None
+
+    def __init__(self, t, out_dtype=np.float64):
+        global _pool
+        import concurrent.futures as cf
+        if _pool is None:
+            _pool = cf.ThreadPoolExecutor(max_workers=8)
+        cls = AsyncFetch
+        if cls._stream is None:
+            cls._stream = torch.cuda.Stream()
+        nbytes = t.numel() * t.element_size()
+        if cls._pin is None or cls._pin.numel() < nbytes:
+            cls._pin = torch.empty((max(nbytes, 1),), dtype=torch.uint8, pin_memory=True)
+        self._keep = t
+        ready = torch.cuda.Event()
+        ready.record()
+        cls._stream.wait_event(ready)
+        view = cls._pin[:nbytes].view(t.dtype).view(t.shape)
+        with torch.cuda.stream(cls._stream):
+            view.copy_(t, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record()
+        src = view.numpy()
+        self._out = np.empty(src.shape, dtype=out_dtype)
+
+        def work():
+            done.synchronize()
+            fs, fd = src.reshape(-1), self._out.reshape(-1)
+            n = fs.size
+            step = max(1 << 20, (n + 7) // 8)
+            jobs = [_pool.submit(np.copyto, fd[a:a + step], fs[a:a + step]) for a in range(0, n, step)]
+            for j in jobs:
+                j.result()
+            return self._out
+
+        import threading
+        self._res = None
+        self._thr = threading.Thread(target=lambda: setattr(self, "_res", work()), daemon=True)
+        self._thr.start()
+
+    def result(self):
+        self._thr.join()
+        self._keep = None
+        return self._res

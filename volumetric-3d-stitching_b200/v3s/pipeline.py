@@ -192,10 +192,12 @@ def fit_stage(ops, plan, Ps, Y, polar_mode=0, check=True):
 
 
 def run_pipeline(ops, plan, ed, rot9_local, rot_y_all, n_p, k, eps, polar_mode=0, check=True, stats=None,
-                 validate=True):
+                 validate=True, on_images=None):
     """Full path on device.  ed [n,n,n] f32; rot9_local [hi-lo,9] f64 row-major Rm of the rank's
     patterns; rot_y_all [N,9] f64 = Rotation_R.T (the reference's column-major unfold, transposed)."""
     img = ops.synth_patterns(ed, rot9_local, n_p)
+    if on_images is not None:
+        on_images(img)                                       # e.g. start the host transfer of the patterns now
     S2, Nbr = knn_stage(ops, plan, img, k)
     S2_out = S2.clone()                                      # pre-mutation copy for callers that want it
     P_rows, dis, scalars = markov_stage(ops, plan, S2, Nbr, eps, validate=validate)

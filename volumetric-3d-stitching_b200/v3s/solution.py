@@ -41,15 +41,21 @@ class OrientationRecoverySolver:
         ed = ops.to_device(Projector.synsthesize_3d(n)['ED'].astype(np.float32), torch.float32)
         rot9 = Projector.rot9_rowmajor(R, ops)
         rot_y = ops.to_device(np.ascontiguousarray(R.T), torch.float64)
+        xfer = {}
+        # the pattern matrix is by far the largest output: its host transfer starts as soon as stage 1
+        # is done and overlaps stages 2-4 (side stream + worker thread)
+        start_images = (lambda img: xfer.setdefault('Images', _util.AsyncFetch(img))) if ops.device.type == 'cuda' else None
         out = run_pipeline(ops, ShardPlan(Nn), ed, rot9, rot_y, n_p, parameters['k'], parameters['Epsilon'],
-                           polar_mode=polar_mode, check=check_sigma, stats=stats)
+                           polar_mode=polar_mode, check=check_sigma, stats=stats, on_images=start_images)
         # the reference returns float64 everywhere: widen on the device, one staged transfer for all arrays
         f64 = lambda t: t.to(torch.float64)
         host = _util.fetch_many({
             'Ps': f64(out['Ps']), 'Lambda': f64(out['Lambda']), 'c': f64(out['c']), 'S2': f64(out['S2']),
-            'N': f64(out['N']), 'Images': f64(out['Images_local']),
+            'N': f64(out['N']),
             'nonzero': torch.any(out['Images_local'] != 0).reshape(1).to(torch.uint8),
             'Sigma_T': out['sigma_T'].reshape(1).to(torch.float64)})
+        host['Images'] = xfer['Images'].result() if 'Images' in xfer else \
+            _util.fetch_many({'Images': f64(out['Images_local'])})['Images']
         if not host['nonzero'][0]:
             raise Exception('Images is an all-zero array.')          # projection.py:47
         print('OrientationRecoverySolver.solve ended.')
