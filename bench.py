@@ -241,6 +241,8 @@ def main():
         sampler.start()
     ops.profile = True
     ops.pop_timings()
+    from v3s import eig as _eig
+    _eig.HOST_TIMERS.update({"ritz_s": 0.0, "wait_s": 0.0})
     launches0 = _lib.launches
     stats = {}
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -311,6 +313,8 @@ def main():
         "kernel_ms_per_pass": stage_ms,
         "eigen": {k_: stats.get(k_) for k_ in ("driver", "matvecs", "probe_steps", "cheb_steps", "degree", "krylov_dim",
                                                "ritz_checks", "locking_rounds", "residual_max", "converged")},
+        "host_ms_per_pass": {"ritz_extraction": round(_eig.HOST_TIMERS["ritz_s"] / args.steps * 1e3, 3),
+                             "waiting_for_gpu_in_eigensolver": round(_eig.HOST_TIMERS["wait_s"] / args.steps * 1e3, 3)},
         "result": {"sigma_T_deg": round(sigma_T, 4), "lambda_1_9": [round(float(x), 8) for x in lam[:10]]},
         "cpu_baseline": cpu_base,
     }

@@ -20,14 +20,25 @@ import numpy as np
 import scipy.linalg as sla
 import torch
 
+import time
+
 try:                                     # small LAPACK calls are faster and far more predictable on one thread
-    from threadpoolctl import threadpool_limits as _tp_limits
+    from threadpoolctl import ThreadpoolController as _TPC
 except Exception:                        # pragma: no cover
-    _tp_limits = None
+    _TPC = None
+_tp_controller = None
+HOST_TIMERS = {"ritz_s": 0.0, "wait_s": 0.0}     # accumulated host time (diagnostics, bench.py)
 
 
 def _one_thread():
-    return _tp_limits(limits=1) if _tp_limits is not None else contextlib.nullcontext()
+    """Context limiting BLAS/LAPACK to one thread.  The controller (a scan of the loaded shared
+    libraries) is built once; entering the context afterwards only calls the libraries' setters."""
+    global _tp_controller
+    if _TPC is None:
+        return contextlib.nullcontext()
+    if _tp_controller is None:
+        _tp_controller = _TPC()
+    return _tp_controller.limit(limits=1)
 
 
 def _chol_qr(W):
@@ -44,8 +55,11 @@ def _chol_qr(W):
 
 
 def _ritz_from_band(band, m, b, nev, both_ends=True):
+    t0 = time.perf_counter()
     with _one_thread():
-        return _ritz_from_band_impl(band, m, b, nev, both_ends)
+        r = _ritz_from_band_impl(band, m, b, nev, both_ends)
+    HOST_TIMERS["ritz_s"] += time.perf_counter() - t0
+    return r
 
 
 def _ritz_from_band_impl(band, m, b, nev, both_ends=True):
@@ -171,7 +185,9 @@ def block_lanczos_device(ops, op, N, nev, tol=1e-8, max_dim=None, first_check=6,
                 m += b
                 do_step()
                 n_spec += 1
+            t0 = time.perf_counter()
             blks, status = ops.lanczos_snapshot_wait(snap)
+            HOST_TIMERS["wait_s"] += time.perf_counter() - t0
             blks = blks.reshape(-1, 2 * b, b)
             if status != 0:
                 raise Exception("block Lanczos broke down (Cholesky-QR of a rank-deficient block)")
