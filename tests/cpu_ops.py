@@ -142,8 +142,12 @@ class OracleOps:
     def alloc_xf(self, N):
         return torch.zeros((N, 8), dtype=torch.float32)
 
-    def block_matvec_f32(self, P_rows, N, Xf):
-        return (P_rows[:, :N].to(torch.float32) @ Xf).to(torch.float64)
+    def block_matvec_f32(self, P_rows, N, Xf, out=None):
+        Y = (P_rows[:, :N].to(torch.float32) @ Xf).to(torch.float64)
+        if out is not None:
+            out.copy_(Y)
+            return out
+        return Y
 
     def lanczos_alloc(self, N, max_dim, max_steps):
         return {"N": N, "max_dim": max_dim, "V": torch.zeros((max_dim, N), dtype=torch.float64),

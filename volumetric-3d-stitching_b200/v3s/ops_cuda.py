@@ -287,10 +287,10 @@ class CudaOps:
         """FP32 operand block of the mat-vec in strip layout (opaque to the host logic), zeroed."""
         return self.zeros((int(_lib.lib.v3s_xf_floats(N)),), torch.float32)
 
-    def block_matvec_f32(self, P_rows, N, Xf):
+    def block_matvec_f32(self, P_rows, N, Xf, out=None):
         """Y_rows [n_rows,8] f64 = P_rows[:, :N] (f32) @ X, X given as the FP32 strip-layout block."""
         n_rows, ldp = P_rows.shape
-        Y = self.empty((n_rows, 8), torch.float64)
+        Y = out if out is not None else self.empty((n_rows, 8), torch.float64)
         ws = self._mv_workspace(n_rows, N)
         h = self._tic("matvec")
         call("v3s_block_matvec_f32", ptr(P_rows), ldp, n_rows, N, ptr(Xf), ptr(Y), ptr(ws), stream_ptr())

@@ -47,15 +47,17 @@ class ShardPlan:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
         return t
 
-    def all_gather_rows(self, t_local):
-        """Concatenate per-rank row blocks [count_r, ...] into [N, ...] on every rank."""
+    def all_gather_rows(self, t_local, out=None):
+        """Concatenate per-rank row blocks [count_r, ...] into [N, ...] on every rank.
+        `out` (optional, [N, ...]) avoids an allocation per call when the blocks are equal-sized."""
         if self.world == 1:
             return t_local
         import torch.distributed as dist
         cmax = max(self.counts)
         tail = tuple(t_local.shape[1:])
         if all(c == cmax for c in self.counts):
-            out = torch.empty((self.N,) + tail, dtype=t_local.dtype, device=t_local.device)
+            if out is None:
+                out = torch.empty((self.N,) + tail, dtype=t_local.dtype, device=t_local.device)
             dist.all_gather_into_tensor(out, t_local.contiguous(), group=self.group)
             return out
         pad = torch.zeros((cmax,) + tail, dtype=t_local.dtype, device=t_local.device)
@@ -136,8 +138,11 @@ def eigen_stage(ops, plan, P_rows, dis, nev=NEV, validate=True, tol=None, stats=
         if stats is not None:
             stats.update({"matvecs": len(cols), "dense": True})
     elif hasattr(ops, "lanczos_step") and N >= 64:
+        y_loc = ops.empty((plan.hi - plan.lo, 8), torch.float64)       # reused every step: no allocation in the loop
+        w_all = ops.empty((N, 8), torch.float64) if plan.world > 1 else None
+
         def matvec_f32(Xf):
-            return plan.all_gather_rows(ops.block_matvec_f32(P_rows, N, Xf))
+            return plan.all_gather_rows(ops.block_matvec_f32(P_rows, N, Xf, out=y_loc), out=w_all)
         tol_ = 1e-8 if tol is None else tol
 
         def run(lock):
