@@ -405,6 +405,31 @@ def test_solve_default_parameters_shapes(v3s_mod, golden_dir):
     assert np.allclose(res["Lambda"], 1.0, atol=1e-6)                              # lambda = 1 has multiplicity 182
 
 
+@pytest.mark.parametrize("cfg", [(3, 3, 9), (3, 2, 12), (4, 5, 20), (5, 7, 124)])
+def test_tiny_and_extreme_configurations(v3s_mod, cfg):
+    """Smallest legal runs (N = nRot1D^3 barely above k, k up to N - 2, odd tiny detectors): every
+    kernel with extents far below its tile sizes, checked against the oracle on identical inputs."""
+    nrot, n, k = cfg
+    N = nrot ** 3
+    Images, R, Axis, Quat = v3s_mod.Projector.generate(nrot, n)
+    oImages = orc.generate(nrot, n)[0]
+    assert np.max(np.abs(Images - oImages)) <= 2e-5 * max(np.max(np.abs(oImages)), 1e-30)
+    S2, Nn = v3s_mod.DistanceMatrix.knn(oImages, k)
+    oS2, oN = orc.knn(oImages, k)
+    assert (orc.almost_equal_hybrid(S2, oS2, 1e-5) | (np.abs(S2 - oS2) < 5e-7)).all()
+    a, b = oS2.copy(), oS2.copy()
+    try:
+        oPs, oLam = orc.diffusion_coordinate(a, oN, 0.7, validate=False)
+    except Exception as e:                                   # degenerate kernel scale: same error on both sides
+        with pytest.raises(Exception, match=str(e)[:10]):
+            v3s_mod.DiffusionMapSolver.diffusion_coordinate(b, oN, 0.7, validate=False)
+        return
+    Ps, Lam = v3s_mod.DiffusionMapSolver.diffusion_coordinate(b, oN, 0.7, validate=False)
+    assert np.array_equal(np.isinf(a), np.isinf(b))
+    assert np.allclose(Lam, oLam, atol=2e-6)
+    assert Ps.shape == (N, 10)
+
+
 def test_full_size_invariants(ops):
     """BASELINE config 2 size (N=10k, 64x64): size-independent properties of every stage."""
     from v3s.pipeline import ShardPlan, knn_stage, markov_stage
