@@ -411,8 +411,13 @@ def test_tiny_and_extreme_configurations(v3s_mod, cfg):
     kernel with extents far below its tile sizes, checked against the oracle on identical inputs."""
     nrot, n, k = cfg
     N = nrot ** 3
+    try:
+        oImages = orc.generate(nrot, n)[0]
+    except Exception as e:                                   # e.g. 'Images is an all-zero array.' (projection.py:47)
+        with pytest.raises(Exception, match=str(e)[:12]):
+            v3s_mod.Projector.generate(nrot, n)
+        return
     Images, R, Axis, Quat = v3s_mod.Projector.generate(nrot, n)
-    oImages = orc.generate(nrot, n)[0]
     assert np.max(np.abs(Images - oImages)) <= 2e-5 * max(np.max(np.abs(oImages)), 1e-30)
     S2, Nn = v3s_mod.DistanceMatrix.knn(oImages, k)
     oS2, oN = orc.knn(oImages, k)
