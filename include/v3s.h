@@ -51,6 +51,13 @@ int v3s_synth_prepare(int n, int n_p, const v3s_geometry* geom /* host */, void*
 int v3s_synth_patterns(const float* ed, int n, const double* rot9, long long N, int n_p, const void* ws_dev, int z0,
                        int nz, float* out, long long out_stride, void* stream);
 
+/* Poisson photon noise, in place (BASELINE config 5; the reference has no noise model -- a
+ * builder-defined input transform applied before stage 2).  Each pattern is scaled to
+ * photons_per_pattern expected counts and every pixel replaced by a Poisson draw (Philox-4x32-10
+ * keyed by seed, global pattern index row0_global + r, pixel): independent of the sharding.       */
+int v3s_poisson_noise(float* img, long long n_rows, int P, long long stride, long long row0_global,
+                      double photons_per_pattern, unsigned long long seed, void* stream);
+
 /* ---- stage 2: distances + k nearest neighbours ----------------------------------------- */
 
 /* DistanceMatrix.remove_offset (distance.py:70-71), first half: per-pixel sums over the local

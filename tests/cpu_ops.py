@@ -190,3 +190,13 @@ class OracleOps:
         Y_out.copy_(v)
         if Xf_out is not None:
             Xf_out.copy_(v.to(torch.float32))
+
+    def poisson_noise_(self, img, photons_per_pattern, seed=0, row0_global=0):
+        # stand-in: numpy Poisson keyed by (seed, global row) -- sharding-independent like the kernel
+        a = img.numpy()
+        for r in range(a.shape[0]):
+            rng = np.random.default_rng([int(seed), int(row0_global) + r])
+            s = a[r].sum()
+            if s > 0:
+                a[r] = rng.poisson(a[r] * (photons_per_pattern / s))
+        return img

@@ -76,6 +76,34 @@ def test_synth_free_detector_and_hopf(v3s_mod, golden_dir):
     assert np.max(np.abs(img - ref)) < 2e-5 * np.max(np.abs(ref))
 
 
+def test_poisson_noise_statistics_and_sharding(v3s_mod, ops):
+    """BASELINE config 5 ingredient: Poisson photon noise.  Mean/variance of the counts, determinism,
+    independence of the row sharding, and the full path on noisy patterns against the oracle."""
+    rng = np.random.default_rng(0)
+    lam = np.concatenate([np.full(20000, 0.3), np.full(20000, 4.0), np.full(20000, 50.0), np.full(20000, 3000.0)])
+    img = np.tile(lam, (4, 1)).astype(np.float32)
+    total = float(lam.sum())
+    out = v3s_mod.Projector.add_poisson_noise(img, total, seed=7)              # scale = 1: expectation == lam
+    assert out.shape == img.shape and np.all(out >= 0) and np.all(out == np.round(out))
+    for v in (0.3, 4.0, 50.0, 3000.0):
+        x = out[:, lam == v].ravel()
+        assert abs(x.mean() - v) < 5 * np.sqrt(v / x.size) + 1e-3 * v
+        assert abs(x.var() - v) < 0.05 * v
+    assert np.array_equal(out, v3s_mod.Projector.add_poisson_noise(img, total, seed=7))
+    assert not np.array_equal(out, v3s_mod.Projector.add_poisson_noise(img, total, seed=8))
+    assert not np.array_equal(out[0], out[1])                                  # rows are independent streams
+    part = v3s_mod.Projector.add_poisson_noise(img[2:], total, seed=7, row0=2)  # a rank owning rows 2..3
+    assert np.array_equal(part, out[2:])
+    # noisy patterns through stages 2-3 vs the oracle on the identical noisy input
+    R9, _ = orc.random_rotations(400, seed=21)
+    clean = v3s_mod.Projector.generate_from_rotations(R9, 15)
+    noisy = v3s_mod.Projector.add_poisson_noise(clean, 2e5, seed=1)
+    S2, Nn = v3s_mod.DistanceMatrix.knn(noisy, 60)
+    oS2, oN = orc.knn(noisy, 60)
+    assert (orc.almost_equal_hybrid(S2, oS2, 1e-5) | (np.abs(S2 - oS2) < 5e-7)).all()
+    assert np.mean(Nn == oN) > 0.999
+
+
 # ------------------------------------------------------------------ stage 2
 
 def test_distance_helpers_golden(v3s_mod):

@@ -108,6 +108,27 @@ def test_locking_resolves_multiplicity_beyond_block_size(golden_dir):
     assert np.max(np.abs(Pb.numpy() @ Vn - Vn)) < 1e-6
 
 
+def test_stage_handoff_roundtrip_and_orientation_metric(tmp_path):
+    rng = np.random.default_rng(0)
+    res = {k: rng.standard_normal((5, 3)) for k in v3s.extras.RESULT_KEYS}
+    v3s.save_stage_outputs(str(tmp_path / "run.npz"), res)
+    back = v3s.load_stage_outputs(str(tmp_path / "run.npz"))
+    assert all(np.array_equal(back[k], res[k]) for k in res)
+    with pytest.raises(Exception, match="lacks"):
+        v3s.save_stage_outputs(str(tmp_path / "bad.npz"), {"Ps": np.zeros(2)})
+    # orientation metric: truth rotated by one global rotation and perturbed by 2 degrees -> ~2 degrees
+    R9, _ = orc.random_rotations(200, seed=1)
+    Rt = R9.T.reshape(-1, 3, 3)
+    A = orc.project_so3(rng.standard_normal((1, 3, 3)))[0]
+    ax = rng.standard_normal((200, 3)); ax /= np.linalg.norm(ax, axis=1)[:, None]
+    th = np.radians(2.0)
+    K = np.zeros((200, 3, 3)); K[:, 0, 1], K[:, 0, 2], K[:, 1, 0], K[:, 1, 2], K[:, 2, 0], K[:, 2, 1] = -ax[:, 2], ax[:, 1], ax[:, 2], -ax[:, 0], -ax[:, 1], ax[:, 0]
+    dR = np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * (K @ K)
+    est = (Rt @ A) @ dR
+    err = v3s.orientation_errors_deg(est.reshape(-1, 9) * 1.3, R9)          # a scale factor must not matter
+    assert np.all(np.abs(err - 2.0) < 0.35) and abs(np.median(err) - 2.0) < 0.1
+
+
 def test_stage_api_golden_vectors():
     """The reference's own unit-test vectors through the product's adapters (CPU backend)."""
     S2 = np.array([[0.0, 16.0, 9.0, 25.0], [16.0, 0.0, 25.0, 9.0], [9.0, 25.0, 0.0, 16.0], [25.0, 9.0, 16.0, 0.0]])

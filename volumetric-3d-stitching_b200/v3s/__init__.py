@@ -14,6 +14,7 @@ from .distance import DistanceMatrix
 from .projection import Projector
 from .rotation import Rotation
 from .solution import OrientationRecoverySolver
+from .extras import load_stage_outputs, orientation_errors_deg, save_stage_outputs
 
 __all__ = ["Projector", "DistanceMatrix", "DiffusionMapSolver", "OrientationRecoverySolver", "Rotation",
-           "ComputeUtils"]
+           "ComputeUtils", "save_stage_outputs", "load_stage_outputs", "orientation_errors_deg"]

@@ -106,6 +106,12 @@ class CudaOps:
         self._toc(h)
         return out
 
+    def poisson_noise_(self, img, photons_per_pattern, seed=0, row0_global=0):
+        """In-place Poisson photon noise on patterns [n,P] f32 (BASELINE config 5)."""
+        call("v3s_poisson_noise", ptr(img), img.shape[0], img.shape[1], img.stride(0), int(row0_global),
+             float(photons_per_pattern), int(seed), stream_ptr())
+        return img
+
     # ---- stage 2 -----------------------------------------------------------------------------
     def column_sums(self, img):
         sums = self.empty((img.shape[1],), torch.float64)

@@ -197,10 +197,12 @@ def fit_stage(ops, plan, Ps, Y, polar_mode=0, check=True):
 
 
 def run_pipeline(ops, plan, ed, rot9_local, rot_y_all, n_p, k, eps, polar_mode=0, check=True, stats=None,
-                 validate=True, on_images=None):
+                 validate=True, on_images=None, photons_per_pattern=None, noise_seed=0):
     """Full path on device.  ed [n,n,n] f32; rot9_local [hi-lo,9] f64 row-major Rm of the rank's
     patterns; rot_y_all [N,9] f64 = Rotation_R.T (the reference's column-major unfold, transposed)."""
     img = ops.synth_patterns(ed, rot9_local, n_p)
+    if photons_per_pattern is not None:                      # BASELINE config 5: Poisson photon noise
+        ops.poisson_noise_(img, photons_per_pattern, noise_seed, plan.lo)
     if on_images is not None:
         on_images(img)                                       # e.g. start the host transfer of the patterns now
     S2, Nbr = knn_stage(ops, plan, img, k)

@@ -40,6 +40,17 @@ class Projector:
         return Images
 
     @staticmethod
+    def add_poisson_noise(Images, photons_per_pattern, seed=0, row0=0):
+        """Poisson photon noise (not in the reference; BASELINE config 5).  Images (N,P); returns
+        the photon counts in the caller's kind (numpy float64 or device tensor)."""
+        ops = _util.get_ops()
+        img = _util.to_dev(Images, torch.float32)
+        if _util.is_torch(Images) and img.data_ptr() == Images.data_ptr():
+            img = img.clone()
+        ops.poisson_noise_(img, photons_per_pattern, seed, row0)
+        return _util.back(img, Images)
+
+    @staticmethod
     def rot9_rowmajor(R, ops):
         """R (9,N) with column c = Rm.T.flatten()  ->  [N,9] row-major Rm (= R[:,c].reshape(3,3).T,
         projection.py:38) as an FP64 device tensor."""

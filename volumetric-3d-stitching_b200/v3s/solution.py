@@ -16,11 +16,13 @@ class OrientationRecoverySolver:
         return OrientationRecoverySolver.solve(parameters)
 
     @staticmethod
-    def solve(parameters, rotations=None, N_p=None, polar_mode=0, stats=None, check_sigma=True):
+    def solve(parameters, rotations=None, N_p=None, polar_mode=0, stats=None, check_sigma=True,
+              photons_per_pattern=None, noise_seed=0):
         """solution.py:34-61 -> dict of numpy float64 arrays with the reference's 11 keys.
         Extensions that never change reference-mode results: `rotations` = explicit
         R (9,N) instead of the Hopf grid, `N_p` = free detector size, `check_sigma=False` = report
-        Sigma_T > 60 instead of raising (diffusion.py:175-176)."""
+        Sigma_T > 60 instead of raising (diffusion.py:175-176), `photons_per_pattern` = Poisson photon
+        noise on the patterns (BASELINE config 5; the reference has no noise model)."""
         print('OrientationRecoverySolver.solve started.')
         if not OrientationRecoverySolver.validate_parameters(parameters):
             parameters = OrientationRecoverySolver.default_parameters()
@@ -46,7 +48,8 @@ class OrientationRecoverySolver:
         # is done and overlaps stages 2-4 (side stream + worker thread)
         start_images = (lambda img: xfer.setdefault('Images', _util.AsyncFetch(img))) if ops.device.type == 'cuda' else None
         out = run_pipeline(ops, ShardPlan(Nn), ed, rot9, rot_y, n_p, parameters['k'], parameters['Epsilon'],
-                           polar_mode=polar_mode, check=check_sigma, stats=stats, on_images=start_images)
+                           polar_mode=polar_mode, check=check_sigma, stats=stats, on_images=start_images,
+                           photons_per_pattern=photons_per_pattern, noise_seed=noise_seed)
         # the reference returns float64 everywhere: widen on the device, one staged transfer for all arrays
         f64 = lambda t: t.to(torch.float64)
         host = _util.fetch_many({
