@@ -51,6 +51,14 @@ int v3s_synth_prepare(int n, int n_p, const v3s_geometry* geom /* host */, void*
 int v3s_synth_patterns(const float* ed, int n, const double* rot9, long long N, int n_p, const void* ws_dev, int z0,
                        int nz, float* out, long long out_stride, void* stream);
 
+/* Direct mode (BASELINE north_star kernel 1; not the reference's numbers): the
+ * analytical amplitude | sum_ijk F[i,j,k] exp(-2 pi i (R Pm kappa).(a_i,a_j,a_k)) | evaluated on
+ * each orientation's rotated Ewald-sphere q-grid, without the reference's two trilinear
+ * interpolations.  Same arguments as v3s_synth_patterns; ws_dev: v3s_synth_workspace_bytes(n_p). */
+int v3s_synth_patterns_direct(const float* ed, int n, const double* rot9, long long N, int n_p,
+                              const v3s_geometry* geom /* host */, void* ws_dev, float* out, long long out_stride,
+                              void* stream);
+
 /* Poisson photon noise, in place (BASELINE config 5; the reference has no noise model -- a
  * builder-defined input transform applied before stage 2).  Each pattern is scaled to
  * photons_per_pattern expected counts and every pixel replaced by a Poisson draw (Philox-4x32-10

@@ -415,6 +415,33 @@ def generate_from_rotations(R9, n_voxel_1d, N_p=None):
     return Images
 
 
+def generate_direct(R9, n_voxel_1d, N_p=None):
+    """Direct-sum form of the patterns (verified there against the reference:
+    corr 0.998): I = | sum_ijk F[i,j,k] exp(-2 pi i (M kappa).(a_i,a_j,a_k)) |, M = R Pm,
+    Pm:(c0,c1,c2)->(c1,c2,c0), a = 2e-7 U.  Not a reference function: the checker of the optional
+    `direct` synthesis mode.  Proper rotations only."""
+    n = n_voxel_1d
+    Experiment = experiment_parameters(n, N_p)["Experiment"]
+    F = synthesize_3d(n)["ED"]
+    Q, mask = q_and_mask(Experiment)
+    U = (np.linspace(1, n, n) - (n + 1) / 2) / (n / 2)
+    a = 2e-7 * U
+    kap = np.stack([Q["x"].ravel(), Q["y"].ravel(), Q["z"].ravel()])          # (3, P)
+    out = np.empty((R9.shape[1], kap.shape[1]))
+    for c in range(R9.shape[1]):
+        Rm = R9[:, c].reshape(3, 3).T
+        M = Rm[:, [2, 0, 1]]                                                   # (M x) = R (x1, x2, x0)
+        kp = M @ kap
+        e0 = np.exp(-2j * np.pi * np.outer(kp[0], a))                          # (P, n)
+        e1 = np.exp(-2j * np.pi * np.outer(kp[1], a))
+        e2 = np.exp(-2j * np.pi * np.outer(kp[2], a))
+        t = np.einsum("ijk,pk->pij", F, e2)
+        t = np.einsum("pij,pj->pi", t, e1)
+        out[c] = np.abs(np.einsum("pi,pi->p", t, e0))
+    out[:, mask.ravel()] = 0.0
+    return out
+
+
 def generate(nRot1D, n_voxel_1d, clip_bug=True):
     """projection.py:17-51 -> [Images (N,P), R (9,N), Axis (3,N), Quat (4,N)]."""
     R, Axis, Quat = all_rot_variables(nRot1D ** 3, clip_bug)

@@ -76,6 +76,23 @@ def test_synth_free_detector_and_hopf(v3s_mod, golden_dir):
     assert np.max(np.abs(img - ref)) < 2e-5 * np.max(np.abs(ref))
 
 
+@pytest.mark.parametrize("n,n_p", [(15, 31), (31, 64), (7, 16)])
+def test_synth_direct_mode(v3s_mod, n, n_p):
+    """Optional direct mode (north_star kernel 1): the analytical amplitude on the rotated q-grid
+    against the float64 direct sum, and its agreement with the reference-exact mode."""
+    R9, _ = orc.random_rotations(5, seed=31 + n)
+    got = v3s_mod.Projector.generate_from_rotations(R9, n, N_p=n_p, mode="direct")
+    ref = orc.generate_direct(R9, n, n_p)
+    err = np.max(np.abs(got - ref)) / ref.max()
+    print(f"direct n={n} n_p={n_p}: max err / max = {err:.2e}")
+    assert err < 5e-5
+    if n >= 15:
+        exact = v3s_mod.Projector.generate_from_rotations(R9, n, N_p=n_p)
+        for i in range(5):
+            m = exact[i] > 0
+            assert np.corrcoef(exact[i][m], got[i][m])[0, 1] > 0.99
+
+
 def test_poisson_noise_statistics_and_sharding(v3s_mod, ops):
     """BASELINE config 5 ingredient: Poisson photon noise.  Mean/variance of the counts, determinism,
     independence of the row sharding, and the full path on noisy patterns against the oracle."""

@@ -221,6 +221,102 @@ static int build_taps(int n, int n_p, const v3s_geometry* g, std::vector<PixelTa
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Direct mode: the analytical scattering amplitude on each orientation's rotated Ewald-sphere
+// q-grid (BASELINE north_star kernel 1; closed form verified in SURVEY Appendix A.1):
+//   I(u,v) = | sum_{ijk} F[i,j,k] exp(-2 pi i (M kappa) . (a_i, a_j, a_k)) |,  M = R Pm,
+//   Pm: (c0,c1,c2) -> (c1,c2,c0), a_i = grid_scale * U_i, kappa = (Q_x,Q_y,Q_z)[u,v].
+// It is the same physical image as the reference's rotate -> FFT -> interpolate chain without its
+// two trilinear interpolations (corr 0.998, not the same numbers), so it is an option, not the
+// default.  One CTA per (pattern, 128-pixel tile), one pixel per thread; the object sits in
+// shared memory and is read as warp-wide broadcasts, the triple sum is evaluated separably
+// (n^3 real x complex FMAs per pixel: FP32-pipe bound), phases by SFU sincospi.
+constexpr int kDirectThreads = 128;
+constexpr int kDirectMaxN = 32;
+
+struct DirectPixel { float kx, ky, kz, valid; };   // kappa * 2 * grid_scale: phase / pi = k . U
+
+__global__ void __launch_bounds__(kDirectThreads)
+synth_direct_kernel(const float* __restrict__ ed, const double* __restrict__ rot, const DirectPixel* __restrict__ pix,
+                    float* __restrict__ out, long long out_stride, int n, int P, long long N) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n2 = n * n, n3 = n2 * n;
+  const int kpad = (n + 3) & ~3;                                   // rows of F padded to float4
+  float* F = reinterpret_cast<float*>(smem_raw);                    // n*n*kpad
+  float2* e1s = reinterpret_cast<float2*>(F + n2 * kpad);           // [n][threads]
+  __shared__ float Mrot[9];
+  const int tid = threadIdx.x;
+  for (int e = tid; e < n2 * kpad; e += kDirectThreads) {
+    const int ij = e / kpad, k = e - ij * kpad;
+    F[e] = k < n ? ed[ij * n + k] : 0.f;
+  }
+  (void)n3;
+  const long long pat = blockIdx.y;
+  if (tid < 9) {
+    // M = R Pm: column c of M is column (c+2)%3 ... (M x)_r = sum_c R[r][c] (Pm x)_c with Pm x = (x1, x2, x0)
+    const int r = tid / 3, c = tid % 3;
+    const int src = (c + 2) % 3;            // M[r][c] multiplies x_c; (Pm x)_src = x_c  <=>  src = (c + 2) % 3
+    Mrot[tid] = (float)rot[pat * 9 + r * 3 + src];
+  }
+  __syncthreads();
+  const int p = blockIdx.x * kDirectThreads + tid;
+  float result = 0.f;
+  const bool active = p < P && pix[p < P ? p : 0].valid != 0.f;
+  if (active) {
+    const DirectPixel q = pix[p];
+    const float k0 = Mrot[0] * q.kx + Mrot[1] * q.ky + Mrot[2] * q.kz;
+    const float k1 = Mrot[3] * q.kx + Mrot[4] * q.ky + Mrot[5] * q.kz;
+    const float k2 = Mrot[6] * q.kx + Mrot[7] * q.ky + Mrot[8] * q.kz;
+    const float half_n = 0.5f * (float)n;
+    float2 e2[kDirectMaxN];
+#pragma unroll
+    for (int k = 0; k < kDirectMaxN; ++k) {
+      if (k < n) {
+        const float U = ((float)(k + 1) - 0.5f * (float)(n + 1)) / half_n;
+        float sn, cs;
+        sincospif(-k2 * U, &sn, &cs);
+        e2[k] = make_float2(cs, sn);
+      } else {
+        e2[k] = make_float2(0.f, 0.f);
+      }
+    }
+    for (int j = 0; j < n; ++j) {
+      const float U = ((float)(j + 1) - 0.5f * (float)(n + 1)) / half_n;
+      float sn, cs;
+      sincospif(-k1 * U, &sn, &cs);
+      e1s[j * kDirectThreads + tid] = make_float2(cs, sn);
+    }
+    float ar = 0.f, ai = 0.f;
+    for (int i = 0; i < n; ++i) {
+      float br = 0.f, bi = 0.f;
+      for (int j = 0; j < n; ++j) {
+        const float4* f4 = reinterpret_cast<const float4*>(F + (i * n + j) * kpad);
+        float cr = 0.f, ci = 0.f;
+#pragma unroll
+        for (int k4 = 0; k4 < kDirectMaxN / 4; ++k4) {
+          if (k4 * 4 < n) {
+            const float4 f = f4[k4];                                // warp-wide broadcast
+            cr = fmaf(f.x, e2[4 * k4].x, cr);     ci = fmaf(f.x, e2[4 * k4].y, ci);
+            cr = fmaf(f.y, e2[4 * k4 + 1].x, cr); ci = fmaf(f.y, e2[4 * k4 + 1].y, ci);
+            cr = fmaf(f.z, e2[4 * k4 + 2].x, cr); ci = fmaf(f.z, e2[4 * k4 + 2].y, ci);
+            cr = fmaf(f.w, e2[4 * k4 + 3].x, cr); ci = fmaf(f.w, e2[4 * k4 + 3].y, ci);
+          }
+        }
+        const float2 w = e1s[j * kDirectThreads + tid];
+        br += cr * w.x - ci * w.y;
+        bi += cr * w.y + ci * w.x;
+      }
+      const float U = ((float)(i + 1) - 0.5f * (float)(n + 1)) / half_n;
+      float sn, cs;
+      sincospif(-k0 * U, &sn, &cs);
+      ar += br * cs - bi * sn;
+      ai += br * sn + bi * cs;
+    }
+    result = sqrtf(ar * ar + ai * ai);
+  }
+  if (p < P) out[pat * out_stride + p] = result;
+}
+
 }  // namespace v3s
 
 using namespace v3s;
@@ -269,5 +365,47 @@ extern "C" int v3s_synth_patterns(const float* ed, int n, const double* rot9, lo
   int grid = (int)(N < (long long)kNumSMs ? N : kNumSMs);
   synth_kernel<<<grid, kSynthThreads, smem, (cudaStream_t)stream>>>(ed, rot9, (const PixelTap*)ws_dev, out, out_stride, prm);
   V3S_CHECK_LAUNCH();
+  return 0;
+}
+
+// Direct mode (see synth_direct_kernel).  ws_dev: n_p*n_p*16 bytes (same size as the exact mode's).
+extern "C" int v3s_synth_patterns_direct(const float* ed, int n, const double* rot9, long long N, int n_p,
+                                         const v3s_geometry* geom, void* ws_dev, float* out, long long out_stride,
+                                         void* stream) {
+  V3S_REQUIRE(n >= 2 && n <= kDirectMaxN, "v3s_synth_patterns_direct: n_voxel_1d=%d outside [2,%d]", n, kDirectMaxN);
+  V3S_REQUIRE(n_p >= 2 && N >= 0 && N < 65536LL * 65535LL && ws_dev != nullptr, "v3s_synth_patterns_direct: bad arguments");
+  v3s_geometry g;
+  if (geom) g = *geom; else v3s_default_geometry(&g);
+  const int P = n_p * n_p;
+  std::vector<DirectPixel> pix(P);
+  const double width = g.pixel * ((double)g.n_p_nobin / (double)n_p) * (double)n_p;
+  for (int u = 0; u < n_p; ++u)
+    for (int v = 0; v < n_p; ++v) {
+      const double cx = (width / (n_p - 1)) * ((double)(v + 1) - (n_p + 1) / 2.0);
+      const double cy = (width / (n_p - 1)) * ((double)(u + 1) - (n_p + 1) / 2.0);
+      const double T = g.lambda * sqrt(cx * cx + cy * cy + g.zd * g.zd);
+      const bool masked = (cx * cx + cy * cy) > (width / 2) * (width / 2);
+      const double sc = 2.0 * g.grid_scale;                       // phase / pi = (2 a kappa) with a = grid_scale * U
+      pix[u * n_p + v] = DirectPixel{(float)(sc * cx / T), (float)(sc * cy / T), (float)(sc * (g.zd / T - 1.0 / g.lambda)),
+                                     masked ? 0.f : 1.f};
+    }
+  cudaStream_t st = (cudaStream_t)stream;
+  V3S_CUDA(cudaMemcpyAsync(ws_dev, pix.data(), sizeof(DirectPixel) * P, cudaMemcpyHostToDevice, st));
+  if (N == 0) return 0;
+  const int kpad = (n + 3) & ~3;
+  const size_t smem = sizeof(float) * n * n * kpad + sizeof(float2) * n * kDirectThreads;
+  V3S_REQUIRE(smem <= 227 * 1024, "v3s_synth_patterns_direct: shared memory %zu B too large", smem);
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    V3S_CUDA(cudaFuncSetAttribute(synth_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  for (long long p0 = 0; p0 < N; p0 += 65535) {     // grid.y limit
+    const long long np = (N - p0 < 65535) ? (N - p0) : 65535;
+    dim3 grid((unsigned)((P + kDirectThreads - 1) / kDirectThreads), (unsigned)np);
+    synth_direct_kernel<<<grid, kDirectThreads, smem, st>>>(ed, rot9 + p0 * 9, (const DirectPixel*)ws_dev,
+                                                            out + p0 * out_stride, out_stride, n, P, np);
+    V3S_CHECK_LAUNCH();
+  }
   return 0;
 }

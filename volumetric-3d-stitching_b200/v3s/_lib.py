@@ -32,6 +32,7 @@ SIGNATURES = {
     "v3s_synth_workspace_bytes": (i64, [i32]),
     "v3s_synth_prepare": (i32, [i32, i32, C.POINTER(Geometry), p, C.POINTER(i32), p]),
     "v3s_synth_patterns": (i32, [p, i32, p, i64, i32, p, i32, i32, p, i64, p]),
+    "v3s_synth_patterns_direct": (i32, [p, i32, p, i64, i32, C.POINTER(Geometry), p, p, i64, p]),
     "v3s_poisson_noise": (i32, [p, i64, i32, i64, i64, f64, C.c_ulonglong, p]),
     "v3s_column_sums": (i32, [p, i64, i32, i64, p, p]),
     "v3s_center_normalize": (i32, [p, i64, i32, i64, p, p, p, p, i32, p, p, p]),

@@ -81,11 +81,19 @@ class CudaOps:
         return t.to(self.device, non_blocking=True).contiguous()
 
     # ---- stage 1 -----------------------------------------------------------------------------
-    def synth_patterns(self, ed, rot9, n_p, geom=None):
-        """ed [n,n,n] f32, rot9 [N,9] f64 (row-major Rm) -> patterns [N, n_p^2] f32."""
+    def synth_patterns(self, ed, rot9, n_p, geom=None, mode="exact"):
+        """ed [n,n,n] f32, rot9 [N,9] f64 (row-major Rm) -> patterns [N, n_p^2] f32.
+        mode "exact" = the reference's rotate -> FFT -> interpolate chain; "direct" = analytical
+        amplitude on the rotated q-grid (north_star kernel 1; proper rotations only)."""
         n = ed.shape[0]
         N = rot9.shape[0]
         out = self.empty((N, n_p * n_p), torch.float32)
+        if mode == "direct":
+            ws = self.empty((int(_lib.lib.v3s_synth_workspace_bytes(n_p)),), torch.uint8)
+            h = self._tic("synth_direct")
+            call("v3s_synth_patterns_direct", ptr(ed), n, ptr(rot9), N, n_p, None, ptr(ws), ptr(out), n_p * n_p, stream_ptr())
+            self._toc(h)
+            return out
         key = (n, n_p, tuple(sorted(geom.items())) if geom else None)
         prep = self._synth_prep.get(key)
         if prep is None:                       # geometry set-up once per (n, n_p, geometry)

@@ -22,16 +22,18 @@ class Projector:
         return [Images, R, Axis, Quat]
 
     @staticmethod
-    def generate_from_rotations(R, n_voxel_1d, N_p=None, as_tensor=False):
+    def generate_from_rotations(R, n_voxel_1d, N_p=None, as_tensor=False, mode="exact"):
         """The hot loop of `generate` for an explicit rotation array R (9,N) in the reference's
-        column-major unfold (any N, free detector size N_p).  Images (N, N_p^2)."""
+        column-major unfold (any N, free detector size N_p).  Images (N, N_p^2).
+        mode="direct" evaluates the analytical amplitude on the rotated q-grid instead (no
+        interpolation; proper rotations only; the same image up to ~7 % rel-L2)."""
         ops = _util.get_ops()
         Experiment = Projector.experiment_parameters(n_voxel_1d)['Experiment']
         n_p = Experiment['N_p'] if N_p is None else int(N_p)
         ED = Projector.synsthesize_3d(n_voxel_1d)['ED']
         ed = ops.to_device(ED.astype(np.float32), torch.float32)
         rot9 = Projector.rot9_rowmajor(R, ops)
-        img = ops.synth_patterns(ed, rot9, n_p)
+        img = ops.synth_patterns(ed, rot9, n_p, mode=mode)
         if as_tensor:
             return img
         Images = img.cpu().numpy().astype(np.float64)
