@@ -228,10 +228,10 @@ static int build_taps(int n, int n_p, const v3s_geometry* g, std::vector<PixelTa
 //   Pm: (c0,c1,c2) -> (c1,c2,c0), a_i = grid_scale * U_i, kappa = (Q_x,Q_y,Q_z)[u,v].
 // It is the same physical image as the reference's rotate -> FFT -> interpolate chain without its
 // two trilinear interpolations (corr 0.998, not the same numbers), so it is an option, not the
-// default.  One CTA per (pattern, 128-pixel tile), one pixel per thread; the object sits in
+// default.  One CTA per (pattern, 512-pixel tile), one pixel per thread; the object sits in
 // shared memory and is read as warp-wide broadcasts, the triple sum is evaluated separably
 // (n^3 real x complex FMAs per pixel: FP32-pipe bound), phases by SFU sincospi.
-constexpr int kDirectThreads = 128;
+constexpr int kDirectThreads = 512;
 constexpr int kDirectMaxN = 32;
 
 struct DirectPixel { float kx, ky, kz, valid; };   // kappa * 2 * grid_scale: phase / pi = k . U
@@ -243,7 +243,6 @@ synth_direct_kernel(const float* __restrict__ ed, const double* __restrict__ rot
   const int n2 = n * n, n3 = n2 * n;
   const int kpad = (n + 3) & ~3;                                   // rows of F padded to float4
   float* F = reinterpret_cast<float*>(smem_raw);                    // n*n*kpad
-  float2* e1s = reinterpret_cast<float2*>(F + n2 * kpad);           // [n][threads]
   __shared__ float Mrot[9];
   const int tid = threadIdx.x;
   for (int e = tid; e < n2 * kpad; e += kDirectThreads) {
@@ -280,15 +279,15 @@ synth_direct_kernel(const float* __restrict__ ed, const double* __restrict__ rot
         e2[k] = make_float2(0.f, 0.f);
       }
     }
-    for (int j = 0; j < n; ++j) {
-      const float U = ((float)(j + 1) - 0.5f * (float)(n + 1)) / half_n;
-      float sn, cs;
-      sincospif(-k1 * U, &sn, &cs);
-      e1s[j * kDirectThreads + tid] = make_float2(cs, sn);
-    }
+    // e1(j) = exp(-i pi k1 U_j) by rotation: U_{j+1} - U_j = 2/n
+    const float U_first = (1.f - 0.5f * (float)(n + 1)) / half_n;
+    float e1r0, e1i0, w1r, w1i;
+    sincospif(-k1 * U_first, &e1i0, &e1r0);
+    sincospif(-k1 * (2.f / (float)n), &w1i, &w1r);
     float ar = 0.f, ai = 0.f;
     for (int i = 0; i < n; ++i) {
       float br = 0.f, bi = 0.f;
+      float e1r = e1r0, e1i = e1i0;
       for (int j = 0; j < n; ++j) {
         const float4* f4 = reinterpret_cast<const float4*>(F + (i * n + j) * kpad);
         float cr = 0.f, ci = 0.f;
@@ -302,9 +301,11 @@ synth_direct_kernel(const float* __restrict__ ed, const double* __restrict__ rot
             cr = fmaf(f.w, e2[4 * k4 + 3].x, cr); ci = fmaf(f.w, e2[4 * k4 + 3].y, ci);
           }
         }
-        const float2 w = e1s[j * kDirectThreads + tid];
-        br += cr * w.x - ci * w.y;
-        bi += cr * w.y + ci * w.x;
+        br += cr * e1r - ci * e1i;
+        bi += cr * e1i + ci * e1r;
+        const float t = e1r * w1r - e1i * w1i;
+        e1i = e1r * w1i + e1i * w1r;
+        e1r = t;
       }
       const float U = ((float)(i + 1) - 0.5f * (float)(n + 1)) / half_n;
       float sn, cs;
@@ -393,7 +394,7 @@ extern "C" int v3s_synth_patterns_direct(const float* ed, int n, const double* r
   V3S_CUDA(cudaMemcpyAsync(ws_dev, pix.data(), sizeof(DirectPixel) * P, cudaMemcpyHostToDevice, st));
   if (N == 0) return 0;
   const int kpad = (n + 3) & ~3;
-  const size_t smem = sizeof(float) * n * n * kpad + sizeof(float2) * n * kDirectThreads;
+  const size_t smem = sizeof(float) * n * n * kpad;
   V3S_REQUIRE(smem <= 227 * 1024, "v3s_synth_patterns_direct: shared memory %zu B too large", smem);
   static size_t smem_set = 0;
   if (smem > smem_set) {
