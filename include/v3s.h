@@ -84,6 +84,10 @@ int v3s_center_normalize(const float* img, long long n_rows, int P, long long st
 int v3s_gram_rows(const void* all_hi, const void* all_lo, long long n_cols, const void* rows_hi, const void* rows_lo,
                   long long n_rows, int Ppad, float* G, long long ldg, void* stream);
 
+/* Pipeline shape of the tcgen05 Gram kernel: 32 = 4 stages x 48 kB, SWIZZLE_64B (default);
+ * 64 = 2 stages x 96 kB, SWIZZLE_128B.  Same results to rounding.                                */
+int v3s_set_gram_kblock(int bk);
+
 /* The whole symmetric Gram matrix G [n, ldg] with half the tensor-core work: only the tiles
  * (column block of 128, row block of 256) listed in tile_list_xy (int pairs x = column block,
  * y = row block, those on or above the diagonal, in the caller's L2-friendly order) are computed;

@@ -59,6 +59,20 @@ def main():
                 print("  Gt[0,:8]", Gt[0, :8].tolist(), "\n  ref[0,:8]", ref[0, :8].tolist())
                 hh = hi.float().double()
                 print("  hi.hi^T[0,:8]", (hh @ hh.T)[0, :8].tolist())
+        from v3s import _lib
+        for (N, P) in ((10000, 4096), (30000, 16384)):
+            A = (rng.random((N, P)).astype(np.float32)) ** 3
+            img = ops.to_device(A, torch.float32)
+            a32, hi, lo, zf = ops.center_normalize(img, ops.column_sums(img) / N)
+            del img
+            G = ops.empty((N, (N + 3) // 4 * 4), torch.float32)
+            for bk in (64, 32):
+                _lib.call("v3s_set_gram_kblock", bk)
+                _, ms = timed(lambda: ops.gram_rows(hi, lo, a32, 0, N, out=G))
+                _, ms2 = timed(lambda: ops.gram_symmetric(hi, lo, N, out=G))
+                print(f"gram N={N} P={P} bk={bk}: full {ms:.3f} ms ({2*N*N*P/ms/1e9:.0f} TF/s alg, issued {6*N*N*P/ms/1e9:.0f}) | symmetric {ms2:.3f} ms ({2*N*N*P/ms2/1e9:.0f} TF/s alg)")
+            del a32, hi, lo, G
+        _lib.call("v3s_set_gram_kblock", 32)
         N, P = 10000, 4096
         A = (rng.random((N, P)).astype(np.float32)) ** 3
         img = ops.to_device(A, torch.float32)

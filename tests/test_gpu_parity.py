@@ -174,6 +174,14 @@ def test_gram_tcgen05_vs_fp64(ops, shape):
     miss = sum(len(set(top_64[r]) - set(top_tc[r])) for r in range(N))
     print(f"  candidate misses: {miss} of {N * k}")
     assert miss == 0
+    # the other pipeline shape (2 stages x 96 kB, SWIZZLE_128B) gives the same matrix to rounding
+    from v3s import _lib
+    _lib.call("v3s_set_gram_kblock", 64)
+    try:
+        G_64 = ops.gram_rows(hi, lo, a32, 0, N)[:, :N].cpu().numpy()
+    finally:
+        _lib.call("v3s_set_gram_kblock", 32)
+    assert np.max(np.abs(G_64 - G_tc)) < 2e-6
     # symmetric mode (upper-triangle tiles + mirrored stores) gives the same matrix
     G_sym = ops.gram_symmetric(hi, lo, N)[:, :N].cpu().numpy()
     assert np.max(np.abs(G_sym - G_sym.T)) < 2e-6

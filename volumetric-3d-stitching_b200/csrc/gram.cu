@@ -20,14 +20,18 @@ namespace v3s {
 
 constexpr int BM = 128;        // TMEM lanes   <-> c (all patterns)
 constexpr int BN = 256;        // TMEM columns <-> r (panel rows)
-constexpr int BK = 64;         // bf16 elements per k-block = one 128-byte swizzle atom
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 2;
-constexpr int A_BYTES = BM * BK * 2;
-constexpr int B_BYTES = BN * BK * 2;
-constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // hi+lo for both operands = 96 KB
 constexpr int GRAM_THREADS = 192;
-constexpr int GRAM_SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+// Two pipeline shapes with the same 192 KB of operand staging:
+//   BK = 64: one 128-byte swizzle atom per row, 2 stages of 96 KB
+//   BK = 32: one  64-byte swizzle atom per row, 4 stages of 48 KB (finer refills hide TMA latency better)
+template <int BK> struct GramCfg {
+  static constexpr int STAGES = (BK == 64) ? 2 : 4;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // hi+lo for both operands
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -43,14 +47,16 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (8-row groups 1024 B apart)
-__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+// K-major swizzled shared-memory matrix descriptor: rows of BK bf16 (128 B -> SWIZZLE_128B, 64 B ->
+// SWIZZLE_64B), 8-row groups 8 * row-bytes apart
+template <int BK>
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);       // start address, bits [0,14)
   d |= (uint64_t)0 << 16;                           // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset, bits [32,46)
+  d |= (uint64_t)((8 * BK * 2) >> 4) << 32;         // stride byte offset, bits [32,46)
   d |= (uint64_t)1 << 46;                           // descriptor version (sm_100)
-  d |= (uint64_t)2 << 61;                           // layout type: SWIZZLE_128B
+  d |= (uint64_t)(BK == 64 ? 2 : 4) << 61;          // layout type: SWIZZLE_128B = 2, SWIZZLE_64B = 4
   return d;
 }
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
@@ -84,11 +90,14 @@ __device__ __forceinline__ void gram_decode_tile(int tile, int tiles_c, int tile
 // instruction descriptor: D=F32, A=B=BF16, both K-major, N=256, M=128
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
+template <int BK>
 __global__ void __launch_bounds__(GRAM_THREADS, 1)
 gram_tc_kernel(const __grid_constant__ CUtensorMap tm_c_hi, const __grid_constant__ CUtensorMap tm_c_lo,
                const __grid_constant__ CUtensorMap tm_r_hi, const __grid_constant__ CUtensorMap tm_r_lo,
                float* __restrict__ G, long long ldg, int n_cols, int n_rows, int num_kb, int tiles_c, int tiles_r,
                int num_tiles, const int2* __restrict__ tile_list, int mirror) {
+  constexpr int STAGES = GramCfg<BK>::STAGES, A_BYTES = GramCfg<BK>::A_BYTES, B_BYTES = GramCfg<BK>::B_BYTES,
+                STAGE_BYTES = GramCfg<BK>::STAGE_BYTES;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -155,10 +164,10 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tm_c_hi, const __grid_constan
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t s = smem_u32(smem + stage * STAGE_BYTES);
-          const uint64_t a_hi = make_kmajor_sw128_desc(s);
-          const uint64_t a_lo = make_kmajor_sw128_desc(s + A_BYTES);
-          const uint64_t b_hi = make_kmajor_sw128_desc(s + 2 * A_BYTES);
-          const uint64_t b_lo = make_kmajor_sw128_desc(s + 2 * A_BYTES + B_BYTES);
+          const uint64_t a_hi = make_kmajor_desc<BK>(s);
+          const uint64_t a_lo = make_kmajor_desc<BK>(s + A_BYTES);
+          const uint64_t b_hi = make_kmajor_desc<BK>(s + 2 * A_BYTES);
+          const uint64_t b_lo = make_kmajor_desc<BK>(s + 2 * A_BYTES + B_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t ko = (uint64_t)((k * UMMA_K * 2) >> 4);   // 32 B per K step, in 16-byte units
@@ -325,9 +334,11 @@ int make_tmap_2d(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const
   return 0;
 }
 
+static int g_gram_bk = 32;
+
 static int make_bf16_map(CUtensorMap* map, const void* base, long long rows, int Ppad, int box_rows) {
-  return make_tmap_2d(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, rows, Ppad, (long long)Ppad * 2, BK, box_rows,
-                      CU_TENSOR_MAP_SWIZZLE_128B);
+  return make_tmap_2d(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, rows, Ppad, (long long)Ppad * 2, g_gram_bk, box_rows,
+                      g_gram_bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
 }
 
 }  // namespace v3s
@@ -337,7 +348,7 @@ using namespace v3s;
 static int gram_launch(const void* all_hi, const void* all_lo, long long n_cols, const void* rows_hi, const void* rows_lo,
                        long long n_rows, int Ppad, float* G, long long ldg, const int2* tile_list, int num_list_tiles,
                        int mirror, void* stream) {
-  V3S_REQUIRE(Ppad > 0 && Ppad % BK == 0, "v3s_gram_rows: Ppad=%d must be a positive multiple of %d", Ppad, BK);
+  V3S_REQUIRE(Ppad > 0 && Ppad % 64 == 0, "v3s_gram_rows: Ppad=%d must be a positive multiple of 64", Ppad);
   V3S_REQUIRE(n_cols >= 0 && n_rows >= 0 && ldg >= n_cols, "v3s_gram_rows: bad shape");
   V3S_REQUIRE(n_cols < (1LL << 31) && n_rows < (1LL << 31), "v3s_gram_rows: extents must fit int32");
   if (n_cols == 0 || n_rows == 0) return 0;
@@ -351,16 +362,27 @@ static int gram_launch(const void* all_hi, const void* all_lo, long long n_cols,
   V3S_REQUIRE(nt < (1LL << 31), "v3s_gram_rows: too many tiles");
   static bool attr_set = false;
   if (!attr_set) {
-    V3S_CUDA(cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM));
+    V3S_CUDA(cudaFuncSetAttribute(gram_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, GramCfg<64>::SMEM));
+    V3S_CUDA(cudaFuncSetAttribute(gram_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, GramCfg<32>::SMEM));
     attr_set = true;
   }
   const long long ntl = tile_list ? (long long)num_list_tiles : nt;
   if (ntl == 0) return 0;
   const int grid = (int)(ntl < kNumSMs ? ntl : kNumSMs);
-  gram_tc_kernel<<<grid, GRAM_THREADS, GRAM_SMEM, (cudaStream_t)stream>>>(mc_hi, mc_lo, mr_hi, mr_lo, G, ldg, (int)n_cols,
-                                                                          (int)n_rows, Ppad / BK, tiles_c, tiles_r, (int)ntl,
-                                                                          tile_list, mirror);
+  if (g_gram_bk == 64)
+    gram_tc_kernel<64><<<grid, GRAM_THREADS, GramCfg<64>::SMEM, (cudaStream_t)stream>>>(
+        mc_hi, mc_lo, mr_hi, mr_lo, G, ldg, (int)n_cols, (int)n_rows, Ppad / 64, tiles_c, tiles_r, (int)ntl, tile_list, mirror);
+  else
+    gram_tc_kernel<32><<<grid, GRAM_THREADS, GramCfg<32>::SMEM, (cudaStream_t)stream>>>(
+        mc_hi, mc_lo, mr_hi, mr_lo, G, ldg, (int)n_cols, (int)n_rows, Ppad / 32, tiles_c, tiles_r, (int)ntl, tile_list, mirror);
   V3S_CHECK_LAUNCH();
+  return 0;
+}
+
+// Pipeline shape of the Gram kernel: 64 (2 stages, SWIZZLE_128B) or 32 (4 stages, SWIZZLE_64B; default).
+extern "C" int v3s_set_gram_kblock(int bk) {
+  V3S_REQUIRE(bk == 32 || bk == 64, "v3s_set_gram_kblock: 32 or 64");
+  g_gram_bk = bk;
   return 0;
 }
 
