@@ -31,6 +31,8 @@ for p in (os.path.join(ROOT, "volumetric-3d-stitching_b200"), os.path.join(ROOT,
 WORKLOADS = {
     "cfg2": dict(N=10000, n=31, n_p=64, k=150, eps=0.7, desc="BASELINE config 2: N=10k patterns 64x64, full pipeline, 1 B200"),
     "cfg3": dict(N=50000, n=31, n_p=128, k=150, eps=0.7, desc="BASELINE config 3: N=50k patterns 128x128, row-sharded"),
+    "cfg4": dict(N=100000, n=31, n_p=128, k=150, eps=0.7, desc="BASELINE config 4: N=100k patterns 128x128, 8 B200, row-sharded ~40 GB Markov matrix"),
+    "cfg5": dict(N=200000, n=31, n_p=256, k=150, eps=0.7, photons=1e6, desc="BASELINE config 5: N=200k patterns 256x256 with Poisson noise, Gram streamed in panels, 8 B200"),
     "small": dict(N=2000, n=15, n_p=31, k=150, eps=0.7, desc="debug size"),
 }
 METRIC = "end_to_end_seconds_patterns_to_orientations"
@@ -245,7 +247,8 @@ def main():
     def one_pass(stats=None):
         if stats is not None:
             stats.clear()
-        return run_pipeline(ops, plan, ed, rot9, rot_y, n_p, k, eps, polar_mode=0, check=False, stats=stats, validate=False)
+        return run_pipeline(ops, plan, ed, rot9, rot_y, n_p, k, eps, polar_mode=0, check=False, stats=stats, validate=False,
+                            photons_per_pattern=wl.get("photons"))
 
     for _ in range(args.warmup):
         out = one_pass()
