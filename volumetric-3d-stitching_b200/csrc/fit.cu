@@ -192,7 +192,10 @@ fit_project_kernel(const double* __restrict__ Ps, int ldx, const double* __restr
   }
 }
 
-// sum over i in [row0,row0+n_rows), j in [0,N) of |acos(clip(q1_i.q1_j)) - acos(clip(q2_i.q2_j))|
+// sum over i in [row0,row0+n_rows), j in [0,N) of |acos(clip(q1_i.q1_j)) - acos(clip(q2_i.q2_j))|.
+// The summand is symmetric in (i,j) and zero on the diagonal, so each unordered pair is evaluated
+// once -- by the row i with (i < j and i+j even) or (i > j and i+j odd), which balances the work
+// over row blocks -- and counted twice.
 constexpr int SG_T = 256;
 __global__ void __launch_bounds__(SG_T)
 sigma_pairs_kernel(const double* __restrict__ q1, const double* __restrict__ q2, long long N, long long row0,
@@ -217,11 +220,14 @@ sigma_pairs_kernel(const double* __restrict__ q1, const double* __restrict__ q2,
     const int lim = (int)((j1 - jb) < SG_T ? (j1 - jb) : SG_T);
     if (i_ok) {
       for (int jj = 0; jj < lim; ++jj) {
+        const long long jg = jb + jj;
+        const bool mine = (i < jg) ? (((i + jg) & 1) == 0) : (i > jg && ((i + jg) & 1) == 1);
+        if (!mine) continue;
         double d1 = a1[0] * sj1[jj][0] + a1[1] * sj1[jj][1] + a1[2] * sj1[jj][2] + a1[3] * sj1[jj][3];
         double d2 = a2[0] * sj2[jj][0] + a2[1] * sj2[jj][1] + a2[2] * sj2[jj][2] + a2[3] * sj2[jj][3];
         d1 = fmin(fmax(d1, 0.0), 1.0);
         d2 = fmin(fmax(d2, 0.0), 1.0);
-        acc += fabs(acos(d1) - acos(d2));
+        acc += 2.0 * fabs(acos(d1) - acos(d2));
       }
     }
   }
