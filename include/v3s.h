@@ -21,6 +21,9 @@ const char* v3s_last_error(void);
 int v3s_version(void);
 int v3s_check_device(void);
 
+/* fill n floats at dst, which may be a peer-mapped address on another GPU (peer-mapping check) */
+int v3s_peer_fill(float* dst, float value, long long n, void* stream);
+
 /* ---- stage 1: pattern synthesis ------------------------------------------------------- */
 
 /* experiment constants of projection.py:96-107 (Projector.experiment_parameters) */

@@ -34,3 +34,18 @@ extern "C" int v3s_check_device(void) {
   V3S_REQUIRE(prop.major == 10, "v3s needs an sm_100a device (B200); found sm_%d%d (%s)", prop.major, prop.minor, prop.name);
   return 0;
 }
+
+// Fill n floats at dst (which may be a peer-mapped address of another GPU) -- used to validate the
+// NVLink peer mapping before the sharded symmetric Gram stores through it.
+namespace v3s {
+__global__ void peer_fill_kernel(float* dst, float value, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] = value;
+}
+}  // namespace v3s
+extern "C" int v3s_peer_fill(float* dst, float value, long long n, void* stream) {
+  V3S_REQUIRE(dst != nullptr && n >= 0, "v3s_peer_fill: bad arguments");
+  if (n == 0) return 0;
+  v3s::peer_fill_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(dst, value, n);
+  V3S_CHECK_LAUNCH();
+  return 0;
+}

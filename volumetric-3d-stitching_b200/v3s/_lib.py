@@ -28,6 +28,7 @@ SIGNATURES = {
     "v3s_last_error": (C.c_char_p, []),
     "v3s_version": (i32, []),
     "v3s_check_device": (i32, []),
+    "v3s_peer_fill": (i32, [p, C.c_float, i64, p]),
     "v3s_default_geometry": (None, [C.POINTER(Geometry)]),
     "v3s_synth_workspace_bytes": (i64, [i32]),
     "v3s_synth_prepare": (i32, [i32, i32, C.POINTER(Geometry), p, C.POINTER(i32), p]),
