@@ -98,6 +98,18 @@ int v3s_set_gram_kblock(int bk);
 int v3s_gram_symmetric(const void* a_hi, const void* a_lo, long long n, int Ppad, float* G, long long ldg,
                        const int* tile_list_xy, int num_tiles, void* stream);
 
+/* Row-sharded symmetric Gram fused with its exchange (one kernel: tcgen05 tiles + NVLink peer
+ * stores).  This rank computes the tiles in tile_list_xy (its share of the global upper-triangle
+ * list; operands a_hi/a_lo are the all-gathered [n, Ppad] matrices) and stores every value twice
+ * from the epilogue: G[r][c] into the row block of the rank owning r and the mirror G[c][r] into
+ * the row block of the rank owning c.  peer_bases (host array [world]): base address of each
+ * rank's [cnt_o, ldg] FP32 row block as mapped in THIS process (peer memory for o != rank, e.g.
+ * torch.distributed._symmetric_memory buffer_ptrs); rank o owns cnt_base + (o < rem) rows.  The
+ * caller synchronises the ranks before reading its block.                                       */
+int v3s_gram_symmetric_sharded(const void* a_hi, const void* a_lo, long long n, int Ppad,
+                               const unsigned long long* peer_bases /* host [world] */, int world, long long cnt_base,
+                               int rem, long long ldg, const int* tile_list_xy, int num_tiles, void* stream);
+
 /* Same contraction on CUDA cores in plain FP32 -- the validation path of v3s_gram_rows.       */
 int v3s_gram_rows_simt(const float* a_all, long long n_cols, const float* a_rows, long long n_rows, int P, float* G,
                        long long ldg, void* stream);

@@ -46,7 +46,7 @@ class OracleOps:
         lo = (a - hi.to(torch.float32)).to(torch.bfloat16) if want_split else None
         return a, hi, lo, zf
 
-    def knn_rows(self, hi_all, lo_all, a32_all, zero_flag, r0, r1, k):
+    def knn_rows(self, hi_all, lo_all, a32_all, zero_flag, r0, r1, k, plan=None):
         A = _np(a32_all).astype(np.float64)
         if k > A.shape[0]:
             raise Exception("Number of nearest neighbors to preserve is too high.")

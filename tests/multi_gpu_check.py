@@ -1,0 +1,65 @@
+"""Multi-GPU parity check (run under torchrun on a multi-GPU box; not a pytest file, the driver's
+`-m gpu` suite is single-process).  Compares the row-sharded pipeline -- including the fused
+tcgen05 + NVLink symmetric Gram -- with the same job on one GPU.
+
+    python -m torch.distributed.run --nproc-per-node 2 tests/multi_gpu_check.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "volumetric-3d-stitching_b200"))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import v3s_oracle as orc
+
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+lr = int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(lr)
+dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+from v3s import _util
+from v3s.pipeline import ShardPlan, knn_stage, run_pipeline
+from v3s.projection import Projector
+
+ops = _util.get_ops()
+ok = True
+for (N, n, n_p, k) in ((3001, 15, 31, 100), (5000, 15, 48, 120)):
+    R9, _ = orc.random_rotations(N, seed=3)
+    ed = ops.to_device(orc.synthesize_3d(n)["ED"].astype(np.float32), torch.float32)
+    rot9_all = Projector.rot9_rowmajor(R9, ops)
+    rot_y = ops.to_device(np.ascontiguousarray(R9.T), torch.float64)
+    plan = ShardPlan.from_env(N)
+    one = ShardPlan(N)
+    img_all = ops.synth_patterns(ed, rot9_all, n_p)
+    # --- Gram row block: fused symmetric + peer stores vs rectangular panel
+    sums = ops.column_sums(img_all)
+    a32, hi, lo, zf = ops.center_normalize(img_all, sums / N)
+    Gs = ops.gram_symmetric_sharded(hi, lo, plan)
+    if Gs is None:
+        print(rank, "symmetric memory unavailable:", ops.symm_error, flush=True)
+        ok = False
+    else:
+        Gr = ops.gram_rows(hi, lo, a32, plan.lo, plan.hi)
+        d = (Gs[:, :N] - Gr[:, :N]).abs().max().item()
+        print(f"rank {rank} N={N}: |G_sharded_symmetric - G_panel| max = {d:.2e}", flush=True)
+        ok &= d < 3e-6
+    # --- whole pipeline: sharded (peer Gram) vs single GPU
+    out_s = run_pipeline(ops, plan, ed, rot9_all[plan.lo:plan.hi].contiguous(), rot_y, n_p, k, 0.7, check=False)
+    out_1 = run_pipeline(ops, one, ed, rot9_all, rot_y, n_p, k, 0.7, check=False)
+    S2s, S21 = out_s["S2_unmutated"].cpu().numpy(), out_1["S2_unmutated"].cpu().numpy()
+    okS = (orc.almost_equal_hybrid(S2s, S21, 1e-6) | (np.abs(S2s - S21) < 1e-9)).all()
+    same_idx = float((out_s["N"] == out_1["N"]).float().mean().item())
+    lam_err = float((out_s["Lambda"] - out_1["Lambda"]).abs().max().item())
+    ang = float(np.max(orc.principal_angles(out_s["Ps"].cpu().numpy(), out_1["Ps"].cpu().numpy())))
+    print(f"rank {rank} N={N}: S2 equal {bool(okS)}, same neighbours {same_idx:.6f}, |dLambda| {lam_err:.2e}, "
+          f"subspace angle {ang:.2e}, sigma_T {out_s['sigma_T'].item():.4f} vs {out_1['sigma_T'].item():.4f}", flush=True)
+    ok &= bool(okS) and same_idx > 0.9999 and lam_err < 1e-6 and ang < 1e-4
+flag = torch.tensor([1 if ok else 0], device="cuda")
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print("MULTI_GPU_CHECK", "PASS" if int(flag.item()) == 1 else "FAIL", flush=True)
+dist.destroy_process_group()
+sys.exit(0 if int(flag.item()) == 1 else 1)

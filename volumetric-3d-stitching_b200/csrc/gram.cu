@@ -90,12 +90,26 @@ __device__ __forceinline__ void gram_decode_tile(int tile, int tiles_c, int tile
 // instruction descriptor: D=F32, A=B=BF16, both K-major, N=256, M=128
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
+// Row-sharded output: rank o owns rows [lo_o, lo_o + cnt_o) of G in its own buffer base[o]
+// (peer-mapped over NVLink for o != this rank).  world == 0: one local buffer (base[0], all rows).
+struct GramPeers {
+  float* base[8];
+  int world;
+  int rem;                 // the first `rem` ranks own cnt_base + 1 rows
+  long long cnt_base;
+};
+__device__ __forceinline__ void gram_owner(const GramPeers& pr, long long x, int& o, long long& lo, long long& hi) {
+  const long long big = pr.cnt_base + 1, split = big * pr.rem;
+  if (x < split) { o = (int)(x / big); lo = o * big; hi = lo + big; }
+  else { o = pr.rem + (int)((x - split) / pr.cnt_base); lo = split + (long long)(o - pr.rem) * pr.cnt_base; hi = lo + pr.cnt_base; }
+}
+
 template <int BK>
 __global__ void __launch_bounds__(GRAM_THREADS, 1)
 gram_tc_kernel(const __grid_constant__ CUtensorMap tm_c_hi, const __grid_constant__ CUtensorMap tm_c_lo,
                const __grid_constant__ CUtensorMap tm_r_hi, const __grid_constant__ CUtensorMap tm_r_lo,
                float* __restrict__ G, long long ldg, int n_cols, int n_rows, int num_kb, int tiles_c, int tiles_r,
-               int num_tiles, const int2* __restrict__ tile_list, int mirror) {
+               int num_tiles, const int2* __restrict__ tile_list, int mirror, const GramPeers peers) {
   constexpr int STAGES = GramCfg<BK>::STAGES, A_BYTES = GramCfg<BK>::A_BYTES, B_BYTES = GramCfg<BK>::B_BYTES,
                 STAGE_BYTES = GramCfg<BK>::STAGE_BYTES;
   extern __shared__ unsigned char smem_raw[];
@@ -202,13 +216,42 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tm_c_hi, const __grid_constan
         tmem_ld_32x32b_x32(t_row + (uint32_t)(ch * 32), v);
         tmem_ld_wait();
         const int r0 = tr * BN + ch * 32;
-        float* dst = G + (long long)r0 * ldg + c;
+        if (peers.world == 0) {
+          float* dst = G + (long long)r0 * ldg + c;
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (c_ok && r0 + j < n_rows) dst[(long long)j * ldg] = __uint_as_float(v[j]);
-        if (mirror && c_ok) {
-          // symmetric mode: only tiles on / above the diagonal are computed; G[c][r] = G[r][c]
-          float* mdst = G + (long long)c * ldg + r0;
+          for (int j = 0; j < 32; ++j)
+            if (c_ok && r0 + j < n_rows) dst[(long long)j * ldg] = __uint_as_float(v[j]);
+          if (mirror && c_ok) {
+            // symmetric mode: only tiles on / above the diagonal are computed; G[c][r] = G[r][c]
+            float* mdst = G + (long long)c * ldg + r0;
+            if (r0 + 32 <= n_rows) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(mdst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                   __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (r0 + j < n_rows) mdst[j] = __uint_as_float(v[j]);
+            }
+          }
+        } else if (c_ok) {
+          // sharded symmetric mode: every store goes to the buffer of the rank that owns the row --
+          // local memory or a peer GPU's HBM over NVLink (the transfer overlaps the next tile's MMAs)
+          int o; long long lo, hi;
+          gram_owner(peers, r0, o, lo, hi);
+          float* dst = peers.base[o] + (r0 - lo) * ldg + c;          // row r0 in its owner's block
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const long long r = r0 + j;
+            if (r < n_rows) {
+              if (r >= hi) { gram_owner(peers, r, o, lo, hi); dst = peers.base[o] + (r - lo) * ldg + c - (long long)j * ldg; }
+              dst[(long long)j * ldg] = __uint_as_float(v[j]);
+            }
+          }
+          int oc; long long loc, hic;
+          gram_owner(peers, c, oc, loc, hic);
+          float* mdst = peers.base[oc] + (c - loc) * ldg + r0;       // mirror: row c in its owner's block
           if (r0 + 32 <= n_rows) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
@@ -347,7 +390,7 @@ using namespace v3s;
 
 static int gram_launch(const void* all_hi, const void* all_lo, long long n_cols, const void* rows_hi, const void* rows_lo,
                        long long n_rows, int Ppad, float* G, long long ldg, const int2* tile_list, int num_list_tiles,
-                       int mirror, void* stream) {
+                       int mirror, const GramPeers& peers, void* stream) {
   V3S_REQUIRE(Ppad > 0 && Ppad % 64 == 0, "v3s_gram_rows: Ppad=%d must be a positive multiple of 64", Ppad);
   V3S_REQUIRE(n_cols >= 0 && n_rows >= 0 && ldg >= n_cols, "v3s_gram_rows: bad shape");
   V3S_REQUIRE(n_cols < (1LL << 31) && n_rows < (1LL << 31), "v3s_gram_rows: extents must fit int32");
@@ -371,10 +414,12 @@ static int gram_launch(const void* all_hi, const void* all_lo, long long n_cols,
   const int grid = (int)(ntl < kNumSMs ? ntl : kNumSMs);
   if (g_gram_bk == 64)
     gram_tc_kernel<64><<<grid, GRAM_THREADS, GramCfg<64>::SMEM, (cudaStream_t)stream>>>(
-        mc_hi, mc_lo, mr_hi, mr_lo, G, ldg, (int)n_cols, (int)n_rows, Ppad / 64, tiles_c, tiles_r, (int)ntl, tile_list, mirror);
+        mc_hi, mc_lo, mr_hi, mr_lo, G, ldg, (int)n_cols, (int)n_rows, Ppad / 64, tiles_c, tiles_r, (int)ntl, tile_list, mirror,
+        peers);
   else
     gram_tc_kernel<32><<<grid, GRAM_THREADS, GramCfg<32>::SMEM, (cudaStream_t)stream>>>(
-        mc_hi, mc_lo, mr_hi, mr_lo, G, ldg, (int)n_cols, (int)n_rows, Ppad / 32, tiles_c, tiles_r, (int)ntl, tile_list, mirror);
+        mc_hi, mc_lo, mr_hi, mr_lo, G, ldg, (int)n_cols, (int)n_rows, Ppad / 32, tiles_c, tiles_r, (int)ntl, tile_list, mirror,
+        peers);
   V3S_CHECK_LAUNCH();
   return 0;
 }
@@ -388,7 +433,8 @@ extern "C" int v3s_set_gram_kblock(int bk) {
 
 extern "C" int v3s_gram_rows(const void* all_hi, const void* all_lo, long long n_cols, const void* rows_hi,
                              const void* rows_lo, long long n_rows, int Ppad, float* G, long long ldg, void* stream) {
-  return gram_launch(all_hi, all_lo, n_cols, rows_hi, rows_lo, n_rows, Ppad, G, ldg, nullptr, 0, 0, stream);
+  GramPeers none{};
+  return gram_launch(all_hi, all_lo, n_cols, rows_hi, rows_lo, n_rows, Ppad, G, ldg, nullptr, 0, 0, none, stream);
 }
 
 // Whole symmetric Gram matrix G [n, ldg] of one operand set: only the (column block 128 x row block
@@ -398,8 +444,30 @@ extern "C" int v3s_gram_rows(const void* all_hi, const void* all_lo, long long n
 extern "C" int v3s_gram_symmetric(const void* a_hi, const void* a_lo, long long n, int Ppad, float* G, long long ldg,
                                   const int* tile_list_xy, int num_tiles, void* stream) {
   V3S_REQUIRE(tile_list_xy != nullptr && num_tiles >= 0, "v3s_gram_symmetric: tile list required");
+  GramPeers none{};
   return gram_launch(a_hi, a_lo, n, a_hi, a_lo, n, Ppad, G, ldg, reinterpret_cast<const int2*>(tile_list_xy), num_tiles, 1,
-                     stream);
+                     none, stream);
+}
+
+// Row-sharded symmetric Gram, fused with its exchange: this rank computes the tiles of its share of
+// the global upper-triangle tile list (any rank can compute any tile: the operands are all-gathered)
+// and stores every value twice -- G[r][c] into the buffer of the rank owning row r and the mirror
+// G[c][r] into the buffer of the rank owning row c -- straight from the tensor-core epilogue through
+// NVLink peer mappings (peer_bases[o] = base of rank o's [cnt_o, ldg] row block, e.g. from
+// torch.distributed._symmetric_memory).  Rank o owns cnt_base + (o < rem) consecutive rows.
+// The caller synchronises the ranks (a barrier) before reading its block.
+extern "C" int v3s_gram_symmetric_sharded(const void* a_hi, const void* a_lo, long long n, int Ppad,
+                                          const unsigned long long* peer_bases /* host [world] */, int world,
+                                          long long cnt_base, int rem, long long ldg, const int* tile_list_xy,
+                                          int num_tiles, void* stream) {
+  V3S_REQUIRE(world >= 1 && world <= 8 && cnt_base >= 1 && rem >= 0 && rem < world, "v3s_gram_symmetric_sharded: bad sharding");
+  V3S_REQUIRE(cnt_base * world + rem == n, "v3s_gram_symmetric_sharded: counts do not add up to n");
+  V3S_REQUIRE(tile_list_xy != nullptr && num_tiles >= 0 && ldg >= n, "v3s_gram_symmetric_sharded: bad arguments");
+  GramPeers pr{};
+  for (int i = 0; i < world; ++i) pr.base[i] = reinterpret_cast<float*>(peer_bases[i]);
+  pr.world = world; pr.rem = rem; pr.cnt_base = cnt_base;
+  return gram_launch(a_hi, a_lo, n, a_hi, a_lo, n, Ppad, pr.base[0], ldg, reinterpret_cast<const int2*>(tile_list_xy),
+                     num_tiles, 1, pr, stream);
 }
 
 extern "C" int v3s_gram_rows_simt(const float* a_all, long long n_cols, const float* a_rows, long long n_rows, int P,

@@ -42,6 +42,9 @@ class CudaOps:
         self._events = []
         self._synth_prep = {}
         self._sym_tile_cache = {}
+        self._symm_G = {}
+        self.use_peer_gram = True    # sharded jobs: symmetric Gram with NVLink peer stores (else rectangular panels)
+        self.symm_error = None
         self._pin = None
 
     # ---- per-kernel device timing (CUDA events on the launching stream) ------------------------
@@ -183,7 +186,46 @@ class CudaOps:
         self._toc(h)
         return G
 
-    def knn_rows(self, hi_all, lo_all, a32_all, zero_flag, r0, r1, k):
+    def gram_symmetric_sharded(self, hi_all, lo_all, plan):
+        """Row block [n_loc, ldg] of the symmetric Gram in a sharded job, with half the tensor-core
+        work per rank: each rank computes 1/world of the global upper-triangle tiles and stores every
+        tile (and its mirror) straight into the owning ranks' buffers over NVLink from the kernel's
+        epilogue (torch symmetric memory provides the peer mappings).  Returns None when symmetric
+        memory is unavailable (the caller then uses rectangular panels)."""
+        import torch.distributed as dist
+        N = plan.N
+        ldg = round_up(N, 4)
+        cmax = max(plan.counts)
+        key = (N, plan.world, plan.rank)
+        ent = self._symm_G.get(key)
+        if ent is None:
+            try:
+                import torch.distributed._symmetric_memory as symm
+                buf = symm.empty((cmax, ldg), dtype=torch.float32, device=self.device)
+                hdl = symm.rendezvous(buf, plan.group if plan.group is not None else dist.group.WORLD)
+                ptrs = (C.c_ulonglong * plan.world)(*[int(x) for x in hdl.buffer_ptrs])
+            except Exception as e:                      # no peer access / API missing: not an error
+                self._symm_G[key] = False
+                self.symm_error = repr(e)
+                return None
+            tiles, nt = self._sym_tiles(N)
+            per = (nt + plan.world - 1) // plan.world
+            t0, t1 = min(plan.rank * per, nt), min((plan.rank + 1) * per, nt)
+            ent = (buf, ptrs, tiles[t0:t1].contiguous(), t1 - t0)
+            self._symm_G[key] = ent
+        if ent is False:
+            return None
+        buf, ptrs, my_tiles, my_nt = ent
+        base, rem = divmod(N, plan.world)
+        dist.barrier(group=plan.group)                   # nobody is still reading its block from the previous pass
+        h = self._tic("gram")
+        call("v3s_gram_symmetric_sharded", ptr(hi_all), ptr(lo_all), N, hi_all.shape[1], ptrs, plan.world, base, rem, ldg,
+             ptr(my_tiles), my_nt, stream_ptr())
+        self._toc(h)
+        dist.barrier(group=plan.group)                   # every rank's tiles (incl. peer stores into this block) are done
+        return buf[: plan.hi - plan.lo]
+
+    def knn_rows(self, hi_all, lo_all, a32_all, zero_flag, r0, r1, k, plan=None):
         """k nearest neighbours (round distance) of rows [r0,r1) against all rows.
         -> S2 [r1-r0,k] f64 ascending, Nbr [r1-r0,k] i32.  Gram panels are streamed."""
         N, P = a32_all.shape
@@ -197,17 +239,23 @@ class CudaOps:
         ldg = round_up(N, 4)
         sym = (self.gram_impl == "tcgen05" and r0 == 0 and r1 == N and 4 * ldg * N <= SYM_BYTES
                and 4 * ldg * N <= 0.6 * torch.cuda.mem_get_info()[0])
-        panel = nr if sym else max(256, min(nr, (PANEL_BYTES // (4 * ldg)) // 256 * 256))
+        G_shard = None
+        if (self.gram_impl == "tcgen05" and plan is not None and plan.world > 1 and plan.world <= 8 and self.use_peer_gram
+                and r0 == plan.lo and r1 == plan.hi and N // plan.world >= 1 and 4 * ldg * max(plan.counts) <= SYM_BYTES):
+            G_shard = self.gram_symmetric_sharded(hi_all, lo_all, plan)
+        panel = nr if (sym or G_shard is not None) else max(256, min(nr, (PANEL_BYTES // (4 * ldg)) // 256 * 256))
         cap = min(k + KNN_MARGIN + KNN_EXTRA_CAP, N)
         eps_g = 2.0 * gram_error_bound(P) if self.gram_impl == "tcgen05" else 2e-5
-        G = self.empty((min(panel, nr), ldg), torch.float32)
+        G = G_shard if G_shard is not None else self.empty((min(panel, nr), ldg), torch.float32)
         cand = self.empty((min(panel, nr), cap), torch.int32)
         cnt = self.empty((min(panel, nr),), torch.int32)
         self.knn_overflow = self.zeros((1,), torch.int32)
         zf = zero_flag if (zero_flag is not None) else None
         for p0 in range(r0, r1, panel):
             p1 = min(p0 + panel, r1)
-            if sym:
+            if G_shard is not None:
+                pass                                     # already complete (computed by all ranks, stored over NVLink)
+            elif sym:
                 self.gram_symmetric(hi_all, lo_all, N, out=G)
             else:
                 self.gram_rows(hi_all, lo_all, a32_all, p0, p1, out=G)

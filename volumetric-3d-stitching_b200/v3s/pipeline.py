@@ -86,7 +86,7 @@ def knn_stage(ops, plan, img_local, k):
     hi_all = _bf16_gather(plan, hi)
     lo_all = _bf16_gather(plan, lo)
     zf_all = plan.all_gather_rows(zf)
-    S2_loc, Nbr_loc = ops.knn_rows(hi_all, lo_all, a32_all, zf_all, plan.lo, plan.hi, k)
+    S2_loc, Nbr_loc = ops.knn_rows(hi_all, lo_all, a32_all, zf_all, plan.lo, plan.hi, k, plan=plan)
     S2_all = plan.all_gather_rows(S2_loc)
     Nbr_all = plan.all_gather_rows(Nbr_loc)
     return S2_all, Nbr_all
