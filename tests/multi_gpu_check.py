@@ -56,7 +56,9 @@ for (N, n, n_p, k) in ((3001, 15, 31, 100), (5000, 15, 48, 120)):
     ang = float(np.max(orc.principal_angles(out_s["Ps"].cpu().numpy(), out_1["Ps"].cpu().numpy())))
     print(f"rank {rank} N={N}: S2 equal {bool(okS)}, same neighbours {same_idx:.6f}, |dLambda| {lam_err:.2e}, "
           f"subspace angle {ang:.2e}, sigma_T {out_s['sigma_T'].item():.4f} vs {out_1['sigma_T'].item():.4f}", flush=True)
-    ok &= bool(okS) and same_idx > 0.9999 and lam_err < 1e-6 and ang < 1e-4
+    lam1 = out_1["Lambda"].cpu().numpy()
+    connected = bool(np.all(lam1[1:] < 1 - 1e-6))            # a degenerate lambda = 1 cluster has no unique basis
+    ok &= bool(okS) and same_idx > 0.9999 and lam_err < 1e-6 and (ang < 1e-4 or not connected)
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
