@@ -194,8 +194,9 @@ fit_project_kernel(const double* __restrict__ Ps, int ldx, const double* __restr
 
 // sum over i in [row0,row0+n_rows), j in [0,N) of |acos(clip(q1_i.q1_j)) - acos(clip(q2_i.q2_j))|.
 // The summand is symmetric in (i,j) and zero on the diagonal, so each unordered pair is evaluated
-// once -- by the row i with (i < j and i+j even) or (i > j and i+j odd), which balances the work
-// over row blocks -- and counted twice.
+// once and counted twice.  Who evaluates it is decided on 32-index blocks (bi = i/32, bj = j/32) so
+// the choice is uniform across a warp: bi != bj -> the row whose block satisfies (bi < bj and bi+bj
+// even) or (bi > bj and bi+bj odd) (balanced over row blocks); bi == bj -> the row with i < j.
 constexpr int SG_T = 256;
 __global__ void __launch_bounds__(SG_T)
 sigma_pairs_kernel(const double* __restrict__ q1, const double* __restrict__ q2, long long N, long long row0,
@@ -221,7 +222,8 @@ sigma_pairs_kernel(const double* __restrict__ q1, const double* __restrict__ q2,
     if (i_ok) {
       for (int jj = 0; jj < lim; ++jj) {
         const long long jg = jb + jj;
-        const bool mine = (i < jg) ? (((i + jg) & 1) == 0) : (i > jg && ((i + jg) & 1) == 1);
+        const long long bi = i >> 5, bj = jg >> 5;
+        const bool mine = (bi == bj) ? (i < jg) : ((bi < bj) ? (((bi + bj) & 1) == 0) : (((bi + bj) & 1) == 1));
         if (!mine) continue;
         double d1 = a1[0] * sj1[jj][0] + a1[1] * sj1[jj][1] + a1[2] * sj1[jj][2] + a1[3] * sj1[jj][3];
         double d2 = a2[0] * sj2[jj][0] + a2[1] * sj2[jj][1] + a2[2] * sj2[jj][2] + a2[3] * sj2[jj][3];
