@@ -81,6 +81,10 @@ int v3s_column_sums(const float* img, long long n_rows, int P, long long stride,
 int v3s_center_normalize(const float* img, long long n_rows, int P, long long stride, const double* mean /* [P] */,
                          float* a_f32, void* a_hi, void* a_lo, int Ppad, double* norms, int* zero_flag, void* stream);
 
+/* BF16 hi/lo split of already centred unit rows a_f32 [n_rows,P] -> a_hi, a_lo [n_rows,Ppad]
+ * (identical to what v3s_center_normalize emits; used on the all-gathered rows of a sharded job). */
+int v3s_split_bf16(const float* a_f32, long long n_rows, int P, int Ppad, void* a_hi, void* a_lo, void* stream);
+
 /* np.matmul(A, A.T) of DistanceMatrix.convert_to_round_distance (distance.py:56) for a row
  * panel: G[r, c] = <a_rows[r], a_all[c]>, r < n_rows, c < n_cols, tcgen05/TMEM/TMA kernel on
  * the split BF16 operands (FP32-equivalent).  Ppad must be a multiple of 64.                */

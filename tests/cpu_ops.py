@@ -200,3 +200,7 @@ class OracleOps:
             if s > 0:
                 a[r] = rng.poisson(a[r] * (photons_per_pattern / s))
         return img
+
+    def split_bf16(self, a32):
+        hi = a32.to(torch.bfloat16)
+        return hi, (a32 - hi.to(torch.float32)).to(torch.bfloat16)

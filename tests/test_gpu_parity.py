@@ -153,6 +153,8 @@ def test_gram_tcgen05_vs_fp64(ops, shape):
     a32, hi, lo, zf = ops.center_normalize(img, mean)
     ref_a = orc.set_norm_to_one(orc.remove_offset(A.astype(np.float64)))
     assert np.max(np.abs(a32.cpu().numpy() - ref_a)) < 3e-7
+    hi2, lo2 = ops.split_bf16(a32)                                   # the sharded path splits after the all-gather
+    assert torch.equal(hi2, hi) and torch.equal(lo2, lo)
     G64 = ref_a @ ref_a.T
     G_tc = ops.gram_rows(hi, lo, a32, 0, N)[:, :N].cpu().numpy()
     ops.gram_impl = "simt"

@@ -71,9 +71,34 @@ center_normalize_kernel(const float* __restrict__ img, long long n_rows, int P, 
   }
 }
 
+// BF16 hi/lo split of already-normalised rows (used after an all-gather of the FP32 rows: shipping
+// 4 B/element and splitting locally is cheaper than shipping the 4 + 2 + 2 B/element of all three)
+__global__ void split_bf16_kernel(const float* __restrict__ a, long long n_rows, int P, int Ppad,
+                                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  const long long total = n_rows * (long long)Ppad;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / Ppad;
+    const int c = (int)(e - r * Ppad);
+    const float v = c < P ? a[r * P + c] : 0.f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[e] = h;
+    lo[e] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
 }  // namespace v3s
 
 using namespace v3s;
+
+extern "C" int v3s_split_bf16(const float* a_f32, long long n_rows, int P, int Ppad, void* a_hi, void* a_lo, void* stream) {
+  V3S_REQUIRE(n_rows >= 0 && P > 0 && Ppad >= P && Ppad % 8 == 0 && a_hi && a_lo, "v3s_split_bf16: bad arguments");
+  if (n_rows == 0) return 0;
+  long long g = ceil_div64(n_rows * (long long)Ppad, 256);
+  if (g > 16LL * kNumSMs) g = 16LL * kNumSMs;
+  split_bf16_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(a_f32, n_rows, P, Ppad, (__nv_bfloat16*)a_hi, (__nv_bfloat16*)a_lo);
+  V3S_CHECK_LAUNCH();
+  return 0;
+}
 
 extern "C" int v3s_column_sums(const float* img, long long n_rows, int P, long long stride, double* sums,
                                void* stream) {

@@ -143,6 +143,15 @@ class CudaOps:
         self._toc(h)
         return a32, hi, lo, zf
 
+    def split_bf16(self, a32):
+        """BF16 hi/lo Gram operands of centred unit rows a32 [n,P] (same values as center_normalize's)."""
+        n, P = a32.shape
+        Ppad = round_up(P, GRAM_KPAD)
+        hi = self.empty((n, Ppad), torch.bfloat16)
+        lo = self.empty((n, Ppad), torch.bfloat16)
+        call("v3s_split_bf16", ptr(a32), n, P, Ppad, ptr(hi), ptr(lo), stream_ptr())
+        return hi, lo
+
     def gram_rows(self, hi_all, lo_all, a32_all, r0, r1, out=None):
         """G[r0:r1, :] as f32 [r1-r0, ldg]."""
         N = a32_all.shape[0]

@@ -5,7 +5,8 @@ functions drive one GPU or a row-sharded job (one process per GPU, torch.distrib
 every N x N object (Gram panel, P_ep) is split by contiguous row blocks, rank g owning rows
 [lo_g, hi_g).  Exchanges:
     all-reduce  per-pixel sums (mean image)                    P doubles
-    all-gather  centred unit rows + their BF16 split           N x P x 8 B
+    all-gather  centred unit rows (BF16 split done locally)    N x P x 4 B
+    peer stores symmetric Gram tiles into the owners' blocks   N x N x 4 B / world per rank (NVLink, in-kernel)
     all-gather  kNN lists                                      N x k x 12 B
     all-gather  block mat-vec result, once per Lanczos step    N x b x 8 B
     all-reduce  Sigma_T partial sum                            1 double
@@ -67,13 +68,6 @@ class ShardPlan:
         return torch.cat([buf[r * cmax: r * cmax + self.counts[r]] for r in range(self.world)], dim=0)
 
 
-def _bf16_gather(plan, t):
-    # not every backend build moves bfloat16; ship the raw bytes
-    if plan.world == 1 or t is None:
-        return t
-    return plan.all_gather_rows(t.view(torch.uint8)).view(torch.bfloat16)
-
-
 def knn_stage(ops, plan, img_local, k):
     """distance.py:17-22 (DistanceMatrix.knn) on the rank's pattern rows.
     -> S2_all [N,k] f64, Nbr_all [N,k] i32 (replicated), a32_all."""
@@ -81,11 +75,14 @@ def knn_stage(ops, plan, img_local, k):
     sums = ops.column_sums(img_local)
     plan.all_reduce_sum(sums)
     mean = sums / N
-    a32, hi, lo, zf = ops.center_normalize(img_local, mean)
-    a32_all = plan.all_gather_rows(a32)
-    hi_all = _bf16_gather(plan, hi)
-    lo_all = _bf16_gather(plan, lo)
-    zf_all = plan.all_gather_rows(zf)
+    if plan.world == 1:
+        a32_all, hi_all, lo_all, zf_all = ops.center_normalize(img_local, mean)
+    else:
+        # ship the FP32 unit rows only (4 B/element) and split them locally: half the all-gather volume
+        a32, _, _, zf = ops.center_normalize(img_local, mean, want_split=False)
+        a32_all = plan.all_gather_rows(a32)
+        zf_all = plan.all_gather_rows(zf)
+        hi_all, lo_all = ops.split_bf16(a32_all)
     S2_loc, Nbr_loc = ops.knn_rows(hi_all, lo_all, a32_all, zf_all, plan.lo, plan.hi, k, plan=plan)
     S2_all = plan.all_gather_rows(S2_loc)
     Nbr_all = plan.all_gather_rows(Nbr_loc)
