@@ -353,6 +353,24 @@ def test_block_matvec_shapes(ops, shape):
         assert (W0.T @ W0 - torch.eye(8, dtype=torch.float64, device="cuda")).abs().max().item() < 1e-12
 
 
+def test_lanczos_large_krylov_dimension(ops):
+    """A slowly converging spectrum drives the Krylov basis to its cap (1024 vectors): exercises the
+    device step kernels at large m (shared-memory opt-in of the update kernel, projection splits)."""
+    from v3s.eig import block_lanczos_device
+    N = 4096
+    g = torch.Generator(device="cpu").manual_seed(0)
+    Q, _ = torch.linalg.qr(torch.randn((N, N), generator=g, dtype=torch.float64))
+    lam = torch.cat([1.0 - 2e-4 * torch.arange(40, dtype=torch.float64), torch.linspace(0.9, -0.2, N - 40, dtype=torch.float64)])
+    Pm = ((Q * lam[None, :]) @ Q.T).to(torch.float32)
+    Pd = torch.zeros((N, N), dtype=torch.float32, device="cuda")
+    Pd.copy_(Pm)
+    stats = {}
+    w, Y, res = block_lanczos_device(ops, lambda Xf, Qb: ops.block_matvec_f32(Pd, N, Xf), N, 10, tol=1e-9, stats=stats)
+    print("large-m lanczos:", stats)
+    assert stats["krylov_dim"] > 640
+    assert np.max(np.abs(np.sort(w)[::-1] - lam[:10].numpy())) < 5e-6
+
+
 def test_eigen_connected(v3s_mod, golden_dir):
     g = np.load(os.path.join(golden_dir, "connected_n15.npz"))
     stats = {}

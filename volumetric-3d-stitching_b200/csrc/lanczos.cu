@@ -338,10 +338,14 @@ extern "C" int v3s_lanczos_step(double* V, long long ldv, long long N, int m, in
   const int nsplit = lz_nsplit(m, N);
   const long long rows_per = ceil_div64(N, nsplit);
   const size_t up_smem = (size_t)m * LB * sizeof(double);
+  // static (9 kB) + dynamic shared memory exceeds the 48 kB default from m ~ 620 on: opt in once
   static size_t up_set = 0;
-  if (up_smem > 48 * 1024 && up_smem > up_set) {
-    V3S_CUDA(cudaFuncSetAttribute(lz_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(max_dim * LB * sizeof(double))));
-    up_set = (size_t)max_dim * LB * sizeof(double);
+  if (up_smem > up_set) {
+    size_t want = (size_t)max_dim * LB * sizeof(double);
+    if (want < 64 * 1024) want = 64 * 1024;
+    V3S_REQUIRE(want <= 200 * 1024, "v3s_lanczos_step: max_dim=%d needs %zu B of shared memory", max_dim, want);
+    V3S_CUDA(cudaFuncSetAttribute(lz_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want));
+    up_set = want;
   }
   for (int pass = 0; pass < 2; ++pass) {
     lz_proj_kernel<<<dim3((m + PJ_VECS - 1) / PJ_VECS, nsplit), PJ_T, 0, st>>>(V, ldv, m, W, N, rows_per, Hpart);
