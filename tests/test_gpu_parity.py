@@ -360,14 +360,14 @@ def test_lanczos_large_krylov_dimension(ops):
     N = 4096
     g = torch.Generator(device="cpu").manual_seed(0)
     Q, _ = torch.linalg.qr(torch.randn((N, N), generator=g, dtype=torch.float64))
-    lam = torch.cat([1.0 - 2e-4 * torch.arange(40, dtype=torch.float64), torch.linspace(0.9, -0.2, N - 40, dtype=torch.float64)])
+    lam = torch.cat([1.0 - 1e-4 * torch.arange(40, dtype=torch.float64), torch.linspace(0.9, -0.2, N - 40, dtype=torch.float64)])
     Pm = ((Q * lam[None, :]) @ Q.T).to(torch.float32)
     Pd = torch.zeros((N, N), dtype=torch.float32, device="cuda")
     Pd.copy_(Pm)
     stats = {}
     w, Y, res = block_lanczos_device(ops, lambda Xf, Qb: ops.block_matvec_f32(Pd, N, Xf), N, 10, tol=1e-9, stats=stats)
     print("large-m lanczos:", stats)
-    assert stats["krylov_dim"] > 640
+    assert stats["krylov_dim"] > 624          # beyond the point where static + dynamic smem crosses 48 kB
     assert np.max(np.abs(np.sort(w)[::-1] - lam[:10].numpy())) < 5e-6
 
 
