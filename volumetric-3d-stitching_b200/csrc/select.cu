@@ -174,7 +174,19 @@ refine_sort_kernel(const float* __restrict__ a_rows, const float* __restrict__ a
       if (vec4) {
         const float4* x4 = reinterpret_cast<const float4*>(xr);
         const float4* y4 = reinterpret_cast<const float4*>(aj);
-        for (int p = lane; p < P / 4; p += 32) {
+        const int n4 = P / 4;
+        int p = lane;
+        // 4 independent 128-bit loads in flight per lane (2 kB per warp): the gather is HBM/L2-latency bound
+        for (; p + 96 < n4; p += 128) {
+          const float4 y0 = __ldg(&y4[p]), y1 = __ldg(&y4[p + 32]), y2 = __ldg(&y4[p + 64]), y3 = __ldg(&y4[p + 96]);
+          const float4 x0 = x4[p], x1 = x4[p + 32], x2 = x4[p + 64], x3 = x4[p + 96];
+          float d;
+          d = x0.x - y0.x; a0 = fmaf(d, d, a0); d = x0.y - y0.y; a1 = fmaf(d, d, a1); d = x0.z - y0.z; a2 = fmaf(d, d, a2); d = x0.w - y0.w; a3 = fmaf(d, d, a3);
+          d = x1.x - y1.x; a0 = fmaf(d, d, a0); d = x1.y - y1.y; a1 = fmaf(d, d, a1); d = x1.z - y1.z; a2 = fmaf(d, d, a2); d = x1.w - y1.w; a3 = fmaf(d, d, a3);
+          d = x2.x - y2.x; a0 = fmaf(d, d, a0); d = x2.y - y2.y; a1 = fmaf(d, d, a1); d = x2.z - y2.z; a2 = fmaf(d, d, a2); d = x2.w - y2.w; a3 = fmaf(d, d, a3);
+          d = x3.x - y3.x; a0 = fmaf(d, d, a0); d = x3.y - y3.y; a1 = fmaf(d, d, a1); d = x3.z - y3.z; a2 = fmaf(d, d, a2); d = x3.w - y3.w; a3 = fmaf(d, d, a3);
+        }
+        for (; p < n4; p += 32) {
           const float4 x = x4[p], y = __ldg(&y4[p]);
           const float d0 = x.x - y.x, d1 = x.y - y.y, d2 = x.z - y.z, d3 = x.w - y.w;
           a0 = fmaf(d0, d0, a0); a1 = fmaf(d1, d1, a1); a2 = fmaf(d2, d2, a2); a3 = fmaf(d3, d3, a3);
