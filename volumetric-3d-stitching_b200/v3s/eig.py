@@ -130,7 +130,7 @@ def _next_check(steps, res_max, target, prev, max_gap):
 
 
 def block_lanczos_device(ops, op, N, nev, tol=1e-8, max_dim=None, first_check=6, seed=0, max_gap=16,
-                         stats=None, start_block=None, both_ends=True, lock=None):
+                         stats=None, start_block=None, both_ends=True, lock=None, want_theta_min=False):
     """Same algorithm as `block_lanczos_topk`, with every per-step operation enqueued on the GPU by
     the C-ABI (`v3s_lanczos_start` / `v3s_lanczos_step`, csrc/lanczos.cu): the host only launches,
     and reads back the small (A_j, B_j) blocks when it extracts Ritz pairs.
@@ -208,6 +208,12 @@ def block_lanczos_device(ops, op, N, nev, tol=1e-8, max_dim=None, first_check=6,
         m += b
     St = torch.from_numpy(np.ascontiguousarray(S)).to(ops.device)
     Y = st["V"][L:L + m].T @ St
+    if stats is not None and want_theta_min:
+        Tb = band[:, :m].copy()
+        for i in range(1, b + 1):
+            Tb[i, max(m - i, 0):] = 0.0
+        with _one_thread():
+            stats["theta_min"] = float(sla.eig_banded(Tb, lower=True, eigvals_only=True, select="i", select_range=(0, 0))[0])
     if stats is not None:
         stats.update({"matvecs": steps, "block": b, "krylov_dim": m, "ritz_checks": n_checks, "speculative_steps": n_spec,
                       "residual_max": float(res.max()),
@@ -215,13 +221,14 @@ def block_lanczos_device(ops, op, N, nev, tol=1e-8, max_dim=None, first_check=6,
     return w, Y, res
 
 
-def chebyshev_lanczos_device(ops, matvec_f32, matvec_f64, N, nev, tol=1e-8, degree=8, probe_steps=10, seed=0,
-                             stats=None, lock=None):
+def chebyshev_lanczos_device(ops, matvec_f32, matvec_f64, N, nev, tol=1e-8, degree=6, probe_steps=10, seed=0,
+                             stats=None, lock=None, safe_lower=False):
     """Largest eigenpairs of the symmetric operator P by block Lanczos on a Chebyshev polynomial
     of P (device driver).  Clustered top eigenvalues (gaps ~1e-4 at N = 10^4) make plain Lanczos
     need a Krylov space of ~600 vectors, whose Ritz extraction is O(m^2 b) host work per check;
     Lanczos on T_d((P - c)/e), with [c-e, c+e] = [-1, cut] the unwanted part of the spectrum,
-    converges in ~4x fewer steps for ~1.8x more (HBM-bound, host-free) mat-vecs.
+    converges in ~4x fewer steps for ~1.5x more (HBM-bound, host-free) mat-vecs (degree 6 and the
+    probe-estimated lower end minimise mat-vecs x 80 us + steps x 100 us at cfg 2).
 
       1. probe: `probe_steps` plain block-Lanczos steps.  Ritz values are lower bounds of the
          eigenvalues (Cauchy interlacing), so cut = theta_nev(probe) <= lambda_nev: the wanted
@@ -237,7 +244,7 @@ def chebyshev_lanczos_device(ops, matvec_f32, matvec_f64, N, nev, tol=1e-8, degr
     st1 = {}
     plain_op = lambda Xf, Q: matvec_f32(Xf)
     w0, Y0, res0 = block_lanczos_device(ops, plain_op, N, nev, tol=tol, max_dim=probe_steps * b, seed=seed,
-                                        first_check=probe_steps, stats=st1, both_ends=True, lock=lock)
+                                        first_check=probe_steps, stats=st1, both_ends=True, lock=lock, want_theta_min=True)
     n_mv = st1["matvecs"]
     info = {"probe_steps": st1["matvecs"], "degree": degree}
     if st1["converged"]:
@@ -252,7 +259,14 @@ def chebyshev_lanczos_device(ops, matvec_f32, matvec_f64, N, nev, tol=1e-8, degr
             stats["driver"] = "device-plain(LM)"
         return lam, Y, res
     else:
-        cut, lo = float(np.min(w0)), -1.0
+        cut = float(np.min(w0))
+        # lower end of the damped interval: the spectrum of a normalised Markov matrix is inside [-1, 1];
+        # the probe's smallest Ritz value (extremal values converge first) minus a 15 % safety margin is
+        # much tighter and amplifies the wanted end far more per degree.  Guarded below: if an eigenvalue
+        # under `lo` existed it would be amplified too and show up in the Rayleigh-Ritz step -> safe rerun.
+        lo = -1.0
+        if safe_lower is False and "theta_min" in st1:
+            lo = max(-1.0, st1["theta_min"] - 0.15 * (float(np.max(w0)) - st1["theta_min"]))
         c, e = 0.5 * (cut + lo), 0.5 * (cut - lo)
         bufs = [ops.empty((N, b), torch.float64) for _ in range(3)]
         Xf = ops.alloc_xf(N)
@@ -273,7 +287,7 @@ def chebyshev_lanczos_device(ops, matvec_f32, matvec_f64, N, nev, tol=1e-8, degr
         order = np.argsort(-w0, kind="stable")[:b]
         start = Y0[:, torch.as_tensor(order.copy(), device=Y0.device)].contiguous()
         st2 = {}
-        _, Y, res = block_lanczos_device(ops, cheb_op, N, nev, tol=tol, seed=seed, first_check=4, max_gap=8, stats=st2,
+        _, Y, res = block_lanczos_device(ops, cheb_op, N, nev, tol=tol, seed=seed, first_check=4, max_gap=4, stats=st2,
                                          start_block=start, both_ends=False, lock=lock)
         n_mv += count[0]
         info.update({"cheb_steps": st2["matvecs"], "krylov_dim": st2["krylov_dim"], "cut": cut,
@@ -291,6 +305,11 @@ def chebyshev_lanczos_device(ops, matvec_f32, matvec_f64, N, nev, tol=1e-8, degr
         lam, res = lam[idx], res[idx]
         Y = Y[:, torch.as_tensor(idx.copy(), device=Y.device)]
         info["true_residual_max"] = float(res.max())
+        info["damped_interval"] = [lo, cut]
+        if lo > -1.0 and float(np.min(lam)) < cut - 1e-6 * max(1.0, abs(cut)):
+            # something from the supposedly damped region was amplified: the lower bound was not a bound
+            return chebyshev_lanczos_device(ops, matvec_f32, matvec_f64, N, nev, tol=tol, degree=degree,
+                                            probe_steps=probe_steps, seed=seed, stats=stats, lock=lock, safe_lower=True)
     if stats is not None:
         stats.update(info)
         stats.update({"matvecs": n_mv, "block": b, "residual_max": float(np.max(res)), "driver": "device-chebyshev",
