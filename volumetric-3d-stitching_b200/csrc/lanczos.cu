@@ -155,12 +155,15 @@ lz_gram8_kernel(const double* __restrict__ W, long long N, double* __restrict__ 
   }
 }
 
-// one warp: G = sum of partials; G = L L^T; Linv; R = L^T.  small[0..63]=Linv (row-major),
-// small[64..127]=R of this round, small[128..191]=R_total (R_round * R_total_prev when round>0)
+// 64 threads: G = sum of partials; G = L L^T (column by column, thread i owns row i); Linv (thread j
+// owns column j); R = L^T.  small[0..63]=Linv (row-major), small[64..127]=R of this round,
+// small[128..191]=R_total (R_round * R_total_prev when round>0; thread (i,j) owns one entry)
 __global__ void lz_chol_kernel(const double* __restrict__ Gpart, int nparts, int round, double* __restrict__ small,
                                int* __restrict__ status) {
-  __shared__ double G[LB][LB], L[LB][LB], Li[LB][LB];
+  __shared__ double G[LB][LB], L[LB][LB], Li[LB][LB], Rprev[LB][LB];
+  __shared__ int bad;
   const int t = threadIdx.x;
+  if (t == 0) bad = 0;
   if (t < 36) {
     double s = 0.0;
     for (int p = 0; p < nparts; ++p) s += Gpart[(long long)p * 36 + t];
@@ -168,44 +171,46 @@ __global__ void lz_chol_kernel(const double* __restrict__ Gpart, int nparts, int
     for (int i = 0; i < LB; ++i) for (int j = i; j < LB; ++j) { if (e == t) { ii = i; jj = j; } ++e; }
     G[ii][jj] = s; G[jj][ii] = s;
   }
+  { const int i = t / LB, j = t % LB; L[i][j] = 0.0; Li[i][j] = 0.0; if (round > 0) Rprev[i][j] = small[128 + t]; }
   __syncthreads();
-  if (t == 0) {
-    bool bad = false;
-    for (int i = 0; i < LB; ++i) for (int j = 0; j < LB; ++j) { L[i][j] = 0.0; Li[i][j] = 0.0; }
-    for (int j = 0; j < LB; ++j) {
+  // right-looking Cholesky: after step j, column j of L is final
+  for (int j = 0; j < LB; ++j) {
+    if (t == j) {
       double d = G[j][j];
       for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k];
-      if (!(d > 0.0)) { bad = true; d = 1.0; }
-      const double l = sqrt(d);
-      L[j][j] = l;
-      for (int i = j + 1; i < LB; ++i) {
-        double s = G[i][j];
-        for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k];
-        L[i][j] = s / l;
-      }
+      if (!(d > 0.0)) { bad = 1; d = 1.0; }
+      L[j][j] = sqrt(d);
     }
-    for (int j = 0; j < LB; ++j) {            // inverse of lower-triangular L, column by column
-      Li[j][j] = 1.0 / L[j][j];
-      for (int i = j + 1; i < LB; ++i) {
-        double s = 0.0;
-        for (int k = j; k < i; ++k) s -= L[i][k] * Li[k][j];
-        Li[i][j] = s / L[i][i];
-      }
+    __syncthreads();
+    if (t > j && t < LB) {
+      double s = G[t][j];
+      for (int k = 0; k < j; ++k) s -= L[t][k] * L[j][k];
+      L[t][j] = s / L[j][j];
     }
-    if (bad) atomicExch(status, 1);
-    for (int i = 0; i < LB; ++i) for (int j = 0; j < LB; ++j) { small[i * LB + j] = Li[i][j]; small[64 + i * LB + j] = L[j][i]; }
-    if (round == 0) {
-      for (int e = 0; e < 64; ++e) small[128 + e] = small[64 + e];
-    } else {                                   // R_total = R_round * R_total_prev
-      double Rt[64];
-      for (int i = 0; i < LB; ++i) for (int j = 0; j < LB; ++j) {
-        double s = 0.0;
-        for (int k = 0; k < LB; ++k) s += small[64 + i * LB + k] * small[128 + k * LB + j];
-        Rt[i * LB + j] = s;
-      }
-      for (int e = 0; e < 64; ++e) small[128 + e] = Rt[e];
+    __syncthreads();
+  }
+  if (t < LB) {                                // inverse of lower-triangular L, column t
+    const int j = t;
+    Li[j][j] = 1.0 / L[j][j];
+    for (int i = j + 1; i < LB; ++i) {
+      double s = 0.0;
+      for (int k = j; k < i; ++k) s -= L[i][k] * Li[k][j];
+      Li[i][j] = s / L[i][i];
     }
   }
+  __syncthreads();
+  {
+    const int i = t / LB, j = t % LB;
+    small[t] = Li[i][j];
+    small[64 + t] = L[j][i];                   // R = L^T
+    double rt = L[j][i];
+    if (round > 0) {                           // R_total = R_round * R_total_prev
+      rt = 0.0;
+      for (int k = 0; k < LB; ++k) rt += L[k][i] * Rprev[k][j];
+    }
+    small[128 + t] = rt;
+  }
+  if (t == 0 && bad) atomicExch(status, 1);
 }
 
 // W <- W L^-T  (row n: w_j = sum_{k<=j} w_k Linv[j][k]); on the final round also append to the
