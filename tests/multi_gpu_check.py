@@ -56,9 +56,22 @@ for (N, n, n_p, k) in ((3001, 15, 31, 100), (5000, 15, 48, 120)):
     ang = float(np.max(orc.principal_angles(out_s["Ps"].cpu().numpy(), out_1["Ps"].cpu().numpy())))
     print(f"rank {rank} N={N}: S2 equal {bool(okS)}, same neighbours {same_idx:.6f}, |dLambda| {lam_err:.2e}, "
           f"subspace angle {ang:.2e}, sigma_T {out_s['sigma_T'].item():.4f} vs {out_1['sigma_T'].item():.4f}", flush=True)
+    # --- the eigen-solver's fused mat-vec (peer stores + flag barrier) vs the NCCL all-gather form
+    ops.use_fused_matvec = False
+    st_n = {}
+    out_n = run_pipeline(ops, plan, ed, rot9_all[plan.lo:plan.hi].contiguous(), rot_y, n_p, k, 0.7, check=False, stats=st_n)
+    ops.use_fused_matvec = True
+    st_f = {}
+    out_f = run_pipeline(ops, plan, ed, rot9_all[plan.lo:plan.hi].contiguous(), rot_y, n_p, k, 0.7, check=False, stats=st_f)
+    lam_fn = float((out_f["Lambda"] - out_n["Lambda"]).abs().max().item())
+    ang_fn = float(np.max(orc.principal_angles(out_f["Ps"].cpu().numpy(), out_n["Ps"].cpu().numpy())))
+    print(f"rank {rank} N={N}: fused vs NCCL mat-vec exchange: |dLambda| {lam_fn:.2e}, subspace angle {ang_fn:.2e}, "
+          f"fused={st_f.get('fused_matvec')} matvecs {st_f.get('matvecs')} vs {st_n.get('matvecs')}", flush=True)
+    ok &= bool(st_f.get("fused_matvec")) and not st_n.get("fused_matvec") and lam_fn < 1e-9
     lam1 = out_1["Lambda"].cpu().numpy()
     connected = bool(np.all(lam1[1:] < 1 - 1e-6))            # a degenerate lambda = 1 cluster has no unique basis
     ok &= bool(okS) and same_idx > 0.9999 and lam_err < 1e-6 and (ang < 1e-4 or not connected)
+    ok &= (ang_fn < 1e-6 or not connected)
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:

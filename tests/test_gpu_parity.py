@@ -353,6 +353,57 @@ def test_block_matvec_shapes(ops, shape):
         assert (W0.T @ W0 - torch.eye(8, dtype=torch.float64, device="cuda")).abs().max().item() < 1e-12
 
 
+@pytest.mark.parametrize("shape", [(1000, 1000, 0), (477, 1003, 200), (3000, 20000, 17000), (1, 128, 5)])
+def test_fused_operator_plain_and_chebyshev(ops, shape):
+    """v3s_matvec_combine / v3s_cheb_filter (reduction + three-term recurrence + result stores in one
+    kernel after the mat-vec) against an FP64 evaluation of the same recurrence; row blocks of a
+    sharded matrix write only their rows [row0, row0+n_rows) of the [N,8] result."""
+    from v3s.pipeline import ShardPlan
+    n_rows, N, row0 = shape
+    g = torch.Generator(device="cpu").manual_seed(7 * n_rows + N)
+    ld = (N + 3) // 4 * 4
+    Pm = torch.zeros((n_rows, ld), dtype=torch.float32)
+    Pm[:, :N] = torch.rand((n_rows, N), generator=g) * (torch.rand((n_rows, N), generator=g) < 0.05) / max(1.0, 0.025 * N)
+    Pd = Pm.cuda()
+    plan = ShardPlan(N)
+    plan.lo, plan.hi = row0, row0 + n_rows                   # a single-process stand-in for one rank's row block
+    fo = ops.fused_operator(Pd, N, plan)
+    st = ops.lanczos_alloc(max(N, 8), 8, 1)
+    W0 = torch.randn((N, 8), generator=g, dtype=torch.float64).cuda()
+    ops.lanczos_start(st, W0)                                # W0 <- Q (orthonormal), st["Xf"] <- float(Q), strip layout
+    Q = W0
+    Qf = Q.float().double().cpu()                            # the operand the kernel multiplies (FP32 copy)
+    Pref = Pm[:, :N].double()
+    rows = slice(row0, row0 + n_rows)
+    for b_ in fo.a["ybufs"]:
+        b_.fill_(-7.0)
+    Y = fo.plain(st["Xf"], Q)
+    ref = Pref @ Qf
+    scale = ref.abs().max().item() + 1e-30
+    assert (Y[rows].cpu() - ref).abs().max().item() < 3e-6 * scale
+    untouched = torch.ones(N, dtype=torch.bool)
+    untouched[rows] = False
+    assert bool((Y.cpu()[untouched] == -7.0).all())          # other ranks' rows are theirs to write
+    if n_rows == N:                                          # the recurrence needs the whole block on this rank
+        c, e, degree = 0.1, 0.7, 5
+        Yc = fo.cheb(st["Xf"], Q, degree, c, e)
+        Qd = Q.cpu()
+        prev, cur = Qd, (Pref @ Qf - c * Qd) / e
+        for _ in range(degree - 1):
+            prev, cur = cur, 2.0 * (Pref @ cur.float().double() - c * cur) / e - prev
+        assert Yc.data_ptr() != Q.data_ptr()
+        assert (Yc.cpu() - cur).abs().max().item() < 2e-5 * (cur.abs().max().item() + 1e-30)
+        # the filter applied to one of its own rotating buffers (the steady state of the Lanczos loop)
+        Q2 = Yc
+        ops.lanczos_start(st, Q2)
+        Yc2 = fo.cheb(st["Xf"], Q2, 2, c, e)
+        Q2d, Q2f = Q2.cpu(), Q2.float().double().cpu()
+        y1 = (Pref @ Q2f - c * Q2d) / e
+        y2 = 2.0 * (Pref @ y1.float().double() - c * y1) / e - Q2d
+        assert Yc2.data_ptr() != Q2.data_ptr()
+        assert (Yc2.cpu() - y2).abs().max().item() < 2e-5 * (y2.abs().max().item() + 1e-30)
+
+
 def test_lanczos_large_krylov_dimension(ops):
     """A slowly converging spectrum drives the Krylov basis to its cap (1024 vectors): exercises the
     device step kernels at large m (shared-memory opt-in of the update kernel, projection splits)."""

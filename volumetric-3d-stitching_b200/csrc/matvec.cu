@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "v3s.h"
 #include "tma.cuh"
+#include <vector>
 
 namespace v3s {
 
@@ -181,9 +182,14 @@ static inline MvPlan mv_plan(long long n_rows, long long N) {
 
 static inline size_t mv_xf_bytes(long long N) { return ((size_t)xf_strip_floats(N) * sizeof(float) + 255) & ~(size_t)255; }
 
-static int mv_run(const float* P_rows, long long ldp, long long n_rows, long long N, const float* XfS, int b,
-                  double* Y_rows, double* Ypart, cudaStream_t st) {
-  const MvPlan pl = mv_plan(n_rows, N);
+// ---- per-launch device timing of the mat-vec kernel (bench.py's roofline): CUDA events recorded on
+// the launching stream around block_matvec_kernel alone, owned by the library ------------------
+static bool g_prof_on = false;
+static std::vector<cudaEvent_t> g_prof_ev;      // pairs (start, stop)
+static size_t g_prof_used = 0;
+
+static int mv_launch(const float* P_rows, long long ldp, long long n_rows, long long N, const float* XfS, double* Ypart,
+                     const MvPlan& pl, cudaStream_t st) {
   CUtensorMap tm;
   if (make_tmap_2d(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, P_rows, n_rows, N, ldp * 4, MV_STRIP, MV_TILE_ROWS,
                    CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
@@ -193,14 +199,101 @@ static int mv_run(const float* P_rows, long long ldp, long long n_rows, long lon
     attr_set = true;
   }
   static unsigned launch_parity = 0;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (g_prof_on) {
+    if (g_prof_used + 2 > g_prof_ev.size()) {
+      for (int i = 0; i < 2; ++i) { cudaEvent_t e; V3S_CUDA(cudaEventCreate(&e)); g_prof_ev.push_back(e); }
+    }
+    e0 = g_prof_ev[g_prof_used]; e1 = g_prof_ev[g_prof_used + 1];
+    g_prof_used += 2;
+    V3S_CUDA(cudaEventRecord(e0, st));
+  }
   block_matvec_kernel<<<pl.grid, MV_THREADS, MV_SMEM, st>>>(tm, XfS, n_rows, N, pl.nstrips_row, pl.units_per_cta,
                                                            pl.total_units, pl.maxseg, Ypart, (int)(launch_parity++ & 1));
   V3S_CHECK_LAUNCH();
+  if (e1) V3S_CUDA(cudaEventRecord(e1, st));
+  return 0;
+}
+
+static int mv_run(const float* P_rows, long long ldp, long long n_rows, long long N, const float* XfS, int b,
+                  double* Y_rows, double* Ypart, cudaStream_t st) {
+  const MvPlan pl = mv_plan(n_rows, N);
+  if (int rc = mv_launch(P_rows, ldp, n_rows, N, XfS, Ypart, pl, st)) return rc;
   long long g2 = ceil_div64(n_rows * MV_B, 256);
   if (g2 > 8LL * kNumSMs) g2 = 8LL * kNumSMs;
   reduce_segments_kernel<<<(int)g2, 256, 0, st>>>(Ypart, n_rows, pl.nstrips_row, pl.units_per_cta, pl.maxseg, b, Y_rows);
   V3S_CHECK_LAUNCH();
   return 0;
+}
+
+// Fused tail of a sharded mat-vec inside the Lanczos / Chebyshev recurrence: segment reduction of
+// the rank's rows, the three-term combination  v = alpha * (P X) + beta * Yk + gamma * Ykm1  (FP64),
+// and the "all-gather": every value is stored straight into the [N,8] result block -- and, as FP32,
+// into the strip-layout operand of the next mat-vec -- of EVERY rank (local HBM or NVLink peer
+// mappings), so no collective follows; `v3s_peer_barrier` orders the steps.
+struct PeerPtrs { unsigned long long p[8]; };
+
+__global__ void reduce_combine_scatter_kernel(const double* __restrict__ Ypart, long long n_rows, long long row0,
+                                              int nstrips_row, long long units_per_cta, int maxseg,
+                                              const double* __restrict__ Yk, const double* __restrict__ Ykm1, double alpha,
+                                              double beta, double gamma, PeerPtrs yout, PeerPtrs xfout, int world,
+                                              int write_xf) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n_rows * MV_B; e += (long long)gridDim.x * blockDim.x) {
+    const long long i = e / MV_B;
+    const int j = (int)(e - i * MV_B);
+    const long long rg = i / MV_TILE_ROWS;
+    const int rr = (int)(i - rg * MV_TILE_ROWS);
+    const long long c_first = (rg * nstrips_row) / units_per_cta;
+    const long long c_last = ((rg + 1) * nstrips_row - 1) / units_per_cta;
+    double py = 0.0;
+    for (long long c = c_first; c <= c_last; ++c) {
+      const long long first_rg = (c * units_per_cta) / nstrips_row;
+      py += Ypart[((c * maxseg + (rg - first_rg)) * MV_TILE_ROWS + rr) * MV_B + j];
+    }
+    const long long ge = (row0 + i) * MV_B + j;
+    double v = Yk ? fma(alpha, py, beta * Yk[ge]) : alpha * py;
+    if (Ykm1) v = fma(gamma, Ykm1[ge], v);
+#pragma unroll 1
+    for (int r = 0; r < world; ++r) reinterpret_cast<double*>(yout.p[r])[ge] = v;
+    if (write_xf) {
+      const long long xi = xf_strip_index(row0 + i, j);
+      const float f = (float)v;
+#pragma unroll 1
+      for (int r = 0; r < world; ++r) reinterpret_cast<float*>(xfout.p[r])[xi] = f;
+    }
+  }
+}
+
+static int mv_combine(const float* P_rows, long long ldp, long long n_rows, long long N, long long row0, const float* XfS,
+                      const double* Yk, const double* Ykm1, double alpha, double beta, double gamma, const PeerPtrs& yout,
+                      const PeerPtrs& xfout, int world, int write_xf, double* Ypart, cudaStream_t st) {
+  const MvPlan pl = mv_plan(n_rows, N);
+  if (int rc = mv_launch(P_rows, ldp, n_rows, N, XfS, Ypart, pl, st)) return rc;
+  long long g2 = ceil_div64(n_rows * MV_B, 256);
+  if (g2 > 8LL * kNumSMs) g2 = 8LL * kNumSMs;
+  reduce_combine_scatter_kernel<<<(int)g2, 256, 0, st>>>(Ypart, n_rows, row0, pl.nstrips_row, pl.units_per_cta, pl.maxseg, Yk,
+                                                         Ykm1, alpha, beta, gamma, yout, xfout, world, write_xf);
+  V3S_CHECK_LAUNCH();
+  return 0;
+}
+
+// All ranks have stored their rows: signal every peer's flag word and wait for every peer's signal.
+// flags.p[r] = rank r's int[world] flag array (zero-initialised once); epochs grow monotonically.
+// A peer that never arrives (a crashed rank) ends the wait after ~2 s and raises *status.
+__global__ void peer_barrier_kernel(PeerPtrs flags, int rank, int world, int epoch, int* status) {
+  const int r = threadIdx.x;
+  if (r >= world) return;
+  __threadfence_system();
+  int* dst = reinterpret_cast<int*>(flags.p[r]) + rank;
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(dst), "r"(epoch) : "memory");
+  const int* src = reinterpret_cast<const int*>(flags.p[rank]) + r;
+  int v = 0;
+  const long long t0 = clock64();
+  for (;;) {
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
+    if (v - epoch >= 0) break;
+    if (clock64() - t0 > 4000000000LL) { if (status) atomicExch(status, 3); break; }
+  }
 }
 
 }  // namespace v3s
@@ -242,4 +335,110 @@ extern "C" int v3s_block_matvec_f32(const float* P_rows, long long ldp, long lon
   if (n_rows == 0) return 0;
   double* Ypart = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(workspace) + mv_xf_bytes(N));
   return mv_run(P_rows, ldp, n_rows, N, XfS, MV_B, Y_rows, Ypart, (cudaStream_t)stream);
+}
+
+// ---- fused (sharded) forms used inside the eigen-solver ---------------------------------------
+
+static inline int load_peers(PeerPtrs& dst, const unsigned long long* src, int world) {
+  for (int r = 0; r < 8; ++r) dst.p[r] = (src && r < world) ? src[r] : 0ULL;
+  return 0;
+}
+
+extern "C" int v3s_peer_barrier(const unsigned long long* flag_ptrs, int rank, int world, int epoch, int* status_dev,
+                                void* stream) {
+  V3S_REQUIRE(flag_ptrs && world >= 1 && world <= 8 && rank >= 0 && rank < world, "v3s_peer_barrier: bad arguments");
+  if (world == 1) return 0;
+  PeerPtrs f;
+  load_peers(f, flag_ptrs, world);
+  peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(f, rank, world, epoch, status_dev);
+  V3S_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int v3s_matvec_combine(const float* P_rows, long long ldp, long long n_rows, long long N, long long row0,
+                                  const float* XfS, const double* Yk, const double* Ykm1, double alpha, double beta,
+                                  double gamma, const unsigned long long* yout_ptrs, const unsigned long long* xfout_ptrs,
+                                  int world, void* workspace, void* stream) {
+  V3S_REQUIRE(n_rows >= 0 && N >= 1 && ldp >= N && ldp % 4 == 0 && row0 >= 0 && row0 + n_rows <= N,
+              "v3s_matvec_combine: bad shape (ldp must be a multiple of 4)");
+  V3S_REQUIRE(((uintptr_t)P_rows & 15) == 0 && ((uintptr_t)XfS & 15) == 0, "v3s_matvec_combine: pointers must be 16-byte aligned");
+  V3S_REQUIRE(N < (1LL << 31) && n_rows < (1LL << 31), "v3s_matvec_combine: extents must fit int32");
+  V3S_REQUIRE(yout_ptrs && world >= 1 && world <= 8, "v3s_matvec_combine: 1..8 ranks, result pointers required");
+  if (n_rows == 0) return 0;
+  PeerPtrs yo, xo;
+  load_peers(yo, yout_ptrs, world);
+  load_peers(xo, xfout_ptrs, world);
+  double* Ypart = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(workspace) + mv_xf_bytes(N));
+  return mv_combine(P_rows, ldp, n_rows, N, row0, XfS, Yk, Ykm1, alpha, beta, gamma, yo, xo, world, xfout_ptrs != nullptr,
+                    Ypart, (cudaStream_t)stream);
+}
+
+// One application of the Chebyshev-filtered operator T_degree((P - c)/e) to the block Q, enqueued by
+// ONE host call:  Y1 = (P Q - c Q)/e,  Y_{k+1} = 2 (P Y_k - c Y_k)/e - Y_{k-1}.  Every step is
+// mat-vec kernel -> fused reduce/combine/scatter kernel -> (sharded) peer barrier; no collective.
+// ybuf_ptrs[b * world + r] = address of rotating result buffer b (0..2) on rank r ([N,8] FP64),
+// xf_ptrs[p * world + r]   = address of ping-pong FP32 strip operand p (0..1) on rank r.
+// Q may be one of the rotating buffers (q_index 0..2) or a separate block (q_index = -1).
+// *result_index = the rotating buffer that holds the result.
+extern "C" int v3s_cheb_filter(const float* P_rows, long long ldp, long long n_rows, long long N, long long row0,
+                               const float* Xf0, const double* Q, int q_index, int degree, double c, double e,
+                               const unsigned long long* ybuf_ptrs, const unsigned long long* xf_ptrs,
+                               const unsigned long long* flag_ptrs, int rank, int world, int epoch0, int* status_dev,
+                               void* workspace, int* result_index, void* stream) {
+  V3S_REQUIRE(degree >= 1 && q_index >= -1 && q_index <= 2 && e != 0.0, "v3s_cheb_filter: bad degree / buffer index / interval");
+  V3S_REQUIRE(ybuf_ptrs && xf_ptrs && world >= 1 && world <= 8 && rank >= 0 && rank < world && (world == 1 || flag_ptrs),
+              "v3s_cheb_filter: bad rank layout");
+  V3S_REQUIRE(n_rows >= 0 && N >= 1 && ldp >= N && ldp % 4 == 0 && row0 >= 0 && row0 + n_rows <= N && N < (1LL << 31),
+              "v3s_cheb_filter: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  double* Ypart = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(workspace) + mv_xf_bytes(N));
+  auto local_y = [&](int b) { return reinterpret_cast<const double*>(ybuf_ptrs[(size_t)b * world + rank]); };
+  auto local_x = [&](int p_) { return reinterpret_cast<const float*>(xf_ptrs[(size_t)p_ * world + rank]); };
+  int prev = -2, cur = q_index;                    // -2: none, -1: the external Q
+  const float* xin = Xf0;
+  for (int s = 1; s <= degree; ++s) {
+    int out = 0;
+    while (out == cur || out == prev) ++out;       // lowest rotating buffer not read by this step
+    PeerPtrs yo, xo;
+    load_peers(yo, ybuf_ptrs + (size_t)out * world, world);
+    const int write_xf = s < degree;
+    load_peers(xo, xf_ptrs + (size_t)(s & 1) * world, world);
+    const double* Yk = cur == -1 ? Q : local_y(cur);
+    const double* Ykm1 = prev == -2 ? nullptr : (prev == -1 ? Q : local_y(prev));
+    const double alpha = (s == 1 ? 1.0 : 2.0) / e, beta = (s == 1 ? -1.0 : -2.0) * c / e, gamma = s == 1 ? 0.0 : -1.0;
+    if (n_rows > 0)
+      if (int rc = mv_combine(P_rows, ldp, n_rows, N, row0, xin, Yk, Ykm1, alpha, beta, gamma, yo, xo, world, write_xf, Ypart, st))
+        return rc;
+    if (world > 1) {
+      PeerPtrs f;
+      load_peers(f, flag_ptrs, world);
+      peer_barrier_kernel<<<1, 32, 0, st>>>(f, rank, world, epoch0 + s, status_dev);
+      V3S_CHECK_LAUNCH();
+    }
+    xin = local_x(s & 1);
+    prev = cur;
+    cur = out;
+  }
+  if (result_index) *result_index = cur;
+  return 0;
+}
+
+extern "C" int v3s_profile_matvec(int enable) {
+  g_prof_on = enable != 0;
+  g_prof_used = 0;
+  return 0;
+}
+
+// Elapsed milliseconds of the block_matvec_kernel launches recorded since v3s_profile_matvec(1)
+// (synchronises on the last event); returns the number of launches, writes min(count, cap) values.
+extern "C" int v3s_profile_matvec_read(float* ms_out, int cap) {
+  const int n = (int)(g_prof_used / 2);
+  if (n > 0) cudaEventSynchronize(g_prof_ev[g_prof_used - 1]);
+  for (int i = 0; i < n && i < cap; ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, g_prof_ev[2 * i], g_prof_ev[2 * i + 1]) != cudaSuccess) ms = -1.f;
+    ms_out[i] = ms;
+  }
+  g_prof_used = 0;
+  return n;
 }

@@ -130,7 +130,7 @@ def _next_check(steps, res_max, target, prev, max_gap):
 
 
 def block_lanczos_device(ops, op, N, nev, tol=1e-8, max_dim=None, first_check=6, seed=0, max_gap=16,
-                         stats=None, start_block=None, both_ends=True, lock=None, want_theta_min=False):
+                         stats=None, start_block=None, both_ends=True, lock=None, want_theta_min=False, pre_sync=None):
     """Same algorithm as `block_lanczos_topk`, with every per-step operation enqueued on the GPU by
     the C-ABI (`v3s_lanczos_start` / `v3s_lanczos_step`, csrc/lanczos.cu): the host only launches,
     and reads back the small (A_j, B_j) blocks when it extracts Ritz pairs.
@@ -140,8 +140,12 @@ def block_lanczos_device(ops, op, N, nev, tol=1e-8, max_dim=None, first_check=6,
     returns [N,8] float64 (all-gathered when sharded), which the step overwrites with the next block.
     lock: optional [L,N] orthonormal rows (L a multiple of 8, zero rows allowed) that every block is
     kept orthogonal to -- converged eigenvectors of earlier runs (see `topk_with_locking`).
+    pre_sync: optional callable enqueuing a cross-rank barrier before the first step (operators that
+    store into peers' buffers, `FusedOperator.sync`).
     """
     b = 8
+    if pre_sync is not None:
+        pre_sync()
     if max_dim is None:
         max_dim = min(N, 1024)
     max_dim = max(b, (min(max_dim, N) // b) * b)
@@ -222,7 +226,7 @@ def block_lanczos_device(ops, op, N, nev, tol=1e-8, max_dim=None, first_check=6,
 
 
 def chebyshev_lanczos_device(ops, matvec_f32, matvec_f64, N, nev, tol=1e-8, degree=6, probe_steps=10, seed=0,
-                             stats=None, lock=None, safe_lower=False):
+                             stats=None, lock=None, safe_lower=False, fused=None):
     """Largest eigenpairs of the symmetric operator P by block Lanczos on a Chebyshev polynomial
     of P (device driver).  Clustered top eigenvalues (gaps ~1e-4 at N = 10^4) make plain Lanczos
     need a Krylov space of ~600 vectors, whose Ritz extraction is O(m^2 b) host work per check;
@@ -237,14 +241,18 @@ def chebyshev_lanczos_device(ops, matvec_f32, matvec_f64, N, nev, tol=1e-8, degr
       3. Rayleigh-Ritz of P itself on the converged subspace (eigenvalues of P, not of p(P)).
 
     matvec_f32: Xf [N,8] f32 -> P Xf [N,8] f64;  matvec_f64: X [N,b<=8] f64 -> P X.
+    fused: optional `FusedOperator` -- the mat-vecs of phases 1 and 2 then run through it (reduction,
+    recurrence and the cross-rank exchange inside the kernels, one host call per filter application).
     Falls back to plain largest-magnitude Lanczos when the probe shows a negative eigenvalue whose
     magnitude competes with the wanted ones (the filter targets the algebraically largest).
     """
     b = 8
     st1 = {}
-    plain_op = lambda Xf, Q: matvec_f32(Xf)
+    plain_op = (lambda Xf, Q: matvec_f32(Xf)) if fused is None else fused.plain
+    pre_sync = None if fused is None else fused.sync
     w0, Y0, res0 = block_lanczos_device(ops, plain_op, N, nev, tol=tol, max_dim=probe_steps * b, seed=seed,
-                                        first_check=probe_steps, stats=st1, both_ends=True, lock=lock, want_theta_min=True)
+                                        first_check=probe_steps, stats=st1, both_ends=True, lock=lock, want_theta_min=True,
+                                        pre_sync=pre_sync)
     n_mv = st1["matvecs"]
     info = {"probe_steps": st1["matvecs"], "degree": degree}
     if st1["converged"]:
@@ -252,7 +260,7 @@ def chebyshev_lanczos_device(ops, matvec_f32, matvec_f64, N, nev, tol=1e-8, degr
         info.update({"cheb_steps": 0, "krylov_dim": st1["krylov_dim"]})
     elif np.any(w0 < 0) or len(w0) < nev:
         st2 = {}
-        lam, Y, res = block_lanczos_device(ops, plain_op, N, nev, tol=tol, seed=seed, stats=st2, lock=lock)
+        lam, Y, res = block_lanczos_device(ops, plain_op, N, nev, tol=tol, seed=seed, stats=st2, lock=lock, pre_sync=pre_sync)
         if stats is not None:
             stats.update(st2)
             stats["matvecs"] += n_mv
@@ -268,9 +276,14 @@ def chebyshev_lanczos_device(ops, matvec_f32, matvec_f64, N, nev, tol=1e-8, degr
         if safe_lower is False and "theta_min" in st1:
             lo = max(-1.0, st1["theta_min"] - 0.15 * (float(np.max(w0)) - st1["theta_min"]))
         c, e = 0.5 * (cut + lo), 0.5 * (cut - lo)
-        bufs = [ops.empty((N, b), torch.float64) for _ in range(3)]
-        Xf = ops.alloc_xf(N)
         count = [0]
+        if fused is None:
+            bufs = [ops.empty((N, b), torch.float64) for _ in range(3)]
+            Xf = ops.alloc_xf(N)
+
+        def cheb_fused(Xf0, Q):
+            count[0] += degree
+            return fused.cheb(Xf0, Q, degree, c, e)
 
         def cheb_op(Xf0, Q):
             # Y0 = Q, Y1 = (P Y0 - c Y0)/e, Y_{k+1} = 2 (P Y_k - c Y_k)/e - Y_{k-1}
@@ -287,8 +300,9 @@ def chebyshev_lanczos_device(ops, matvec_f32, matvec_f64, N, nev, tol=1e-8, degr
         order = np.argsort(-w0, kind="stable")[:b]
         start = Y0[:, torch.as_tensor(order.copy(), device=Y0.device)].contiguous()
         st2 = {}
-        _, Y, res = block_lanczos_device(ops, cheb_op, N, nev, tol=tol, seed=seed, first_check=4, max_gap=4, stats=st2,
-                                         start_block=start, both_ends=False, lock=lock)
+        _, Y, res = block_lanczos_device(ops, cheb_op if fused is None else cheb_fused, N, nev, tol=tol, seed=seed,
+                                         first_check=4, max_gap=4, stats=st2, start_block=start, both_ends=False, lock=lock,
+                                         pre_sync=pre_sync)
         n_mv += count[0]
         info.update({"cheb_steps": st2["matvecs"], "krylov_dim": st2["krylov_dim"], "cut": cut,
                      "ritz_checks": st2["ritz_checks"], "converged": st2["converged"]})
@@ -309,7 +323,8 @@ def chebyshev_lanczos_device(ops, matvec_f32, matvec_f64, N, nev, tol=1e-8, degr
         if lo > -1.0 and float(np.min(lam)) < cut - 1e-6 * max(1.0, abs(cut)):
             # something from the supposedly damped region was amplified: the lower bound was not a bound
             return chebyshev_lanczos_device(ops, matvec_f32, matvec_f64, N, nev, tol=tol, degree=degree,
-                                            probe_steps=probe_steps, seed=seed, stats=stats, lock=lock, safe_lower=True)
+                                            probe_steps=probe_steps, seed=seed, stats=stats, lock=lock, safe_lower=True,
+                                            fused=fused)
     if stats is not None:
         stats.update(info)
         stats.update({"matvecs": n_mv, "block": b, "residual_max": float(np.max(res)), "driver": "device-chebyshev",

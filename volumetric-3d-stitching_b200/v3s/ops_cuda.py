@@ -38,16 +38,27 @@ class CudaOps:
         self._mv_ws = None
         self._sigma_ws = None
         self.gram_impl = "tcgen05"   # "simt" = FP32 CUDA-core validation path
-        self.profile = False         # when True, CUDA events bracket the named kernels (bench.py)
+        self._profile = False        # when True, CUDA events bracket the named kernels (bench.py)
         self._events = []
         self._synth_prep = {}
         self._sym_tile_cache = {}
         self._symm_G = {}
+        self.use_fused_matvec = True # eigen-solver mat-vecs with the reduction / recurrence / exchange fused (FusedOperator)
         self.use_peer_gram = True    # sharded jobs: symmetric Gram with NVLink peer stores (else rectangular panels)
         self.symm_error = None
         self._pin = None
 
     # ---- per-kernel device timing (CUDA events on the launching stream) ------------------------
+    @property
+    def profile(self):
+        return self._profile
+
+    @profile.setter
+    def profile(self, on):
+        # the mat-vec kernel is launched from inside multi-kernel C calls: its events are recorded by the library
+        self._profile = bool(on)
+        _lib.lib.v3s_profile_matvec(1 if on else 0)
+
     def _tic(self, name):
         if not self.profile:
             return None
@@ -68,6 +79,12 @@ class CudaOps:
         for name, e0, e1 in self._events:
             out.setdefault(name, []).append(e0.elapsed_time(e1))
         self._events = []
+        if self._profile:
+            cap = 1 << 16
+            buf = (C.c_float * cap)()
+            n = min(int(_lib.lib.v3s_profile_matvec_read(buf, cap)), cap)
+            if n:
+                out["matvec"] = [float(buf[i]) for i in range(n)]
         return out
 
     # ---- allocation helpers ---------------------------------------------------------------
@@ -343,9 +360,7 @@ class CudaOps:
         b = X.shape[1]
         ws = self._mv_workspace(n_rows, N)
         Y = self.empty((n_rows, b), torch.float64)
-        h = self._tic("matvec")
         call("v3s_block_matvec", ptr(P_rows), ldp, n_rows, N, ptr(X), b, ptr(Y), ptr(ws), stream_ptr())
-        self._toc(h)
         return Y
 
     def _mv_workspace(self, n_rows, N):
@@ -363,10 +378,19 @@ class CudaOps:
         n_rows, ldp = P_rows.shape
         Y = out if out is not None else self.empty((n_rows, 8), torch.float64)
         ws = self._mv_workspace(n_rows, N)
-        h = self._tic("matvec")
         call("v3s_block_matvec_f32", ptr(P_rows), ldp, n_rows, N, ptr(Xf), ptr(Y), ptr(ws), stream_ptr())
-        self._toc(h)
         return Y
+
+    def fused_operator(self, P_rows, N, plan=None):
+        """The eigen-solver's operator with the result exchange fused into the kernels (`FusedOperator`)."""
+        try:
+            return FusedOperator(self, P_rows, N, plan)
+        except Exception as e:                      # symmetric memory / peer access unavailable: NCCL path instead
+            if plan is None or plan.world == 1:
+                raise
+            self.symm_error = repr(e)
+            self._symm_G[("fused", int(N), plan.world, plan.rank)] = False
+            return None
 
     # device-side block-Lanczos state and steps (lanczos.cu)
     def lanczos_alloc(self, N, max_dim, max_steps):
@@ -438,3 +462,101 @@ class CudaOps:
         call("v3s_sigma_pairs", ptr(qe), ptr(qt), qe.shape[0], r0, r1 - r0, ptr(self._sigma_ws), ptr(out), stream_ptr())
         self._toc(h)
         return out
+
+
+class FusedOperator:
+    """P (and Chebyshev polynomials of P) applied to a Lanczos block with no collective and no
+    separate reduction / combination launches: `v3s_matvec_combine` / `v3s_cheb_filter` store each
+    rank's rows of the result -- FP64 block and FP32 operand of the next mat-vec -- straight into every
+    rank's buffers (NVLink peer mappings from torch symmetric memory when sharded) and order the steps
+    with `v3s_peer_barrier`.  One arena per (N, world) is cached on the ops object: three rotating
+    [N,8] FP64 result blocks, two ping-pong FP32 strip operands, the barrier flag words.
+
+    plain(Xf, Q) -> P X;  cheb(Xf, Q, degree, c, e) -> T_degree((P - c)/e) X;  both return one of the
+    rotating blocks (complete on every rank), never the block Q itself."""
+
+    def __init__(self, ops, P_rows, N, plan=None):
+        import torch.distributed as dist
+        self.ops, self.P_rows, self.N = ops, P_rows, int(N)
+        self.world = 1 if plan is None else plan.world
+        self.rank = 0 if plan is None else plan.rank
+        self.row0 = 0 if plan is None else plan.lo
+        self.group = None if plan is None else plan.group
+        if self.world > 8:
+            raise Exception("FusedOperator: at most 8 ranks (one NVLink domain)")
+        key = ("fused", self.N, self.world, self.rank)
+        arena = ops._symm_G.get(key)
+        if arena is False:
+            raise Exception("symmetric memory unavailable (earlier attempt failed)")
+        if arena is None:
+            xf_floats = int(_lib.lib.v3s_xf_floats(self.N))
+            y_bytes = round_up(self.N * 8 * 8, 256)
+            x_bytes = round_up(xf_floats * 4, 256)
+            total = 3 * y_bytes + 2 * x_bytes + 256
+            if self.world > 1:
+                import torch.distributed._symmetric_memory as symm
+                buf = symm.empty((total,), dtype=torch.uint8, device=ops.device)
+                hdl = symm.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
+                bases = [int(x) for x in hdl.buffer_ptrs]
+            else:
+                buf = torch.empty((total,), dtype=torch.uint8, device=ops.device)
+                bases = [buf.data_ptr()]
+            buf.zero_()                                   # strip padding columns and flag words start at zero
+            if self.world > 1:
+                torch.cuda.synchronize()
+                dist.barrier(group=self.group)            # nobody stores into a buffer that is still being zeroed
+            ybufs = [buf[b * y_bytes: b * y_bytes + self.N * 64].view(torch.float64).view(self.N, 8) for b in range(3)]
+            xfs = [buf[3 * y_bytes + q * x_bytes: 3 * y_bytes + q * x_bytes + xf_floats * 4].view(torch.float32) for q in range(2)]
+            flag_off = 3 * y_bytes + 2 * x_bytes
+            arena = {
+                "buf": buf, "ybufs": ybufs, "xfs": xfs,
+                "yptrs": (C.c_ulonglong * (3 * self.world))(*[bases[r] + b * y_bytes for b in range(3) for r in range(self.world)]),
+                "xptrs": (C.c_ulonglong * (2 * self.world))(*[bases[r] + 3 * y_bytes + q * x_bytes for q in range(2) for r in range(self.world)]),
+                "fptrs": (C.c_ulonglong * self.world)(*[bases[r] + flag_off for r in range(self.world)]),
+                "status": torch.zeros((1,), dtype=torch.int32, device=ops.device), "epoch": 0, "next_out": 0,
+            }
+            ops._symm_G[key] = arena
+        self.a = arena
+        self.n_matvec = 0
+
+    def _index_of(self, Q):
+        for b, t in enumerate(self.a["ybufs"]):
+            if t.data_ptr() == Q.data_ptr():
+                return b
+        return -1
+
+    def sync(self):
+        """Cross-rank barrier on the stream: everything this rank enqueued so far is complete before any
+        peer's later stores into this rank's buffers (phase changes of the solver)."""
+        if self.world > 1:
+            self.a["epoch"] += 1
+            call("v3s_peer_barrier", self.a["fptrs"], self.rank, self.world, self.a["epoch"], ptr(self.a["status"]), stream_ptr())
+
+    def plain(self, Xf, Q):
+        a, w = self.a, self.world
+        qi = self._index_of(Q)
+        out = min(b for b in range(3) if b != qi)
+        yout = (C.c_ulonglong * w)(*[a["yptrs"][out * w + r] for r in range(w)])
+        ws = self.ops._mv_workspace(self.P_rows.shape[0], self.N)
+        call("v3s_matvec_combine", ptr(self.P_rows), self.P_rows.shape[1], self.P_rows.shape[0], self.N, self.row0, ptr(Xf),
+             None, None, 1.0, 0.0, 0.0, yout, None, w, ptr(ws), stream_ptr())
+        self.sync()
+        self.n_matvec += 1
+        return a["ybufs"][out]
+
+    def cheb(self, Xf0, Q, degree, c, e):
+        a = self.a
+        res = C.c_int(0)
+        ws = self.ops._mv_workspace(self.P_rows.shape[0], self.N)
+        call("v3s_cheb_filter", ptr(self.P_rows), self.P_rows.shape[1], self.P_rows.shape[0], self.N, self.row0, ptr(Xf0),
+             ptr(Q), self._index_of(Q), int(degree), float(c), float(e), a["yptrs"], a["xptrs"], a["fptrs"], self.rank,
+             self.world, a["epoch"], ptr(a["status"]), ptr(ws), C.byref(res), stream_ptr())
+        if self.world > 1:
+            a["epoch"] += int(degree)
+        self.n_matvec += int(degree)
+        return a["ybufs"][res.value]
+
+    def check(self):
+        """Raise if a peer barrier timed out (one small D2H; call once after the solve)."""
+        if self.world > 1 and int(self.a["status"].item()) != 0:
+            raise Exception("v3s: a peer rank never reached the mat-vec barrier (status %d)" % int(self.a["status"].item()))

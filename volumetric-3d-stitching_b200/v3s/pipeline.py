@@ -141,11 +141,18 @@ def eigen_stage(ops, plan, P_rows, dis, nev=NEV, validate=True, tol=None, stats=
         def matvec_f32(Xf):
             return plan.all_gather_rows(ops.block_matvec_f32(P_rows, N, Xf, out=y_loc), out=w_all)
         tol_ = 1e-8 if tol is None else tol
+        # reduction + recurrence + cross-rank exchange inside the mat-vec's own kernels (no NCCL per step)
+        fused = ops.fused_operator(P_rows, N, plan) if (hasattr(ops, "fused_operator") and plan.world <= 8
+                                                        and getattr(ops, "use_fused_matvec", True)) else None
 
         def run(lock):
             st_ = {}
             if N >= 2048 and nev <= 16:
-                r = chebyshev_lanczos_device(ops, matvec_f32, matvec, N, nev, tol=tol_, stats=st_, seed=seed, lock=lock)
+                r = chebyshev_lanczos_device(ops, matvec_f32, matvec, N, nev, tol=tol_, stats=st_, seed=seed, lock=lock,
+                                             fused=fused)
+            elif fused is not None:
+                r = block_lanczos_device(ops, fused.plain, N, nev, tol=tol_, stats=st_, seed=seed, lock=lock,
+                                         pre_sync=fused.sync)
             else:
                 r = block_lanczos_device(ops, lambda Xf, Q: matvec_f32(Xf), N, nev, tol=tol_, stats=st_, seed=seed,
                                          lock=lock)
@@ -156,6 +163,12 @@ def eigen_stage(ops, plan, P_rows, dis, nev=NEV, validate=True, tol=None, stats=
             return r
 
         lam, V, _ = topk_with_locking(run, nev, stats=stats)
+        if fused is not None:
+            fused.sync()
+            if validate:
+                fused.check()
+            if stats is not None:
+                stats["fused_matvec"] = True
     else:
         lam, V, _ = block_lanczos_topk(matvec, N, nev, dev, tol=(1e-8 if tol is None else tol), stats=stats, seed=seed)
     V = -V                                                   # diffusion.py:62 (sign is arbitrary upstream)
