@@ -281,25 +281,32 @@ def main():
     sigma_T = float(out["sigma_T"].item())
     lam = out["Lambda"].cpu().numpy()
 
-    # ---- e2e: reference-facing call, host inputs -> host outputs (rank 0 of a 1-GPU run) ----
+    # ---- e2e: reference-facing call, host inputs -> host outputs, on every rank of the job ----
     e2e = None
-    if world == 1 and not args.no_e2e:
+    if not args.no_e2e:
         params = {"n_voxel_1d": n, "nRot1D": 22, "k": k, "Epsilon": eps, "plot": False, "aPrioriFlag": True}
         def call():
             with contextlib.redirect_stdout(io.StringIO()):
-                return OrientationRecoverySolver.solve(params, rotations=R9, N_p=n_p, check_sigma=False)
+                return OrientationRecoverySolver.solve(params, rotations=R9, N_p=n_p, check_sigma=False,
+                                                       photons_per_pattern=wl.get("photons"))
         for _ in range(2):
             res = call()
-        torch.cuda.synchronize()
+        barrier()
         t0 = time.perf_counter()
         reps = max(2, min(args.steps, 3))
         for _ in range(reps):
             res = call()
-        torch.cuda.synchronize()
-        e2e_s = (time.perf_counter() - t0) / reps
+        barrier()
+        t_e2e = torch.tensor([(time.perf_counter() - t0) / reps], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+        e2e_s = float(t_e2e.item())
+        # bytes actually copied: rotations (two layouts) + object in; the pattern rows travel as FP32 (widened
+        # to the reference's float64 on the host), everything else as FP64
         h2d = R9.nbytes * 2 + ed.numel() * 4
-        d2h = sum(v.nbytes for kk_, v in res.items() if kk_ not in ("R", "Axis", "Quat"))
-        e2e = {"value": round(e2e_s, 5), "unit": "s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
+        d2h = res["Images"].size * 4 + sum(v.nbytes for kk_, v in res.items() if kk_ not in ("R", "Axis", "Quat", "Images", "rows", "c0"))
+        e2e = {"value": round(e2e_s, 5), "unit": "s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "note": "OrientationRecoverySolver.solve with numpy inputs/outputs on each rank; max over ranks; bytes per rank"}
 
     if rank != 0:
         if world > 1:

@@ -238,6 +238,13 @@ int v3s_fit_solve(const double* in162, double* c81, void* stream);
  * polar_mode 0: U.Vh^T (reference form), 1: U.Vh, 2: nearest rotation.                          */
 int v3s_fit_project(const double* Ps, int ldx, const double* Y, long long n_rows, const double* c81, int polar_mode,
                     double* recon_pre, double* rproj, double* quat_est, double* quat_true, void* stream);
+/* DiffusionMapSolver.or_func (diffusion.py:265-287; src/octave/CalculateDiffusion.m:136-157): the
+ * rotation-matrix constraint residuals of the fit without known orientations, G [n_rows], for
+ * C = c81 (row-major 9x9) and psi_l = Ps[l,1:10]; r_total = the r of the 1/sqrt(r) factor (N when
+ * sharded); form 0 = the Python expression, 1 = the Octave expression.  J (may be NULL) [n_rows,81]
+ * = forward-difference Jacobian with steps rel_step * max(1,|c_p|) (scipy least_squares '2-point'). */
+int v3s_or_func(const double* c81, const double* Ps, int ldx, long long n_rows, long long r_total, int form,
+                double rel_step, double* G, double* J, void* stream);
 /* Rotation.mean_geodesic_distance (rotation.py:228-244) inner sum over rows [row0,row0+n_rows)
  * against all N columns; partials_ws: 65536 doubles; out_sum[0] = sum |acos - acos|.            */
 int v3s_sigma_pairs(const double* quat_est, const double* quat_true, long long N, long long row0, long long n_rows,

@@ -681,3 +681,32 @@ def solve(parameters, check=True):
     c, c0, Sigma_T = dm_fit_all(Ps, R, parameters["aPrioriFlag"], check=check)
     return {"Ps": Ps, "Lambda": Lambda, "c0": c0, "c": c, "S2": S2, "N": N, "Images": Images,
             "R": R, "Sigma_T": np.array([Sigma_T]), "Axis": Axis.T, "Quat": Quat.T}
+
+
+# ------------------------------------------------------------------------------------------
+# fit WITHOUT known orientations.  Parity unpinned for this block: the Python
+# reference's branch cannot run (diffusion.py:231 `np.random.rand((81, 1))` and :283 `math.abs`
+# raise), Octave is not available here; the functions restate the code as written, minus the two
+# defects, and `form="octave"` gives src/octave/CalculateDiffusion.m:136-157.
+# ------------------------------------------------------------------------------------------
+
+def or_func(c, PsMod, form="python"):
+    """diffusion.py:265-287: rotation-matrix constraint residuals G (r,) for C = c.reshape(9,9) and
+    PsMod = Ps[:, 1:10].T (9, r)."""
+    r = PsMod.shape[1]
+    C = np.asarray(c, dtype=np.float64).reshape(9, 9)
+    RB = (C @ PsMod).T.reshape(-1, 3, 3)                      # R = R_Big[:, l].reshape((3, 3))
+    T = np.einsum('nki,nkj->nij', RB, RB) - np.eye(3)         # R.T @ R - I
+    s2 = np.sum(T * T, axis=(1, 2))
+    d = np.abs(np.linalg.det(RB) - 1.0)
+    G = np.sqrt(s2 + d) if form == "python" else np.sqrt(s2) + d     # diffusion.py:283 / CalculateDiffusion.m:153
+    return np.sqrt(G) / math.sqrt(r)                          # diffusion.py:285
+
+
+def fit_without_prior(Ps, x0, form="python", max_nfev=250):
+    """diffusion.py:124-141: scipy least_squares (trust-region reflective) on or_func from x0 (81,);
+    -> c = pinv(c_1D.reshape(9,9)), c0 = pinv((x0/5).reshape(9,9)), final cost."""
+    from scipy.optimize import least_squares
+    X = np.asarray(Ps, dtype=np.float64)[:, 1:10]
+    res = least_squares(or_func, np.asarray(x0, dtype=np.float64).ravel(), args=(X.T, form), method='trf', max_nfev=max_nfev)
+    return np.linalg.pinv(res.x.reshape(9, 9)), np.linalg.pinv((np.asarray(x0).ravel() / 5.0).reshape(9, 9)), float(res.cost), res.x

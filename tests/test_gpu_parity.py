@@ -493,6 +493,42 @@ def test_fit_connected(v3s_mod, golden_dir):
         v3s_mod.DiffusionMapSolver.dm_fit_all(g["Ps"], g["R9"], False)
 
 
+def test_or_func_and_fit_without_prior(v3s_mod, ops, golden_dir):
+    """the constraint residuals of the fit without known orientations against the
+    oracle's restatement (both the Python and the Octave expression), the kernel's forward-difference
+    Jacobian against central differences of the oracle, and the device Levenberg-Marquardt fit against
+    scipy's trust-region fit of the same functional from the same start (same minimum, other path)."""
+    g = np.load(os.path.join(golden_dir, "connected_n15.npz"))
+    Ps = g["Ps"]
+    X = Ps[:, 1:10]
+    rng = np.random.default_rng(5)
+    for form in ("python", "octave"):
+        for trial in range(3):
+            c = rng.standard_normal(81) * (1.0 if trial else 5.0)
+            G = v3s_mod.or_func(c, X.T, form=form)
+            Go = orc.or_func(c, X.T, form=form)
+            assert G.shape == Go.shape and np.max(np.abs(G - Go)) < 1e-12 * max(1.0, np.max(np.abs(Go)))
+    c = g["c"].T.ravel() * (1 + 0.05 * rng.standard_normal(81))
+    _, J = ops.or_func(ops.to_device(c, torch.float64), ops.to_device(Ps, torch.float64), Ps.shape[0], 0, want_jac=True)
+    J = J.cpu().numpy()
+    for p_ in (0, 13, 40, 80):
+        h = 1e-6 * max(1.0, abs(c[p_]))
+        e = np.zeros(81)
+        e[p_] = h
+        col = (orc.or_func(c + e, X.T) - orc.or_func(c - e, X.T)) / (2 * h)
+        assert np.max(np.abs(J[:, p_] - col)) < 1e-4 * max(np.max(np.abs(col)), 1e-12)
+    x0 = 5.0 * np.random.default_rng(0).random(81)                                  # diffusion.py:231 start (c_scale * rand)
+    info = {}
+    c_fit, c0_fit, cost = v3s_mod.fit_without_prior(Ps, x0=x0, info=info)
+    c_ref, c0_ref, cost_ref, _ = orc.fit_without_prior(Ps, x0)
+    print("fit without prior: cost %.5f (%d iterations) vs scipy trf %.5f; at the a-priori c %.5f"
+          % (cost, info["iterations"], cost_ref, 0.5 * np.sum(orc.or_func(g["c"].T.ravel(), X.T) ** 2)))
+    assert np.allclose(c0_fit, c0_ref, rtol=1e-9, atol=1e-12)
+    assert cost <= 1.03 * cost_ref + 1e-12
+    assert abs(0.5 * np.sum(orc.or_func(info["x"], X.T) ** 2) - cost) < 1e-10 * max(cost, 1.0)   # the kernel's cost is the oracle's
+    assert np.allclose(c_fit, np.linalg.pinv(info["x"].reshape(9, 9)))
+
+
 # ------------------------------------------------------------------ whole path
 
 def test_solve_connected_end_to_end(v3s_mod, golden_dir):

@@ -245,6 +245,65 @@ __global__ void sum_partials_kernel(const double* __restrict__ partials, int n, 
   if (threadIdx.x == 0) out[0] = acc * scale;
 }
 
+// ---- rotation-matrix constraint functional of the fit WITHOUT known orientations -----------------
+// DiffusionMapSolver.or_func (diffusion.py:265-287; src/octave/CalculateDiffusion.m:136-157):
+//   R_l = reshape(C psi_l, 3, 3),  T = R_l^T R_l - I,
+//   form 0 (the Python expression):  g_l = (sum T^2 + |det R_l - 1|)^(1/4) / sqrt(r)
+//   form 1 (the Octave expression):  g_l = (sqrt(sum T^2) + |det R_l - 1|)^(1/2) / sqrt(r)
+// C = c.reshape(9,9) row-major (numpy), psi_l = Ps[l, 1:10].  ||R^T R - I||_F and det R do not depend on
+// whether the 9-vector is folded row- or column-major, so Octave's column-major reshape gives the same g.
+__device__ __forceinline__ double or_value(const double* R, int form, double inv_sqrt_r) {
+  double s2 = 0.0;
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      const double t = R[a] * R[b] + R[3 + a] * R[3 + b] + R[6 + a] * R[6 + b] - (a == b ? 1.0 : 0.0);   // (R^T R - I)[a][b]
+      s2 = fma(t, t, s2);
+    }
+  const double det = R[0] * (R[4] * R[8] - R[5] * R[7]) - R[1] * (R[3] * R[8] - R[5] * R[6]) + R[2] * (R[3] * R[7] - R[4] * R[6]);
+  const double d = fabs(det - 1.0);
+  const double inner = form == 0 ? sqrt(s2 + d) : sqrt(s2) + d;
+  return sqrt(inner) * inv_sqrt_r;
+}
+
+// G [n] and (optional) the forward-difference Jacobian J [n,81] with step h_p = rel_step * max(1,|c_p|)
+// (scipy.optimize.least_squares '2-point'); one thread per pattern, c in shared memory.
+__global__ void __launch_bounds__(128)
+or_func_kernel(const double* __restrict__ c81, const double* __restrict__ Ps, int ldx, long long n, long long r_total,
+               int form, double rel_step, double* __restrict__ G, double* __restrict__ J) {
+  __shared__ double cs[81];
+  if (threadIdx.x < 81) cs[threadIdx.x] = c81[threadIdx.x];
+  __syncthreads();
+  const long long l = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (l >= n) return;
+  const double inv_sqrt_r = 1.0 / sqrt((double)r_total);
+  double psi[9], R[9];
+#pragma unroll
+  for (int q = 0; q < 9; ++q) psi[q] = Ps[l * ldx + 1 + q];
+#pragma unroll
+  for (int a = 0; a < 9; ++a) {
+    double v = 0.0;
+#pragma unroll
+    for (int q = 0; q < 9; ++q) v = fma(cs[a * 9 + q], psi[q], v);
+    R[a] = v;
+  }
+  const double g0 = or_value(R, form, inv_sqrt_r);
+  G[l] = g0;
+  if (!J) return;
+  for (int a = 0; a < 9; ++a) {
+    const double keep = R[a];
+    for (int q = 0; q < 9; ++q) {
+      const double cp = cs[a * 9 + q];
+      const double h = rel_step * fmax(1.0, fabs(cp));
+      const double cph = cp + h;                       // the step actually taken in floating point
+      R[a] = keep + (cph - cp) * psi[q];
+      J[l * 81 + a * 9 + q] = (or_value(R, form, inv_sqrt_r) - g0) / (cph - cp);
+    }
+    R[a] = keep;
+  }
+}
+
 }  // namespace v3s
 
 using namespace v3s;
@@ -294,6 +353,16 @@ extern "C" int v3s_sigma_pairs(const double* quat_est, const double* quat_true, 
   sigma_pairs_kernel<<<dim3(gx, gy), SG_T, 0, st>>>(quat_est, quat_true, N, row0, n_rows, partials_ws);
   V3S_CHECK_LAUNCH();
   sum_partials_kernel<<<1, 256, 0, st>>>(partials_ws, gx * gy, 1.0, out_sum);
+  V3S_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int v3s_or_func(const double* c81, const double* Ps, int ldx, long long n_rows, long long r_total, int form,
+                           double rel_step, double* G, double* J, void* stream) {
+  V3S_REQUIRE(c81 && Ps && G && ldx >= 10 && n_rows >= 0 && r_total >= 1 && (form == 0 || form == 1),
+              "v3s_or_func: bad arguments (Ps needs the trivial + 9 non-trivial columns)");
+  if (n_rows == 0) return 0;
+  or_func_kernel<<<(int)ceil_div64(n_rows, 128), 128, 0, (cudaStream_t)stream>>>(c81, Ps, ldx, n_rows, r_total, form, rel_step, G, J);
   V3S_CHECK_LAUNCH();
   return 0;
 }

@@ -14,7 +14,8 @@ from .distance import DistanceMatrix
 from .projection import Projector
 from .rotation import Rotation
 from .solution import OrientationRecoverySolver
-from .extras import load_stage_outputs, orientation_errors_deg, save_stage_outputs
+from .extras import fit_without_prior, load_stage_outputs, or_func, orientation_errors_deg, save_stage_outputs
 
 __all__ = ["Projector", "DistanceMatrix", "DiffusionMapSolver", "OrientationRecoverySolver", "Rotation",
-           "ComputeUtils", "save_stage_outputs", "load_stage_outputs", "orientation_errors_deg"]
+           "ComputeUtils", "save_stage_outputs", "load_stage_outputs", "orientation_errors_deg",
+           "or_func", "fit_without_prior"]

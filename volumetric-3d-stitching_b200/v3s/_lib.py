@@ -70,6 +70,7 @@ SIGNATURES = {
     "v3s_fit_gram": (i32, [p, i32, p, i64, p, p]),
     "v3s_fit_solve": (i32, [p, p, p]),
     "v3s_fit_project": (i32, [p, i32, p, i64, p, i32, p, p, p, p, p]),
+    "v3s_or_func": (i32, [p, p, i32, i64, i64, i32, f64, p, p, p]),
     "v3s_sigma_pairs": (i32, [p, p, i64, i64, i64, p, p, p]),
 }
 

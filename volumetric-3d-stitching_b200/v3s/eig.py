@@ -75,8 +75,18 @@ def _ritz_from_band_impl(band, m, b, nev, both_ends=True):
     for i in range(1, b + 1):
         Tb[i, max(m - i, 0):] = 0.0
     want = min(nev, m)
-    if m <= 200:
-        w, S = sla.eig_banded(Tb, lower=True)
+    if m <= 320:
+        # small projected matrices: dense LAPACK on the m x m matrix (dsyevr on the wanted end only when
+        # the caller targets the algebraically largest) beats the banded driver with vectors
+        T = np.zeros((m, m))
+        for i in range(b + 1):
+            ii = np.arange(m - i)
+            T[ii + i, ii] = Tb[i, : m - i]
+        if both_ends or m <= want:
+            w, S = sla.eigh(T, lower=True, check_finite=False, overwrite_a=True)
+            _ritz_from_band_impl.last_min = float(w[0])
+        else:
+            w, S = sla.eigh(T, lower=True, check_finite=False, overwrite_a=True, subset_by_index=[m - want, m - 1])
         idx = np.argsort(-np.abs(w), kind="stable")[:want]
         return w[idx], S[:, idx]
     w = sla.eig_banded(Tb, lower=True, eigvals_only=True, select="i", select_range=(m - want, m - 1))
@@ -112,12 +122,21 @@ def _ritz_from_band_impl(band, m, b, nev, both_ends=True):
     return wz[idx], Q @ Z[:, idx]
 
 
+_FILL_IDX = {}
+
+
 def _fill_band(band, b, m_of_block, blk):
-    for c in range(b):
-        col = m_of_block - b + c
-        for i in range(0, b + 1):
-            r = c + i                           # row offset inside the [A; B] stack
-            band[i, col] = blk[r, c] if (r < b or (r - b) <= c) else 0.0
+    """Columns [m_of_block-b, m_of_block) of the lower band storage from the step's [A_j; B_j] stack
+    (A_j symmetric b x b, B_j upper triangular): band[i, col_c] = stack[c + i, c]."""
+    idx = _FILL_IDX.get(b)
+    if idx is None:
+        c = np.arange(b)[None, :]
+        i = np.arange(b + 1)[:, None]
+        r = c + i
+        idx = (r, np.broadcast_to(c, r.shape), (r < b) | ((r - b) <= c))
+        _FILL_IDX[b] = idx
+    r, c, keep = idx
+    band[:, m_of_block - b:m_of_block] = np.where(keep, blk[r, c], 0.0)
 
 
 def _next_check(steps, res_max, target, prev, max_gap):
@@ -130,7 +149,8 @@ def _next_check(steps, res_max, target, prev, max_gap):
 
 
 def block_lanczos_device(ops, op, N, nev, tol=1e-8, max_dim=None, first_check=6, seed=0, max_gap=16,
-                         stats=None, start_block=None, both_ends=True, lock=None, want_theta_min=False, pre_sync=None):
+                         stats=None, start_block=None, both_ends=True, lock=None, want_theta_min=False, pre_sync=None,
+                         step_cost_s=None):
     """Same algorithm as `block_lanczos_topk`, with every per-step operation enqueued on the GPU by
     the C-ABI (`v3s_lanczos_start` / `v3s_lanczos_step`, csrc/lanczos.cu): the host only launches,
     and reads back the small (A_j, B_j) blocks when it extracts Ritz pairs.
@@ -142,6 +162,8 @@ def block_lanczos_device(ops, op, N, nev, tol=1e-8, max_dim=None, first_check=6,
     kept orthogonal to -- converged eigenvectors of earlier runs (see `topk_with_locking`).
     pre_sync: optional callable enqueuing a cross-rank barrier before the first step (operators that
     store into peers' buffers, `FusedOperator.sync`).
+    step_cost_s: optional estimate of the device time of one step (operator + orthogonalisation); sizes
+    the speculation that hides the host's Ritz extraction.  Must be identical on every rank.
     """
     b = 8
     if pre_sync is not None:
@@ -177,18 +199,34 @@ def block_lanczos_device(ops, op, N, nev, tol=1e-8, max_dim=None, first_check=6,
         steps += 1
 
     n_spec = 0
+    _ritz_from_band_impl.last_min = None
+    # The host's Ritz extraction (~1 ms) is hidden behind speculative Lanczos steps.  How many: enough to
+    # cover a model of the host time (grows with m^2) with the caller's estimate of the device time per
+    # step -- both deterministic, so every rank of a sharded job takes the same decision -- but one only
+    # when the observed convergence rate predicts that this check is the last (its speculative steps are
+    # then wasted device time in front of the next stage).
+    rate = None
     while True:
         do_step()
         last = (m + b > max_dim)
         if steps >= next_check or last:
-            # snapshot the new (A_j, B_j) blocks asynchronously, keep the GPU busy with one speculative
-            # step while the host extracts Ritz pairs, then wait for the snapshot only
+            # snapshot the new (A_j, B_j) blocks asynchronously, keep the GPU busy with speculative
+            # steps while the host extracts Ritz pairs, then wait for the snapshot only
             s_chk, m_chk = steps, m
             snap = ops.lanczos_snapshot(st, copied, s_chk)
-            if not last and m + 2 * b <= max_dim:
-                m += b
-                do_step()
-                n_spec += 1
+            want_spec = 1
+            if step_cost_s is not None and step_cost_s > 0:
+                host_model_s = 4e-4 + 9e-4 * (m_chk / 128.0) ** 2
+                want_spec = int(min(2, max(1, np.ceil(host_model_s / step_cost_s))))
+                if rate is not None and prev is not None:
+                    predicted = prev[1] * np.exp(-rate * (s_chk - prev[0]))
+                    if predicted <= 10.0 * tol * max(np.abs(w).max(), 1e-300):
+                        want_spec = 1
+            for _ in range(want_spec):
+                if not last and m + 2 * b <= max_dim:
+                    m += b
+                    do_step()
+                    n_spec += 1
             t0 = time.perf_counter()
             blks, status = ops.lanczos_snapshot_wait(snap)
             HOST_TIMERS["wait_s"] += time.perf_counter() - t0
@@ -207,17 +245,22 @@ def block_lanczos_device(ops, op, N, nev, tol=1e-8, max_dim=None, first_check=6,
             if res.max() <= target or last or m + b > max_dim:
                 m = m_chk
                 break
+            if prev is not None and res.max() < prev[1] and s_chk > prev[0]:
+                rate = np.log(prev[1] / res.max()) / (s_chk - prev[0])
             next_check = max(steps + 1, _next_check(s_chk, res.max(), target, prev, max_gap))
             prev = (s_chk, res.max())
         m += b
     St = torch.from_numpy(np.ascontiguousarray(S)).to(ops.device)
     Y = st["V"][L:L + m].T @ St
     if stats is not None and want_theta_min:
-        Tb = band[:, :m].copy()
-        for i in range(1, b + 1):
-            Tb[i, max(m - i, 0):] = 0.0
-        with _one_thread():
-            stats["theta_min"] = float(sla.eig_banded(Tb, lower=True, eigvals_only=True, select="i", select_range=(0, 0))[0])
+        if both_ends and m <= 320 and getattr(_ritz_from_band_impl, "last_min", None) is not None:
+            stats["theta_min"] = _ritz_from_band_impl.last_min     # the last check diagonalised this very matrix
+        else:
+            Tb = band[:, :m].copy()
+            for i in range(1, b + 1):
+                Tb[i, max(m - i, 0):] = 0.0
+            with _one_thread():
+                stats["theta_min"] = float(sla.eig_banded(Tb, lower=True, eigvals_only=True, select="i", select_range=(0, 0))[0])
     if stats is not None:
         stats.update({"matvecs": steps, "block": b, "krylov_dim": m, "ritz_checks": n_checks, "speculative_steps": n_spec,
                       "residual_max": float(res.max()),
@@ -226,7 +269,7 @@ def block_lanczos_device(ops, op, N, nev, tol=1e-8, max_dim=None, first_check=6,
 
 
 def chebyshev_lanczos_device(ops, matvec_f32, matvec_f64, N, nev, tol=1e-8, degree=6, probe_steps=10, seed=0,
-                             stats=None, lock=None, safe_lower=False, fused=None):
+                             stats=None, lock=None, safe_lower=False, fused=None, matvec_cost_s=None):
     """Largest eigenpairs of the symmetric operator P by block Lanczos on a Chebyshev polynomial
     of P (device driver).  Clustered top eigenvalues (gaps ~1e-4 at N = 10^4) make plain Lanczos
     need a Krylov space of ~600 vectors, whose Ritz extraction is O(m^2 b) host work per check;
@@ -302,7 +345,8 @@ def chebyshev_lanczos_device(ops, matvec_f32, matvec_f64, N, nev, tol=1e-8, degr
         st2 = {}
         _, Y, res = block_lanczos_device(ops, cheb_op if fused is None else cheb_fused, N, nev, tol=tol, seed=seed,
                                          first_check=4, max_gap=4, stats=st2, start_block=start, both_ends=False, lock=lock,
-                                         pre_sync=pre_sync)
+                                         pre_sync=pre_sync,
+                                         step_cost_s=(None if matvec_cost_s is None else degree * matvec_cost_s + 1e-4))
         n_mv += count[0]
         info.update({"cheb_steps": st2["matvecs"], "krylov_dim": st2["krylov_dim"], "cut": cut,
                      "ritz_checks": st2["ritz_checks"], "converged": st2["converged"]})
@@ -310,11 +354,14 @@ def chebyshev_lanczos_device(ops, matvec_f32, matvec_f64, N, nev, tol=1e-8, degr
         PY = torch.cat([matvec_f64(Y[:, j:j + b].contiguous()) for j in range(0, Y.shape[1], b)], dim=1)
         n_mv += (Y.shape[1] + b - 1) // b
         H = Y.T @ PY
-        lam_t, Z = torch.linalg.eigh(0.5 * (H + H.T))
+        # nev x nev eigenproblem on the host (a device syevd is ~10 latency-bound launches plus its own sync)
+        Hh = H.cpu().numpy()
+        lam_h, Zh = np.linalg.eigh(0.5 * (Hh + Hh.T))
+        Z = torch.from_numpy(Zh).to(Y.device)
+        lam_t = torch.from_numpy(lam_h).to(Y.device)
         Y = Y @ Z
         R = PY @ Z - Y * lam_t[None, :]
-        both = torch.stack([lam_t, torch.linalg.norm(R, dim=0)]).cpu().numpy()      # one D2H
-        lam, res = both[0], both[1]
+        lam, res = lam_h, torch.linalg.norm(R, dim=0).cpu().numpy()
         idx = np.argsort(-np.abs(lam), kind="stable")
         lam, res = lam[idx], res[idx]
         Y = Y[:, torch.as_tensor(idx.copy(), device=Y.device)]
@@ -324,7 +371,7 @@ def chebyshev_lanczos_device(ops, matvec_f32, matvec_f64, N, nev, tol=1e-8, degr
             # something from the supposedly damped region was amplified: the lower bound was not a bound
             return chebyshev_lanczos_device(ops, matvec_f32, matvec_f64, N, nev, tol=tol, degree=degree,
                                             probe_steps=probe_steps, seed=seed, stats=stats, lock=lock, safe_lower=True,
-                                            fused=fused)
+                                            fused=fused, matvec_cost_s=matvec_cost_s)
     if stats is not None:
         stats.update(info)
         stats.update({"matvecs": n_mv, "block": b, "residual_max": float(np.max(res)), "driver": "device-chebyshev",

@@ -5,7 +5,11 @@
   with the result map of `OrientationRecoverySolver.solve`, so a run can be resumed or cross-checked;
 * a *correct* orientation metric next to the bug-compatible Sigma_T: per-pattern geodesic error of
   the recovered rotations after the best global alignment (the diffusion map fixes orientations only
-  up to one global rotation / reflection of the frame).
+  up to one global rotation / reflection of the frame);
+* the orientation fit WITHOUT known orientations (`or_func`, `fit_without_prior`): dead code in the
+  Python reference (diffusion.py:124-141, 228-240, 265-287 raise before doing anything), live in
+  Octave (src/octave/CalculateDiffusion.m:29-38, 136-157).  `DiffusionMapSolver.dm_fit_all(..., False)`
+  keeps raising like the reference; these are separate entry points.
 """
 import numpy as np
 import torch
@@ -54,3 +58,79 @@ def orientation_errors_deg(Recon, R_true):
     tr = torch.einsum('nij,nij->n', Re, Rt @ A)
     ang = torch.rad2deg(torch.arccos(torch.clamp((tr - 1) / 2, -1, 1)))
     return ang.cpu().numpy()
+
+
+def or_func(c, PsMod, form="python"):
+    """DiffusionMapSolver.or_func (diffusion.py:265-287): residuals G (r,) of the rotation-matrix
+    constraints for C = c.reshape(9,9) and PsMod = Ps[:, 1:10].T (9, r).  form "octave" evaluates
+    src/octave/CalculateDiffusion.m:153 instead of diffusion.py:283 (they differ in a parenthesis)."""
+    ops = _util.get_ops()
+    X = _util.to_dev(PsMod, torch.float64).T
+    Ps = torch.cat([torch.zeros((X.shape[0], 1), dtype=torch.float64, device=X.device), X], dim=1).contiguous()
+    cd = _util.to_dev(np.asarray(c, dtype=np.float64).reshape(81) if not _util.is_torch(c) else c.reshape(81), torch.float64)
+    G, _ = ops.or_func(cd, Ps, Ps.shape[0], 0 if form == "python" else 1, want_jac=False)
+    return _util.back(G, PsMod)
+
+
+def fit_without_prior(Ps, x0=None, c_scale=5.0, seed=0, max_iter=250, form="python", ftol=1e-10, xtol=1e-10, info=None):
+    """The `aPrioriFlag=False` branch of dm_fit_all as written upstream (diffusion.py:124-141;
+    CalculateDiffusion.m:29-38): minimise sum or_func(C)^2 over the 81 entries of C from
+    x0 = c_scale * rand(81), then c = pinv(C), c0 = pinv(x0 / c_scale).  The residuals and their
+    forward-difference Jacobian are one CUDA kernel (csrc/fit.cu `or_func_kernel`); the 81 x 81
+    Levenberg-Marquardt system is solved on the host (upstream: scipy 'trf' / lsqnonlin -- another
+    trust-region least-squares method, so iterates differ while the minimised functional is the same).
+    -> [c (9,9), c0 (9,9), cost]; `info` (dict) receives iterations / final x."""
+    ops = _util.get_ops()
+    Psd = _util.to_dev(Ps, torch.float64)
+    if Psd.shape[1] < 10:
+        raise Exception('Ps needs the trivial + 9 non-trivial eigenvectors (10 columns)')
+    n = Psd.shape[0]
+    if x0 is None:
+        x0 = c_scale * np.random.default_rng(seed).random(81)
+    x0 = np.asarray(x0, dtype=np.float64).reshape(81).copy()
+    fm = 0 if form == "python" else 1
+    x = x0.copy()
+
+    def evaluate(xv, jac):
+        G, J = ops.or_func(ops.to_device(xv, torch.float64), Psd, n, fm, want_jac=jac)
+        if not jac:
+            return float((G @ G).item()) * 0.5, None, None
+        pack = torch.cat([(J.T @ J).reshape(-1), J.T @ G, (G @ G).reshape(1)]).cpu().numpy()      # one D2H
+        return 0.5 * pack[-1], pack[:81 * 81].reshape(81, 81), pack[81 * 81:81 * 81 + 81]
+
+    cost, A, g = evaluate(x, True)
+    mu = 1e-3 * max(np.max(np.diag(A)), 1e-300)
+    it, nfev = 0, 1
+    while it < max_iter:
+        it += 1
+        D = np.maximum(np.diag(A), 1e-12 * np.max(np.diag(A)))
+        accepted = False
+        for _ in range(12):
+            try:
+                dx = np.linalg.solve(A + mu * np.diag(D / np.max(D)), -g)
+            except np.linalg.LinAlgError:
+                mu *= 4.0
+                continue
+            new_cost, _, _ = evaluate(x + dx, False)
+            nfev += 1
+            pred = -(g @ dx) - 0.5 * dx @ (A @ dx)
+            rho = (cost - new_cost) / max(pred, 1e-300)
+            if new_cost < cost and np.isfinite(new_cost):
+                accepted = True
+                mu *= max(1.0 / 3.0, 1.0 - (2.0 * rho - 1.0) ** 3)
+                break
+            mu *= 2.5
+        if not accepted:
+            break
+        small_step = np.linalg.norm(dx) <= xtol * (xtol + np.linalg.norm(x))
+        small_gain = (cost - new_cost) <= ftol * cost
+        x = x + dx
+        cost, A, g = evaluate(x, True)
+        nfev += 1
+        if small_step or small_gain:
+            break
+    if info is not None:
+        info.update({"iterations": it, "nfev": nfev, "x": x, "x0": x0, "cost": cost})
+    c = np.linalg.pinv(x.reshape(9, 9))
+    c0 = np.linalg.pinv((x0 / c_scale).reshape(9, 9))
+    return [c, c0, cost]

@@ -454,6 +454,16 @@ class CudaOps:
              ptr(qt), stream_ptr())
         return recon, rproj, qe, qt
 
+    def or_func(self, c81, Ps, r_total, form=0, want_jac=True, rel_step=1.4901161193847656e-08):
+        """Residuals G [n] of DiffusionMapSolver.or_func and (optionally) its forward-difference
+        Jacobian J [n,81] (rel_step = sqrt(eps), scipy's '2-point' default)."""
+        n = Ps.shape[0]
+        G = self.empty((n,), torch.float64)
+        J = self.empty((n, 81), torch.float64) if want_jac else None
+        call("v3s_or_func", ptr(c81), ptr(Ps), Ps.stride(0), n, int(r_total), int(form), float(rel_step), ptr(G), ptr(J),
+             stream_ptr())
+        return G, J
+
     def sigma_pairs(self, qe, qt, r0, r1):
         if self._sigma_ws is None:
             self._sigma_ws = self.empty((65536,), torch.float64)

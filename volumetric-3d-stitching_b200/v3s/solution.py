@@ -22,7 +22,10 @@ class OrientationRecoverySolver:
         Extensions that never change reference-mode results: `rotations` = explicit
         R (9,N) instead of the Hopf grid, `N_p` = free detector size, `check_sigma=False` = report
         Sigma_T > 60 instead of raising (diffusion.py:175-176), `photons_per_pattern` = Poisson photon
-        noise on the patterns (BASELINE config 5; the reference has no noise model)."""
+        noise on the patterns (BASELINE config 5; the reference has no noise model).
+        Under torch.distributed (one process per GPU, world > 1) the job is row-sharded: every rank calls
+        solve with the same arguments and gets the same replicated results, except 'Images', which holds
+        the rank's own pattern rows [rows[0], rows[1]) (key 'rows'; the full matrix never leaves the GPUs)."""
         print('OrientationRecoverySolver.solve started.')
         if not OrientationRecoverySolver.validate_parameters(parameters):
             parameters = OrientationRecoverySolver.default_parameters()
@@ -47,7 +50,10 @@ class OrientationRecoverySolver:
         # the pattern matrix is by far the largest output: its host transfer starts as soon as stage 1
         # is done and overlaps stages 2-4 (side stream + worker thread)
         start_images = (lambda img: xfer.setdefault('Images', _util.AsyncFetch(img))) if ops.device.type == 'cuda' else None
-        out = run_pipeline(ops, ShardPlan(Nn), ed, rot9, rot_y, n_p, parameters['k'], parameters['Epsilon'],
+        plan = ShardPlan.from_env(Nn)
+        if plan.world > 1:
+            rot9 = rot9[plan.lo:plan.hi].contiguous()
+        out = run_pipeline(ops, plan, ed, rot9, rot_y, n_p, parameters['k'], parameters['Epsilon'],
                            polar_mode=polar_mode, check=check_sigma, stats=stats, on_images=start_images,
                            photons_per_pattern=photons_per_pattern, noise_seed=noise_seed)
         # the reference returns float64 everywhere: widen on the device, one staged transfer for all arrays
@@ -55,14 +61,16 @@ class OrientationRecoverySolver:
         host = _util.fetch_many({
             'Ps': f64(out['Ps']), 'Lambda': f64(out['Lambda']), 'c': f64(out['c']), 'S2': f64(out['S2']),
             'N': f64(out['N']),
-            'nonzero': torch.any(out['Images_local'] != 0).reshape(1).to(torch.uint8),
+            'nonzero': plan.all_reduce_sum(torch.any(out['Images_local'] != 0).reshape(1).to(torch.int32)).to(torch.uint8),
             'Sigma_T': out['sigma_T'].reshape(1).to(torch.float64)})
         host['Images'] = xfer['Images'].result() if 'Images' in xfer else \
             _util.fetch_many({'Images': f64(out['Images_local'])})['Images']
         if not host['nonzero'][0]:
             raise Exception('Images is an all-zero array.')          # projection.py:47
         print('OrientationRecoverySolver.solve ended.')
+        extra = {'rows': np.array([plan.lo, plan.hi])} if plan.world > 1 else {}
         return {
+            **extra,
             'Ps': host['Ps'], 'Lambda': host['Lambda'], 'c0': host['c'].copy(), 'c': host['c'],
             'S2': host['S2'], 'N': host['N'], 'Images': host['Images'], 'R': R,
             'Sigma_T': np.array([out.get('sigma_T_host', float(host['Sigma_T'][0]))]), 'Axis': Axis.T, 'Quat': Quat.T,
