@@ -336,7 +336,7 @@ def main():
         "roofline": None, "roofline_other": None,
         "kernel_ms_per_pass": stage_ms,
         "eigen": {k_: stats.get(k_) for k_ in ("driver", "matvecs", "probe_steps", "cheb_steps", "degree", "krylov_dim",
-                                               "ritz_checks", "locking_rounds", "residual_max", "converged")},
+                                               "ritz_checks", "locking_rounds", "residual_max", "converged", "fused_matvec", "cheb_check_history")},
         "host_ms_per_pass": {"ritz_extraction": round(_eig.HOST_TIMERS["ritz_s"] / args.steps * 1e3, 3),
                              "waiting_for_gpu_in_eigensolver": round(_eig.HOST_TIMERS["wait_s"] / args.steps * 1e3, 3)},
         "result": {"sigma_T_deg": round(sigma_T, 4), "lambda_1_9": [round(float(x), 8) for x in lam[:10]]},

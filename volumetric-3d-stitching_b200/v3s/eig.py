@@ -149,8 +149,7 @@ def _next_check(steps, res_max, target, prev, max_gap):
 
 
 def block_lanczos_device(ops, op, N, nev, tol=1e-8, max_dim=None, first_check=6, seed=0, max_gap=16,
-                         stats=None, start_block=None, both_ends=True, lock=None, want_theta_min=False, pre_sync=None,
-                         step_cost_s=None):
+                         stats=None, start_block=None, both_ends=True, lock=None, want_theta_min=False, pre_sync=None):
     """Same algorithm as `block_lanczos_topk`, with every per-step operation enqueued on the GPU by
     the C-ABI (`v3s_lanczos_start` / `v3s_lanczos_step`, csrc/lanczos.cu): the host only launches,
     and reads back the small (A_j, B_j) blocks when it extracts Ritz pairs.
@@ -162,8 +161,6 @@ def block_lanczos_device(ops, op, N, nev, tol=1e-8, max_dim=None, first_check=6,
     kept orthogonal to -- converged eigenvectors of earlier runs (see `topk_with_locking`).
     pre_sync: optional callable enqueuing a cross-rank barrier before the first step (operators that
     store into peers' buffers, `FusedOperator.sync`).
-    step_cost_s: optional estimate of the device time of one step (operator + orthogonalisation); sizes
-    the speculation that hides the host's Ritz extraction.  Must be identical on every rank.
     """
     b = 8
     if pre_sync is not None:
@@ -200,33 +197,21 @@ def block_lanczos_device(ops, op, N, nev, tol=1e-8, max_dim=None, first_check=6,
 
     n_spec = 0
     _ritz_from_band_impl.last_min = None
-    # The host's Ritz extraction (~1 ms) is hidden behind speculative Lanczos steps.  How many: enough to
-    # cover a model of the host time (grows with m^2) with the caller's estimate of the device time per
-    # step -- both deterministic, so every rank of a sharded job takes the same decision -- but one only
-    # when the observed convergence rate predicts that this check is the last (its speculative steps are
-    # then wasted device time in front of the next stage).
-    rate = None
+    history = []                         # (step, max residual estimate) of every check (diagnostics)
     while True:
         do_step()
         last = (m + b > max_dim)
         if steps >= next_check or last:
-            # snapshot the new (A_j, B_j) blocks asynchronously, keep the GPU busy with speculative
-            # steps while the host extracts Ritz pairs, then wait for the snapshot only
+            # snapshot the new (A_j, B_j) blocks asynchronously, keep the GPU busy with one speculative
+            # step while the host extracts Ritz pairs, then wait for the snapshot only.  (More than one
+            # speculative step hides more host time at intermediate checks but is wasted device time in
+            # front of the next stage at the last one: measured net loss at cfg 2.)
             s_chk, m_chk = steps, m
             snap = ops.lanczos_snapshot(st, copied, s_chk)
-            want_spec = 1
-            if step_cost_s is not None and step_cost_s > 0:
-                host_model_s = 4e-4 + 9e-4 * (m_chk / 128.0) ** 2
-                want_spec = int(min(2, max(1, np.ceil(host_model_s / step_cost_s))))
-                if rate is not None and prev is not None:
-                    predicted = prev[1] * np.exp(-rate * (s_chk - prev[0]))
-                    if predicted <= 10.0 * tol * max(np.abs(w).max(), 1e-300):
-                        want_spec = 1
-            for _ in range(want_spec):
-                if not last and m + 2 * b <= max_dim:
-                    m += b
-                    do_step()
-                    n_spec += 1
+            if not last and m + 2 * b <= max_dim:
+                m += b
+                do_step()
+                n_spec += 1
             t0 = time.perf_counter()
             blks, status = ops.lanczos_snapshot_wait(snap)
             HOST_TIMERS["wait_s"] += time.perf_counter() - t0
@@ -242,11 +227,10 @@ def block_lanczos_device(ops, op, N, nev, tol=1e-8, max_dim=None, first_check=6,
                 raise Exception("block Lanczos broke down (non-finite residuals)")
             target = tol * max(np.abs(w).max(), 1e-300)
             n_checks += 1
+            history.append((s_chk, float(res.max() / max(np.abs(w).max(), 1e-300))))
             if res.max() <= target or last or m + b > max_dim:
                 m = m_chk
                 break
-            if prev is not None and res.max() < prev[1] and s_chk > prev[0]:
-                rate = np.log(prev[1] / res.max()) / (s_chk - prev[0])
             next_check = max(steps + 1, _next_check(s_chk, res.max(), target, prev, max_gap))
             prev = (s_chk, res.max())
         m += b
@@ -263,13 +247,13 @@ def block_lanczos_device(ops, op, N, nev, tol=1e-8, max_dim=None, first_check=6,
                 stats["theta_min"] = float(sla.eig_banded(Tb, lower=True, eigvals_only=True, select="i", select_range=(0, 0))[0])
     if stats is not None:
         stats.update({"matvecs": steps, "block": b, "krylov_dim": m, "ritz_checks": n_checks, "speculative_steps": n_spec,
-                      "residual_max": float(res.max()),
+                      "residual_max": float(res.max()), "check_history": history,
                       "converged": bool(res.max() <= tol * max(np.abs(w).max(), 1e-300)), "driver": "device"})
     return w, Y, res
 
 
 def chebyshev_lanczos_device(ops, matvec_f32, matvec_f64, N, nev, tol=1e-8, degree=6, probe_steps=10, seed=0,
-                             stats=None, lock=None, safe_lower=False, fused=None, matvec_cost_s=None):
+                             stats=None, lock=None, safe_lower=False, fused=None):
     """Largest eigenpairs of the symmetric operator P by block Lanczos on a Chebyshev polynomial
     of P (device driver).  Clustered top eigenvalues (gaps ~1e-4 at N = 10^4) make plain Lanczos
     need a Krylov space of ~600 vectors, whose Ritz extraction is O(m^2 b) host work per check;
@@ -345,10 +329,10 @@ def chebyshev_lanczos_device(ops, matvec_f32, matvec_f64, N, nev, tol=1e-8, degr
         st2 = {}
         _, Y, res = block_lanczos_device(ops, cheb_op if fused is None else cheb_fused, N, nev, tol=tol, seed=seed,
                                          first_check=4, max_gap=4, stats=st2, start_block=start, both_ends=False, lock=lock,
-                                         pre_sync=pre_sync,
-                                         step_cost_s=(None if matvec_cost_s is None else degree * matvec_cost_s + 1e-4))
+                                         pre_sync=pre_sync)
         n_mv += count[0]
         info.update({"cheb_steps": st2["matvecs"], "krylov_dim": st2["krylov_dim"], "cut": cut,
+                     "cheb_check_history": st2.get("check_history"),
                      "ritz_checks": st2["ritz_checks"], "converged": st2["converged"]})
         # Rayleigh-Ritz with P itself
         PY = torch.cat([matvec_f64(Y[:, j:j + b].contiguous()) for j in range(0, Y.shape[1], b)], dim=1)
@@ -371,7 +355,7 @@ def chebyshev_lanczos_device(ops, matvec_f32, matvec_f64, N, nev, tol=1e-8, degr
             # something from the supposedly damped region was amplified: the lower bound was not a bound
             return chebyshev_lanczos_device(ops, matvec_f32, matvec_f64, N, nev, tol=tol, degree=degree,
                                             probe_steps=probe_steps, seed=seed, stats=stats, lock=lock, safe_lower=True,
-                                            fused=fused, matvec_cost_s=matvec_cost_s)
+                                            fused=fused)
     if stats is not None:
         stats.update(info)
         stats.update({"matvecs": n_mv, "block": b, "residual_max": float(np.max(res)), "driver": "device-chebyshev",

@@ -148,10 +148,8 @@ def eigen_stage(ops, plan, P_rows, dis, nev=NEV, validate=True, tol=None, stats=
         def run(lock):
             st_ = {}
             if N >= 2048 and nev <= 16:
-                # device time of one mat-vec step (same on every rank): row block at ~5.5 TB/s + launches / exchange
-                mv_cost = 4.0 * (N / plan.world) * N / 5.5e12 + 1.5e-5
                 r = chebyshev_lanczos_device(ops, matvec_f32, matvec, N, nev, tol=tol_, stats=st_, seed=seed, lock=lock,
-                                             fused=fused, matvec_cost_s=mv_cost)
+                                             fused=fused)
             elif fused is not None:
                 r = block_lanczos_device(ops, fused.plain, N, nev, tol=tol_, stats=st_, seed=seed, lock=lock,
                                          pre_sync=fused.sync)
