@@ -13,7 +13,7 @@ from v3s import _util
 
 ops = _util.get_ops()
 pts = []
-for (rows, N) in ((1250, 10000), (5000, 10000), (10000, 10000), (6250, 50000), (12500, 50000), (12500, 100000)):
+for (rows, N) in ((1250, 10000), (2500, 10000), (5000, 10000), (10000, 10000), (6250, 50000), (12500, 50000), (12500, 100000)):
     P = torch.rand((rows, (N + 3) // 4 * 4), dtype=torch.float32, device="cuda")
     Xf = ops.alloc_xf(N)
     Xf.normal_()
@@ -31,6 +31,6 @@ for (rows, N) in ((1250, 10000), (5000, 10000), (10000, 10000), (6250, 50000), (
     pts.append((mb, us))
     print("rows %6d x N %6d (%7.0f MB): %7.1f us  %6.0f GB/s" % (rows, N, mb, us, mb / us * 1e3), flush=True)
     del P
-A = np.array([[1.0, m] for m, _ in pts[2:]])
-t0, slope = np.linalg.lstsq(A, np.array([u for _, u in pts[2:]]), rcond=None)[0]
+A = np.array([[1.0, m] for m, _ in pts[3:]])
+t0, slope = np.linalg.lstsq(A, np.array([u for _, u in pts[3:]]), rcond=None)[0]
 print("fit over the blocks >= 400 MB: fixed %.1f us per launch, streaming %.0f GB/s" % (t0, 1e3 / slope))
