@@ -72,14 +72,26 @@ __global__ void lz_reduce_h_kernel(const double* __restrict__ Hpart, int m, int 
   Hsum[e] = accumulate ? Hsum[e] + s : s;
 }
 
-// W[n][:] -= sum_i V[i][n] * H[i][:] ; CTA = 32 rows n x 4 warps, each warp a quarter of the basis
+// W[n][:] -= sum_i V[i][n] * H[i][:] ; CTA = 32 rows n x 4 warps, each warp a quarter of the basis.
+// nsplit > 0: H is still in `nsplit` partial sums (Hpart, from lz_proj_kernel) and every CTA adds them up
+// itself while staging H in shared memory (block 0 also stores H into Hsum: overwrite on the first
+// Gram-Schmidt pass, accumulate on the second) -- one launch less per pass when the partials are small.
 constexpr int UP_WARPS = 4;
 __global__ void __launch_bounds__(UP_WARPS * 32)
-lz_update_kernel(const double* __restrict__ V, long long ldv, int m, const double* __restrict__ H,
-                 double* __restrict__ W, long long N) {
+lz_update_kernel(const double* __restrict__ V, long long ldv, int m, const double* __restrict__ H, int nsplit,
+                 int accumulate, double* __restrict__ Hsum, double* __restrict__ W, long long N) {
   extern __shared__ double hs[];                         // m * 8
   __shared__ double part[UP_WARPS][32][LB + 1];
-  for (int e = threadIdx.x; e < m * LB; e += UP_WARPS * 32) hs[e] = H[e];
+  if (nsplit > 0) {
+    for (int e = threadIdx.x; e < m * LB; e += UP_WARPS * 32) {
+      double sum = 0.0;
+      for (int p = 0; p < nsplit; ++p) sum += H[(long long)p * m * LB + e];
+      hs[e] = sum;
+      if (blockIdx.x == 0) Hsum[e] = accumulate ? Hsum[e] + sum : sum;
+    }
+  } else {
+    for (int e = threadIdx.x; e < m * LB; e += UP_WARPS * 32) hs[e] = H[e];
+  }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long n = (long long)blockIdx.x * 32 + lane;
@@ -123,55 +135,26 @@ lz_update_kernel(const double* __restrict__ V, long long ldv, int m, const doubl
   }
 }
 
-// Gpart[cta][36] = upper triangle of W^T W over the CTA's rows
-constexpr int GR_T = 256;
-__global__ void __launch_bounds__(GR_T)
-lz_gram8_kernel(const double* __restrict__ W, long long N, double* __restrict__ Gpart) {
-  __shared__ double red[GR_T / 32][36];
-  double acc[36];
-#pragma unroll
-  for (int e = 0; e < 36; ++e) acc[e] = 0.0;
-  for (long long n = (long long)blockIdx.x * GR_T + threadIdx.x; n < N; n += (long long)gridDim.x * GR_T) {
-    const double2* w2 = reinterpret_cast<const double2*>(W + n * LB);
-    const double2 a = w2[0], b = w2[1], c = w2[2], d = w2[3];
-    const double w[LB] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
-    int e = 0;
-#pragma unroll
-    for (int i = 0; i < LB; ++i)
-#pragma unroll
-      for (int j = i; j < LB; ++j) { acc[e] = fma(w[i], w[j], acc[e]); ++e; }
-  }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int e = 0; e < 36; ++e) {
-    const double s = warp_sum(acc[e]);
-    if (lane == 0) red[warp][e] = s;
-  }
-  __syncthreads();
-  if (threadIdx.x < 36) {
-    double s = 0.0;
-    for (int w_ = 0; w_ < GR_T / 32; ++w_) s += red[w_][threadIdx.x];
-    Gpart[(long long)blockIdx.x * 36 + threadIdx.x] = s;
-  }
-}
-
-// 64 threads: G = sum of partials; G = L L^T (column by column, thread i owns row i); Linv (thread j
-// owns column j); R = L^T.  small[0..63]=Linv (row-major), small[64..127]=R of this round,
-// small[128..191]=R_total (R_round * R_total_prev when round>0; thread (i,j) owns one entry)
-__global__ void lz_chol_kernel(const double* __restrict__ Gpart, int nparts, int round, double* __restrict__ small,
-                               int* __restrict__ status) {
+// 8 x 8 Cholesky-QR factors from the partial Gram sums, executed by threads t < 64 of ONE block (all
+// threads of the block must call it: it synchronises).  G = sum of partials; G = L L^T (column by
+// column, thread i owns row i); Linv (thread j owns column j); R = L^T.  small[0..63] = Linv
+// (row-major), small[64..127] = R of this round, small[128..191] = R_total (R_round * R_total_prev when
+// round > 0; thread (i,j) owns one entry).  Tblk != NULL (final round of a step): also
+// Tblk[0..63] = sym(Hsum[m-8 .. m)), Tblk[64..127] = R_total, and the breakdown flag is published.
+__device__ void chol8_block(const double* Gpart, int nparts, int round, double* __restrict__ small, int* __restrict__ status,
+                            const double* __restrict__ Hsum, int m, double* __restrict__ Tblk, int* __restrict__ status_out) {
   __shared__ double G[LB][LB], L[LB][LB], Li[LB][LB], Rprev[LB][LB];
   __shared__ int bad;
   const int t = threadIdx.x;
   if (t == 0) bad = 0;
   if (t < 36) {
     double s = 0.0;
-    for (int p = 0; p < nparts; ++p) s += Gpart[(long long)p * 36 + t];
+    for (int p = 0; p < nparts; ++p) s += __ldcg(Gpart + (long long)p * 36 + t);
     int e = 0, ii = 0, jj = 0;
     for (int i = 0; i < LB; ++i) for (int j = i; j < LB; ++j) { if (e == t) { ii = i; jj = j; } ++e; }
     G[ii][jj] = s; G[jj][ii] = s;
   }
-  { const int i = t / LB, j = t % LB; L[i][j] = 0.0; Li[i][j] = 0.0; if (round > 0) Rprev[i][j] = small[128 + t]; }
+  if (t < 64) { const int i = t / LB, j = t % LB; L[i][j] = 0.0; Li[i][j] = 0.0; if (round > 0) Rprev[i][j] = small[128 + t]; }
   __syncthreads();
   // right-looking Cholesky: after step j, column j of L is final
   for (int j = 0; j < LB; ++j) {
@@ -199,7 +182,7 @@ __global__ void lz_chol_kernel(const double* __restrict__ Gpart, int nparts, int
     }
   }
   __syncthreads();
-  {
+  if (t < 64) {
     const int i = t / LB, j = t % LB;
     small[t] = Li[i][j];
     small[64 + t] = L[j][i];                   // R = L^T
@@ -209,8 +192,62 @@ __global__ void lz_chol_kernel(const double* __restrict__ Gpart, int nparts, int
       for (int k = 0; k < LB; ++k) rt += L[k][i] * Rprev[k][j];
     }
     small[128 + t] = rt;
+    if (Tblk) {
+      Tblk[t] = 0.5 * (Hsum[(m - LB + i) * LB + j] + Hsum[(m - LB + j) * LB + i]);
+      Tblk[64 + t] = rt;
+    }
   }
-  if (t == 0 && bad) atomicExch(status, 1);
+  if (t == 0) {
+    if (bad) atomicExch(status, 1);
+    if (status_out) *status_out = bad ? 1 : *status;
+  }
+}
+
+// Gpart[cta][36] = upper triangle of W^T W over the CTA's rows; the block that finishes last (ticket
+// counter) goes on to the Cholesky factors, so the Gram reduction and the 8 x 8 factorisation are one launch.
+constexpr int GR_T = 256;
+__global__ void __launch_bounds__(GR_T)
+lz_gram8_chol_kernel(const double* __restrict__ W, long long N, double* __restrict__ Gpart, unsigned* __restrict__ ticket,
+                     int round, double* __restrict__ small, int* __restrict__ status, const double* __restrict__ Hsum, int m,
+                     double* __restrict__ Tblk, int* __restrict__ status_out) {
+  __shared__ double red[GR_T / 32][36];
+  __shared__ int is_last;
+  double acc[36];
+#pragma unroll
+  for (int e = 0; e < 36; ++e) acc[e] = 0.0;
+  for (long long n = (long long)blockIdx.x * GR_T + threadIdx.x; n < N; n += (long long)gridDim.x * GR_T) {
+    const double2* w2 = reinterpret_cast<const double2*>(W + n * LB);
+    const double2 a = w2[0], b = w2[1], c = w2[2], d = w2[3];
+    const double w[LB] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
+    int e = 0;
+#pragma unroll
+    for (int i = 0; i < LB; ++i)
+#pragma unroll
+      for (int j = i; j < LB; ++j) { acc[e] = fma(w[i], w[j], acc[e]); ++e; }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int e = 0; e < 36; ++e) {
+    const double s = warp_sum(acc[e]);
+    if (lane == 0) red[warp][e] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 36) {
+    double s = 0.0;
+    for (int w_ = 0; w_ < GR_T / 32; ++w_) s += red[w_][threadIdx.x];
+    Gpart[(long long)blockIdx.x * 36 + threadIdx.x] = s;
+    __threadfence();                            // the partial is visible before the ticket is taken
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned tk = atomicAdd(ticket, 1u);
+    is_last = (tk == gridDim.x - 1);
+    if (is_last) *ticket = 0;                   // ready for the next launch
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  chol8_block(Gpart, (int)gridDim.x, round, small, status, Hsum, m, Tblk, status_out);
 }
 
 // W <- W L^-T  (row n: w_j = sum_{k<=j} w_k Linv[j][k]); on the final round also append to the
@@ -245,17 +282,6 @@ __global__ void lz_scale_kernel(double* __restrict__ W, long long N, const doubl
   }
 }
 
-// Tblk[0..63] = sym(Hsum[m-8 .. m)) , Tblk[64..127] = R_total
-__global__ void lz_store_blocks_kernel(const double* __restrict__ Hsum, int m, const double* __restrict__ small,
-                                       double* __restrict__ Tblk) {
-  const int t = threadIdx.x;
-  if (t < 64) {
-    const int i = t / LB, j = t % LB;
-    Tblk[t] = 0.5 * (Hsum[(m - LB + i) * LB + j] + Hsum[(m - LB + j) * LB + i]);
-    Tblk[64 + t] = small[128 + t];
-  }
-}
-
 // Chebyshev three-term recurrence on a block [N,8]: Y_out = alpha * PY + beta * Yk + gamma * Ykm1
 // (FP64), plus the FP32 strip-layout copy the next mat-vec reads.  Y_out may alias Ykm1.
 __global__ void lz_cheb_combine_kernel(const double* __restrict__ PY, const double* __restrict__ Yk,
@@ -272,6 +298,7 @@ __global__ void lz_cheb_combine_kernel(const double* __restrict__ PY, const doub
 struct LzWs {
   double *Hpart, *Hcur, *Hsum, *Gpart, *small;
   int* status;
+  unsigned* ticket;
 };
 static inline LzWs lz_carve(double* ws, int max_dim) {
   LzWs w;
@@ -281,6 +308,7 @@ static inline LzWs lz_carve(double* ws, int max_dim) {
   w.Gpart = w.Hsum + (long long)max_dim * LB;
   w.small = w.Gpart + 1024LL * 36;
   w.status = reinterpret_cast<int*>(w.small + 192);
+  w.ticket = reinterpret_cast<unsigned*>(w.status + 1);
   return w;
 }
 }  // namespace v3s
@@ -303,17 +331,17 @@ extern "C" long long v3s_lanczos_workspace_doubles(long long N, int max_dim) {
   return 32LL * max_dim * LB + 2LL * max_dim * LB + 1024LL * 36 + 192 + 8;
 }
 
-static int lz_cholqr(double* W, long long N, double* Gpart, double* small, int* status, double* Vnext, long long ldv,
-                     float* Xf, cudaStream_t st) {
+static int lz_cholqr(double* W, long long N, const LzWs& w, double* Vnext, long long ldv, float* Xf, const double* Hsum, int m,
+                     double* Tblk, int* status_out, cudaStream_t st) {
   long long g = ceil_div64(N, GR_T * 4);
   if (g > 1024) g = 1024;
   if (g < 1) g = 1;
   for (int round = 0; round < 2; ++round) {
-    lz_gram8_kernel<<<(int)g, GR_T, 0, st>>>(W, N, Gpart);
+    const bool fin = round == 1;
+    lz_gram8_chol_kernel<<<(int)g, GR_T, 0, st>>>(W, N, w.Gpart, w.ticket, round, w.small, w.status, Hsum, m,
+                                                 fin ? Tblk : nullptr, fin ? status_out : nullptr);
     V3S_CHECK_LAUNCH();
-    lz_chol_kernel<<<1, 64, 0, st>>>(Gpart, (int)g, round, small, status);
-    V3S_CHECK_LAUNCH();
-    lz_scale_kernel<<<(int)ceil_div64(N, 256), 256, 0, st>>>(W, N, small, round == 1, Vnext, ldv, Xf);
+    lz_scale_kernel<<<(int)ceil_div64(N, 256), 256, 0, st>>>(W, N, w.small, fin, Vnext, ldv, Xf);
     V3S_CHECK_LAUNCH();
   }
   return 0;
@@ -325,8 +353,8 @@ extern "C" int v3s_lanczos_start(double* V, long long ldv, long long N, int max_
   V3S_REQUIRE(N >= LB && ldv >= N && max_dim >= LB, "v3s_lanczos_start: bad shape");
   const LzWs w = lz_carve(ws, max_dim);
   cudaStream_t st = (cudaStream_t)stream;
-  V3S_CUDA(cudaMemsetAsync(w.status, 0, sizeof(int), st));
-  return lz_cholqr(W, N, w.Gpart, w.small, w.status, V, ldv, Xf, st);
+  V3S_CUDA(cudaMemsetAsync(w.status, 0, 2 * sizeof(int), st));      // breakdown flag + the Gram kernel's ticket counter
+  return lz_cholqr(W, N, w, V, ldv, Xf, nullptr, 0, nullptr, nullptr, st);
 }
 
 // One Lanczos step after W = P @ Q_j has been formed (and all-gathered): m = current basis size
@@ -338,8 +366,7 @@ extern "C" int v3s_lanczos_step(double* V, long long ldv, long long N, int m, in
   V3S_REQUIRE(m >= LB && m % LB == 0 && m <= max_dim && N >= LB && ldv >= N, "v3s_lanczos_step: bad shape (m=%d)", m);
   cudaStream_t st = (cudaStream_t)stream;
   const LzWs w = lz_carve(ws, max_dim);
-  double *Hpart = w.Hpart, *Hcur = w.Hcur, *Hsum = w.Hsum, *Gpart = w.Gpart, *small = w.small;
-  int* status = w.status;
+  double *Hpart = w.Hpart, *Hcur = w.Hcur, *Hsum = w.Hsum;
   const int nsplit = lz_nsplit(m, N);
   const long long rows_per = ceil_div64(N, nsplit);
   const size_t up_smem = (size_t)m * LB * sizeof(double);
@@ -352,20 +379,22 @@ extern "C" int v3s_lanczos_step(double* V, long long ldv, long long N, int m, in
     V3S_CUDA(cudaFuncSetAttribute(lz_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want));
     up_set = want;
   }
+  // every update CTA can add up the projection partials itself while that re-read stays small
+  const bool fuse_reduce = (double)nsplit * m * LB * sizeof(double) * (double)ceil_div64(N, 32) <= 48e6;
   for (int pass = 0; pass < 2; ++pass) {
     lz_proj_kernel<<<dim3((m + PJ_VECS - 1) / PJ_VECS, nsplit), PJ_T, 0, st>>>(V, ldv, m, W, N, rows_per, Hpart);
     V3S_CHECK_LAUNCH();
-    lz_reduce_h_kernel<<<(m * LB + 255) / 256, 256, 0, st>>>(Hpart, m, nsplit, pass, Hcur, Hsum);
-    V3S_CHECK_LAUNCH();
-    lz_update_kernel<<<(int)ceil_div64(N, 32), UP_WARPS * 32, up_smem, st>>>(V, ldv, m, Hcur, W, N);
+    if (fuse_reduce) {
+      lz_update_kernel<<<(int)ceil_div64(N, 32), UP_WARPS * 32, up_smem, st>>>(V, ldv, m, Hpart, nsplit, pass, Hsum, W, N);
+    } else {
+      lz_reduce_h_kernel<<<(m * LB + 255) / 256, 256, 0, st>>>(Hpart, m, nsplit, pass, Hcur, Hsum);
+      V3S_CHECK_LAUNCH();
+      lz_update_kernel<<<(int)ceil_div64(N, 32), UP_WARPS * 32, up_smem, st>>>(V, ldv, m, Hcur, 0, pass, Hsum, W, N);
+    }
     V3S_CHECK_LAUNCH();
   }
   double* Vnext = (m + LB <= max_dim) ? V + (long long)m * ldv : nullptr;
-  if (lz_cholqr(W, N, Gpart, small, status, Vnext, ldv, Xf, st)) return 1;
-  lz_store_blocks_kernel<<<1, 64, 0, st>>>(Hsum, m, small, Tblk);
-  V3S_CHECK_LAUNCH();
-  if (status_out_dev) V3S_CUDA(cudaMemcpyAsync(status_out_dev, status, sizeof(int), cudaMemcpyDeviceToDevice, st));
-  return 0;
+  return lz_cholqr(W, N, w, Vnext, ldv, Xf, Hsum, m, Tblk, status_out_dev, st);
 }
 
 extern "C" int v3s_cheb_combine(const double* PY, const double* Yk, const double* Ykm1, double alpha, double beta,
