@@ -203,23 +203,27 @@ int v3s_cheb_combine(const double* PY, const double* Yk, const double* Ykm1, dou
  *     v = alpha * (P X) + beta * Yk + gamma * Ykm1        (FP64; Yk / Ykm1 [N,8] may be NULL)
  * and stores v into the [N,8] result block of EVERY rank (yout_ptrs[r], peer-mapped addresses) and,
  * when xfout_ptrs != NULL, float(v) into every rank's strip-layout operand of the next mat-vec:
- * the all-gather of the Lanczos block is part of the kernel's stores, not a collective.
- * v3s_peer_barrier (flag words in peer-mapped memory, monotonically growing epoch) then orders
- * the step against the peers; *status_dev becomes 3 if a peer never arrives.                    */
+ * the all-gather of the Lanczos block is part of the kernel's stores, not a collective.  When
+ * sharded, the block of that kernel that finishes last signals every peer's flag word
+ * (flag_ptrs[r] = rank r's int[world] array in peer-mapped memory, zero-initialised; epochs grow
+ * monotonically) and waits for every peer's signal, so the stream only moves on when the whole
+ * block has arrived; ticket_dev = a zero-initialised word of the rank's own memory;
+ * *status_dev becomes 3 if a peer never arrives.  v3s_peer_barrier is the same barrier stand-alone. */
 int v3s_matvec_combine(const float* P_rows, long long ldp, long long n_rows, long long N, long long row0,
                        const float* Xf_strips, const double* Yk, const double* Ykm1, double alpha, double beta,
                        double gamma, const unsigned long long* yout_ptrs, const unsigned long long* xfout_ptrs,
-                       int world, void* workspace, void* stream);
+                       const unsigned long long* flag_ptrs, int rank, int world, int epoch, unsigned* ticket_dev,
+                       int* status_dev, void* workspace, void* stream);
 int v3s_peer_barrier(const unsigned long long* flag_ptrs, int rank, int world, int epoch, int* status_dev, void* stream);
 /* T_degree((P - c)/e) applied to the block Q [N,8] by one host call (degree x {mat-vec, fused
- * combine/scatter, barrier}).  ybuf_ptrs[b*world + r]: rotating FP64 result buffer b = 0..2 on rank
+ * combine / scatter / barrier}).  ybuf_ptrs[b*world + r]: rotating FP64 result buffer b = 0..2 on rank
  * r; xf_ptrs[p*world + r]: ping-pong FP32 strip operand p = 0..1 on rank r; Xf0 = float(Q) in strip
  * layout; q_index = which rotating buffer Q is (-1: a separate block); the barriers use epochs
  * epoch0+1 .. epoch0+degree.  *result_index (host) = rotating buffer holding the result.       */
 int v3s_cheb_filter(const float* P_rows, long long ldp, long long n_rows, long long N, long long row0, const float* Xf0,
                     const double* Q, int q_index, int degree, double c, double e, const unsigned long long* ybuf_ptrs,
                     const unsigned long long* xf_ptrs, const unsigned long long* flag_ptrs, int rank, int world,
-                    int epoch0, int* status_dev, void* workspace, int* result_index, void* stream);
+                    int epoch0, unsigned* ticket_dev, int* status_dev, void* workspace, int* result_index, void* stream);
 /* per-launch device time of block_matvec_kernel (CUDA events owned by the library, recorded on the
  * launching stream): enable/reset, then read the elapsed milliseconds (returns the launch count). */
 int v3s_profile_matvec(int enable);

@@ -235,11 +235,30 @@ static int mv_run(const float* P_rows, long long ldp, long long n_rows, long lon
 // mappings), so no collective follows; `v3s_peer_barrier` orders the steps.
 struct PeerPtrs { unsigned long long p[8]; };
 
+// thread r of the caller: publish `epoch` in rank r's flag word for this rank, then wait until rank r has
+// published at least `epoch` in ours.  flags.p[r] = rank r's int[world] flag array (zero-initialised once);
+// epochs grow monotonically.  A peer that never arrives (a crashed rank) ends the wait after ~2 s and
+// raises *status.
+__device__ __forceinline__ void peer_signal_wait(const PeerPtrs& flags, int rank, int r, int epoch, int* status) {
+  __threadfence_system();
+  int* dst = reinterpret_cast<int*>(flags.p[r]) + rank;
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(dst), "r"(epoch) : "memory");
+  const int* src = reinterpret_cast<const int*>(flags.p[rank]) + r;
+  int v = 0;
+  const long long t0 = clock64();
+  for (;;) {
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
+    if (v - epoch >= 0) break;
+    if (clock64() - t0 > 4000000000LL) { if (status) atomicExch(status, 3); break; }
+  }
+}
+
 __global__ void reduce_combine_scatter_kernel(const double* __restrict__ Ypart, long long n_rows, long long row0,
                                               int nstrips_row, long long units_per_cta, int maxseg,
                                               const double* __restrict__ Yk, const double* __restrict__ Ykm1, double alpha,
                                               double beta, double gamma, PeerPtrs yout, PeerPtrs xfout, int world,
-                                              int write_xf) {
+                                              int write_xf, PeerPtrs flags, int rank, int epoch, unsigned* ticket,
+                                              int* status) {
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n_rows * MV_B; e += (long long)gridDim.x * blockDim.x) {
     const long long i = e / MV_B;
     const int j = (int)(e - i * MV_B);
@@ -264,38 +283,40 @@ __global__ void reduce_combine_scatter_kernel(const double* __restrict__ Ypart, 
       for (int r = 0; r < world; ++r) reinterpret_cast<float*>(xfout.p[r])[xi] = f;
     }
   }
+  if (!ticket) return;
+  // Sharded job: the block that finishes last signals every peer (all stores of this grid are ordered
+  // before it by the fences around the ticket) and waits for every peer's signal, so the kernel -- and
+  // with it the stream -- only moves on when all rows of the block have arrived from all ranks.
+  __shared__ int is_last;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned tk = atomicAdd(ticket, 1u);
+    is_last = (tk == gridDim.x - 1);
+    if (is_last) *ticket = 0;
+  }
+  __syncthreads();
+  if (is_last && threadIdx.x < world) peer_signal_wait(flags, rank, threadIdx.x, epoch, status);
 }
 
 static int mv_combine(const float* P_rows, long long ldp, long long n_rows, long long N, long long row0, const float* XfS,
                       const double* Yk, const double* Ykm1, double alpha, double beta, double gamma, const PeerPtrs& yout,
-                      const PeerPtrs& xfout, int world, int write_xf, double* Ypart, cudaStream_t st) {
+                      const PeerPtrs& xfout, int world, int write_xf, double* Ypart, const PeerPtrs& flags, int rank, int epoch,
+                      unsigned* ticket, int* status, cudaStream_t st) {
   const MvPlan pl = mv_plan(n_rows, N);
   if (int rc = mv_launch(P_rows, ldp, n_rows, N, XfS, Ypart, pl, st)) return rc;
   long long g2 = ceil_div64(n_rows * MV_B, 256);
   if (g2 > 8LL * kNumSMs) g2 = 8LL * kNumSMs;
   reduce_combine_scatter_kernel<<<(int)g2, 256, 0, st>>>(Ypart, n_rows, row0, pl.nstrips_row, pl.units_per_cta, pl.maxseg, Yk,
-                                                         Ykm1, alpha, beta, gamma, yout, xfout, world, write_xf);
+                                                         Ykm1, alpha, beta, gamma, yout, xfout, world, write_xf, flags, rank,
+                                                         epoch, world > 1 ? ticket : nullptr, status);
   V3S_CHECK_LAUNCH();
   return 0;
 }
 
-// All ranks have stored their rows: signal every peer's flag word and wait for every peer's signal.
-// flags.p[r] = rank r's int[world] flag array (zero-initialised once); epochs grow monotonically.
-// A peer that never arrives (a crashed rank) ends the wait after ~2 s and raises *status.
+// Stand-alone form of the same barrier (phase changes of the solver).
 __global__ void peer_barrier_kernel(PeerPtrs flags, int rank, int world, int epoch, int* status) {
-  const int r = threadIdx.x;
-  if (r >= world) return;
-  __threadfence_system();
-  int* dst = reinterpret_cast<int*>(flags.p[r]) + rank;
-  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(dst), "r"(epoch) : "memory");
-  const int* src = reinterpret_cast<const int*>(flags.p[rank]) + r;
-  int v = 0;
-  const long long t0 = clock64();
-  for (;;) {
-    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
-    if (v - epoch >= 0) break;
-    if (clock64() - t0 > 4000000000LL) { if (status) atomicExch(status, 3); break; }
-  }
+  if (threadIdx.x < world) peer_signal_wait(flags, rank, threadIdx.x, epoch, status);
 }
 
 }  // namespace v3s
@@ -360,19 +381,22 @@ extern "C" int v3s_peer_barrier(const unsigned long long* flag_ptrs, int rank, i
 extern "C" int v3s_matvec_combine(const float* P_rows, long long ldp, long long n_rows, long long N, long long row0,
                                   const float* XfS, const double* Yk, const double* Ykm1, double alpha, double beta,
                                   double gamma, const unsigned long long* yout_ptrs, const unsigned long long* xfout_ptrs,
-                                  int world, void* workspace, void* stream) {
-  V3S_REQUIRE(n_rows >= 0 && N >= 1 && ldp >= N && ldp % 4 == 0 && row0 >= 0 && row0 + n_rows <= N,
-              "v3s_matvec_combine: bad shape (ldp must be a multiple of 4)");
+                                  const unsigned long long* flag_ptrs, int rank, int world, int epoch, unsigned* ticket_dev,
+                                  int* status_dev, void* workspace, void* stream) {
+  V3S_REQUIRE(n_rows >= 1 && N >= 1 && ldp >= N && ldp % 4 == 0 && row0 >= 0 && row0 + n_rows <= N,
+              "v3s_matvec_combine: bad shape (ldp must be a multiple of 4, at least one row per rank)");
   V3S_REQUIRE(((uintptr_t)P_rows & 15) == 0 && ((uintptr_t)XfS & 15) == 0, "v3s_matvec_combine: pointers must be 16-byte aligned");
   V3S_REQUIRE(N < (1LL << 31) && n_rows < (1LL << 31), "v3s_matvec_combine: extents must fit int32");
-  V3S_REQUIRE(yout_ptrs && world >= 1 && world <= 8, "v3s_matvec_combine: 1..8 ranks, result pointers required");
-  if (n_rows == 0) return 0;
-  PeerPtrs yo, xo;
+  V3S_REQUIRE(yout_ptrs && world >= 1 && world <= 8 && rank >= 0 && rank < world && (world == 1 || (flag_ptrs && ticket_dev)),
+              "v3s_matvec_combine: 1..8 ranks, result pointers (and flag words + ticket when sharded) required");
+  PeerPtrs yo, xo, fl;
   load_peers(yo, yout_ptrs, world);
   load_peers(xo, xfout_ptrs, world);
-  double* Ypart = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(workspace) + mv_xf_bytes(N));
+  load_peers(fl, flag_ptrs, world);
+  unsigned char* wsb = reinterpret_cast<unsigned char*>(workspace);
+  double* Ypart = reinterpret_cast<double*>(wsb + mv_xf_bytes(N));
   return mv_combine(P_rows, ldp, n_rows, N, row0, XfS, Yk, Ykm1, alpha, beta, gamma, yo, xo, world, xfout_ptrs != nullptr,
-                    Ypart, (cudaStream_t)stream);
+                    Ypart, fl, rank, epoch, ticket_dev, status_dev, (cudaStream_t)stream);
 }
 
 // One application of the Chebyshev-filtered operator T_degree((P - c)/e) to the block Q, enqueued by
@@ -385,13 +409,14 @@ extern "C" int v3s_matvec_combine(const float* P_rows, long long ldp, long long 
 extern "C" int v3s_cheb_filter(const float* P_rows, long long ldp, long long n_rows, long long N, long long row0,
                                const float* Xf0, const double* Q, int q_index, int degree, double c, double e,
                                const unsigned long long* ybuf_ptrs, const unsigned long long* xf_ptrs,
-                               const unsigned long long* flag_ptrs, int rank, int world, int epoch0, int* status_dev,
-                               void* workspace, int* result_index, void* stream) {
+                               const unsigned long long* flag_ptrs, int rank, int world, int epoch0, unsigned* ticket_dev,
+                               int* status_dev, void* workspace, int* result_index, void* stream) {
   V3S_REQUIRE(degree >= 1 && q_index >= -1 && q_index <= 2 && e != 0.0, "v3s_cheb_filter: bad degree / buffer index / interval");
-  V3S_REQUIRE(ybuf_ptrs && xf_ptrs && world >= 1 && world <= 8 && rank >= 0 && rank < world && (world == 1 || flag_ptrs),
+  V3S_REQUIRE(ybuf_ptrs && xf_ptrs && world >= 1 && world <= 8 && rank >= 0 && rank < world &&
+                  (world == 1 || (flag_ptrs && ticket_dev)),
               "v3s_cheb_filter: bad rank layout");
-  V3S_REQUIRE(n_rows >= 0 && N >= 1 && ldp >= N && ldp % 4 == 0 && row0 >= 0 && row0 + n_rows <= N && N < (1LL << 31),
-              "v3s_cheb_filter: bad shape");
+  V3S_REQUIRE(n_rows >= 1 && N >= 1 && ldp >= N && ldp % 4 == 0 && row0 >= 0 && row0 + n_rows <= N && N < (1LL << 31),
+              "v3s_cheb_filter: bad shape (at least one row per rank)");
   cudaStream_t st = (cudaStream_t)stream;
   double* Ypart = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(workspace) + mv_xf_bytes(N));
   auto local_y = [&](int b) { return reinterpret_cast<const double*>(ybuf_ptrs[(size_t)b * world + rank]); };
@@ -408,15 +433,11 @@ extern "C" int v3s_cheb_filter(const float* P_rows, long long ldp, long long n_r
     const double* Yk = cur == -1 ? Q : local_y(cur);
     const double* Ykm1 = prev == -2 ? nullptr : (prev == -1 ? Q : local_y(prev));
     const double alpha = (s == 1 ? 1.0 : 2.0) / e, beta = (s == 1 ? -1.0 : -2.0) * c / e, gamma = s == 1 ? 0.0 : -1.0;
-    if (n_rows > 0)
-      if (int rc = mv_combine(P_rows, ldp, n_rows, N, row0, xin, Yk, Ykm1, alpha, beta, gamma, yo, xo, world, write_xf, Ypart, st))
-        return rc;
-    if (world > 1) {
-      PeerPtrs f;
-      load_peers(f, flag_ptrs, world);
-      peer_barrier_kernel<<<1, 32, 0, st>>>(f, rank, world, epoch0 + s, status_dev);
-      V3S_CHECK_LAUNCH();
-    }
+    PeerPtrs fl;
+    load_peers(fl, flag_ptrs, world);
+    if (int rc = mv_combine(P_rows, ldp, n_rows, N, row0, xin, Yk, Ykm1, alpha, beta, gamma, yo, xo, world, write_xf, Ypart, fl,
+                            rank, epoch0 + s, ticket_dev, status_dev, st))
+      return rc;
     xin = local_x(s & 1);
     prev = cur;
     cur = out;

@@ -61,10 +61,10 @@ SIGNATURES = {
     "v3s_lanczos_step": (i32, [p, i64, i64, i32, i32, p, p, p, p, p, p]),
     "v3s_cheb_combine": (i32, [p, p, p, f64, f64, f64, p, p, i64, p]),
     "v3s_matvec_combine": (i32, [p, i64, i64, i64, i64, p, p, p, f64, f64, f64, C.POINTER(C.c_ulonglong),
-                                 C.POINTER(C.c_ulonglong), i32, p, p]),
+                                 C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), i32, i32, i32, p, p, p, p]),
     "v3s_peer_barrier": (i32, [C.POINTER(C.c_ulonglong), i32, i32, i32, p, p]),
     "v3s_cheb_filter": (i32, [p, i64, i64, i64, i64, p, p, i32, i32, f64, f64, C.POINTER(C.c_ulonglong),
-                              C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), i32, i32, i32, p, p, C.POINTER(i32), p]),
+                              C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), i32, i32, i32, p, p, p, C.POINTER(i32), p]),
     "v3s_profile_matvec": (i32, [i32]),
     "v3s_profile_matvec_read": (i32, [C.POINTER(C.c_float), i32]),
     "v3s_fit_gram": (i32, [p, i32, p, i64, p, p]),

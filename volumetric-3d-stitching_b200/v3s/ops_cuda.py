@@ -523,7 +523,8 @@ class FusedOperator:
                 "yptrs": (C.c_ulonglong * (3 * self.world))(*[bases[r] + b * y_bytes for b in range(3) for r in range(self.world)]),
                 "xptrs": (C.c_ulonglong * (2 * self.world))(*[bases[r] + 3 * y_bytes + q * x_bytes for q in range(2) for r in range(self.world)]),
                 "fptrs": (C.c_ulonglong * self.world)(*[bases[r] + flag_off for r in range(self.world)]),
-                "status": torch.zeros((1,), dtype=torch.int32, device=ops.device), "epoch": 0, "next_out": 0,
+                "ticket": buf[flag_off + 128: flag_off + 132],            # last-block ticket of the fused combine kernel
+                "status": torch.zeros((1,), dtype=torch.int32, device=ops.device), "epoch": 0,
             }
             ops._symm_G[key] = arena
         self.a = arena
@@ -548,9 +549,10 @@ class FusedOperator:
         out = min(b for b in range(3) if b != qi)
         yout = (C.c_ulonglong * w)(*[a["yptrs"][out * w + r] for r in range(w)])
         ws = self.ops._mv_workspace(self.P_rows.shape[0], self.N)
+        a["epoch"] += 1 if w > 1 else 0
         call("v3s_matvec_combine", ptr(self.P_rows), self.P_rows.shape[1], self.P_rows.shape[0], self.N, self.row0, ptr(Xf),
-             None, None, 1.0, 0.0, 0.0, yout, None, w, ptr(ws), stream_ptr())
-        self.sync()
+             None, None, 1.0, 0.0, 0.0, yout, None, a["fptrs"], self.rank, w, a["epoch"], ptr(a["ticket"]), ptr(a["status"]),
+             ptr(ws), stream_ptr())
         self.n_matvec += 1
         return a["ybufs"][out]
 
@@ -560,7 +562,7 @@ class FusedOperator:
         ws = self.ops._mv_workspace(self.P_rows.shape[0], self.N)
         call("v3s_cheb_filter", ptr(self.P_rows), self.P_rows.shape[1], self.P_rows.shape[0], self.N, self.row0, ptr(Xf0),
              ptr(Q), self._index_of(Q), int(degree), float(c), float(e), a["yptrs"], a["xptrs"], a["fptrs"], self.rank,
-             self.world, a["epoch"], ptr(a["status"]), ptr(ws), C.byref(res), stream_ptr())
+             self.world, a["epoch"], ptr(a["ticket"]), ptr(a["status"]), ptr(ws), C.byref(res), stream_ptr())
         if self.world > 1:
             a["epoch"] += int(degree)
         self.n_matvec += int(degree)

@@ -143,6 +143,7 @@ def eigen_stage(ops, plan, P_rows, dis, nev=NEV, validate=True, tol=None, stats=
         tol_ = 1e-8 if tol is None else tol
         # reduction + recurrence + cross-rank exchange inside the mat-vec's own kernels (no NCCL per step)
         fused = ops.fused_operator(P_rows, N, plan) if (hasattr(ops, "fused_operator") and plan.world <= 8
+                                                        and min(plan.counts) >= 1
                                                         and getattr(ops, "use_fused_matvec", True)) else None
 
         def run(lock):
