@@ -3,6 +3,7 @@ import numpy as np
 import torch
 
 _ops = None
+TIMERS = {"widen_s": 0.0, "result_wait_s": 0.0, "fetch_many_s": 0.0}     # host-side diagnostics (bench.py)
 
 
 def get_ops():
@@ -50,6 +51,8 @@ def fetch_many(tensors):
     caller owns the results and the next call may reuse the staging buffer."""
     global _pool
     import concurrent.futures as cf
+    import time
+    t_start = time.perf_counter()
     items = [(k, t.contiguous()) for k, t in tensors.items()]
     offs, total = [], 0
     for _, t in items:
@@ -79,6 +82,7 @@ def fetch_many(tensors):
             jobs.append(_pool.submit(np.copyto, flat_d[a:a + step], flat_s[a:a + step]))
     for j in jobs:
         j.result()
+    TIMERS["fetch_many_s"] += time.perf_counter() - t_start
     return out
 
 
@@ -114,13 +118,16 @@ class AsyncFetch:
         self._out = np.empty(src.shape, dtype=out_dtype)
 
         def work():
+            import time
             done.synchronize()
+            t0 = time.perf_counter()
             fs, fd = src.reshape(-1), self._out.reshape(-1)
             n = fs.size
             step = max(1 << 20, (n + 7) // 8)
             jobs = [_pool.submit(np.copyto, fd[a:a + step], fs[a:a + step]) for a in range(0, n, step)]
             for j in jobs:
                 j.result()
+            TIMERS["widen_s"] += time.perf_counter() - t0
             return self._out
 
         import threading
@@ -129,6 +136,9 @@ class AsyncFetch:
         self._thr.start()
 
     def result(self):
+        import time
+        t0 = time.perf_counter()
         self._thr.join()
+        TIMERS["result_wait_s"] += time.perf_counter() - t0
         self._keep = None
         return self._res

@@ -43,7 +43,7 @@ class OrientationRecoverySolver:
             Quat = np.full((4, R.shape[1]), np.nan)
         Nn = R.shape[1]
         n_p = (1 + 2 * n) if N_p is None else int(N_p)
-        ed = ops.to_device(Projector.synsthesize_3d(n)['ED'].astype(np.float32), torch.float32)
+        ed = Projector.object_on_device(n, ops)
         rot9 = Projector.rot9_rowmajor(R, ops)
         rot_y = ops.to_device(np.ascontiguousarray(R.T), torch.float64)
         xfer = {}
