@@ -19,6 +19,8 @@ extern "C" {
 
 const char* v3s_last_error(void);
 int v3s_version(void);
+/* CUDA kernels launched by the library since it was loaded (bench.py reports launches per step) */
+long long v3s_kernel_launches(void);
 int v3s_check_device(void);
 
 /* fill n floats at dst, which may be a peer-mapped address on another GPU (peer-mapping check) */

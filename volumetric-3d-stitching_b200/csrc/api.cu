@@ -6,6 +6,7 @@
 namespace v3s {
 
 static thread_local char g_err[512] = "";
+long long g_kernel_launches = 0;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -24,6 +25,9 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
 extern "C" const char* v3s_last_error(void) { return v3s::g_err; }
 
 extern "C" int v3s_version(void) { return 100; }
+
+// number of CUDA kernels this library has launched so far (bench.py's gpu_launches)
+extern "C" long long v3s_kernel_launches(void) { return v3s::g_kernel_launches; }
 
 // 0 when a compute-capability-10.x device is current; the product path refuses anything else.
 extern "C" int v3s_check_device(void) {

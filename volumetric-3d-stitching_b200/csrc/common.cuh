@@ -22,7 +22,14 @@ int  cuda_fail(cudaError_t e, const char* what, const char* file, int line);
     if (_e != cudaSuccess) return v3s::cuda_fail(_e, #call, __FILE__, __LINE__);   \
   } while (0)
 
-#define V3S_CHECK_LAUNCH() V3S_CUDA(cudaGetLastError())
+extern long long g_kernel_launches;   // kernels launched by this library since it was loaded (api.cu)
+}  // namespace v3s
+#define V3S_CHECK_LAUNCH()                      \
+  do {                                          \
+    ++v3s::g_kernel_launches;                   \
+    V3S_CUDA(cudaGetLastError());               \
+  } while (0)
+namespace v3s {
 
 #define V3S_REQUIRE(cond, ...)                                                     \
   do {                                                                             \

@@ -27,6 +27,7 @@ class Geometry(C.Structure):
 SIGNATURES = {
     "v3s_last_error": (C.c_char_p, []),
     "v3s_version": (i32, []),
+    "v3s_kernel_launches": (i64, []),
     "v3s_check_device": (i32, []),
     "v3s_peer_fill": (i32, [p, C.c_float, i64, p]),
     "v3s_default_geometry": (None, [C.POINTER(Geometry)]),
