@@ -202,20 +202,20 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-sample", type=int, default=3000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-baseline-only", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         return run_reference_arm(args, wl)
+    if args.cpu_baseline_only:                       # child process of the v3s arm (see below)
+        return emit(cpu_baseline_block(wl, args.cpu_sample))
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
-    # CPU baseline first (rank 0, N=1 only): it forks worker processes, so it runs before CUDA is touched
     cpu_base = None
-    if world == 1 and rank == 0 and not args.no_cpu_baseline:
-        cpu_base = cpu_baseline_block(wl, args.cpu_sample)
 
     import numpy as np
     import torch
@@ -317,6 +317,15 @@ def main():
         if world > 1:
             dist.destroy_process_group()
         return
+    # CPU baseline (rank 0, N=1 only) in a child process, after the GPU measurements: its BLAS thread pools,
+    # forked workers and multi-GB temporaries stay out of the process (and of the time window) being measured
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-baseline-only", "--workload", args.workload,
+                                "--cpu-sample", str(args.cpu_sample)], capture_output=True, text=True, timeout=900)
+            cpu_base = json.loads(r.stdout.strip().splitlines()[-1])
+        except Exception as e:
+            cpu_base = {"value": None, "unit": "s", "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (e,)}
     peaks, peak_src = load_peaks()
     P = n_p * n_p
     gram_ms = kt.get("gram", [])

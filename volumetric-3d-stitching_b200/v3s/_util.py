@@ -92,9 +92,9 @@ class AsyncFetch:
     worker thread widens / copies it into a fresh numpy array (`out_dtype`) while the main stream
     keeps computing.  `result()` returns the array."""
     _stream = None
-    _pin = None
+    _pins = {}                      # one cached pinned staging buffer per slot (transfers of different slots overlap)
 
-    def __init__(self, t, out_dtype=np.float64):
+    def __init__(self, t, out_dtype=np.float64, slot="images"):
         global _pool
         import concurrent.futures as cf
         if _pool is None:
@@ -103,13 +103,15 @@ class AsyncFetch:
         if cls._stream is None:
             cls._stream = torch.cuda.Stream()
         nbytes = t.numel() * t.element_size()
-        if cls._pin is None or cls._pin.numel() < nbytes:
-            cls._pin = torch.empty((max(nbytes, 1),), dtype=torch.uint8, pin_memory=True)
+        pin = cls._pins.get(slot)
+        if pin is None or pin.numel() < nbytes:
+            pin = torch.empty((max(nbytes, 1),), dtype=torch.uint8, pin_memory=True)
+            cls._pins[slot] = pin
         self._keep = t
         ready = torch.cuda.Event()
         ready.record()
         cls._stream.wait_event(ready)
-        view = cls._pin[:nbytes].view(t.dtype).view(t.shape)
+        view = pin[:nbytes].view(t.dtype).view(t.shape)
         with torch.cuda.stream(cls._stream):
             view.copy_(t, non_blocking=True)
             done = torch.cuda.Event()

@@ -208,7 +208,7 @@ def fit_stage(ops, plan, Ps, Y, polar_mode=0, check=True):
 
 
 def run_pipeline(ops, plan, ed, rot9_local, rot_y_all, n_p, k, eps, polar_mode=0, check=True, stats=None,
-                 validate=True, on_images=None, photons_per_pattern=None, noise_seed=0):
+                 validate=True, on_images=None, photons_per_pattern=None, noise_seed=0, on_lists=None):
     """Full path on device.  ed [n,n,n] f32; rot9_local [hi-lo,9] f64 row-major Rm of the rank's
     patterns; rot_y_all [N,9] f64 = Rotation_R.T (the reference's column-major unfold, transposed)."""
     img = ops.synth_patterns(ed, rot9_local, n_p)
@@ -219,6 +219,8 @@ def run_pipeline(ops, plan, ed, rot9_local, rot_y_all, n_p, k, eps, polar_mode=0
     S2, Nbr = knn_stage(ops, plan, img, k)
     S2_out = S2.clone()                                      # pre-mutation copy for callers that want it
     P_rows, dis, scalars = markov_stage(ops, plan, S2, Nbr, eps, validate=validate)
+    if on_lists is not None:
+        on_lists(S2, Nbr)                                    # final (thresholded) kNN lists: their host transfer can start now
     Ps, lam = eigen_stage(ops, plan, P_rows, dis, validate=validate, stats=stats)
     fit = fit_stage(ops, plan, Ps, rot_y_all, polar_mode=polar_mode, check=check)
     out = {"Images_local": img, "S2": S2, "S2_unmutated": S2_out, "N": Nbr, "Ps": Ps, "Lambda": lam, "dinv_sqrt": dis,

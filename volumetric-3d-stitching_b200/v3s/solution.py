@@ -49,22 +49,33 @@ class OrientationRecoverySolver:
         xfer = {}
         # the pattern matrix is by far the largest output: its host transfer starts as soon as stage 1
         # is done and overlaps stages 2-4 (side stream + worker thread)
-        start_images = (lambda img: xfer.setdefault('Images', _util.AsyncFetch(img))) if ops.device.type == 'cuda' else None
+        on_gpu = ops.device.type == 'cuda'
+        start_images = (lambda img: xfer.setdefault('Images', _util.AsyncFetch(img))) if on_gpu else None
+        # so are the kNN lists (final once the Markov matrix is built): they travel during the eigen-solver
+
+        def start_lists(S2_dev, N_dev):
+            xfer['S2'] = _util.AsyncFetch(S2_dev, slot='S2')
+            xfer['N'] = _util.AsyncFetch(N_dev, slot='N')            # int32 on the wire, float64 (distance.py:37) on the host
         plan = ShardPlan.from_env(Nn)
         if plan.world > 1:
             rot9 = rot9[plan.lo:plan.hi].contiguous()
         out = run_pipeline(ops, plan, ed, rot9, rot_y, n_p, parameters['k'], parameters['Epsilon'],
                            polar_mode=polar_mode, check=check_sigma, stats=stats, on_images=start_images,
-                           photons_per_pattern=photons_per_pattern, noise_seed=noise_seed)
+                           photons_per_pattern=photons_per_pattern, noise_seed=noise_seed,
+                           on_lists=start_lists if on_gpu else None)
         # the reference returns float64 everywhere: widen on the device, one staged transfer for all arrays
         f64 = lambda t: t.to(torch.float64)
+        small = {'Ps': f64(out['Ps']), 'Lambda': f64(out['Lambda']), 'c': f64(out['c'])}
+        if 'S2' not in xfer:
+            small.update({'S2': f64(out['S2']), 'N': f64(out['N'])})
         host = _util.fetch_many({
-            'Ps': f64(out['Ps']), 'Lambda': f64(out['Lambda']), 'c': f64(out['c']), 'S2': f64(out['S2']),
-            'N': f64(out['N']),
+            **small,
             'nonzero': plan.all_reduce_sum(torch.any(out['Images_local'] != 0).reshape(1).to(torch.int32)).to(torch.uint8),
             'Sigma_T': out['sigma_T'].reshape(1).to(torch.float64)})
         host['Images'] = xfer['Images'].result() if 'Images' in xfer else \
             _util.fetch_many({'Images': f64(out['Images_local'])})['Images']
+        if 'S2' in xfer:
+            host['S2'], host['N'] = xfer['S2'].result(), xfer['N'].result()
         if not host['nonzero'][0]:
             raise Exception('Images is an all-zero array.')          # projection.py:47
         print('OrientationRecoverySolver.solve ended.')
