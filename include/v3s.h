@@ -137,12 +137,14 @@ int v3s_knn_from_dense(const double* B, long long n, int k, int margin, float* k
  * most `cap` per row (cand_ws int [n_rows,cap], count_ws int [n_rows]); *overflow_flag (device,
  * may be NULL) counts rows whose band exceeded cap and fell back to exactly k+margin candidates.
  * Their distances are recomputed from the FP32 rows as 2 asin(|a_r - a_c|/2) and sorted.
+ * dist_ws (may be NULL): FP64 [n_rows,cap]; with it every unordered pair of rows of this call that
+ * list each other is evaluated once instead of twice (same values bit for bit, ~1/3 fewer row reads).
  * Fails with the reference's message "Number of nearest neighbors to preserve is too high."
  * when k > n_cols.                                                                              */
 int v3s_knn_from_gram(const float* G, long long ldg, long long n_rows, long long n_cols, long long row0,
                       const float* a_rows, const float* a_all, int P, int k, int margin, float eps_g, int cap,
                       const int* zero_flag, int* cand_ws, int* count_ws, int* overflow_flag, double* S2, int* Nbr,
-                      void* stream);
+                      double* dist_ws, void* stream);
 
 /* ---- stage 3: diffusion map ---------------------------------------------------------------- */
 

@@ -255,6 +255,48 @@ def test_knn_zero_rows_and_panels(ops):
     finally:
         ops_cuda.PANEL_BYTES = old
     assert np.array_equal(S2p.cpu().numpy(), S2) and np.array_equal(Np.cpu().numpy(), N)
+    # mutual candidate pairs evaluated once (two-launch refinement) == every pair evaluated by both rows
+    try:
+        ops.dedup_refine = False
+        S2n, Nn_ = knn_stage(ops, ShardPlan(700), ops.to_device(A, torch.float32), 20)
+    finally:
+        ops.dedup_refine = True
+    assert np.array_equal(S2n.cpu().numpy(), S2) and np.array_equal(Nn_.cpu().numpy(), N)
+
+
+def test_refinement_pair_dedup_bit_identical(ops):
+    """The refinement evaluates a pair of rows that list each other once (select.cu, phases 1 / 2):
+    same distances and neighbours bit for bit as the one-launch form, for the whole matrix, for a row
+    block of a sharded job (partners outside the block are evaluated locally) and for streamed panels."""
+    from v3s import ops_cuda
+    rng = np.random.default_rng(11)
+    N, P, k = 3000, 640, 150
+    base = rng.standard_normal((60, P)).astype(np.float32)
+    A = (base[rng.integers(0, 60, N)] + 0.35 * rng.standard_normal((N, P))).astype(np.float32)   # clustered: dense mutual lists
+    img = ops.to_device(A, torch.float32)
+    a32, hi, lo, zf = ops.center_normalize(img, ops.column_sums(img) / N)
+    out = {}
+    for dedup in (True, False):
+        ops.dedup_refine = dedup
+        try:
+            whole = ops.knn_rows(hi, lo, a32, zf, 0, N, k)
+            block = ops.knn_rows(hi, lo, a32, zf, 1000, 2177, k)
+            old = ops_cuda.PANEL_BYTES
+            try:
+                ops_cuda.PANEL_BYTES = 256 * 4 * 3000                    # panels of 256 rows
+                panels = ops.knn_rows(hi, lo, a32, zf, 500, 1500, k)
+            finally:
+                ops_cuda.PANEL_BYTES = old
+        finally:
+            ops.dedup_refine = True
+        out[dedup] = [t.cpu().numpy() for pair in (whole, block, panels) for t in pair]
+    for x, y in zip(out[True], out[False]):
+        assert np.array_equal(x, y)
+    S2w, Nw = out[True][0], out[True][1]
+    assert np.array_equal(out[True][2], S2w[1000:2177]) and np.array_equal(out[True][3], Nw[1000:2177])
+    assert np.all(np.diff(S2w, axis=1) >= 0) and np.all(Nw[:, 0] == np.arange(N))
+    mutual = np.mean([i in Nw[j] for i in range(0, N, 37) for j in Nw[i, 1:20]])
+    print("mutual fraction among the 20 nearest:", mutual)
 
 
 # ------------------------------------------------------------------ stage 3

@@ -52,6 +52,40 @@ def test_block_lanczos_matches_dense_eigh(golden_dir):
     assert stats["converged"] and stats["matvecs"] < 60
 
 
+def test_ritz_extraction_paths_agree():
+    """The projected block-tridiagonal matrix: vectorised band fill == the element-wise definition, and the
+    dense (m <= 320) and banded (m > 320) Ritz extractions return the same extreme eigenpairs."""
+    from v3s import eig
+    b = 8
+    rng = np.random.default_rng(3)
+    for m in (40, 320, 336):
+        band = np.zeros((b + 1, 512))
+        ref = np.zeros_like(band)
+        T = np.zeros((m, m))
+        for s_ in range(m // b):
+            A = rng.standard_normal((b, b))
+            A = 0.5 * (A + A.T)
+            Bj = np.triu(rng.standard_normal((b, b)))
+            blk = np.concatenate([A, Bj], axis=0)
+            eig._fill_band(band, b, (s_ + 1) * b, blk)
+            for c in range(b):                                   # the definition: band[i, col] = stack[c + i, c]
+                col = s_ * b + c
+                for i in range(b + 1):
+                    r = c + i
+                    ref[i, col] = blk[r, c] if (r < b or (r - b) <= c) else 0.0
+            T[s_ * b:(s_ + 1) * b, s_ * b:(s_ + 1) * b] = A
+            if (s_ + 1) * b < m:
+                T[(s_ + 1) * b:(s_ + 2) * b, s_ * b:(s_ + 1) * b] = Bj
+                T[s_ * b:(s_ + 1) * b, (s_ + 1) * b:(s_ + 2) * b] = Bj.T
+        assert np.array_equal(band, ref)
+        w_all, U = np.linalg.eigh(T)
+        for both in (False, True):
+            w, S = eig._ritz_from_band(band, m, b, 10, both)
+            want = w_all[np.argsort(-np.abs(w_all), kind="stable")[:10]] if both else w_all[::-1][:10]
+            assert np.allclose(np.sort(w), np.sort(want), rtol=0, atol=1e-10 * np.abs(w_all).max())
+            assert np.max(np.abs(T @ S - S * w[None, :])) < 1e-8 * np.abs(w_all).max()
+
+
 def test_device_driver_lanczos_host_logic(golden_dir):
     """block_lanczos_device (the host side of csrc/lanczos.cu) against dense eigh, CPU stand-in steps."""
     from v3s.eig import block_lanczos_device

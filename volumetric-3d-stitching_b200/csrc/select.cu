@@ -8,6 +8,11 @@
 //                      well-conditioned form d = 2 asin(|a_r - a_c| / 2) (== arccos(<a_r,a_c>) for
 //                      unit vectors; arccos(g) itself amplifies FP32 error by 1/(d sin d)),
 //                      bitonic-sort by (d, index) and keep the first k.
+//                      With a distance workspace the refinement runs in two launches and every
+//                      unordered pair (i, j) of rows of the same call that list each other is
+//                      evaluated ONCE (by the lower row; the other row fetches the value) -- the
+//                      refinement is bound by the reads of the candidate rows, and most kNN pairs
+//                      are mutual.  Values are bit-identical to the one-launch form.
 // Zero-norm rows (0/0 -> NaN in the reference, then NaN -> 0 at distance.py:58) get distance 0 to
 // every pattern, as in the reference.
 #include "common.cuh"
@@ -135,7 +140,10 @@ refine_sort_kernel(const float* __restrict__ a_rows, const float* __restrict__ a
                    const int* __restrict__ cand, const int* __restrict__ cand_count, int cap, int kk_pad, int k,
                    const int* __restrict__ zero_flag,
                    int cache_row, const double* __restrict__ Bd, long long ldb, double* __restrict__ S2,
-                   int* __restrict__ Nbr) {
+                   int* __restrict__ Nbr, double* Dws, int phase) {
+  // phase 0: distances + sort in one launch.  phase 1: distances only, into Dws [n_rows, cap] in candidate
+  // order; a pair whose partner row j < i of this call lists i too is skipped and stored as -(t + 1),
+  // t = position of i in j's list.  phase 2: fetch the skipped values from the partner rows, sort, emit.
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* sd = reinterpret_cast<double*>(smem_raw);          // kk_pad
   int* si = reinterpret_cast<int*>(sd + kk_pad);              // kk_pad
@@ -155,7 +163,7 @@ refine_sort_kernel(const float* __restrict__ a_rows, const float* __restrict__ a
         si[s] = j;
       }
     }
-    if (!Bd && cache_row) {
+    if (!Bd && cache_row && phase != 2) {
       for (int p = tid; p < P; p += kRefThreads) srow[p] = arow[p];
     }
     if (!Bd) {
@@ -167,8 +175,35 @@ refine_sort_kernel(const float* __restrict__ a_rows, const float* __restrict__ a
     __syncthreads();
     const float* xr = cache_row ? srow : arow;
     const bool rz = zero_flag ? (zero_flag[row0 + r] != 0) : false;
-    for (int s = warp; s < (Bd ? 0 : kk); s += kRefThreads / 32) {
+    if (phase == 2) {
+      for (int s = tid; s < kk; s += kRefThreads) {
+        const int j = cand[(long long)r * cap + s];
+        double d = Dws[(long long)r * cap + s];
+        if (d < 0.0) d = Dws[(long long)(j - row0) * cap + (long long)(-d) - 1];   // evaluated by the partner row
+        sd[s] = d;
+        si[s] = j;
+      }
+    }
+    for (int s = warp; s < ((Bd || phase == 2) ? 0 : kk); s += kRefThreads / 32) {
       const int j = cand[(long long)r * cap + s];
+      if (phase == 1) {
+        const long long lj = (long long)j - row0;
+        if (lj >= 0 && lj < r) {                              // partner row of this call with a lower index
+          const int* cj = cand + lj * cap;
+          const int cntj = cand_count[lj];
+          const int me = (int)(row0 + r);
+          int pos = -1;
+          for (int t0 = 0; t0 < cntj && pos < 0; t0 += 32) {
+            const int t = t0 + lane;
+            const unsigned hit = __ballot_sync(0xffffffffu, t < cntj && cj[t] == me);
+            if (hit) pos = t0 + __ffs(hit) - 1;
+          }
+          if (pos >= 0) {
+            if (lane == 0) Dws[(long long)r * cap + s] = -(double)(pos + 1);
+            continue;
+          }
+        }
+      }
       const float* aj = a_all + (long long)j * P;
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
       if (vec4) {
@@ -204,10 +239,15 @@ refine_sort_kernel(const float* __restrict__ a_rows, const float* __restrict__ a
         if (half > 1.0) half = 1.0;
         double d = 2.0 * asin(half);
         if (zero_flag && (rz || zero_flag[j])) d = 0.0;
-        sd[s] = d;
-        si[s] = j;
+        if (phase == 1) {
+          Dws[(long long)r * cap + s] = d;
+        } else {
+          sd[s] = d;
+          si[s] = j;
+        }
       }
     }
+    if (phase == 1) continue;
     __syncthreads();
     // bitonic sort of kk_pad (d, idx) pairs, ascending by d then idx
     for (int size = 2; size <= kk_pad; size <<= 1) {
@@ -238,7 +278,7 @@ using namespace v3s;
 extern "C" int v3s_knn_from_gram(const float* G, long long ldg, long long n_rows, long long n_cols, long long row0,
                                  const float* a_rows, const float* a_all, int P, int k, int margin, float eps_g, int cap,
                                  const int* zero_flag, int* cand_ws, int* count_ws, int* overflow_flag, double* S2,
-                                 int* Nbr, void* stream) {
+                                 int* Nbr, double* dist_ws, void* stream) {
   V3S_REQUIRE(k >= 1 && margin >= 0, "v3s_knn_from_gram: bad k/margin");
   V3S_REQUIRE(k <= n_cols, "Number of nearest neighbors to preserve is too high.");   // distance.py:33-34
   V3S_REQUIRE(n_rows >= 0 && n_cols < (1LL << 31) && n_rows < (1LL << 31) && ldg >= n_cols, "v3s_knn_from_gram: bad shape");
@@ -264,8 +304,17 @@ extern "C" int v3s_knn_from_gram(const float* G, long long ldg, long long n_rows
     smem_set = smem;
   }
   const int grid2 = (int)(n_rows < 8LL * kNumSMs ? n_rows : 8LL * kNumSMs);
+  if (dist_ws) {
+    refine_sort_kernel<<<grid2, kRefThreads, smem, st>>>(a_rows, a_all, P, row0, (int)n_rows, cand_ws, count_ws, cap, kk_pad,
+                                                        k, zero_flag, cache_row, nullptr, 0, S2, Nbr, dist_ws, 1);
+    V3S_CHECK_LAUNCH();
+    refine_sort_kernel<<<grid2, kRefThreads, base, st>>>(a_rows, a_all, P, row0, (int)n_rows, cand_ws, count_ws, cap, kk_pad,
+                                                        k, zero_flag, 0, nullptr, 0, S2, Nbr, dist_ws, 2);
+    V3S_CHECK_LAUNCH();
+    return 0;
+  }
   refine_sort_kernel<<<grid2, kRefThreads, smem, st>>>(a_rows, a_all, P, row0, (int)n_rows, cand_ws, count_ws, cap, kk_pad,
-                                                      k, zero_flag, cache_row, nullptr, 0, S2, Nbr);
+                                                      k, zero_flag, cache_row, nullptr, 0, S2, Nbr, nullptr, 0);
   V3S_CHECK_LAUNCH();
   return 0;
 }
@@ -300,7 +349,7 @@ extern "C" int v3s_knn_from_dense(const double* B, long long n, int k, int margi
   V3S_CHECK_LAUNCH();
   const size_t smem = (size_t)kk_pad * (sizeof(double) + sizeof(int));
   refine_sort_kernel<<<grid, kRefThreads, smem, st>>>(nullptr, nullptr, 0, 0, (int)n, cand_ws, count_ws, (int)kk, kk_pad, k,
-                                                     nullptr, 0, B, n, S2, Nbr);
+                                                     nullptr, 0, B, n, S2, Nbr, nullptr, 0);
   V3S_CHECK_LAUNCH();
   return 0;
 }

@@ -45,7 +45,7 @@ SIGNATURES = {
     "v3s_gram_symmetric_sharded": (i32, [p, p, i64, i32, C.POINTER(C.c_ulonglong), i32, i64, i32, i64, p, i32, p]),
     "v3s_gram_rows_simt": (i32, [p, i64, p, i64, i32, p, i64, p]),
     "v3s_round_distance_dense": (i32, [p, i64, i32, p, p, p]),
-    "v3s_knn_from_gram": (i32, [p, i64, i64, i64, i64, p, p, i32, i32, i32, C.c_float, i32, p, p, p, p, p, p, p]),
+    "v3s_knn_from_gram": (i32, [p, i64, i64, i64, i64, p, p, i32, i32, i32, C.c_float, i32, p, p, p, p, p, p, p, p]),
     "v3s_knn_from_dense": (i32, [p, i64, i32, i32, p, p, p, p, p, p]),
     "v3s_s2_scalars": (i32, [p, i64, i32, f64, i32, i32, p, p]),
     "v3s_s2_threshold": (i32, [p, i64, i32, p, p]),

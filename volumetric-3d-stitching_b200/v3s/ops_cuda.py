@@ -43,6 +43,7 @@ class CudaOps:
         self._synth_prep = {}
         self._sym_tile_cache = {}
         self._symm_G = {}
+        self.dedup_refine = True     # exact-distance refinement: mutual candidate pairs once (select.cu)
         self.use_fused_matvec = True # eigen-solver mat-vecs with the reduction / recurrence / exchange fused (FusedOperator)
         self.use_peer_gram = True    # sharded jobs: symmetric Gram with NVLink peer stores (else rectangular panels)
         self.symm_error = None
@@ -275,6 +276,7 @@ class CudaOps:
         G = G_shard if G_shard is not None else self.empty((min(panel, nr), ldg), torch.float32)
         cand = self.empty((min(panel, nr), cap), torch.int32)
         cnt = self.empty((min(panel, nr),), torch.int32)
+        dws = self.empty((min(panel, nr), cap), torch.float64) if self.dedup_refine else None   # mutual pairs evaluated once
         self.knn_overflow = self.zeros((1,), torch.int32)
         zf = zero_flag if (zero_flag is not None) else None
         for p0 in range(r0, r1, panel):
@@ -288,7 +290,7 @@ class CudaOps:
             h = self._tic("select_refine")
             call("v3s_knn_from_gram", ptr(G), ldg, p1 - p0, N, p0, ptr(a32_all[p0:p1]), ptr(a32_all), P, k, KNN_MARGIN,
                  eps_g, cap, ptr(zf), ptr(cand), ptr(cnt), ptr(self.knn_overflow), ptr(S2[p0 - r0:p1 - r0]),
-                 ptr(Nbr[p0 - r0:p1 - r0]), stream_ptr())
+                 ptr(Nbr[p0 - r0:p1 - r0]), ptr(dws), stream_ptr())
             self._toc(h)
         return S2, Nbr
 
