@@ -170,7 +170,7 @@ def run_reference_arm(args, wl):
         return
     _use_all_host_threads()
     vals, t_start, done = [], time.perf_counter(), 0
-    sample = min(args.cpu_sample, 3000)
+    sample = min(args.cpu_sample, 6000)
     for i in range(args.warmup + args.steps):
         full, t, Ns = cpu_reference_pass(wl, sample, os.cpu_count() or 1)
         done += 1
@@ -200,7 +200,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="v3s", choices=["v3s", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-sample", type=int, default=3000)
+    ap.add_argument("--cpu-sample", type=int, default=6000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-baseline-only", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-e2e", action="store_true")

@@ -70,31 +70,72 @@ __device__ void jacobi_sym(double* A, double* V, int n) {
   }
 }
 
-// c = pinv(X^T X) (X^T Y); numpy's pinv cut-off: singular values <= 1e-15 * max are dropped
-__global__ void fit_solve_kernel(const double* __restrict__ in162, double* __restrict__ c81) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  double A[81], V[81], pinv[81];
-  for (int i = 0; i < 81; ++i) A[i] = in162[i];
-  for (int i = 0; i < 9; ++i) for (int j = i + 1; j < 9; ++j) { const double m = 0.5 * (A[i * 9 + j] + A[j * 9 + i]); A[i * 9 + j] = A[j * 9 + i] = m; }
-  jacobi_sym(A, V, 9);
-  double wmax = 0.0;
-  for (int i = 0; i < 9; ++i) wmax = fmax(wmax, fabs(A[i * 9 + i]));
-  for (int i = 0; i < 9; ++i)
-    for (int j = 0; j < 9; ++j) {
-      double s = 0.0;
-      for (int k = 0; k < 9; ++k) {
-        const double w = A[k * 9 + k];
-        if (fabs(w) > 1e-15 * wmax) s += V[i * 9 + k] * V[j * 9 + k] / w;
+// The same cyclic Jacobi iteration on a 9 x 9 matrix in shared memory, executed by one warp: the rotation
+// parameters are computed redundantly by every lane, lane k < 9 applies the rotation to row / column k.
+// Same rotations in the same order and the same arithmetic per element as jacobi_sym (bit-identical).
+__device__ void jacobi_sym9_warp(double (*A)[9], double (*V)[9]) {
+  const int k = threadIdx.x;
+  if (k < 9) for (int j = 0; j < 9; ++j) V[k][j] = (k == j) ? 1.0 : 0.0;
+  __syncwarp();
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    double off = 0.0, diag = 0.0;
+    for (int i = 0; i < 9; ++i) { diag += A[i][i] * A[i][i]; for (int j = i + 1; j < 9; ++j) off += A[i][j] * A[i][j]; }
+    if (off <= 1e-60 || off <= 1e-34 * diag) break;
+    for (int p = 0; p < 8; ++p)
+      for (int q = p + 1; q < 9; ++q) {
+        const double apq = A[p][q];
+        if (apq == 0.0) continue;                      // uniform across the warp
+        const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+        __syncwarp();
+        if (k < 9) {
+          const double akp = A[k][p], akq = A[k][q];
+          A[k][p] = c * akp - sn * akq; A[k][q] = sn * akp + c * akq;
+        }
+        __syncwarp();
+        if (k < 9) {
+          const double apk = A[p][k], aqk = A[q][k];
+          A[p][k] = c * apk - sn * aqk; A[q][k] = sn * apk + c * aqk;
+          const double vkp = V[k][p], vkq = V[k][q];
+          V[k][p] = c * vkp - sn * vkq; V[k][q] = sn * vkp + c * vkq;
+        }
+        __syncwarp();
       }
-      pinv[i * 9 + j] = s;
+  }
+  __syncwarp();
+}
+
+// c = pinv(X^T X) (X^T Y); numpy's pinv cut-off: singular values <= 1e-15 * max are dropped.  One warp.
+__global__ void fit_solve_kernel(const double* __restrict__ in162, double* __restrict__ c81) {
+  __shared__ double A[9][9], V[9][9], pinv[9][9];
+  const int tid = threadIdx.x;
+  if (blockIdx.x != 0) return;
+  for (int e = tid; e < 81; e += 32) A[e / 9][e % 9] = in162[e];
+  __syncwarp();
+  if (tid < 9)
+    for (int j = tid + 1; j < 9; ++j) { const double m = 0.5 * (A[tid][j] + A[j][tid]); A[tid][j] = m; A[j][tid] = m; }
+  __syncwarp();
+  jacobi_sym9_warp(A, V);
+  double wmax = 0.0;
+  for (int i = 0; i < 9; ++i) wmax = fmax(wmax, fabs(A[i][i]));
+  for (int e = tid; e < 81; e += 32) {
+    const int i = e / 9, j = e % 9;
+    double s = 0.0;
+    for (int k = 0; k < 9; ++k) {
+      const double w = A[k][k];
+      if (fabs(w) > 1e-15 * wmax) s += V[i][k] * V[j][k] / w;
     }
+    pinv[i][j] = s;
+  }
+  __syncwarp();
   const double* xty = in162 + 81;
-  for (int i = 0; i < 9; ++i)
-    for (int j = 0; j < 9; ++j) {
-      double s = 0.0;
-      for (int k = 0; k < 9; ++k) s += pinv[i * 9 + k] * xty[k * 9 + j];
-      c81[i * 9 + j] = s;
-    }
+  for (int e = tid; e < 81; e += 32) {
+    const int i = e / 9, j = e % 9;
+    double s = 0.0;
+    for (int k = 0; k < 9; ++k) s += pinv[i][k] * xty[k * 9 + j];
+    c81[e] = s;
+  }
 }
 
 __device__ __forceinline__ void quat_from_rot(const double* R, double* q) {
