@@ -250,12 +250,18 @@ def main():
         return run_pipeline(ops, plan, ed, rot9, rot_y, n_p, k, eps, polar_mode=0, check=False, stats=stats, validate=False,
                             photons_per_pattern=wl.get("photons"))
 
-    for _ in range(args.warmup):
-        out = one_pass()
-    barrier()
+    # the clock sampler (an nvidia-smi child polling every 100 ms) starts before the warm-up: its start-up
+    # (process spawn, NVML initialisation) must not fall into the timed region
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        out = one_pass()
+    barrier()
+    if rank == 0:
+        time.sleep(0.3)                   # let the sampler reach its steady polling state
+        sampler.lines.clear()             # keep the samples of the timed region only
+    barrier()
     ops.profile = True
     ops.pop_timings()
     from v3s import eig as _eig
