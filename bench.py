@@ -15,6 +15,7 @@ per launch set / its CUDA-event time, against the measured BF16 peak.
 """
 import argparse
 import contextlib
+import gc
 import io
 import json
 import os
@@ -55,49 +56,87 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons during the timed region (B200_PROFILING.md's clocks line).
+    In-process NVML polling from a thread (a few tens of microseconds per sample, every 10 ms); an
+    `nvidia-smi -lms` child costs tens of milliseconds of driver time per poll, which a 100 ms timed region
+    cannot absorb.  Falls back to one nvidia-smi query after the region if NVML cannot be loaded."""
+
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"),
+               (0x80, "hw_power_brake_slowdown"))
 
     def __init__(self, index=0):
         self.index = index
-        self.proc = None
-        self.lines = []
+        self.samples = []          # (sm_mhz, reasons bit mask)
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = None
+        self._nvml = None
+        self._handle = None
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            import pynvml
+            pynvml.nvmlInit()
+            handle = None
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+                handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self._nvml, self._handle = pynvml, handle
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
+            self._sample()         # first call pays NVML's lazy initialisation, outside the timed region
+            self.samples.clear()
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
         except Exception:
-            self.proc = None
+            self._nvml = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _sample(self):
+        nv, h = self._nvml, self._handle
+        sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+        get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        self.samples.append((sm, int(get(h))))
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self._sample()
+            except Exception:
+                break
+            self._stop.wait(0.01)
+
+    def reset(self):
+        self.samples.clear()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        # under load = upper half of the samples (idle samples before/after the region are dropped)
-        load = sm[len(sm) // 2:] if sm else []
-        return {"sm_mhz": (load[len(load) // 2] if load else None), "sm_max_mhz": (max(mx) if mx else None),
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if self._nvml is None:
+            return self._fallback()
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=1.0)
+        sm = sorted(s for s, _ in self.samples)
+        mask = 0
+        for _, m in self.samples:
+            mask |= m
+        reasons = [name for bit, name in self.REASONS if mask & bit]
+        return {"sm_mhz": (sm[len(sm) // 2] if sm else None), "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(sm), "source": "nvml, 10 ms polling inside the timed region"}
+
+    def _fallback(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            r = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                               capture_output=True, text=True, timeout=20)
+            f = [x.strip() for x in r.stdout.strip().splitlines()[0].split(",")]
+            reasons = [n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6])
+                       if v.lower().startswith("active")]
+            return {"sm_mhz": float(f[0]), "sm_max_mhz": float(f[1]), "reasons": reasons, "samples": 1,
+                    "source": "nvidia-smi, one query right after the timed region (NVML python binding unavailable)"}
+        except Exception:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
 
 
 # ------------------------------------------------------------------------------------------
@@ -250,8 +289,7 @@ def main():
         return run_pipeline(ops, plan, ed, rot9, rot_y, n_p, k, eps, polar_mode=0, check=False, stats=stats, validate=False,
                             photons_per_pattern=wl.get("photons"))
 
-    # the clock sampler (an nvidia-smi child polling every 100 ms) starts before the warm-up: its start-up
-    # (process spawn, NVML initialisation) must not fall into the timed region
+    # the clock sampler starts before the warm-up: NVML's initialisation must not fall into the timed region
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -259,9 +297,7 @@ def main():
         out = one_pass()
     barrier()
     if rank == 0:
-        time.sleep(0.3)                   # let the sampler reach its steady polling state
-        sampler.lines.clear()             # keep the samples of the timed region only
-    barrier()
+        sampler.reset()                   # keep the samples of the timed region only
     ops.profile = True
     ops.pop_timings()
     from v3s import eig as _eig
@@ -269,12 +305,17 @@ def main():
     launches0 = int(_lib.lib.v3s_kernel_launches())
     stats = {}
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # a generation-2 collection of the cyclic GC (torch + scipy imported: ~10^5 tracked objects) is a 50-100 ms
+    # pause at a random point of a ~115 ms timed region: collect now, keep the collector off while timing
+    gc.collect()
+    gc.disable()
     barrier()
     e0.record()
     for _ in range(args.steps):
         out = one_pass(stats)
     e1.record()
     barrier()
+    gc.enable()
     ms = e0.elapsed_time(e1) / args.steps
     host_timers = dict(_eig.HOST_TIMERS)                 # of the timed region only (the e2e calls below add to them)
     launches = (int(_lib.lib.v3s_kernel_launches()) - launches0) // args.steps      # kernels of libv3s.so only
@@ -301,11 +342,15 @@ def main():
         barrier()
         for k_ in _util.TIMERS:
             _util.TIMERS[k_] = 0.0
+        del res
+        gc.collect()
+        gc.disable()
         t0 = time.perf_counter()
         reps = max(2, min(args.steps, 3))
         for _ in range(reps):
             res = call()
         barrier()
+        gc.enable()
         host_e2e = {k_: round(v_ / reps * 1e3, 3) for k_, v_ in _util.TIMERS.items()}
         t_e2e = torch.tensor([(time.perf_counter() - t0) / reps], dtype=torch.float64, device="cuda")
         if world > 1:
