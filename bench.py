@@ -423,6 +423,12 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(args.workload, {})
     except Exception:
         traffic = {}
+    try:
+        pipes = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(args.workload + "_ncu_pipes")
+    except Exception:
+        pipes = None
+    if world == 1 and pipes:
+        line["ncu_pipe_utilisation"] = pipes          # committed ncu capture of this workload (not measured in this run)
     if world == 1:
         mv_roof["traffic"] = traffic.get("block_matvec_kernel")
         gram_roof["traffic"] = traffic.get("gram_tc_kernel")
