@@ -243,6 +243,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-baseline-only", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--operator", default="auto", choices=["auto", "dense", "sparse"],
+                    help="Markov operator of the eigen-solver (auto: dense FP32 rows up to 12 GB per rank, FP64 kNN-list form beyond)")
+    ap.add_argument("--no-alt-operator", action="store_true", help="skip the extra passes with the other operator form")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -270,6 +273,7 @@ def main():
     from v3s.rotation import Rotation
     from v3s.solution import OrientationRecoverySolver
     ops = _util.get_ops()
+    ops.operator = args.operator
     N, n, n_p, k, eps = wl["N"], wl["n"], wl["n_p"], wl["k"], wl["eps"]
     plan = ShardPlan.from_env(N)
     R9, _ = Rotation.random_rotations(N, seed=0)
@@ -289,16 +293,30 @@ def main():
         return run_pipeline(ops, plan, ed, rot9, rot_y, n_p, k, eps, polar_mode=0, check=False, stats=stats, validate=False,
                             photons_per_pattern=wl.get("photons"))
 
+    trace = None
+    if os.environ.get("V3S_BENCH_TRACE"):
+        # diagnostic: host timestamps around every C-ABI call (no synchronisation added) -> where a stalled pass lost its time
+        trace = []
+        _orig_call = _lib.call
+
+        def _traced_call(name, *a):
+            t0_ = time.perf_counter()
+            r_ = _orig_call(name, *a)
+            trace.append((name, t0_, time.perf_counter()))
+            return r_
+        import v3s.ops_cuda as _oc
+        _lib.call = _oc.call = _traced_call
+
     # the clock sampler starts before the warm-up: NVML's initialisation must not fall into the timed region
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("V3S_BENCH_NO_SAMPLER"):
         sampler.start()
     for _ in range(args.warmup):
         out = one_pass()
     barrier()
     if rank == 0:
         sampler.reset()                   # keep the samples of the timed region only
-    ops.profile = True
+    ops.profile = not os.environ.get("V3S_BENCH_NO_PROFILE")
     ops.pop_timings()
     from v3s import eig as _eig
     _eig.HOST_TIMERS.update({"ritz_s": 0.0, "wait_s": 0.0})
@@ -311,8 +329,25 @@ def main():
     gc.disable()
     barrier()
     e0.record()
+    pass_wall = [time.perf_counter()]
     for _ in range(args.steps):
+        if trace is not None:
+            trace.append(("PASS", time.perf_counter(), time.perf_counter()))
         out = one_pass(stats)
+        pass_wall.append(time.perf_counter())          # host clock only (no synchronisation): where a stall fell
+    if trace is not None:
+        trace.append(("END", time.perf_counter(), time.perf_counter()))
+        ev = [i for i, r_ in enumerate(trace) if r_[0] in ("PASS", "END")]
+        for a_, b_ in zip(ev[-args.steps - 1:-1], ev[-args.steps:]):
+            seg = trace[a_:b_ + 1]
+            total = (seg[-1][1] - seg[0][1]) * 1e3
+            slow = []
+            for x_, y_ in zip(seg[:-1], seg[1:]):
+                if (x_[2] - x_[1]) > 2e-3:
+                    slow.append("in %s %.1f ms" % (x_[0], (x_[2] - x_[1]) * 1e3))
+                if (y_[1] - x_[2]) > 2e-3:
+                    slow.append("%s -> %s %.1f ms" % (x_[0], y_[0], (y_[1] - x_[2]) * 1e3))
+            sys.stderr.write("TRACE pass %.1f ms: %s\n" % (total, "; ".join(slow)))
     e1.record()
     barrier()
     gc.enable()
@@ -328,6 +363,44 @@ def main():
     ms = float(t_ms.item())
     sigma_T = float(out["sigma_T"].item())
     lam = out["Lambda"].cpu().numpy()
+    sparse_run = stats.get("operator") == "sparse-fp64"
+    nnz_local = None
+    if sparse_run:      # stored entries of the rank's rows: its own lists + the transposed copies of the non-zero entries
+        nnz_local = (plan.hi - plan.lo) * k + int((torch.isfinite(out["S2"]) & (out["N"] >= plan.lo) & (out["N"] < plan.hi)).sum().item())
+    del out
+
+    # ---- the same pass with the other form of the Markov operator (reported beside the headline) ----
+    alt = None
+    if not args.no_alt_operator:
+        try:
+            ops.operator = "dense" if sparse_run else "sparse"
+            alt_stats = {}
+            for _ in range(2):
+                o2 = one_pass(alt_stats)
+            gc.collect()
+            gc.disable()
+            barrier()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(args.steps):
+                o2 = one_pass(alt_stats)
+            a1.record()
+            barrier()
+            gc.enable()
+            t_alt = torch.tensor([a0.elapsed_time(a1) / args.steps], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(t_alt, op=dist.ReduceOp.MAX)
+            lam2 = o2["Lambda"].cpu().numpy()
+            alt = {"operator": alt_stats.get("operator"), "value": round(float(t_alt.item()) / 1e3, 5), "unit": "s",
+                   "matvecs": alt_stats.get("matvecs"), "converged": alt_stats.get("converged"),
+                   "max_abs_lambda_difference_to_headline": float(np.max(np.abs(lam2 - lam))),
+                   "sigma_T_deg": round(float(o2["sigma_T"].item()), 4),
+                   "note": "same device-resident pass, other operator form (dense FP32 row block <-> FP64 kNN-list form); not the headline"}
+            del o2
+        except Exception as e_alt:                      # never lose the headline line over the side measurement
+            gc.enable()
+            alt = {"error": repr(e_alt)}
+        ops.operator = args.operator
 
     # ---- e2e: reference-facing call, host inputs -> host outputs, on every rank of the job ----
     e2e = None
@@ -385,7 +458,8 @@ def main():
     gram_flop = 2.0 * rows_local * N * P                       # algorithmic: no split-precision multiplier
     achieved = gram_flop / (gram_per_pass * 1e-3) / 1e12 if gram_ms else None
     mv = kt.get("matvec", [])
-    mv_gbs = (4.0 * rows_local * N + 8.0 * N * 8 * 2) / (sum(mv) / len(mv) * 1e-3) / 1e9 if mv else None
+    mv_bytes = (12.0 * nnz_local + 64.0 * N + 64.0 * rows_local) if sparse_run else (4.0 * rows_local * N + 8.0 * N * 8 * 2)
+    mv_gbs = mv_bytes / (sum(mv) / len(mv) * 1e-3) / 1e9 if mv else None
     stage_ms = {name: round(sum(v) / args.steps, 3) for name, v in kt.items()}
     line = {
         "metric": METRIC, "value": round(ms / 1e3, 5), "unit": "s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -406,6 +480,9 @@ def main():
                              "waiting_for_gpu_in_eigensolver": round(host_timers["wait_s"] / args.steps * 1e3, 3)},
         "result": {"sigma_T_deg": round(sigma_T, 4), "lambda_1_9": [round(float(x), 8) for x in lam[:10]]},
         "cpu_baseline": cpu_base,
+        "host_wall_ms_of_each_pass": [round((b_ - a_) * 1e3, 2) for a_, b_ in zip(pass_wall[:-1], pass_wall[1:])],
+        "operator": stats.get("operator"),
+        "alt_operator": alt,
     }
     sym = getattr(ops, "_sym_tile_cache", {}).get(N) if world == 1 else None
     tile_frac = (sym[1] / (((N + 127) // 128) * ((N + 255) // 256))) if sym else 1.0
@@ -419,6 +496,10 @@ def main():
                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": (round(mv_gbs / peaks["hbm_gbs"], 4) if mv_gbs else None),
                "traffic": None, "ms_per_pass": round(sum(mv) / args.steps, 3) if mv else None, "launches_per_pass": len(mv) // args.steps,
                "peak_source": peak_src + " hbm_gbs", "note": "algorithmic 4*rows*N + 8*N*8*2 bytes per launch"}
+    if sparse_run:
+        mv_roof["kernel"] = "sparse_block_matvec_kernel (FP64 kNN-list operator, warp per row, shuffle-broadcast entries)"
+        mv_roof["note"] = ("algorithmic HBM bytes per launch: 12 B per stored entry + the FP64 block read once and the rank's rows "
+                           "written once; the kernel itself is bound by L2 gathers of the block (64 B per entry), not by HBM")
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(args.workload, {})
     except Exception:
@@ -430,7 +511,7 @@ def main():
     if world == 1 and pipes:
         line["ncu_pipe_utilisation"] = pipes          # committed ncu capture of this workload (not measured in this run)
     if world == 1:
-        mv_roof["traffic"] = traffic.get("block_matvec_kernel")
+        mv_roof["traffic"] = None if sparse_run else traffic.get("block_matvec_kernel")
         gram_roof["traffic"] = traffic.get("gram_tc_kernel")
         mv_roof["traffic_source"] = gram_roof["traffic_source"] = "profiles/r01_traffic.json (ncu --set full, bytes per launch)"
     dominant_is_mv = bool(mv) and (not gram_ms or sum(mv) >= sum(gram_ms))

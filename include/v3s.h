@@ -228,7 +228,42 @@ int v3s_cheb_filter(const float* P_rows, long long ldp, long long n_rows, long l
                     const double* Q, int q_index, int degree, double c, double e, const unsigned long long* ybuf_ptrs,
                     const unsigned long long* xf_ptrs, const unsigned long long* flag_ptrs, int rank, int world,
                     int epoch0, unsigned* ticket_dev, int* status_dev, void* workspace, int* result_index, void* stream);
-/* per-launch device time of block_matvec_kernel (CUDA events owned by the library, recorded on the
+/* ---- sparse form of the same operator -----------------------------------------------------------
+ * P_ep has at most k + in-degree(i) non-zeros in row i (the reference itself assembles W through
+ * scipy.sparse.csr_array, diffusion.py:317, and only then densifies it): P = A + A^T, A = the kNN
+ * lists with the values h_ij of v3s_build_markov.  FP64 values and FP64 operand, so the operator
+ * carries no FP32 rounding at all; per mat-vec it moves 76 B per non-zero instead of 4 N B per row,
+ * which is what makes BASELINE config 5 (N = 2 10^5: 160 GB dense) affordable.  Device pointers;
+ * the descriptor itself lives on the host.                                                       */
+typedef struct v3s_sparse_markov {
+  const int* nbr;        /* [N,k]   column of entry (i,t): the kNN list                             */
+  const double* a_val;   /* [N,k]   h_it (0 for thresholded entries)                                */
+  const int* t_ptr;      /* [N+1]   row pointers of the transposed lists                            */
+  const int* t_col;      /* [nnz]   source rows, ascending inside a row                             */
+  const double* t_val;   /* [nnz]                                                                   */
+  int k;
+} v3s_sparse_markov;
+/* s2_to_w_matrix + anisotropic_norm + dm_cov on the lists (as v3s_build_markov) -> the arrays of the
+ * descriptor (caller-allocated: a_val [N k], t_ptr [N+1], t_col / t_val [N k]) and dinv_sqrt [N].
+ * ws_2N: 2N doubles; iws: N + N k ints.  Replicated on every rank of a sharded job (O(N k)).     */
+int v3s_build_markov_sparse(const double* S2_thresholded, const int* Nbr, long long N, int k, const double* scalars5,
+                            double* a_val, int* t_ptr, int* t_col, double* t_val, double* dinv_sqrt, double* ws_2N,
+                            int* iws, void* stream);
+/* Y_rows [n_rows,b] = P[row0 .. row0+n_rows, :] . X [N,b] (FP64), b <= 8 */
+int v3s_sparse_block_matvec(const v3s_sparse_markov* op, long long row0, long long n_rows, long long N, const double* X,
+                            int b, double* Y_rows, void* stream);
+/* v3s_matvec_combine / v3s_cheb_filter with the sparse operator: X (Q) is the FP64 block [N,8] itself,
+ * no FP32 strip operands are read or (unless xfout_ptrs is given) written; workspace: 8 n_rows doubles. */
+int v3s_sparse_matvec_combine(const v3s_sparse_markov* op, long long n_rows, long long N, long long row0, const double* X,
+                              const double* Yk, const double* Ykm1, double alpha, double beta, double gamma,
+                              const unsigned long long* yout_ptrs, const unsigned long long* xfout_ptrs,
+                              const unsigned long long* flag_ptrs, int rank, int world, int epoch, unsigned* ticket_dev,
+                              int* status_dev, void* workspace, void* stream);
+int v3s_sparse_cheb_filter(const v3s_sparse_markov* op, long long n_rows, long long N, long long row0, const double* Q,
+                           int q_index, int degree, double c, double e, const unsigned long long* ybuf_ptrs,
+                           const unsigned long long* flag_ptrs, int rank, int world, int epoch0, unsigned* ticket_dev,
+                           int* status_dev, void* workspace, int* result_index, void* stream);
+/* per-launch device time of the mat-vec kernel, dense or sparse (CUDA events owned by the library, recorded on the
  * launching stream): enable/reset, then read the elapsed milliseconds (returns the launch count). */
 int v3s_profile_matvec(int enable);
 int v3s_profile_matvec_read(float* ms_out, int cap);

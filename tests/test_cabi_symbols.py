@@ -32,5 +32,7 @@ def test_error_plumbing_without_gpu():
     # argument validation happens before any CUDA call: a bad shape returns non-zero with a message
     rc = _lib.lib.v3s_block_matvec(None, 3, 1, 10, None, 99, None, None, None)
     assert rc != 0 and "block size" in _lib.last_error()
+    rc = _lib.lib.v3s_sparse_block_matvec(None, 0, 1, 10, None, 8, None, None)
+    assert rc != 0 and "operator descriptor" in _lib.last_error()
     assert _lib.lib.v3s_xf_floats(130) == 2048
     assert _lib.lib.v3s_synth_workspace_bytes(64) == 64 * 64 * 16

@@ -446,6 +446,140 @@ def test_fused_operator_plain_and_chebyshev(ops, shape):
         assert (Yc2.cpu() - y2).abs().max().item() < 2e-5 * (y2.abs().max().item() + 1e-30)
 
 
+def _so3_knn_lists(N, k, seed, hub=False):
+    """kNN lists of N random rotations under the geodesic distance of their quaternions (the
+    geometry the diffusion map is meant for: lambda_0 = 1, a 9-fold cluster, then a clear gap).
+    hub=True puts pattern 0 into the middle of every list (in-degree N)."""
+    rng = np.random.default_rng(seed)
+    q = rng.standard_normal((N, 4))
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    D = np.arccos(np.clip(np.abs(q @ q.T), 0.0, 1.0))
+    np.fill_diagonal(D, 0.0)
+    Nbr = np.argsort(D, axis=1, kind="stable")[:, :k]
+    S2 = np.take_along_axis(D, Nbr, axis=1)
+    if hub:
+        for i in range(1, N):
+            if 0 not in Nbr[i]:
+                Nbr[i, k // 2] = 0
+    return S2, Nbr
+
+
+def test_sparse_markov_operator_connected(ops, golden_dir):
+    """Sparse (list) form of P_ep: same entries as the oracle's dense matrix to FP64 rounding, mat-vec
+    to 1e-13, bit-identical across row blocks, repeated calls and rebuilt operators (the transposed
+    lists are filled with atomics and then ordered), fused plain / Chebyshev forms."""
+    from v3s.pipeline import ShardPlan
+    g = np.load(os.path.join(golden_dir, "connected_n15.npz"))
+    N = g["S2"].shape[0]
+    S2m = g["S2"].copy()
+    _, _, W1o, Wo, Po, dio = orc.diffusion_coordinate(S2m, g["N"], float(g["eps"]), return_all=True)
+    S2d = ops.to_device(g["S2"].copy(), torch.float64)
+    Nd = ops.to_device(g["N"], torch.int32)
+    sc = ops.s2_scalars(S2d, float(g["eps"]))
+    ops.s2_threshold_(S2d, sc)
+    sp, dis = ops.build_markov_sparse(S2d, Nd, sc, 0, N)
+    assert np.allclose(dis.cpu().numpy(), g["D_diag"], rtol=1e-12)
+    P = sp.to_dense().cpu().numpy()
+    nz = Po != 0
+    assert np.array_equal(P != 0, nz)
+    assert np.max(np.abs(P[nz] - Po[nz]) / Po[nz]) < 1e-12
+    tp = sp.t_ptr.cpu().numpy()
+    tc = sp.t_col.cpu().numpy()
+    assert tp[0] == 0 and tp[-1] == int((sp.a_val != 0).sum().item())
+    assert all(np.all(np.diff(tc[tp[j]:tp[j + 1]]) > 0) for j in range(N))        # ascending source rows
+    X = np.stack([g["z"], np.ones(N), 1.0 / dio] + [np.random.default_rng(i).standard_normal(N) for i in range(5)], axis=1)
+    Xd = ops.to_device(X, torch.float64)
+    Yref = Po @ X
+    Y = ops.sparse_block_matvec(sp, Xd)
+    assert np.max(np.abs(Y.cpu().numpy() - Yref)) < 5e-12 * np.max(np.abs(Yref))
+    assert torch.equal(Y, ops.sparse_block_matvec(sp, Xd))
+    for b in (1, 3):
+        Yb = ops.sparse_block_matvec(sp, ops.to_device(X[:, :b].copy(), torch.float64)).cpu().numpy()
+        assert np.max(np.abs(Yb - Yref[:, :b])) < 5e-12 * np.max(np.abs(Yref))
+    assert torch.equal(ops.sparse_block_matvec(sp.rows(300, 777), Xd), Y[300:777])
+    sp2, dis2 = ops.build_markov_sparse(S2d, Nd, sc, 0, N)
+    nnz = int(tp[-1])
+    assert torch.equal(sp2.t_ptr, sp.t_ptr) and torch.equal(sp2.t_col[:nnz], sp.t_col[:nnz])
+    assert torch.equal(sp2.t_val[:nnz], sp.t_val[:nnz]) and torch.equal(sp2.a_val, sp.a_val) and torch.equal(dis2, dis)
+    # fused forms: whole matrix (plain + Chebyshev recurrence) and a row block (plain)
+    fo = ops.fused_operator(sp, N, ShardPlan(N))
+    Q = torch.linalg.qr(Xd)[0].contiguous()
+    Yp = fo.plain(None, Q)
+    Pt = torch.from_numpy(Po)
+    ref = Pt @ Q.cpu()
+    assert Yp.data_ptr() != Q.data_ptr()
+    assert (Yp.cpu() - ref).abs().max().item() < 5e-12 * ref.abs().max().item()
+    c, e, degree = 0.1, 0.7, 5
+    Yc = fo.cheb(None, Q, degree, c, e)
+    prev, cur = Q.cpu(), (Pt @ Q.cpu() - c * Q.cpu()) / e
+    for _ in range(degree - 1):
+        prev, cur = cur, 2.0 * (Pt @ cur - c * cur) / e - prev
+    assert (Yc.cpu() - cur).abs().max().item() < 1e-10 * cur.abs().max().item()
+    Yc2 = fo.cheb(None, Yc, 2, c, e)                         # applied to one of its own rotating buffers
+    y0 = Yc.cpu()
+    y1 = (Pt @ y0 - c * y0) / e
+    y2 = 2.0 * (Pt @ y1 - c * y1) / e - y0
+    assert Yc2.data_ptr() != Yc.data_ptr()
+    assert (Yc2.cpu() - y2).abs().max().item() < 1e-10 * y2.abs().max().item()
+    plan = ShardPlan(N)
+    plan.lo, plan.hi = 300, 777
+    fo2 = ops.fused_operator(sp.rows(300, 777), N, plan)
+    for b_ in fo2.a["ybufs"]:
+        b_.fill_(-7.0)
+    Yr = fo2.plain(None, Q).cpu()
+    assert (Yr[300:777] - ref[300:777]).abs().max().item() < 5e-12 * ref.abs().max().item()
+    assert bool((Yr[:300] == -7.0).all()) and bool((Yr[777:] == -7.0).all())
+
+
+@pytest.mark.parametrize("hub", [False, True])
+def test_sparse_operator_eigenpairs(v3s_mod, ops, hub):
+    """Chebyshev-filtered block Lanczos on the sparse operator (N >= 2048) against a dense FP64
+    eigendecomposition of the oracle's P_ep; hub=True gives one row N transposed entries (the
+    multi-chunk path of the list ordering kernel) and rows of very different lengths."""
+    N, k = 3000, 60
+    S2, Nbr = _so3_knn_lists(N, k, seed=11 + hub, hub=hub)
+    _, _, _, _, Po, dio = orc.diffusion_coordinate(S2.copy(), Nbr, 0.7, validate=False, return_all=True)
+    w, V = np.linalg.eigh(0.5 * (Po + Po.T))
+    idx = np.argsort(-np.abs(w))[:10]
+    prev = ops.operator
+    try:
+        out = {}
+        for mode in ("sparse", "dense"):
+            ops.operator = mode
+            stats = {}
+            Ps, Lam = v3s_mod.DiffusionMapSolver.diffusion_coordinate(S2.copy(), Nbr, 0.7, validate=False, stats=stats)
+            out[mode] = (Ps, Lam, stats)
+            print("sparse-operator eigenpairs", mode, "hub" if hub else "", stats.get("operator"), stats.get("driver"),
+                  stats.get("matvecs"), np.max(np.abs(np.sort(np.abs(Lam))[::-1] - np.abs(w[idx]))))
+    finally:
+        ops.operator = prev
+    assert out["sparse"][2]["operator"] == "sparse-fp64" and out["dense"][2]["operator"] == "dense-fp32"
+    lam_ref = np.sort(np.abs(w[idx]))[::-1]
+    assert np.max(np.abs(np.sort(np.abs(out["sparse"][1]))[::-1] - lam_ref)) < 1e-9
+    assert np.max(np.abs(np.sort(np.abs(out["dense"][1]))[::-1] - lam_ref)) < 1e-6
+    # leading eigenvector (lambda = 1 is simple on a connected graph): Ps[:,0] = lambda * D^-1/2 v
+    v0 = V[:, idx[0]] * dio
+    for mode in ("sparse", "dense"):
+        p0 = out[mode][0][:, 0]
+        cosang = abs(p0 @ v0) / (np.linalg.norm(p0) * np.linalg.norm(v0))
+        assert cosang > 1 - 1e-9
+
+
+def test_eigen_connected_sparse_operator(v3s_mod, ops, golden_dir):
+    g = np.load(os.path.join(golden_dir, "connected_n15.npz"))
+    prev = ops.operator
+    try:
+        ops.operator = "sparse"
+        stats = {}
+        Ps, Lam = v3s_mod.DiffusionMapSolver.diffusion_coordinate(g["S2"].copy(), g["N"], float(g["eps"]), stats=stats)
+    finally:
+        ops.operator = prev
+    print("eigen connected (sparse operator):", stats, "lambda rel err", np.max(np.abs(Lam - g["Lambda"]) / g["Lambda"]))
+    assert stats["operator"] == "sparse-fp64"
+    assert np.max(np.abs(Lam - g["Lambda"]) / g["Lambda"]) < 1e-9
+    assert orc.principal_angles(Ps, g["Ps"]).max() < 1e-6
+
+
 def test_lanczos_large_krylov_dimension(ops):
     """A slowly converging spectrum drives the Krylov basis to its cap (1024 vectors): exercises the
     device step kernels at large m (shared-memory opt-in of the update kernel, projection splits)."""

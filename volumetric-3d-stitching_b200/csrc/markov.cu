@@ -144,6 +144,125 @@ __global__ void scatter_p_kernel(const double* __restrict__ S2, const int* __res
   }
 }
 
+// ---- sparse form of P_ep: the kNN lists ARE the matrix (P = A + A^T, A_ij = h_ij on i's list) ----
+// a_val[e] = g_e = exp(-S2_e/eps') / (2 q_i q_j), the entry before the D^-1/2 scaling; count[j] =
+// in-degree of j over the non-zero entries (thresholded entries are exact zeros and carry no
+// transposed copy).
+__global__ void sp_values_kernel(const double* __restrict__ S2, const int* __restrict__ Nbr, long long N, int k,
+                                 const double* __restrict__ scalars, const double* __restrict__ q,
+                                 double* __restrict__ a_val, int* __restrict__ count) {
+  const double inv_eps = 1.0 / scalars[2];
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < N * k; e += (long long)gridDim.x * blockDim.x) {
+    const long long i = e / k;
+    const long long j = Nbr[e];
+    const double g = 0.5 * exp(-S2[e] * inv_eps) / (q[i] * q[j]);
+    a_val[e] = g;
+    if (g != 0.0) atomicAdd(&count[j], 1);
+  }
+}
+
+// d_i = max(sum of row i of W2 = list part + transposed part, 1/N), dinv_sqrt_i = d_i^-1/2: one warp
+// per row, fixed order (unlike the dense build's atomics this is reproducible to the last bit)
+__global__ void sp_rowsum_d_kernel(const double* __restrict__ a_val, int k, const int* __restrict__ t_ptr,
+                                   const double* __restrict__ t_val, long long N, double* __restrict__ d,
+                                   double* __restrict__ dinv_sqrt) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long i = warp; i < N; i += nwarps) {
+    double s = 0.0;
+    for (int t = lane; t < k; t += 32) s += a_val[i * k + t];
+    const int p0 = t_ptr[i], p1 = t_ptr[i + 1];
+    for (int e = p0 + lane; e < p1; e += 32) s += t_val[e];
+    s = warp_sum(s);
+    if (lane == 0) {
+      const double v = fmax(s, 1.0 / (double)N);
+      d[i] = v;
+      dinv_sqrt[i] = 1.0 / sqrt(v);
+    }
+  }
+}
+
+// h = (g dis_i) dis_j on both copies of every entry (the expression and order of scatter_p_kernel)
+__global__ void sp_scale_kernel(double* __restrict__ a_val, const int* __restrict__ Nbr, int k, long long N,
+                                const int* __restrict__ t_ptr, const int* __restrict__ t_col, double* __restrict__ t_val,
+                                const double* __restrict__ dis) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long i = warp; i < N; i += nwarps) {
+    const double di = dis[i];
+    for (int t = lane; t < k; t += 32) a_val[i * k + t] = a_val[i * k + t] * di * dis[Nbr[i * k + t]];
+    const int p0 = t_ptr[i], p1 = t_ptr[i + 1];
+    for (int e = p0 + lane; e < p1; e += 32) t_val[e] = t_val[e] * dis[t_col[e]] * di;
+  }
+}
+
+// exclusive scan of count[N] -> ptr[N+1]; one block, each thread owns a contiguous chunk
+__global__ void __launch_bounds__(1024) sp_scan_kernel(const int* __restrict__ count, long long N, int* __restrict__ ptr) {
+  __shared__ int wsum[32];
+  __shared__ int total_before;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const long long chunk = (N + 1023) / 1024;
+  const long long b0 = tid * chunk, b1 = b0 + chunk < N ? b0 + chunk : N;
+  int s = 0;
+  for (long long i = b0; i < b1; ++i) s += count[i];
+  int inc = s;                                           // inclusive scan of the per-thread sums
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+  if (lane == 31) wsum[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    int v = wsum[lane], iv = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, iv, o); if (lane >= o) iv += t; }
+    wsum[lane] = iv - v;                                 // exclusive offsets of the warps
+    if (lane == 31) total_before = iv;
+  }
+  __syncthreads();
+  int run = wsum[w] + inc - s;
+  for (long long i = b0; i < b1; ++i) { ptr[i] = run; run += count[i]; }
+  if (tid == 0) ptr[N] = total_before;
+}
+
+// entry e = (i -> j) lands somewhere in row j of the transposed list (order fixed by the sort below)
+__global__ void sp_fill_kernel(const int* __restrict__ Nbr, const double* __restrict__ a_val, long long nk,
+                               const int* __restrict__ ptr, int* __restrict__ cursor, int* __restrict__ tmp) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < nk; e += (long long)gridDim.x * blockDim.x) {
+    if (a_val[e] == 0.0) continue;
+    const int j = Nbr[e];
+    tmp[ptr[j] + atomicAdd(&cursor[j], 1)] = (int)e;
+  }
+}
+
+// Row j of the transposed list in ascending source row (entry indices e = i k + t are unique per
+// source row i, so ordering by e orders by i): rank by counting, one block per row.  Makes the
+// summation order of the mat-vec -- and with it every result -- independent of the atomics above.
+constexpr int SP_SORT_THREADS = 128;
+constexpr int SP_SORT_CHUNK = 2048;
+__global__ void __launch_bounds__(SP_SORT_THREADS)
+sp_sort_rows_kernel(const int* __restrict__ ptr, const int* __restrict__ tmp, const double* __restrict__ a_val, int k,
+                    long long N, int* __restrict__ t_col, double* __restrict__ t_val) {
+  __shared__ int sh[SP_SORT_CHUNK];
+  for (long long j = blockIdx.x; j < N; j += gridDim.x) {
+    const int p0 = ptr[j], d = ptr[j + 1] - p0;
+    for (int m0 = 0; m0 < d; m0 += SP_SORT_THREADS) {
+      const int mi = m0 + threadIdx.x;
+      const int x = mi < d ? tmp[p0 + mi] : 0x7fffffff;
+      int rank = 0;
+      for (int c0 = 0; c0 < d; c0 += SP_SORT_CHUNK) {
+        const int cn = d - c0 < SP_SORT_CHUNK ? d - c0 : SP_SORT_CHUNK;
+        __syncthreads();
+        for (int t = threadIdx.x; t < cn; t += SP_SORT_THREADS) sh[t] = tmp[p0 + c0 + t];
+        __syncthreads();
+        if (mi < d)
+          for (int t = 0; t < cn; ++t) rank += (sh[t] < x);
+      }
+      if (mi < d) { t_col[p0 + rank] = x / k; t_val[p0 + rank] = a_val[x]; }
+    }
+  }
+}
+
 // ---- dense FP64 forms of the three reference functions (API fidelity at small N) ----------
 __global__ void w_dense_scatter_kernel(const double* __restrict__ S2, const int* __restrict__ Nbr, long long N, int k,
                                        double eps_eff, double* __restrict__ W) {
@@ -227,6 +346,36 @@ extern "C" int v3s_build_markov(const double* S2_thresholded, const int* Nbr, lo
                                                           P_rows, ldp);
     V3S_CHECK_LAUNCH();
   }
+  return 0;
+}
+
+extern "C" int v3s_build_markov_sparse(const double* S2_thresholded, const int* Nbr, long long N, int k,
+                                       const double* scalars5, double* a_val, int* t_ptr, int* t_col, double* t_val,
+                                       double* dinv_sqrt, double* ws_2N, int* iws, void* stream) {
+  V3S_REQUIRE(N >= 1 && k >= 1 && N * (long long)k < (1LL << 31), "v3s_build_markov_sparse: need N>=1, k>=1 and N*k < 2^31");
+  V3S_REQUIRE(a_val && t_ptr && t_col && t_val && dinv_sqrt && ws_2N && iws, "v3s_build_markov_sparse: null buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  double* q = ws_2N;
+  double* d = ws_2N + N;
+  int* count = iws;            // [N]   in-degrees, then the fill cursors
+  int* tmp = iws + N;          // [N k] entry indices in arrival order
+  V3S_CUDA(cudaMemsetAsync(count, 0, sizeof(int) * N, st));
+  rowsum_q_kernel<<<grid_for(N * 32, 256), 256, 0, st>>>(S2_thresholded, N, k, scalars5, q);
+  V3S_CHECK_LAUNCH();
+  sp_values_kernel<<<grid_for(N * k, 256), 256, 0, st>>>(S2_thresholded, Nbr, N, k, scalars5, q, a_val, count);
+  V3S_CHECK_LAUNCH();
+  sp_scan_kernel<<<1, 1024, 0, st>>>(count, N, t_ptr);
+  V3S_CHECK_LAUNCH();
+  V3S_CUDA(cudaMemsetAsync(count, 0, sizeof(int) * N, st));
+  sp_fill_kernel<<<grid_for(N * k, 256), 256, 0, st>>>(Nbr, a_val, N * k, t_ptr, count, tmp);
+  V3S_CHECK_LAUNCH();
+  sp_sort_rows_kernel<<<grid_for(N * SP_SORT_THREADS, SP_SORT_THREADS), SP_SORT_THREADS, 0, st>>>(t_ptr, tmp, a_val, k, N,
+                                                                                                t_col, t_val);
+  V3S_CHECK_LAUNCH();
+  sp_rowsum_d_kernel<<<grid_for(N * 32, 256), 256, 0, st>>>(a_val, k, t_ptr, t_val, N, d, dinv_sqrt);
+  V3S_CHECK_LAUNCH();
+  sp_scale_kernel<<<grid_for(N * 32, 256), 256, 0, st>>>(a_val, Nbr, k, N, t_ptr, t_col, t_val, dinv_sqrt);
+  V3S_CHECK_LAUNCH();
   return 0;
 }
 

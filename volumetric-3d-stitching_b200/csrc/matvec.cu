@@ -163,6 +163,56 @@ __global__ void reduce_segments_kernel(const double* __restrict__ Ypart, long lo
   }
 }
 
+// ---- sparse operator ------------------------------------------------------------------------
+// P_ep has at most k + in-degree(i) non-zeros in row i: P = A + A^T with A the kNN lists themselves
+// (v3s_build_markov_sparse).  Y[i,:] = sum_t a[i,t] X[nbr[i,t],:] + sum_{e in T(i)} t_val[e] X[t_col[e],:],
+// FP64 throughout.  One warp per row: a warp-wide coalesced load fetches 32 (column, value) pairs,
+// which are then broadcast by shuffles to 4 groups of 8 lanes -- lane j of a group gathers X[col, j],
+// so a group reads one 64-byte row of X per entry and 8 independent gathers per lane are in flight.
+// Fixed entry order per lane group + fixed shuffle tree => run-to-run deterministic.  Bound by the
+// L2 gathers of X (64 B per non-zero; X itself is N x 64 B and stays in L2) plus 12 B per non-zero
+// of list data from HBM.
+constexpr int SP_THREADS = 256;
+
+__device__ __forceinline__ double sp_segment(const int* __restrict__ cols, const double* __restrict__ vals, int len,
+                                             const double* __restrict__ X, int ldx, int j, int g, int lane, double acc) {
+  for (int base = 0; base < len; base += 32) {
+    const int e = base + lane;
+    const int c = e < len ? cols[e] : 0;
+    const double v = e < len ? vals[e] : 0.0;
+    double xv[8], vv[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int src = it * 4 + g;
+      const int cc = __shfl_sync(0xffffffffu, c, src);
+      vv[it] = __shfl_sync(0xffffffffu, v, src);
+      xv[it] = (vv[it] != 0.0 && j < ldx) ? X[(long long)cc * ldx + j] : 0.0;   // padding / thresholded entries: no load
+    }
+#pragma unroll
+    for (int it = 0; it < 8; ++it) acc = fma(vv[it], xv[it], acc);
+  }
+  return acc;
+}
+
+__global__ void __launch_bounds__(SP_THREADS)
+sparse_block_matvec_kernel(const int* __restrict__ nbr, const double* __restrict__ a_val, int k,
+                           const int* __restrict__ t_ptr, const int* __restrict__ t_col, const double* __restrict__ t_val,
+                           long long row0, long long n_rows, const double* __restrict__ X, int ldx,
+                           double* __restrict__ Y, int ldy) {
+  const int lane = threadIdx.x & 31, j = lane & 7, g = lane >> 3;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp; r < n_rows; r += nwarps) {
+    const long long i = row0 + r;
+    double acc = sp_segment(nbr + i * k, a_val + i * k, k, X, ldx, j, g, lane, 0.0);
+    const int p0 = t_ptr[i];
+    acc = sp_segment(t_col + p0, t_val + p0, t_ptr[i + 1] - p0, X, ldx, j, g, lane, acc);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+    if (g == 0 && j < ldy) Y[r * ldy + j] = acc;
+  }
+}
+
 struct MvPlan { int grid; int nstrips_row; int maxseg; long long units_per_cta, total_units; };
 static inline MvPlan mv_plan(long long n_rows, long long N) {
   MvPlan p;
@@ -190,6 +240,19 @@ static bool g_prof_on = false;
 static std::vector<cudaEvent_t> g_prof_ev;      // pairs (start, stop)
 static size_t g_prof_used = 0;
 
+static int prof_begin(cudaStream_t st, cudaEvent_t* e1) {
+  *e1 = nullptr;
+  if (!g_prof_on) return 0;
+  if (g_prof_used + 2 > g_prof_ev.size()) {
+    for (int i = 0; i < 2; ++i) { cudaEvent_t e; V3S_CUDA(cudaEventCreate(&e)); g_prof_ev.push_back(e); }
+  }
+  cudaEvent_t e0 = g_prof_ev[g_prof_used];
+  *e1 = g_prof_ev[g_prof_used + 1];
+  g_prof_used += 2;
+  V3S_CUDA(cudaEventRecord(e0, st));
+  return 0;
+}
+
 static int mv_launch(const float* P_rows, long long ldp, long long n_rows, long long N, const float* XfS, double* Ypart,
                      const MvPlan& pl, cudaStream_t st) {
   CUtensorMap tm;
@@ -201,17 +264,24 @@ static int mv_launch(const float* P_rows, long long ldp, long long n_rows, long 
     attr_set = true;
   }
   static unsigned launch_parity = 0;
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
-  if (g_prof_on) {
-    if (g_prof_used + 2 > g_prof_ev.size()) {
-      for (int i = 0; i < 2; ++i) { cudaEvent_t e; V3S_CUDA(cudaEventCreate(&e)); g_prof_ev.push_back(e); }
-    }
-    e0 = g_prof_ev[g_prof_used]; e1 = g_prof_ev[g_prof_used + 1];
-    g_prof_used += 2;
-    V3S_CUDA(cudaEventRecord(e0, st));
-  }
+  cudaEvent_t e1 = nullptr;
+  if (int rc = prof_begin(st, &e1)) return rc;
   block_matvec_kernel<<<pl.grid, MV_THREADS, MV_SMEM, st>>>(tm, XfS, n_rows, N, pl.nstrips_row, pl.units_per_cta,
                                                            pl.total_units, pl.maxseg, Ypart, (int)(launch_parity++ & 1));
+  V3S_CHECK_LAUNCH();
+  if (e1) V3S_CUDA(cudaEventRecord(e1, st));
+  return 0;
+}
+
+// sparse operator: Y [n_rows, ldy] = P[row0 .. row0+n_rows, :] X,  X [N, ldx] FP64 (ldx = ldy = b <= 8)
+static int sp_launch(const v3s_sparse_markov& op, long long row0, long long n_rows, const double* X, int ldx, double* Y,
+                     int ldy, cudaStream_t st) {
+  long long g = ceil_div64(n_rows, SP_THREADS / 32);
+  if (g > 8LL * kNumSMs) g = 8LL * kNumSMs;
+  cudaEvent_t e1 = nullptr;
+  if (int rc = prof_begin(st, &e1)) return rc;
+  sparse_block_matvec_kernel<<<(int)g, SP_THREADS, 0, st>>>(op.nbr, op.a_val, op.k, op.t_ptr, op.t_col, op.t_val, row0, n_rows,
+                                                          X, ldx, Y, ldy);
   V3S_CHECK_LAUNCH();
   if (e1) V3S_CUDA(cudaEventRecord(e1, st));
   return 0;
@@ -310,6 +380,22 @@ static int mv_combine(const float* P_rows, long long ldp, long long n_rows, long
   reduce_combine_scatter_kernel<<<(int)g2, 256, 0, st>>>(Ypart, n_rows, row0, pl.nstrips_row, pl.units_per_cta, pl.maxseg, Yk,
                                                          Ykm1, alpha, beta, gamma, yout, xfout, world, write_xf, flags, rank,
                                                          epoch, world > 1 ? ticket : nullptr, status);
+  V3S_CHECK_LAUNCH();
+  return 0;
+}
+
+// The same fused tail behind the sparse mat-vec: its [n_rows,8] result is read as one segment per row
+// group (nstrips_row = units_per_cta = maxseg = 1).
+static int sp_combine(const v3s_sparse_markov& op, long long n_rows, long long row0, const double* X, const double* Yk,
+                      const double* Ykm1, double alpha, double beta, double gamma, const PeerPtrs& yout, const PeerPtrs& xfout,
+                      int world, int write_xf, double* PY, const PeerPtrs& flags, int rank, int epoch, unsigned* ticket,
+                      int* status, cudaStream_t st) {
+  if (int rc = sp_launch(op, row0, n_rows, X, MV_B, PY, MV_B, st)) return rc;
+  long long g2 = ceil_div64(n_rows * MV_B, 256);
+  if (g2 > 8LL * kNumSMs) g2 = 8LL * kNumSMs;
+  reduce_combine_scatter_kernel<<<(int)g2, 256, 0, st>>>(PY, n_rows, row0, 1, 1, 1, Yk, Ykm1, alpha, beta, gamma, yout, xfout,
+                                                         world, write_xf, flags, rank, epoch, world > 1 ? ticket : nullptr,
+                                                         status);
   V3S_CHECK_LAUNCH();
   return 0;
 }
@@ -439,6 +525,76 @@ extern "C" int v3s_cheb_filter(const float* P_rows, long long ldp, long long n_r
                             rank, epoch0 + s, ticket_dev, status_dev, st))
       return rc;
     xin = local_x(s & 1);
+    prev = cur;
+    cur = out;
+  }
+  if (result_index) *result_index = cur;
+  return 0;
+}
+
+// ---- sparse-operator forms (same contracts; the operand is the FP64 block itself) -------------
+
+static inline bool sp_valid(const v3s_sparse_markov* op) {
+  return op && op->nbr && op->a_val && op->t_ptr && op->t_col && op->t_val && op->k >= 1;
+}
+
+extern "C" int v3s_sparse_block_matvec(const v3s_sparse_markov* op, long long row0, long long n_rows, long long N,
+                                       const double* X, int b, double* Y_rows, void* stream) {
+  V3S_REQUIRE(sp_valid(op), "v3s_sparse_block_matvec: incomplete operator descriptor");
+  V3S_REQUIRE(b >= 1 && b <= MV_B, "v3s_sparse_block_matvec: block size b=%d outside [1,%d]", b, MV_B);
+  V3S_REQUIRE(n_rows >= 0 && row0 >= 0 && row0 + n_rows <= N && N < (1LL << 31), "v3s_sparse_block_matvec: bad shape");
+  if (n_rows == 0) return 0;
+  return sp_launch(*op, row0, n_rows, X, b, Y_rows, b, (cudaStream_t)stream);
+}
+
+extern "C" int v3s_sparse_matvec_combine(const v3s_sparse_markov* op, long long n_rows, long long N, long long row0,
+                                         const double* X, const double* Yk, const double* Ykm1, double alpha, double beta,
+                                         double gamma, const unsigned long long* yout_ptrs,
+                                         const unsigned long long* xfout_ptrs, const unsigned long long* flag_ptrs, int rank,
+                                         int world, int epoch, unsigned* ticket_dev, int* status_dev, void* workspace,
+                                         void* stream) {
+  V3S_REQUIRE(sp_valid(op), "v3s_sparse_matvec_combine: incomplete operator descriptor");
+  V3S_REQUIRE(n_rows >= 1 && N >= 1 && row0 >= 0 && row0 + n_rows <= N && N < (1LL << 31) && X && workspace,
+              "v3s_sparse_matvec_combine: bad shape (at least one row per rank)");
+  V3S_REQUIRE(yout_ptrs && world >= 1 && world <= 8 && rank >= 0 && rank < world && (world == 1 || (flag_ptrs && ticket_dev)),
+              "v3s_sparse_matvec_combine: 1..8 ranks, result pointers (and flag words + ticket when sharded) required");
+  PeerPtrs yo, xo, fl;
+  load_peers(yo, yout_ptrs, world);
+  load_peers(xo, xfout_ptrs, world);
+  load_peers(fl, flag_ptrs, world);
+  return sp_combine(*op, n_rows, row0, X, Yk, Ykm1, alpha, beta, gamma, yo, xo, world, xfout_ptrs != nullptr,
+                    reinterpret_cast<double*>(workspace), fl, rank, epoch, ticket_dev, status_dev, (cudaStream_t)stream);
+}
+
+extern "C" int v3s_sparse_cheb_filter(const v3s_sparse_markov* op, long long n_rows, long long N, long long row0,
+                                      const double* Q, int q_index, int degree, double c, double e,
+                                      const unsigned long long* ybuf_ptrs, const unsigned long long* flag_ptrs, int rank,
+                                      int world, int epoch0, unsigned* ticket_dev, int* status_dev, void* workspace,
+                                      int* result_index, void* stream) {
+  V3S_REQUIRE(sp_valid(op), "v3s_sparse_cheb_filter: incomplete operator descriptor");
+  V3S_REQUIRE(degree >= 1 && q_index >= -1 && q_index <= 2 && e != 0.0 && Q, "v3s_sparse_cheb_filter: bad degree / buffer index / interval");
+  V3S_REQUIRE(ybuf_ptrs && world >= 1 && world <= 8 && rank >= 0 && rank < world && (world == 1 || (flag_ptrs && ticket_dev)),
+              "v3s_sparse_cheb_filter: bad rank layout");
+  V3S_REQUIRE(n_rows >= 1 && N >= 1 && row0 >= 0 && row0 + n_rows <= N && N < (1LL << 31) && workspace,
+              "v3s_sparse_cheb_filter: bad shape (at least one row per rank)");
+  cudaStream_t st = (cudaStream_t)stream;
+  double* PY = reinterpret_cast<double*>(workspace);
+  auto local_y = [&](int b) { return reinterpret_cast<const double*>(ybuf_ptrs[(size_t)b * world + rank]); };
+  int prev = -2, cur = q_index;                    // -2: none, -1: the external Q
+  PeerPtrs fl, xo;
+  load_peers(fl, flag_ptrs, world);
+  load_peers(xo, nullptr, world);
+  for (int s = 1; s <= degree; ++s) {
+    int out = 0;
+    while (out == cur || out == prev) ++out;       // lowest rotating buffer not read by this step
+    PeerPtrs yo;
+    load_peers(yo, ybuf_ptrs + (size_t)out * world, world);
+    const double* Yk = cur == -1 ? Q : local_y(cur);
+    const double* Ykm1 = prev == -2 ? nullptr : (prev == -1 ? Q : local_y(prev));
+    const double alpha = (s == 1 ? 1.0 : 2.0) / e, beta = (s == 1 ? -1.0 : -2.0) * c / e, gamma = s == 1 ? 0.0 : -1.0;
+    if (int rc = sp_combine(*op, n_rows, row0, Yk, Yk, Ykm1, alpha, beta, gamma, yo, xo, world, 0, PY, fl, rank, epoch0 + s,
+                            ticket_dev, status_dev, st))
+      return rc;
     prev = cur;
     cur = out;
   }

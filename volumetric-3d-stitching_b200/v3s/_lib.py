@@ -23,6 +23,11 @@ class Geometry(C.Structure):
     _fields_ = [("pixel", f64), ("zd", f64), ("lambda_", f64), ("n_p_nobin", i32), ("grid_scale", f64)]
 
 
+class SparseMarkovDesc(C.Structure):
+    """v3s_sparse_markov (include/v3s.h): device pointers of the sparse operator's arrays."""
+    _fields_ = [("nbr", p), ("a_val", p), ("t_ptr", p), ("t_col", p), ("t_val", p), ("k", i32)]
+
+
 # name -> (restype, argtypes); mirrors include/v3s.h one to one
 SIGNATURES = {
     "v3s_last_error": (C.c_char_p, []),
@@ -66,6 +71,14 @@ SIGNATURES = {
     "v3s_peer_barrier": (i32, [C.POINTER(C.c_ulonglong), i32, i32, i32, p, p]),
     "v3s_cheb_filter": (i32, [p, i64, i64, i64, i64, p, p, i32, i32, f64, f64, C.POINTER(C.c_ulonglong),
                               C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), i32, i32, i32, p, p, p, C.POINTER(i32), p]),
+    "v3s_build_markov_sparse": (i32, [p, p, i64, i32, p, p, p, p, p, p, p, p, p]),
+    "v3s_sparse_block_matvec": (i32, [C.POINTER(SparseMarkovDesc), i64, i64, i64, p, i32, p, p]),
+    "v3s_sparse_matvec_combine": (i32, [C.POINTER(SparseMarkovDesc), i64, i64, i64, p, p, p, f64, f64, f64,
+                                        C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong),
+                                        i32, i32, i32, p, p, p, p]),
+    "v3s_sparse_cheb_filter": (i32, [C.POINTER(SparseMarkovDesc), i64, i64, i64, p, i32, i32, f64, f64,
+                                     C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), i32, i32, i32, p, p, p,
+                                     C.POINTER(i32), p]),
     "v3s_profile_matvec": (i32, [i32]),
     "v3s_profile_matvec_read": (i32, [C.POINTER(C.c_float), i32]),
     "v3s_fit_gram": (i32, [p, i32, p, i64, p, p]),

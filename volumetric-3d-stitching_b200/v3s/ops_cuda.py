@@ -25,8 +25,49 @@ PANEL_BYTES = 4 << 30   # Gram row panel budget when G is streamed in panels
 SYM_BYTES = 48 << 30    # the whole symmetric G is materialised (half the MMA work) up to this size
 
 
+DENSE_OPERATOR_BYTES = 12 << 30   # operator "auto": dense FP32 row block up to this size per rank, sparse beyond
+
+
 def round_up(x, m):
     return (x + m - 1) // m * m
+
+
+class SparseMarkov:
+    """Sparse form of P_ep (v3s_sparse_markov): P = A + A^T on the kNN lists, FP64.  Holds every
+    rank's copy of the whole operator (O(N k)); a rank multiplies its own rows [r0, r1)."""
+
+    def __init__(self, nbr, a_val, t_ptr, t_col, t_val, r0, r1):
+        self.nbr, self.a_val, self.t_ptr, self.t_col, self.t_val = nbr, a_val, t_ptr, t_col, t_val
+        self.N, self.k = int(nbr.shape[0]), int(nbr.shape[1])
+        self.r0, self.r1 = int(r0), int(r1)
+        self.device = nbr.device
+        self.desc = _lib.SparseMarkovDesc(nbr.data_ptr(), a_val.data_ptr(), t_ptr.data_ptr(), t_col.data_ptr(),
+                                          t_val.data_ptr(), self.k)
+
+    @property
+    def n_rows(self):
+        return self.r1 - self.r0
+
+    def nnz(self):
+        """Stored entries of the rank's rows (list part incl. thresholded zeros + transposed part)."""
+        tp = self.t_ptr[[self.r0, self.r1]].cpu()
+        return self.n_rows * self.k + int(tp[1] - tp[0])
+
+    def rows(self, r0, r1):
+        """The same operator restricted to another row block (shares the arrays)."""
+        return SparseMarkov(self.nbr, self.a_val, self.t_ptr, self.t_col, self.t_val, r0, r1)
+
+    def to_dense(self):
+        """[n_rows, N] FP64 (tests / tiny problems)."""
+        N, k = self.N, self.k
+        P = torch.zeros((N, N), dtype=torch.float64, device=self.device)
+        rows = torch.arange(N, device=self.device).repeat_interleave(k)
+        P.index_put_((rows, self.nbr.reshape(-1).long()), self.a_val.reshape(-1), accumulate=True)
+        nnz = int(self.t_ptr[-1].item())
+        cnt = (self.t_ptr[1:] - self.t_ptr[:-1]).long()
+        trow = torch.arange(N, device=self.device).repeat_interleave(cnt)
+        P.index_put_((trow, self.t_col[:nnz].long()), self.t_val[:nnz], accumulate=True)
+        return P[self.r0:self.r1]
 
 
 class CudaOps:
@@ -42,10 +83,13 @@ class CudaOps:
         self._events = []
         self._synth_prep = {}
         self._sym_tile_cache = {}
+        self._sym_fits = {}
+        self._snap_events = []
         self._symm_G = {}
         self.dedup_refine = True     # exact-distance refinement: mutual candidate pairs once (select.cu)
         self.use_fused_matvec = True # eigen-solver mat-vecs with the reduction / recurrence / exchange fused (FusedOperator)
         self.use_peer_gram = True    # sharded jobs: symmetric Gram with NVLink peer stores (else rectangular panels)
+        self.operator = "auto"       # Markov operator of the eigen-solver: "dense" (FP32 rows), "sparse" (FP64 lists), "auto"
         self.symm_error = None
         self._pin = None
 
@@ -264,8 +308,14 @@ class CudaOps:
         if nr == 0:
             return S2, Nbr
         ldg = round_up(N, 4)
-        sym = (self.gram_impl == "tcgen05" and r0 == 0 and r1 == N and 4 * ldg * N <= SYM_BYTES
-               and 4 * ldg * N <= 0.6 * torch.cuda.mem_get_info()[0])
+        sym = self.gram_impl == "tcgen05" and r0 == 0 and r1 == N and 4 * ldg * N <= SYM_BYTES
+        if sym:
+            # cudaMemGetInfo is a kernel-mode driver call (it can queue behind any other RM client of the box, e.g. a
+            # monitoring nvidia-smi, for tens of milliseconds): ask once per problem size, not once per pass
+            fits = self._sym_fits.get(N)
+            if fits is None:
+                fits = self._sym_fits[N] = bool(4 * ldg * N <= 0.6 * torch.cuda.mem_get_info()[0])
+            sym = fits
         G_shard = None
         if (self.gram_impl == "tcgen05" and plan is not None and plan.world > 1 and plan.world <= 8 and self.use_peer_gram
                 and r0 == plan.lo and r1 == plan.hi and N // plan.world >= 1 and 4 * ldg * max(plan.counts) <= SYM_BYTES):
@@ -334,6 +384,34 @@ class CudaOps:
              stream_ptr())
         self._toc(h)
         return P_rows, dis
+
+    def wants_sparse_operator(self, n_rows, N):
+        if self.operator == "sparse":
+            return True
+        return self.operator == "auto" and 4 * n_rows * round_up(N, 4) > DENSE_OPERATOR_BYTES
+
+    def build_markov_sparse(self, S2t, Nbr, scalars, r0, r1):
+        """-> SparseMarkov (rows [r0,r1) of P_ep = A + A^T on the lists, FP64), dinv_sqrt [N]."""
+        N, k = S2t.shape
+        a_val = self.empty((N, k), torch.float64)
+        t_ptr = self.empty((N + 1,), torch.int32)
+        t_col = self.empty((N * k,), torch.int32)
+        t_val = self.empty((N * k,), torch.float64)
+        dis = self.empty((N,), torch.float64)
+        ws = self.empty((2 * N,), torch.float64)
+        iws = self.empty((N + N * k,), torch.int32)
+        h = self._tic("markov")
+        call("v3s_build_markov_sparse", ptr(S2t), ptr(Nbr), N, k, ptr(scalars), ptr(a_val), ptr(t_ptr), ptr(t_col), ptr(t_val),
+             ptr(dis), ptr(ws), ptr(iws), stream_ptr())
+        self._toc(h)
+        return SparseMarkov(Nbr, a_val, t_ptr, t_col, t_val, r0, r1), dis
+
+    def sparse_block_matvec(self, sp, X, out=None):
+        """Y_rows [n_rows,b] f64 = P[r0:r1, :] @ X [N,b] (f64), sparse operator."""
+        b = X.shape[1]
+        Y = out if out is not None else self.empty((sp.n_rows, b), torch.float64)
+        call("v3s_sparse_block_matvec", C.byref(sp.desc), sp.r0, sp.n_rows, sp.N, ptr(X), b, ptr(Y), stream_ptr())
+        return Y
 
     def w_dense(self, S2t, Nbr, eps_eff):
         N, k = S2t.shape
@@ -410,13 +488,14 @@ class CudaOps:
         n = (s1 - s0) * 128
         self._pin[:n].copy_(st["T"][s0:s1].reshape(-1), non_blocking=True)
         self._pin[n:n + 1].copy_(st["status"].to(torch.float64), non_blocking=True)
-        ev = torch.cuda.Event()
+        ev = self._snap_events.pop() if self._snap_events else torch.cuda.Event()     # reused: no event creation per check
         ev.record()
         return (ev, n)
 
     def lanczos_snapshot_wait(self, snap):
         ev, n = snap
         ev.synchronize()
+        self._snap_events.append(ev)
         host = self._pin[:n + 1].numpy()
         return host[:n].copy(), int(host[n])
 
@@ -490,6 +569,7 @@ class FusedOperator:
     def __init__(self, ops, P_rows, N, plan=None):
         import torch.distributed as dist
         self.ops, self.P_rows, self.N = ops, P_rows, int(N)
+        self.sparse = isinstance(P_rows, SparseMarkov)
         self.world = 1 if plan is None else plan.world
         self.rank = 0 if plan is None else plan.rank
         self.row0 = 0 if plan is None else plan.lo
@@ -531,6 +611,10 @@ class FusedOperator:
             ops._symm_G[key] = arena
         self.a = arena
         self.n_matvec = 0
+        if self.sparse:
+            if (P_rows.r0, P_rows.N) != (self.row0, self.N):
+                raise Exception("FusedOperator: the sparse operator's row block does not start at the rank's first row")
+            self._sp_ws = ops.empty((max(P_rows.n_rows, 1) * 8,), torch.float64)
 
     def _index_of(self, Q):
         for b, t in enumerate(self.a["ybufs"]):
@@ -550,8 +634,15 @@ class FusedOperator:
         qi = self._index_of(Q)
         out = min(b for b in range(3) if b != qi)
         yout = (C.c_ulonglong * w)(*[a["yptrs"][out * w + r] for r in range(w)])
-        ws = self.ops._mv_workspace(self.P_rows.shape[0], self.N)
         a["epoch"] += 1 if w > 1 else 0
+        if self.sparse:
+            sp = self.P_rows
+            call("v3s_sparse_matvec_combine", C.byref(sp.desc), sp.n_rows, self.N, self.row0, ptr(Q), None, None, 1.0, 0.0, 0.0,
+                 yout, None, a["fptrs"], self.rank, w, a["epoch"], ptr(a["ticket"]), ptr(a["status"]), ptr(self._sp_ws),
+                 stream_ptr())
+            self.n_matvec += 1
+            return a["ybufs"][out]
+        ws = self.ops._mv_workspace(self.P_rows.shape[0], self.N)
         call("v3s_matvec_combine", ptr(self.P_rows), self.P_rows.shape[1], self.P_rows.shape[0], self.N, self.row0, ptr(Xf),
              None, None, 1.0, 0.0, 0.0, yout, None, a["fptrs"], self.rank, w, a["epoch"], ptr(a["ticket"]), ptr(a["status"]),
              ptr(ws), stream_ptr())
@@ -561,6 +652,15 @@ class FusedOperator:
     def cheb(self, Xf0, Q, degree, c, e):
         a = self.a
         res = C.c_int(0)
+        if self.sparse:
+            sp = self.P_rows
+            call("v3s_sparse_cheb_filter", C.byref(sp.desc), sp.n_rows, self.N, self.row0, ptr(Q), self._index_of(Q), int(degree),
+                 float(c), float(e), a["yptrs"], a["fptrs"], self.rank, self.world, a["epoch"], ptr(a["ticket"]),
+                 ptr(a["status"]), ptr(self._sp_ws), C.byref(res), stream_ptr())
+            if self.world > 1:
+                a["epoch"] += int(degree)
+            self.n_matvec += int(degree)
+            return a["ybufs"][res.value]
         ws = self.ops._mv_workspace(self.P_rows.shape[0], self.N)
         call("v3s_cheb_filter", ptr(self.P_rows), self.P_rows.shape[1], self.P_rows.shape[0], self.N, self.row0, ptr(Xf0),
              ptr(Q), self._index_of(Q), int(degree), float(c), float(e), a["yptrs"], a["xptrs"], a["fptrs"], self.rank,

@@ -100,12 +100,17 @@ def check_scalars(scalars_host):
 
 def markov_stage(ops, plan, S2_all, Nbr_all, eps, med_row=4, idx_off=1, validate=True):
     """diffusion.py:291-325, 89-105, 244-260 fused.  Mutates S2_all in place like the reference.
-    -> P_rows [hi-lo, ldp] f32, dinv_sqrt [N] f64, scalars [5]."""
+    -> P_rows, dinv_sqrt [N] f64, scalars [5].  P_rows is the rank's row block of P_ep: dense
+    [hi-lo, ldp] f32, or -- backend option `operator` = "sparse", or "auto" beyond
+    DENSE_OPERATOR_BYTES per rank -- the FP64 list form (`SparseMarkov`), which never forms N x N."""
     scalars = ops.s2_scalars(S2_all, eps, med_row, idx_off)
     if validate:
         check_scalars(scalars.cpu().numpy())
     ops.s2_threshold_(S2_all, scalars)
-    P_rows, dis = ops.build_markov(S2_all, Nbr_all, scalars, plan.lo, plan.hi)
+    if hasattr(ops, "wants_sparse_operator") and ops.wants_sparse_operator(plan.hi - plan.lo, plan.N):
+        P_rows, dis = ops.build_markov_sparse(S2_all, Nbr_all, scalars, plan.lo, plan.hi)
+    else:
+        P_rows, dis = ops.build_markov(S2_all, Nbr_all, scalars, plan.lo, plan.hi)
     return P_rows, dis, scalars
 
 
@@ -116,9 +121,11 @@ def eigen_stage(ops, plan, P_rows, dis, nev=NEV, validate=True, tol=None, stats=
     if nev >= N - 1:
         raise Exception("No spare-matrix for eigs-calculation")   # diffusion.py:59-60
     dev = P_rows.device
+    sparse = not isinstance(P_rows, torch.Tensor)            # ops_cuda.SparseMarkov
 
     def matvec(X):
-        Y = ops.block_matvec(P_rows, N, X.contiguous())
+        X = X.contiguous()
+        Y = ops.sparse_block_matvec(P_rows, X) if sparse else ops.block_matvec(P_rows, N, X)
         return plan.all_gather_rows(Y)
 
     if N <= dense_below:
@@ -139,6 +146,8 @@ def eigen_stage(ops, plan, P_rows, dis, nev=NEV, validate=True, tol=None, stats=
         w_all = ops.empty((N, 8), torch.float64) if plan.world > 1 else None
 
         def matvec_f32(Xf):
+            if sparse:
+                raise Exception("v3s: the sparse Markov operator needs the fused mat-vec path (symmetric memory unavailable?)")
             return plan.all_gather_rows(ops.block_matvec_f32(P_rows, N, Xf, out=y_loc), out=w_all)
         tol_ = 1e-8 if tol is None else tol
         # reduction + recurrence + cross-rank exchange inside the mat-vec's own kernels (no NCCL per step)
@@ -148,12 +157,14 @@ def eigen_stage(ops, plan, P_rows, dis, nev=NEV, validate=True, tol=None, stats=
 
         def run(lock):
             st_ = {}
-            if N >= 2048 and nev <= 16:
+            if N >= 2048 and nev <= 16 and (fused is not None or not sparse):
                 r = chebyshev_lanczos_device(ops, matvec_f32, matvec, N, nev, tol=tol_, stats=st_, seed=seed, lock=lock,
                                              fused=fused)
             elif fused is not None:
                 r = block_lanczos_device(ops, fused.plain, N, nev, tol=tol_, stats=st_, seed=seed, lock=lock,
                                          pre_sync=fused.sync)
+            elif sparse:
+                r = block_lanczos_device(ops, lambda Xf, Q: matvec(Q), N, nev, tol=tol_, stats=st_, seed=seed, lock=lock)
             else:
                 r = block_lanczos_device(ops, lambda Xf, Q: matvec_f32(Xf), N, nev, tol=tol_, stats=st_, seed=seed,
                                          lock=lock)
@@ -170,6 +181,8 @@ def eigen_stage(ops, plan, P_rows, dis, nev=NEV, validate=True, tol=None, stats=
                 fused.check()
             if stats is not None:
                 stats["fused_matvec"] = True
+        if stats is not None:
+            stats["operator"] = "sparse-fp64" if sparse else "dense-fp32"
     else:
         lam, V, _ = block_lanczos_topk(matvec, N, nev, dev, tol=(1e-8 if tol is None else tol), stats=stats, seed=seed)
     V = -V                                                   # diffusion.py:62 (sign is arbitrary upstream)
