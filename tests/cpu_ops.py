@@ -14,9 +14,18 @@ def _np(t):
     return t.detach().cpu().numpy()
 
 
+class _SparseRows:
+    """Stand-in for ops_cuda.SparseMarkov: the rank's rows of P_ep as a scipy CSR matrix (FP64)."""
+
+    def __init__(self, P_rows_csr, r0, r1, N):
+        self.P, self.r0, self.r1, self.N = P_rows_csr, r0, r1, N
+        self.device = torch.device("cpu")
+
+
 class OracleOps:
     name = "oracle-cpu"
     device = torch.device("cpu")
+    operator = "dense"
 
     def empty(self, shape, dtype):
         return torch.empty(shape, dtype=dtype)
@@ -94,6 +103,17 @@ class OracleOps:
         out = torch.zeros((r1 - r0, ldp), dtype=torch.float32)
         out[:, :N] = torch.from_numpy(P[r0:r1].astype(np.float32))
         return out, torch.from_numpy(di)
+
+    def wants_sparse_operator(self, n_rows, N):
+        return self.operator == "sparse"
+
+    def build_markov_sparse(self, S2t, Nbr, scalars, r0, r1):
+        import scipy.sparse as sps
+        P, di = self._dense_p(S2t, Nbr, scalars)
+        return _SparseRows(sps.csr_matrix(P[r0:r1]), r0, r1, P.shape[0]), torch.from_numpy(di)
+
+    def sparse_block_matvec(self, sp, X, out=None):
+        return torch.from_numpy(sp.P @ _np(X))
 
     def w_dense(self, S2t, Nbr, eps_eff):
         n, d = S2t.shape

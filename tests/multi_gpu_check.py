@@ -26,6 +26,7 @@ from v3s.projection import Projector
 
 ops = _util.get_ops()
 ok = True
+only = os.environ.get("V3S_CHECK_ONLY", "")          # "sparse": only the sparse-operator section (cheap re-check)
 for (N, n, n_p, k) in ((3001, 15, 31, 100), (5000, 15, 48, 120)):
     R9, _ = orc.random_rotations(N, seed=3)
     ed = ops.to_device(orc.synthesize_3d(n)["ED"].astype(np.float32), torch.float32)
@@ -33,6 +34,21 @@ for (N, n, n_p, k) in ((3001, 15, 31, 100), (5000, 15, 48, 120)):
     rot_y = ops.to_device(np.ascontiguousarray(R9.T), torch.float64)
     plan = ShardPlan.from_env(N)
     one = ShardPlan(N)
+    # --- sparse (FP64 kNN-list) Markov operator: sharded fused mat-vec (peer stores + flag barrier) vs one GPU
+    ops.operator = "sparse"
+    st_s, st_1 = {}, {}
+    sp_s = run_pipeline(ops, plan, ed, rot9_all[plan.lo:plan.hi].contiguous(), rot_y, n_p, k, 0.7, check=False, stats=st_s)
+    sp_1 = run_pipeline(ops, one, ed, rot9_all, rot_y, n_p, k, 0.7, check=False, stats=st_1)
+    ops.operator = "auto"
+    lam_sp = float((sp_s["Lambda"] - sp_1["Lambda"]).abs().max().item())
+    ang_sp = float(np.max(orc.principal_angles(sp_s["Ps"].cpu().numpy(), sp_1["Ps"].cpu().numpy())))
+    conn_sp = bool(np.all(sp_1["Lambda"].cpu().numpy()[1:] < 1 - 1e-6))
+    print(f"rank {rank} N={N}: sparse operator sharded vs one GPU: |dLambda| {lam_sp:.2e}, subspace angle {ang_sp:.2e}, "
+          f"operator {st_s.get('operator')} fused={st_s.get('fused_matvec')} matvecs {st_s.get('matvecs')} vs {st_1.get('matvecs')}",
+          flush=True)
+    ok &= st_s.get("operator") == "sparse-fp64" and bool(st_s.get("fused_matvec")) and lam_sp < 1e-9 and (ang_sp < 1e-6 or not conn_sp)
+    if only == "sparse":
+        continue
     img_all = ops.synth_patterns(ed, rot9_all, n_p)
     # --- Gram row block: fused symmetric + peer stores vs rectangular panel
     sums = ops.column_sums(img_all)

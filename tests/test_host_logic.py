@@ -216,7 +216,21 @@ def test_pipeline_single_process_matches_oracle():
     assert np.allclose(out["Lambda"].numpy(), np.clip(Lam, 0, 1), atol=1e-6)
 
 
-def _worker(rank, world, port, q):
+def test_pipeline_sparse_operator_takes_the_lanczos_branch():
+    """N above the dense-eigh cut-off: the sparse operator drives block_lanczos_device with the FP64
+    block itself (no FP32 operand copy), so the eigenvalues agree with the oracle to solver tolerance."""
+    N, n, k, eps = 700, 7, 60, 0.7
+    R9, ed, rot9, rot_y = _pipeline_inputs(N, n)
+    ops = OracleOps()
+    ops.operator = "sparse"
+    stats = {}
+    out = run_pipeline(ops, ShardPlan(N), ed, rot9, rot_y, 2 * n + 1, k, eps, check=False, stats=stats)
+    assert stats["operator"] == "sparse-fp64" and stats["driver"] == "device" and stats["converged"]
+    Ps, Lam = orc.diffusion_coordinate(out["S2_unmutated"].numpy().copy(), out["N"].numpy(), eps, validate=False)
+    assert np.allclose(out["Lambda"].numpy(), np.clip(Lam, 0, 1), rtol=0, atol=1e-9)
+
+
+def _worker(rank, world, port, q, operator="dense"):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -225,7 +239,11 @@ def _worker(rank, world, port, q):
         N, n, k, eps = 301, 7, 60, 0.7     # odd N: uneven row blocks
         R9, ed, rot9, rot_y = _pipeline_inputs(N, n)
         plan = ShardPlan.from_env(N)
-        out = run_pipeline(OracleOps(), plan, ed, rot9[plan.lo:plan.hi], rot_y, 2 * n + 1, k, eps, check=False)
+        ops = OracleOps()
+        ops.operator = operator
+        stats = {}
+        out = run_pipeline(ops, plan, ed, rot9[plan.lo:plan.hi], rot_y, 2 * n + 1, k, eps, check=False, stats=stats)
+        assert stats.get("dense") or stats.get("operator") == ("sparse-fp64" if operator == "sparse" else "dense-fp32"), stats
         q.put((rank, out["S2_unmutated"].numpy(), out["N"].numpy(), out["Lambda"].numpy(), out["Ps"].numpy(),
                float(out["sigma_T"].item())))
     except Exception as e:      # fail fast instead of letting the parent wait for the queue
@@ -235,12 +253,15 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_pipeline_world2_gloo_matches_single():
+@pytest.mark.parametrize("operator", ["dense", "sparse"])
+def test_pipeline_world2_gloo_matches_single(operator):
+    """Row-sharded pipeline (uneven blocks) on two gloo ranks against the single-process run; with
+    the sparse form of the Markov operator the eigen-solver multiplies the FP64 block itself."""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29500 + (os.getpid() % 2000) + (7 if operator == "sparse" else 0)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, operator)) for r in range(2)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=300) for _ in range(2)], key=lambda t: t[0])

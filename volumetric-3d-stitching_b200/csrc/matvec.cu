@@ -169,9 +169,12 @@ __global__ void reduce_segments_kernel(const double* __restrict__ Ypart, long lo
 // FP64 throughout.  One warp per row: a warp-wide coalesced load fetches 32 (column, value) pairs,
 // which are then broadcast by shuffles to 4 groups of 8 lanes -- lane j of a group gathers X[col, j],
 // so a group reads one 64-byte row of X per entry and 8 independent gathers per lane are in flight.
-// Fixed entry order per lane group + fixed shuffle tree => run-to-run deterministic.  Bound by the
-// L2 gathers of X (64 B per non-zero; X itself is N x 64 B and stays in L2) plus 12 B per non-zero
-// of list data from HBM.
+// Fixed entry order per lane group + fixed shuffle tree => run-to-run deterministic and independent
+// of the sharding.  Traffic: 64 B of L2 gathers per non-zero (X itself is N x 64 B and stays in L2)
+// plus 12 B of list data.  Measured at cfg 2 (3.0 M entries): 36 us per launch, 30 MB from DRAM, L2
+// throughput 12 %, warps active 34 % (profiles/r01_ncu_full_summary.txt) -- latency-bound; fetching
+// the next 32 entries ahead of the gathers and one row per warp without a grid-stride tail were tried
+// and changed nothing (36 -> 38 us), so the simple form stays.
 constexpr int SP_THREADS = 256;
 
 __device__ __forceinline__ double sp_segment(const int* __restrict__ cols, const double* __restrict__ vals, int len,
