@@ -10,8 +10,12 @@ Epsilon = 0.7, proper random rotations (seed 0).  A "step" is one pass of the wh
 `value`  = seconds per pass, inputs resident in HBM (strong scaling: the same job on N GPUs).
 `e2e`    = the same pass through the reference-facing call OrientationRecoverySolver.solve with
            host (numpy) inputs and host outputs, copies inside the timed region.
-`roofline` is for the dominant kernel of the pass (the tcgen05 Gram): algorithmic 2 N^2 P flop
-per launch set / its CUDA-event time, against the measured BF16 peak.
+`roofline` is for the kernel with the largest share of the pass (the HBM-bound block mat-vec of the
+eigen-solver at cfg 2: algorithmic 4 rows N + 128 N bytes per launch / its mean CUDA-event time, against the
+measured HBM copy bandwidth); the tcgen05 Gram is reported under `roofline_other` (2 N^2 P flop against
+the measured BF16 peak).  `alt_operator` = the same pass with the other form of the Markov operator
+(dense FP32 rows <-> FP64 kNN lists), `host_wall_ms_of_each_pass` = host clock per timed pass (shows
+where a host stall fell; the value itself is the CUDA-event time of exactly K passes).
 """
 import argparse
 import contextlib
@@ -37,6 +41,7 @@ WORKLOADS = {
     "small": dict(N=2000, n=15, n_p=31, k=150, eps=0.7, desc="debug size"),
 }
 METRIC = "end_to_end_seconds_patterns_to_orientations"
+EXTRA_WARMUP = 4
 
 # stdout carries exactly one JSON line: everything else any library prints (NCCL banners, progress
 # prints of the stage API, ...) is routed to stderr at the file-descriptor level
@@ -223,7 +228,8 @@ def run_reference_arm(args, wl):
     line = {"impl": "reference", "metric": METRIC, "value": round(v, 3), "unit": "s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(v * 1e3, 1), "higher_is_better": False, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl["desc"], "N": wl["N"], "pixels": wl["n_p"] ** 2, "k": wl["k"], "epsilon": wl["eps"]},
+            "config": {"workload": wl["desc"], "N": wl["N"], "pixels": wl["n_p"] ** 2, "object_voxels_1d": wl["n"], "k": wl["k"],
+                       "epsilon": wl["eps"], "rotations": "uniform random SO(3), seed 0"},
             "cpu_baseline": {"value": round(v, 3), "unit": "s", "cores": cores, "kind": "port",
                              "sample": "oracle port on the first %d of %d patterns, stage times extrapolated (synth x N/Ns, rest x (N/Ns)^2); %d of %d steps run (200 s budget)" % (Ns, wl["N"], done, args.warmup + args.steps)},
             "e2e": {"value": round(v, 3), "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -235,7 +241,7 @@ def run_reference_arm(args, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="v3s", choices=["v3s", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
@@ -311,7 +317,9 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0 and not os.environ.get("V3S_BENCH_NO_SAMPLER"):
         sampler.start()
-    for _ in range(args.warmup):
+    # W warm-up passes as asked, plus EXTRA_WARMUP untimed ones: on every box tried the 6th pass of a process is
+    # slower (0.6 ms to >100 ms, one-off driver-side work after ~3000 launches); it belongs to start-up, not to a step
+    for _ in range(args.warmup + EXTRA_WARMUP):
         out = one_pass()
     barrier()
     if rank == 0:
@@ -419,7 +427,7 @@ def main():
         gc.collect()
         gc.disable()
         t0 = time.perf_counter()
-        reps = max(2, min(args.steps, 3))
+        reps = max(2, min(args.steps, 10))
         for _ in range(reps):
             res = call()
         barrier()
@@ -467,6 +475,7 @@ def main():
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl["desc"], "N": N, "pixels": P, "object_voxels_1d": n, "k": k, "epsilon": eps,
                    "rotations": "uniform random SO(3), seed 0", "parallelism": "rows%d" % world,
+                   "untimed_passes_before_the_timed_region": args.warmup + EXTRA_WARMUP,
                    "l2": "inputs larger than L2 (pattern matrix %.0f MB, Markov matrix %.0f MB)" % (N * P * 4 / 1e6, rows_local * N * 4 / 1e6),
                    "arithmetic": "BF16x3 split tcgen05 Gram (FP32 accumulate), FP32 synthesis/mat-vec, FP64 reductions + eigen-solver"},
         "clocks": clocks,

@@ -148,6 +148,23 @@ def test_stage_handoff_roundtrip_and_orientation_metric(tmp_path):
     v3s.save_stage_outputs(str(tmp_path / "run.npz"), res)
     back = v3s.load_stage_outputs(str(tmp_path / "run.npz"))
     assert all(np.array_equal(back[k], res[k]) for k in res)
+    # MATLAB v5 file and the Octave pipeline's artifacts folder (one `save -text` file per variable, N 1-based)
+    res2 = dict(res)
+    res2["N"] = rng.integers(0, 5, size=(5, 3)).astype(float)
+    res2["Lambda"] = rng.random(10)
+    res2["Sigma_T"] = np.array([12.5])
+    v3s.save_stage_outputs(str(tmp_path / "run.mat"), res2)
+    back = v3s.load_stage_outputs(str(tmp_path / "run.mat"))
+    assert all(np.array_equal(back[k], res2[k]) for k in res2)
+    import scipy.io
+    assert np.array_equal(scipy.io.loadmat(str(tmp_path / "run.mat"))["N"], res2["N"] + 1)
+    art = str(tmp_path / "artifacts") + os.sep
+    v3s.save_stage_outputs(art, res2)
+    assert sorted(os.listdir(art)) == sorted(k + ".mat" for k in v3s.extras.RESULT_KEYS)
+    head = open(os.path.join(art, "S2.mat")).read().splitlines()[:5]
+    assert head[1] == "# name: S2" and head[2] == "# type: matrix" and head[3] == "# rows: 5" and head[4] == "# columns: 3"
+    back = v3s.load_stage_outputs(art)
+    assert all(np.array_equal(back[k], res2[k]) for k in res2)             # %.17g round-trips doubles exactly
     with pytest.raises(Exception, match="lacks"):
         v3s.save_stage_outputs(str(tmp_path / "bad.npz"), {"Ps": np.zeros(2)})
     # orientation metric: truth rotated by one global rotation and perturbed by 2 degrees -> ~2 degrees

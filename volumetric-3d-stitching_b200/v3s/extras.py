@@ -1,8 +1,10 @@
 """Rows (f) of the scope table that sit next to the hot path:
 
 * stage hand-off files -- the Octave / MATLAB implementations exchange every intermediate through
-  files (`src/octave/DiffusionMap3dOrientations.m:10-27`: Images, S2, N, Axis, ...); here one `.npz`
-  with the result map of `OrientationRecoverySolver.solve`, so a run can be resumed or cross-checked;
+  files (`src/octave/DiffusionMap3dOrientations.m:10-27`: Images, S2, N, Axis, ...); here the result
+  map of `OrientationRecoverySolver.solve` as one `.npz`, one MATLAB `.mat`, or a folder of Octave
+  `save -text` files named like the Octave pipeline's artifacts, so a run can be resumed or
+  cross-checked against Octave / MATLAB users' files;
 * a *correct* orientation metric next to the bug-compatible Sigma_T: per-pattern geodesic error of
   the recovered rotations after the best global alignment (the diffusion map fixes orientations only
   up to one global rotation / reflection of the frame);
@@ -19,17 +21,100 @@ from . import _util
 RESULT_KEYS = ('Ps', 'Lambda', 'c0', 'c', 'S2', 'N', 'Images', 'R', 'Sigma_T', 'Axis', 'Quat')
 
 
+OCTAVE_ARTIFACTS = ('Images', 'Axis', 'S2', 'N', 'Ps', 'Lambda', 'c0', 'c')   # files of src/octave/DiffusionMap3dOrientations.m:10-27
+
+
 def save_stage_outputs(path, result):
-    """Write the result map of `solve` (solution.py:49-61 keys) to a compressed .npz."""
+    """Write the result map of `solve` (solution.py:49-61 keys).
+
+    path ending in .npz -> one compressed numpy archive; .mat -> one MATLAB v5 file (scipy.io.savemat;
+    Octave and MATLAB `load` both read it); a directory (existing, or a path ending in '/') -> one
+    Octave `save -text` file per variable, `<dir>/<name>.mat`, the layout of the Octave pipeline's
+    `artifacts/` folder.  In the two MATLAB / Octave forms the neighbour indices `N` are written
+    1-based, as DistanceMatrix.m produces them; `load_stage_outputs` undoes that."""
+    import os
     missing = [k for k in RESULT_KEYS if k not in result]
     if missing:
         raise Exception('result map lacks ' + str(missing))
-    np.savez_compressed(path, **{k: np.asarray(result[k]) for k in RESULT_KEYS})
+    arrays = {k: np.asarray(result[k], dtype=np.float64) for k in RESULT_KEYS}
+    if path.endswith(os.sep) or os.path.isdir(path):
+        os.makedirs(path, exist_ok=True)
+        for k in RESULT_KEYS:
+            a = arrays[k] + 1.0 if k == 'N' else arrays[k]
+            _write_octave_text(os.path.join(path, k + '.mat'), k, a)
+    elif path.endswith('.mat'):
+        import scipy.io
+        arrays['N'] = arrays['N'] + 1.0
+        scipy.io.savemat(path, arrays, do_compression=True)
+    else:
+        np.savez_compressed(path, **arrays)
 
 
 def load_stage_outputs(path):
+    """Inverse of `save_stage_outputs` for all three forms (a directory may also hold files written by the
+    Octave pipeline itself: whatever of RESULT_KEYS is present is returned)."""
+    import os
+    if os.path.isdir(path):
+        out = {}
+        for k in RESULT_KEYS:
+            f = os.path.join(path, k + '.mat')
+            if os.path.exists(f):
+                out[k] = _read_octave_text(f)
+                if k == 'N':
+                    out[k] = out[k] - 1.0
+        return out
+    if path.endswith('.mat'):
+        import scipy.io
+        m = scipy.io.loadmat(path)
+        out = {k: np.asarray(m[k], dtype=np.float64) for k in RESULT_KEYS if k in m}
+        if 'N' in out:
+            out['N'] = out['N'] - 1.0
+        for k in ('Lambda', 'Sigma_T'):                  # loadmat returns 1-D arrays as (1, n)
+            if k in out and out[k].ndim == 2 and out[k].shape[0] == 1:
+                out[k] = out[k][0]
+        return out
     with np.load(path) as f:
         return {k: f[k] for k in RESULT_KEYS}
+
+
+def _write_octave_text(fname, name, a):
+    """One variable in Octave's `save -text` format (matrix / scalar), full double precision."""
+    a = np.asarray(a, dtype=np.float64)
+    with open(fname, 'w') as f:
+        f.write('# Created by v3s\n# name: %s\n' % name)
+        if a.ndim == 0:
+            f.write('# type: scalar\n%.17g\n' % float(a))
+        else:
+            a2 = a.reshape(-1, 1) if a.ndim == 1 else a.reshape(a.shape[0], -1)
+            f.write('# type: matrix\n# rows: %d\n# columns: %d\n' % a2.shape)
+            np.savetxt(f, a2, fmt=' %.17g', delimiter='')
+        f.write('\n\n')
+
+
+def _read_octave_text(fname):
+    rows = cols = None
+    kind = None
+    data = []
+    with open(fname) as f:
+        for line in f:
+            t = line.strip()
+            if t.startswith('#'):
+                key, _, val = t[1:].partition(':')
+                key, val = key.strip(), val.strip()
+                if key == 'type':
+                    kind = val
+                elif key == 'rows':
+                    rows = int(val)
+                elif key == 'columns':
+                    cols = int(val)
+            elif t:
+                data.extend(float(x) for x in t.split())
+    if kind == 'scalar':
+        return np.float64(data[0])
+    if kind != 'matrix' or rows is None or cols is None or len(data) != rows * cols:
+        raise Exception('unsupported or truncated Octave text file: ' + fname)
+    a = np.array(data, dtype=np.float64).reshape(rows, cols)
+    return a[:, 0] if cols == 1 else a
 
 
 def orientation_errors_deg(Recon, R_true):
