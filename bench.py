@@ -379,7 +379,7 @@ def main():
 
     # ---- the same pass with the other form of the Markov operator (reported beside the headline) ----
     alt = None
-    if not args.no_alt_operator:
+    if not args.no_alt_operator and world == 1:          # (sharded: tests/multi_gpu_check.py covers the sparse form)
         try:
             ops.operator = "dense" if sparse_run else "sparse"
             alt_stats = {}
