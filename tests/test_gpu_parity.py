@@ -541,6 +541,21 @@ def test_sparse_operator_eigenpairs(v3s_mod, ops, hub):
     _, _, _, _, Po, dio = orc.diffusion_coordinate(S2.copy(), Nbr, 0.7, validate=False, return_all=True)
     w, V = np.linalg.eigh(0.5 * (Po + Po.T))
     idx = np.argsort(-np.abs(w))[:10]
+    # the mat-vec itself (hub: row 0 has > 2048 stored entries and is shared by the 8 warps of a block)
+    S2d = ops.to_device(S2.copy(), torch.float64)
+    Nd = ops.to_device(Nbr, torch.int32)
+    sc = ops.s2_scalars(S2d, 0.7)
+    ops.s2_threshold_(S2d, sc)
+    sp, _ = ops.build_markov_sparse(S2d, Nd, sc, 0, N)
+    tp = sp.t_ptr.cpu().numpy()
+    assert (int(np.max(np.diff(tp))) + k > 2048) == bool(hub)
+    X = np.random.default_rng(5).standard_normal((N, 8))
+    Xd = ops.to_device(X, torch.float64)
+    Y = ops.sparse_block_matvec(sp, Xd)
+    Yref = Po @ X
+    assert np.max(np.abs(Y.cpu().numpy() - Yref)) < 5e-12 * np.max(np.abs(Yref))
+    assert torch.equal(ops.sparse_block_matvec(sp.rows(0, 10), Xd), Y[:10])        # same bits from another launch shape
+    assert torch.equal(ops.sparse_block_matvec(sp.rows(0, N - 3), Xd), Y[:N - 3])
     prev = ops.operator
     try:
         out = {}

@@ -197,22 +197,89 @@ __device__ __forceinline__ double sp_segment(const int* __restrict__ cols, const
   return acc;
 }
 
+// entries [e0, e0+32) of a row's unified range (list part [0,k), transposed part [k,L)): lane -> (column, value)
+__device__ __forceinline__ void sp_fetch(const int* __restrict__ colA, const double* __restrict__ valA, int k,
+                                         const int* __restrict__ colT, const double* __restrict__ valT, int L, int e,
+                                         int& c, double& v) {
+  if (e < k) { c = colA[e]; v = valA[e]; }
+  else if (e < L) { c = colT[e - k]; v = valT[e - k]; }
+  else { c = 0; v = 0.0; }
+}
+
+// 32 entries held one per lane -> 8 x (4 entries, 8 vectors): shuffle-broadcast, gather, accumulate
+__device__ __forceinline__ double sp_chunk(int c, double v, const double* __restrict__ X, int ldx, int j, int g, double acc) {
+  double xv[8], vv[8];
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int src = it * 4 + g;
+    const int cc = __shfl_sync(0xffffffffu, c, src);
+    vv[it] = __shfl_sync(0xffffffffu, v, src);
+    xv[it] = (vv[it] != 0.0 && j < ldx) ? X[(long long)cc * ldx + j] : 0.0;   // padding / thresholded entries: no load
+  }
+#pragma unroll
+  for (int it = 0; it < 8; ++it) acc = fma(vv[it], xv[it], acc);
+  return acc;
+}
+
+constexpr int SP_LONG = 2048;      // rows with more stored entries are shared by the 8 warps of a block (phase 2)
+
 __global__ void __launch_bounds__(SP_THREADS)
 sparse_block_matvec_kernel(const int* __restrict__ nbr, const double* __restrict__ a_val, int k,
                            const int* __restrict__ t_ptr, const int* __restrict__ t_col, const double* __restrict__ t_val,
                            long long row0, long long n_rows, const double* __restrict__ X, int ldx,
                            double* __restrict__ Y, int ldy) {
-  const int lane = threadIdx.x & 31, j = lane & 7, g = lane >> 3;
+  const int lane = threadIdx.x & 31, j = lane & 7, g = lane >> 3, w = threadIdx.x >> 5;
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  // phase 1: one warp per row
   for (long long r = warp; r < n_rows; r += nwarps) {
     const long long i = row0 + r;
-    double acc = sp_segment(nbr + i * k, a_val + i * k, k, X, ldx, j, g, lane, 0.0);
     const int p0 = t_ptr[i];
-    acc = sp_segment(t_col + p0, t_val + p0, t_ptr[i + 1] - p0, X, ldx, j, g, lane, acc);
+    const int d = t_ptr[i + 1] - p0;
+    if (k + d > SP_LONG) continue;                     // a hub of the kNN graph: phase 2
+    double acc = sp_segment(nbr + i * k, a_val + i * k, k, X, ldx, j, g, lane, 0.0);
+    acc = sp_segment(t_col + p0, t_val + p0, d, X, ldx, j, g, lane, acc);
     acc += __shfl_xor_sync(0xffffffffu, acc, 8);
     acc += __shfl_xor_sync(0xffffffffu, acc, 16);
     if (g == 0 && j < ldy) Y[r * ldy + j] = acc;
+  }
+  // phase 2: long rows (in-degree in the thousands: hubs of noisy high-dimensional data), one block per row --
+  // warp w takes the 32-entry chunks w, w+8, ... of the row's unified entry range, the 8 partial sums are added in
+  // warp order.  The order depends on the row alone, so results stay independent of the sharding.
+  __shared__ double part[SP_THREADS / 32][8];
+  const long long per_block = ceil_div64(n_rows, gridDim.x);       // the block looks for long rows in its own contiguous range
+  const long long rb0 = blockIdx.x * per_block;
+  const long long rb1 = rb0 + per_block < n_rows ? rb0 + per_block : n_rows;
+  for (long long rb = rb0; rb < rb1; rb += SP_THREADS) {
+    const long long rt = rb + threadIdx.x;
+    int is_long = 0;
+    if (rt < rb1) is_long = (k + (t_ptr[row0 + rt + 1] - t_ptr[row0 + rt])) > SP_LONG;
+    if (!__syncthreads_or(is_long)) continue;          // the usual case: one test per 256 rows
+    const long long re = rb + SP_THREADS < rb1 ? rb + SP_THREADS : rb1;
+    for (long long r = rb; r < re; ++r) {
+      const long long i = row0 + r;
+      const int p0 = t_ptr[i];
+      const int L = k + (t_ptr[i + 1] - p0);
+      if (L <= SP_LONG) continue;                      // block-uniform
+      double acc = 0.0;
+      for (int base = w * 32; base < L; base += SP_THREADS) {
+        int c;
+        double v;
+        sp_fetch(nbr + i * k, a_val + i * k, k, t_col + p0, t_val + p0, L, base + lane, c, v);
+        acc = sp_chunk(c, v, X, ldx, j, g, acc);
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+      if (g == 0) part[w][j] = acc;
+      __syncthreads();
+      if (w == 0 && g == 0 && j < ldy) {
+        double s_ = part[0][j];
+#pragma unroll
+        for (int q = 1; q < SP_THREADS / 32; ++q) s_ += part[q][j];
+        Y[r * ldy + j] = s_;
+      }
+      __syncthreads();
+    }
   }
 }
 
