@@ -297,3 +297,22 @@ def test_pipeline_world2_gloo_matches_single(operator):
         assert np.max(orc.principal_angles(r[4], ref["Ps"].numpy())) < 1e-5
         assert abs(r[5] - float(ref["sigma_T"].item())) < 1e-3
     assert np.array_equal(res[0][3], res[1][3])      # ranks agree bitwise
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the reference's CPU path, oracle port) needs no GPU: one JSON line on
+    stdout with the contract's keys, same metric / unit / direction as the v3s arm."""
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "small",
+                        "--steps", "1", "--warmup", "0", "--cpu-sample", "300"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1                                   # everything else goes to stderr
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "end_to_end_seconds_patterns_to_orientations"
+    assert d["unit"] == "s" and d["higher_is_better"] is False and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
+    assert d["e2e"] == {"value": d["value"], "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["N"] == 2000 and d["steps"] == 1 and d["warmup"] == 0

@@ -23,11 +23,9 @@ class DiffusionMapSolver:
 
     @staticmethod
     def _lists_to_dev(S2, N):
-        S2d = _util.to_dev(S2, torch.float64)
-        if _util.is_torch(S2) and S2d.data_ptr() == S2.data_ptr():
-            pass                                   # mutate the caller's tensor in place, like the reference
-        Nd = _util.to_dev(N, torch.int32) if not (_util.is_torch(N) and N.dtype == torch.int32) else _util.to_dev(N, torch.int32)
-        return S2d, Nd
+        """kNN lists on the device: S2 as FP64 (a CUDA FP64 tensor is used as is, so the thresholding
+        mutates the caller's tensor like the reference mutates its array), N as int32."""
+        return _util.to_dev(S2, torch.float64), _util.to_dev(N, torch.int32)
 
     @staticmethod
     def diffusion_coordinate(S2, N, Epsilon, k=10, validate=True, stats=None):
