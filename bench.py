@@ -221,7 +221,7 @@ def run_reference_arm(args, wl):
         if i >= args.warmup:
             vals.append(full)
         # keep the whole arm within a few minutes whatever K and W the caller asks for
-        if time.perf_counter() - t_start > 200 and vals:
+        if time.perf_counter() - t_start > 120 and vals:
             break
     v = sum(vals) / len(vals)
     cores = os.cpu_count() or 1
@@ -231,7 +231,7 @@ def run_reference_arm(args, wl):
             "config": {"workload": wl["desc"], "N": wl["N"], "pixels": wl["n_p"] ** 2, "object_voxels_1d": wl["n"], "k": wl["k"],
                        "epsilon": wl["eps"], "rotations": "uniform random SO(3), seed 0"},
             "cpu_baseline": {"value": round(v, 3), "unit": "s", "cores": cores, "kind": "port",
-                             "sample": "oracle port on the first %d of %d patterns, stage times extrapolated (synth x N/Ns, rest x (N/Ns)^2); %d of %d steps run (200 s budget)" % (Ns, wl["N"], done, args.warmup + args.steps)},
+                             "sample": "oracle port on the first %d of %d patterns, stage times extrapolated (synth x N/Ns, rest x (N/Ns)^2); %d of %d steps run (120 s budget)" % (Ns, wl["N"], done, args.warmup + args.steps)},
             "e2e": {"value": round(v, 3), "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
