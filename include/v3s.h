@@ -146,6 +146,51 @@ int v3s_knn_from_gram(const float* G, long long ldg, long long n_rows, long long
                       const int* zero_flag, int* cand_ws, int* count_ws, int* overflow_flag, double* S2, int* Nbr,
                       double* dist_ws, void* stream);
 
+/* ---- stage 2, fused form: the Gram matrix is never materialised --------------------------- */
+
+/* FP16 Gram operand of centred unit rows a_f32 [n_rows,P]: a16 [n_rows,Ppad] = fl16(2^8 a), zero
+ * padded (Ppad a multiple of 64).  One FP16 product ranks candidates; distances come from a_f32.  */
+int v3s_split_f16(const float* a_f32, long long n_rows, int P, int Ppad, void* a16, void* stream);
+
+/* cta_group of the fused kernel: 2 = CTA pairs, tcgen05.mma.cta_group::2 M=256 N=256 with each CTA
+ * staging half of the shared column tile; 1 = one CTA per SM, M=128 N=256; 0 (default) = by size.   */
+int v3s_set_gram_topk_cta_group(int cg);
+
+/* buffer sizes of v3s_gram_topk for a problem: out[0] = S lists per row (column segments),
+ * out[1] = C entries per list, out[2] = padded row count of `lists` / `counts`, out[3] = ints of `ws`. */
+int v3s_gram_topk_plan(long long n_rows, long long n_cols, int k, int* out /* host [4] */);
+
+/* np.matmul(A, A.T) (distance.py:56) FUSED with the selection half of
+ * DistanceMatrix.knn_from_round_distance (distance.py:39-43): tcgen05/TMEM/TMA Gram tiles whose
+ * epilogue keeps, per query row, a running threshold and a candidate list -- G [n_rows, n_cols] is
+ * never written.  a16_all [n_cols,Ppad], a16_rows [n_rows,Ppad] from v3s_split_f16.  Output:
+ * lists [rows_pad*S*C] 64-bit entries (FP32 bits of g~ << 32 | column) and counts [rows_pad*S];
+ * the union of a row's S lists contains every column with g~ >= (k-th largest g~ of the row) -
+ * 2 eps_g, eps_g = the caller's bound on |g~ - g| (2^-10 + accumulation for one FP16 product),
+ * hence the row's exact k nearest.  *overflow (device, may be NULL) counts lists that saturated.
+ * ws int [plan[3]] (zeroed by the call): the rows' shared thresholds and the per-tile arrival counters
+ * that keep the persistent workers' operand streams aligned (each K slice read from HBM once).
+ * Fails with "Number of nearest neighbors to preserve is too high." when k > n_cols.            */
+int v3s_gram_topk(const void* a16_all, long long n_cols, const void* a16_rows, long long n_rows, int Ppad, int k,
+                  float eps_g, unsigned long long* lists, int* counts, int* overflow, int* ws, void* stream);
+
+/* unite the S lists of every row: candidates = entries within 2 eps_g of the k-th largest g~ of the
+ * union -> cand_ws int [n_rows,cap], count_ws int [n_rows] (input of v3s_knn_refine).  Zero-norm
+ * patterns (NaN -> distance 0, distance.py:58; zero_flag [n_cols] may be NULL): a zero query row
+ * gets columns 0..cap-1, and the zero columns (compacted into zero_ws, int [cap + 1]) are appended to
+ * every row.  *overflow counts rows cut at cap.                                                    */
+int v3s_knn_merge_lists(const unsigned long long* lists, const int* counts, int S, int C, long long n_rows,
+                        long long n_cols, long long row0, int k, float eps_g, int cap, const int* zero_flag,
+                        int* zero_ws, int* cand_ws, int* count_ws, int* overflow, void* stream);
+
+/* arccos epilogue (distance.py:56-59) + final ordering (distance.py:39-43) on selected candidates:
+ * d = 2 asin(|a_r - a_c| / 2) from the FP32 rows, sorted by (d, index), first k kept -> S2 [n_rows,k]
+ * FP64, Nbr [n_rows,k] int32.  dist_ws FP64 [n_rows,cap] (may be NULL): mutual pairs evaluated once.  order
+ * (may be NULL, int [n_rows]): processing order of the rows, a cache-locality hint only.            */
+int v3s_knn_refine(const float* a_rows, const float* a_all, int P, long long row0, long long n_rows, long long n_cols,
+                   int k, int cap, const int* zero_flag, const int* cand_ws, const int* count_ws, double* S2, int* Nbr,
+                   double* dist_ws, const int* order, void* stream);
+
 /* ---- stage 3: diffusion map ---------------------------------------------------------------- */
 
 /* scalar part of DiffusionMapSolver.s2_to_w_matrix (diffusion.py:297-313), bug-compatible row

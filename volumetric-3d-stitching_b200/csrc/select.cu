@@ -140,7 +140,7 @@ refine_sort_kernel(const float* __restrict__ a_rows, const float* __restrict__ a
                    const int* __restrict__ cand, const int* __restrict__ cand_count, int cap, int kk_pad, int k,
                    const int* __restrict__ zero_flag,
                    int cache_row, const double* __restrict__ Bd, long long ldb, double* __restrict__ S2,
-                   int* __restrict__ Nbr, double* Dws, int phase) {
+                   int* __restrict__ Nbr, double* Dws, int phase, const int* __restrict__ order) {
   // phase 0: distances + sort in one launch.  phase 1: distances only, into Dws [n_rows, cap] in candidate
   // order; a pair whose partner row j < i of this call lists i too is skipped and stored as -(t + 1),
   // t = position of i in j's list.  phase 2: fetch the skipped values from the partner rows, sort, emit.
@@ -151,7 +151,10 @@ refine_sort_kernel(const float* __restrict__ a_rows, const float* __restrict__ a
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool vec4 = (P % 4 == 0);
 
-  for (int r = blockIdx.x; r < n_rows; r += gridDim.x) {
+  // `order` (optional): processing order of the rows -- rows handled at the same time by the grid then
+  // share candidates (neighbouring patterns), so their row reads hit L2; results do not depend on it
+  for (int it = blockIdx.x; it < n_rows; it += gridDim.x) {
+    const int r = order ? order[it] : it;
     __syncthreads();
     const int kk = cand_count[r];
     const float* arow = a_rows ? a_rows + (long long)r * P : nullptr;
@@ -275,6 +278,8 @@ refine_sort_kernel(const float* __restrict__ a_rows, const float* __restrict__ a
 
 using namespace v3s;
 
+static size_t g_refine_smem_set = 0;   // largest dynamic shared-memory size refine_sort_kernel was opted into
+
 extern "C" int v3s_knn_from_gram(const float* G, long long ldg, long long n_rows, long long n_cols, long long row0,
                                  const float* a_rows, const float* a_all, int P, int k, int margin, float eps_g, int cap,
                                  const int* zero_flag, int* cand_ws, int* count_ws, int* overflow_flag, double* S2,
@@ -298,23 +303,59 @@ extern "C" int v3s_knn_from_gram(const float* G, long long ldg, long long n_rows
   const size_t base = (size_t)kk_pad * (sizeof(double) + sizeof(int));
   const int cache_row = (base + (size_t)P * 4 <= 200 * 1024) ? 1 : 0;
   const size_t smem = base + (cache_row ? (size_t)P * 4 : 0);
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
+  if (smem > g_refine_smem_set) {
     V3S_CUDA(cudaFuncSetAttribute(refine_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
+    g_refine_smem_set = smem;
   }
   const int grid2 = (int)(n_rows < 8LL * kNumSMs ? n_rows : 8LL * kNumSMs);
   if (dist_ws) {
     refine_sort_kernel<<<grid2, kRefThreads, smem, st>>>(a_rows, a_all, P, row0, (int)n_rows, cand_ws, count_ws, cap, kk_pad,
-                                                        k, zero_flag, cache_row, nullptr, 0, S2, Nbr, dist_ws, 1);
+                                                        k, zero_flag, cache_row, nullptr, 0, S2, Nbr, dist_ws, 1, nullptr);
     V3S_CHECK_LAUNCH();
     refine_sort_kernel<<<grid2, kRefThreads, base, st>>>(a_rows, a_all, P, row0, (int)n_rows, cand_ws, count_ws, cap, kk_pad,
-                                                        k, zero_flag, 0, nullptr, 0, S2, Nbr, dist_ws, 2);
+                                                        k, zero_flag, 0, nullptr, 0, S2, Nbr, dist_ws, 2, nullptr);
     V3S_CHECK_LAUNCH();
     return 0;
   }
   refine_sort_kernel<<<grid2, kRefThreads, smem, st>>>(a_rows, a_all, P, row0, (int)n_rows, cand_ws, count_ws, cap, kk_pad,
-                                                      k, zero_flag, cache_row, nullptr, 0, S2, Nbr, nullptr, 0);
+                                                      k, zero_flag, cache_row, nullptr, 0, S2, Nbr, nullptr, 0, nullptr);
+  V3S_CHECK_LAUNCH();
+  return 0;
+}
+
+// Exact distances + sort for candidate lists that are already selected (v3s_gram_topk +
+// v3s_knn_merge_lists): the refinement half of v3s_knn_from_gram.  cand_ws int [n_rows,cap] /
+// count_ws int [n_rows] are inputs; dist_ws FP64 [n_rows,cap] (NULL: one launch, no pair sharing).
+// order (optional, int [n_rows]): processing order of the rows (a locality hint, not a result).
+extern "C" int v3s_knn_refine(const float* a_rows, const float* a_all, int P, long long row0, long long n_rows,
+                              long long n_cols, int k, int cap, const int* zero_flag, const int* cand_ws,
+                              const int* count_ws, double* S2, int* Nbr, double* dist_ws, const int* order, void* stream) {
+  V3S_REQUIRE(k >= 1 && cap >= k && n_rows >= 0 && n_cols < (1LL << 31) && n_rows < (1LL << 31), "v3s_knn_refine: bad arguments");
+  V3S_REQUIRE(k <= n_cols, "Number of nearest neighbors to preserve is too high.");   // distance.py:33-34
+  if (n_rows == 0) return 0;
+  int kk_pad = 4;
+  while (kk_pad < cap) kk_pad <<= 1;
+  V3S_REQUIRE(kk_pad <= 4096, "v3s_knn_refine: candidate capacity %d too large (max 4096)", cap);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t base = (size_t)kk_pad * (sizeof(double) + sizeof(int));
+  const int cache_row = (base + (size_t)P * 4 <= 200 * 1024) ? 1 : 0;
+  const size_t smem = base + (cache_row ? (size_t)P * 4 : 0);
+  if (smem > g_refine_smem_set) {
+    V3S_CUDA(cudaFuncSetAttribute(refine_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    g_refine_smem_set = smem;
+  }
+  const int grid2 = (int)(n_rows < 8LL * kNumSMs ? n_rows : 8LL * kNumSMs);
+  if (!dist_ws) {       // one launch, every pair evaluated by both of its rows
+    refine_sort_kernel<<<grid2, kRefThreads, smem, st>>>(a_rows, a_all, P, row0, (int)n_rows, cand_ws, count_ws, cap, kk_pad, k,
+                                                        zero_flag, cache_row, nullptr, 0, S2, Nbr, nullptr, 0, order);
+    V3S_CHECK_LAUNCH();
+    return 0;
+  }
+  refine_sort_kernel<<<grid2, kRefThreads, smem, st>>>(a_rows, a_all, P, row0, (int)n_rows, cand_ws, count_ws, cap, kk_pad, k,
+                                                      zero_flag, cache_row, nullptr, 0, S2, Nbr, dist_ws, 1, order);
+  V3S_CHECK_LAUNCH();
+  refine_sort_kernel<<<grid2, kRefThreads, base, st>>>(a_rows, a_all, P, row0, (int)n_rows, cand_ws, count_ws, cap, kk_pad, k,
+                                                      zero_flag, 0, nullptr, 0, S2, Nbr, dist_ws, 2, order);
   V3S_CHECK_LAUNCH();
   return 0;
 }
@@ -349,7 +390,7 @@ extern "C" int v3s_knn_from_dense(const double* B, long long n, int k, int margi
   V3S_CHECK_LAUNCH();
   const size_t smem = (size_t)kk_pad * (sizeof(double) + sizeof(int));
   refine_sort_kernel<<<grid, kRefThreads, smem, st>>>(nullptr, nullptr, 0, 0, (int)n, cand_ws, count_ws, (int)kk, kk_pad, k,
-                                                     nullptr, 0, B, n, S2, Nbr, nullptr, 0);
+                                                     nullptr, 0, B, n, S2, Nbr, nullptr, 0, nullptr);
   V3S_CHECK_LAUNCH();
   return 0;
 }

@@ -21,6 +21,15 @@ def gram_error_bound(P):
     """|G_tcgen05 - G_exact| for unit rows of length P: dropped lo.lo^T term (2^-18) + the tensor
     core's truncating FP32 accumulate over 3P/16 steps (validated in test_gram_tcgen05_vs_fp64)."""
     return 1e-5 + 3.0e-8 * (3.0 * P / 16.0)
+
+
+def fused_gram_error_bound(P):
+    """|g~ - g| of the fused Gram / top-k kernel for unit rows of length P (gram_topk.cu): one FP16
+    product, (2^-10 + 2^-22) sum|a_i b_i| <= 2^-10 by Cauchy-Schwarz, + the FP32 accumulation of the
+    P/16 tensor-core steps (<= 2^-23 each) + FP16 subnormal flushes of 2^8-scaled entries."""
+    return 2.0 ** -10 * (1.0 + 2.0 ** -11) + 1.2e-7 * (P / 16.0) + 2e-6
+
+
 PANEL_BYTES = 4 << 30   # Gram row panel budget when G is streamed in panels
 SYM_BYTES = 48 << 30    # the whole symmetric G is materialised (half the MMA work) up to this size
 
@@ -78,7 +87,10 @@ class CudaOps:
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self._mv_ws = None
         self._sigma_ws = None
-        self.gram_impl = "tcgen05"   # "simt" = FP32 CUDA-core validation path
+        # "fused" = tcgen05 Gram tiles with the top-k selection in their epilogue (G never materialised; default),
+        # "tcgen05" = materialised BF16x3 Gram panels + radix select, "simt" = FP32 CUDA-core validation path
+        self.gram_impl = "fused"
+        self.knn_overflow = None
         self._profile = False        # when True, CUDA events bracket the named kernels (bench.py)
         self._events = []
         self._synth_prep = {}
@@ -214,6 +226,49 @@ class CudaOps:
         call("v3s_split_bf16", ptr(a32), n, P, Ppad, ptr(hi), ptr(lo), stream_ptr())
         return hi, lo
 
+    def split_f16(self, a32):
+        """FP16 operand fl16(2^8 a) [n,Ppad] of the fused Gram / top-k kernel."""
+        n, P = a32.shape
+        Ppad = round_up(P, GRAM_KPAD)
+        a16 = self.empty((n, Ppad), torch.float16)
+        call("v3s_split_f16", ptr(a32), n, P, Ppad, ptr(a16), stream_ptr())
+        return a16
+
+    def knn_rows_fused(self, a16_all, a32_all, zero_flag, r0, r1, k, order=None):
+        """k nearest neighbours of rows [r0,r1) with the selection fused into the Gram kernel's epilogue:
+        v3s_gram_topk (candidate lists per row and column segment) -> v3s_knn_merge_lists (value band around
+        the k-th largest) -> v3s_knn_refine (exact distances from the FP32 rows, sort)."""
+        N, P = a32_all.shape
+        nr = r1 - r0
+        S2 = self.empty((nr, k), torch.float64)
+        Nbr = self.empty((nr, k), torch.int32)
+        if nr == 0:
+            return S2, Nbr
+        pl = (C.c_int * 4)()
+        call("v3s_gram_topk_plan", nr, N, k, pl)
+        S, Cc, rows_pad = int(pl[0]), int(pl[1]), int(pl[2])
+        lists = self.empty((rows_pad * S * Cc,), torch.int64)
+        counts = self.empty((rows_pad * S,), torch.int32)
+        tws = self.empty((int(pl[3]),), torch.int32)
+        self.knn_overflow = self.zeros((1,), torch.int32)
+        eps_g = fused_gram_error_bound(P)
+        h = self._tic("gram")
+        call("v3s_gram_topk", ptr(a16_all), N, ptr(a16_all[r0:r1]), nr, a16_all.shape[1], k, eps_g, ptr(lists), ptr(counts),
+             ptr(self.knn_overflow), ptr(tws), stream_ptr())
+        self._toc(h)
+        cap = min(k + KNN_MARGIN + KNN_EXTRA_CAP, N)
+        cand = self.empty((nr, cap), torch.int32)
+        cnt = self.empty((nr,), torch.int32)
+        zws = self.empty((cap + 1,), torch.int32) if zero_flag is not None else None
+        dws = self.empty((nr, cap), torch.float64) if self.dedup_refine else None
+        h = self._tic("select_refine")
+        call("v3s_knn_merge_lists", ptr(lists), ptr(counts), S, Cc, nr, N, r0, k, eps_g, cap, ptr(zero_flag), ptr(zws),
+             ptr(cand), ptr(cnt), ptr(self.knn_overflow), stream_ptr())
+        call("v3s_knn_refine", ptr(a32_all[r0:r1]), ptr(a32_all), P, r0, nr, N, k, cap, ptr(zero_flag), ptr(cand), ptr(cnt),
+             ptr(S2), ptr(Nbr), ptr(dws), ptr(order), stream_ptr())
+        self._toc(h)
+        return S2, Nbr
+
     def gram_rows(self, hi_all, lo_all, a32_all, r0, r1, out=None):
         """G[r0:r1, :] as f32 [r1-r0, ldg]."""
         N = a32_all.shape[0]
@@ -303,6 +358,10 @@ class CudaOps:
         if k > N:
             raise Exception("Number of nearest neighbors to preserve is too high.")   # distance.py:33-34
         nr = r1 - r0
+        if self.gram_impl == "fused":
+            return self.knn_rows_fused(self.split_f16(a32_all), a32_all, zero_flag, r0, r1, k)
+        if hi_all is None:
+            hi_all, lo_all = self.split_bf16(a32_all)
         S2 = self.empty((nr, k), torch.float64)
         Nbr = self.empty((nr, k), torch.int32)
         if nr == 0:

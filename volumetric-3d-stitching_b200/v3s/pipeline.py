@@ -75,14 +75,15 @@ def knn_stage(ops, plan, img_local, k):
     sums = ops.column_sums(img_local)
     plan.all_reduce_sum(sums)
     mean = sums / N
+    fused = getattr(ops, "gram_impl", None) == "fused"       # the Gram operand (FP16) is derived from a32 inside knn_rows
     if plan.world == 1:
-        a32_all, hi_all, lo_all, zf_all = ops.center_normalize(img_local, mean)
+        a32_all, hi_all, lo_all, zf_all = ops.center_normalize(img_local, mean, want_split=not fused)
     else:
         # ship the FP32 unit rows only (4 B/element) and split them locally: half the all-gather volume
         a32, _, _, zf = ops.center_normalize(img_local, mean, want_split=False)
         a32_all = plan.all_gather_rows(a32)
         zf_all = plan.all_gather_rows(zf)
-        hi_all, lo_all = ops.split_bf16(a32_all)
+        hi_all, lo_all = (None, None) if fused else ops.split_bf16(a32_all)
     S2_loc, Nbr_loc = ops.knn_rows(hi_all, lo_all, a32_all, zf_all, plan.lo, plan.hi, k, plan=plan)
     S2_all = plan.all_gather_rows(S2_loc)
     Nbr_all = plan.all_gather_rows(Nbr_loc)
