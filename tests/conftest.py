@@ -4,7 +4,7 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for p in (os.path.join(ROOT, "volumetric-3d-stitching_b200"), os.path.join(ROOT, "oracle"), ROOT):
+for p in (os.path.join(ROOT, "volumetric-3d-stitching_b200"), os.path.join(ROOT, "oracle"), ROOT, os.path.join(ROOT, "tests")):
     if p not in sys.path:
         sys.path.insert(0, p)
 

@@ -104,7 +104,7 @@ class OracleOps:
         out[:, :N] = torch.from_numpy(P[r0:r1].astype(np.float32))
         return out, torch.from_numpy(di)
 
-    def wants_sparse_operator(self, n_rows, N):
+    def wants_sparse_operator(self, n_rows, N, k=150):
         return self.operator == "sparse"
 
     def build_markov_sparse(self, S2t, Nbr, scalars, r0, r1):

@@ -156,10 +156,12 @@ def test_gram_tcgen05_vs_fp64(ops, shape):
     hi2, lo2 = ops.split_bf16(a32)                                   # the sharded path splits after the all-gather
     assert torch.equal(hi2, hi) and torch.equal(lo2, lo)
     G64 = ref_a @ ref_a.T
+    prev_impl = ops.gram_impl
+    ops.gram_impl = "tcgen05"
     G_tc = ops.gram_rows(hi, lo, a32, 0, N)[:, :N].cpu().numpy()
     ops.gram_impl = "simt"
     G_simt = ops.gram_rows(hi, lo, a32, 0, N)[:, :N].cpu().numpy()
-    ops.gram_impl = "tcgen05"
+    ops.gram_impl = prev_impl
     e_tc, e_simt = np.max(np.abs(G_tc - G64)), np.max(np.abs(G_simt - G64))
     print(f"gram {shape}: max|tcgen05-f64|={e_tc:.2e} max|simt-f64|={e_simt:.2e}")
     assert e_simt < 5e-6
@@ -194,6 +196,44 @@ def test_gram_tcgen05_vs_fp64(ops, shape):
     r0, r1 = N // 3, min(N, N // 3 + 300)
     Gp = ops.gram_rows(hi, lo, a32, r0, r1)[:, :N].cpu().numpy()
     assert np.array_equal(Gp, G_tc[r0:r1])
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+def test_fused_gram_topk_lists_vs_fp64(ops, cg):
+    """gram_topk.cu (Gram tiles + selection in the tensor-core epilogue, G never stored): for ragged shapes,
+    a middle row block and clustered data, the union of a row's lists holds the exact FP64 top-k, every listed
+    value is within the documented one-FP16-product bound, no column is listed twice, and the resulting S2 / N
+    equal the materialised-Gram path's bit for bit (tests/gpu_fused_check.py holds the checker)."""
+    import gpu_fused_check as chk
+    from v3s import _lib
+    _lib.call("v3s_set_gram_topk_cta_group", cg)
+    try:
+        chk.check(ops, 301, 225, 50, 0, 301, 1)
+        chk.check(ops, 77, 64, 19, 0, 77, 2)
+        chk.check(ops, 1000, 961, 150, 0, 1000, 3)
+        chk.check(ops, 3000, 640, 150, 1000, 2177, 4, clustered=True)
+        chk.check(ops, 6000, 4096, 150, 0, 6000, 6)
+        chk.check(ops, 20000, 1024, 200, 2500, 5000, 7)
+    finally:
+        _lib.call("v3s_set_gram_topk_cta_group", 0)
+        ops.gram_impl = "fused"
+
+
+def test_fused_gram_topk_saturated_lists_are_reported(ops):
+    """Near-constant Gram rows (all patterns almost identical): the value band around the k-th largest holds
+    more entries than a list / the candidate buffer can keep.  The kernel must say so (knn_overflow) instead of
+    silently truncating; the distances it does return are still exact and sorted."""
+    rng = np.random.default_rng(3)
+    N, P, k = 2000, 256, 20
+    base = rng.random(P).astype(np.float32)
+    A = (base[None, :] + 1e-4 * rng.standard_normal((N, P))).astype(np.float32)
+    A[:, 0] += np.linspace(0, 50, N).astype(np.float32)            # after centring: one dominant direction, g ~ +-1
+    img = ops.to_device(A, torch.float32)
+    a32, _, _, zf = ops.center_normalize(img, ops.column_sums(img) / N, want_split=False)
+    S2, Nb = ops.knn_rows(None, None, a32, zf, 0, N, k)
+    assert int(ops.knn_overflow.item()) > 0
+    S2 = S2.cpu().numpy()
+    assert np.all(np.diff(S2, axis=1) >= 0) and np.all(np.isfinite(S2))
 
 
 def test_knn_connected_fixture(v3s_mod, golden_dir):

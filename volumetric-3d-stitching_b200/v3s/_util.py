@@ -69,7 +69,7 @@ def fetch_many(tensors):
         views.append(v)
     torch.cuda.current_stream().synchronize()
     if _pool is None:
-        _pool = cf.ThreadPoolExecutor(max_workers=8)
+        _pool = cf.ThreadPoolExecutor(max_workers=_host_threads())
     out, jobs = {}, []
     for (k, t), v in zip(items, views):
         src = v.numpy()
@@ -86,61 +86,72 @@ def fetch_many(tensors):
     return out
 
 
+def _host_threads():
+    """Worker threads for host-side copies: the cores of the box shared by the ranks of the job."""
+    import os
+    world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")) or 1)
+    return max(1, min(8, (os.cpu_count() or 1) // max(world, 1)))
+
+
 class AsyncFetch:
-    """Device -> host transfer of one large tensor that overlaps with later GPU work: the copy runs
-    on a side stream into a cached pinned buffer as soon as the producer kernel has finished, and a
-    worker thread widens / copies it into a fresh numpy array (`out_dtype`) while the main stream
-    keeps computing.  `result()` returns the array."""
+    """Device -> host transfer of one large tensor that overlaps with later GPU work.  The tensor is
+    widened to `out_dtype` ON THE GPU (side stream, in chunks through one cached device buffer) and
+    copied straight into a cached pinned host buffer; `result()` waits for the copy and returns a
+    numpy view of that buffer -- no host-side pass over the data, no allocation per call.
+
+    The buffer of a slot is reused: an array returned by `result()` is valid until the second next
+    transfer of the same slot starts (two alternating buffers per slot; one for arrays above
+    `SINGLE_BUFFER_BYTES`, which are then valid until the next transfer).  Callers that keep results
+    across calls copy them (`OrientationRecoverySolver.solve(..., copy_results=True)`)."""
     _stream = None
-    _pins = {}                      # one cached pinned staging buffer per slot (transfers of different slots overlap)
+    _pins = {}                      # slot -> [buffers], [next index]
+    _chunk = {}                     # slot -> cached device staging buffer (uint8)
+    SINGLE_BUFFER_BYTES = 1 << 30
+    CHUNK_BYTES = 256 << 20
 
     def __init__(self, t, out_dtype=np.float64, slot="images"):
-        global _pool
-        import concurrent.futures as cf
-        if _pool is None:
-            _pool = cf.ThreadPoolExecutor(max_workers=8)
         cls = AsyncFetch
         if cls._stream is None:
             cls._stream = torch.cuda.Stream()
-        nbytes = t.numel() * t.element_size()
-        pin = cls._pins.get(slot)
-        if pin is None or pin.numel() < nbytes:
-            pin = torch.empty((max(nbytes, 1),), dtype=torch.uint8, pin_memory=True)
-            cls._pins[slot] = pin
+        tdt = torch.from_numpy(np.empty(0, dtype=out_dtype)).dtype
+        nbytes = t.numel() * tdt.itemsize
+        nbuf = 1 if nbytes > cls.SINGLE_BUFFER_BYTES else 2
+        ent = cls._pins.get(slot)
+        if ent is None or ent[0][0].numel() < nbytes or len(ent[0]) != nbuf:
+            ent = [[torch.empty((max(nbytes, 1),), dtype=torch.uint8, pin_memory=True) for _ in range(nbuf)], 0]
+            cls._pins[slot] = ent
+        pin = ent[0][ent[1] % nbuf]
+        ent[1] += 1
         self._keep = t
         ready = torch.cuda.Event()
         ready.record()
         cls._stream.wait_event(ready)
-        view = pin[:nbytes].view(t.dtype).view(t.shape)
+        view = pin[:nbytes].view(tdt).view(t.shape)
         with torch.cuda.stream(cls._stream):
-            view.copy_(t, non_blocking=True)
-            done = torch.cuda.Event()
-            done.record()
-        src = view.numpy()
-        self._out = np.empty(src.shape, dtype=out_dtype)
-
-        def work():
-            import time
-            done.synchronize()
-            t0 = time.perf_counter()
-            fs, fd = src.reshape(-1), self._out.reshape(-1)
-            n = fs.size
-            step = max(1 << 20, (n + 7) // 8)
-            jobs = [_pool.submit(np.copyto, fd[a:a + step], fs[a:a + step]) for a in range(0, n, step)]
-            for j in jobs:
-                j.result()
-            TIMERS["widen_s"] += time.perf_counter() - t0
-            return self._out
-
-        import threading
-        self._res = None
-        self._thr = threading.Thread(target=lambda: setattr(self, "_res", work()), daemon=True)
-        self._thr.start()
+            if t.dtype == tdt:
+                view.copy_(t, non_blocking=True)
+            else:
+                rows = t.shape[0]
+                row_bytes = max(1, (t.numel() // max(rows, 1)) * tdt.itemsize)
+                step = max(1, cls.CHUNK_BYTES // row_bytes)
+                need = min(rows, step) * row_bytes
+                dev = cls._chunk.get(slot)
+                if dev is None or dev.numel() < need:
+                    dev = torch.empty((max(need, 1),), dtype=torch.uint8, device=t.device)
+                    cls._chunk[slot] = dev
+                for r0 in range(0, rows, step):
+                    r1 = min(rows, r0 + step)
+                    tmp = dev[: (r1 - r0) * row_bytes].view(tdt).view((r1 - r0,) + tuple(t.shape[1:]))
+                    tmp.copy_(t[r0:r1])                       # widening cast on the GPU
+                    view[r0:r1].copy_(tmp, non_blocking=True)
+            self._done = torch.cuda.Event()
+            self._done.record()
+        self._out = view.numpy()
 
     def result(self):
         import time
         t0 = time.perf_counter()
-        self._thr.join()
+        self._done.synchronize()
         TIMERS["result_wait_s"] += time.perf_counter() - t0
         self._keep = None
-        return self._res
+        return self._out

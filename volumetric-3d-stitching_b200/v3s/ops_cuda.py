@@ -444,10 +444,20 @@ class CudaOps:
         self._toc(h)
         return P_rows, dis
 
-    def wants_sparse_operator(self, n_rows, N):
+    def wants_sparse_operator(self, n_rows, N, k=150):
+        """operator "auto": the form a cost model predicts to be faster for one block mat-vec (measured, round 1:
+        dense = 11 us + 4 rows N bytes at ~7 TB/s; sparse = ~10 us + ~12 ps per stored entry, ~2 k per row), with
+        the dense row block also costing its N^2 build and at most DENSE_OPERATOR_BYTES of memory."""
         if self.operator == "sparse":
             return True
-        return self.operator == "auto" and 4 * n_rows * round_up(N, 4) > DENSE_OPERATOR_BYTES
+        if self.operator != "auto":
+            return False
+        dense_bytes = 4.0 * n_rows * round_up(N, 4)
+        if dense_bytes > DENSE_OPERATOR_BYTES:
+            return True
+        t_dense = 11e-6 + dense_bytes / 7.0e12
+        t_sparse = 10e-6 + 2.0 * k * n_rows * 1.2e-11
+        return t_sparse < t_dense
 
     def build_markov_sparse(self, S2t, Nbr, scalars, r0, r1):
         """-> SparseMarkov (rows [r0,r1) of P_ep = A + A^T on the lists, FP64), dinv_sqrt [N]."""
@@ -730,6 +740,11 @@ class FusedOperator:
         return a["ybufs"][res.value]
 
     def check(self):
-        """Raise if a peer barrier timed out (one small D2H; call once after the solve)."""
-        if self.world > 1 and int(self.a["status"].item()) != 0:
-            raise Exception("v3s: a peer rank never reached the mat-vec barrier (status %d)" % int(self.a["status"].item()))
+        """Raise if a peer barrier timed out (one small D2H; called once after every solve).  The status word
+        lives in the cached arena: it is cleared once reported, so one failed solve does not poison the next."""
+        if self.world > 1:
+            st = int(self.a["status"].item())
+            if st != 0:
+                self.a["status"].zero_()
+                raise Exception("v3s: a peer rank never reached the mat-vec barrier (status %d): the result blocks of "
+                                "this solve are incomplete" % st)

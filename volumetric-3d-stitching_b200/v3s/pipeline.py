@@ -108,7 +108,7 @@ def markov_stage(ops, plan, S2_all, Nbr_all, eps, med_row=4, idx_off=1, validate
     if validate:
         check_scalars(scalars.cpu().numpy())
     ops.s2_threshold_(S2_all, scalars)
-    if hasattr(ops, "wants_sparse_operator") and ops.wants_sparse_operator(plan.hi - plan.lo, plan.N):
+    if hasattr(ops, "wants_sparse_operator") and ops.wants_sparse_operator(plan.hi - plan.lo, plan.N, int(S2_all.shape[1])):
         P_rows, dis = ops.build_markov_sparse(S2_all, Nbr_all, scalars, plan.lo, plan.hi)
     else:
         P_rows, dis = ops.build_markov(S2_all, Nbr_all, scalars, plan.lo, plan.hi)
@@ -158,30 +158,49 @@ def eigen_stage(ops, plan, P_rows, dis, nev=NEV, validate=True, tol=None, stats=
 
         def run(lock):
             st_ = {}
+            plain_op = fused.plain if fused is not None else ((lambda Xf, Q: matvec(Q)) if sparse else (lambda Xf, Q: matvec_f32(Xf)))
+            pre = fused.sync if fused is not None else None
             if N >= 2048 and nev <= 16 and (fused is not None or not sparse):
                 r = chebyshev_lanczos_device(ops, matvec_f32, matvec, N, nev, tol=tol_, stats=st_, seed=seed, lock=lock,
                                              fused=fused)
-            elif fused is not None:
-                r = block_lanczos_device(ops, fused.plain, N, nev, tol=tol_, stats=st_, seed=seed, lock=lock,
-                                         pre_sync=fused.sync)
-            elif sparse:
-                r = block_lanczos_device(ops, lambda Xf, Q: matvec(Q), N, nev, tol=tol_, stats=st_, seed=seed, lock=lock)
             else:
-                r = block_lanczos_device(ops, lambda Xf, Q: matvec_f32(Xf), N, nev, tol=tol_, stats=st_, seed=seed,
-                                         lock=lock)
+                r = block_lanczos_device(ops, plain_op, N, nev, tol=tol_, stats=st_, seed=seed, lock=lock, pre_sync=pre)
+            # Krylov cap reached without convergence (ARPACK would restart implicitly): restart from the best
+            # Ritz block, at most three times; what is still unconverged then is reported / raised below
+            restarts, n_mv = 0, st_.get("matvecs", 0)
+            while not st_.get("converged", True) and restarts < 3:
+                start = r[1][:, :8].contiguous()
+                st_ = {}
+                r = block_lanczos_device(ops, plain_op, N, nev, tol=tol_, stats=st_, seed=seed, lock=lock, pre_sync=pre,
+                                         start_block=start)
+                n_mv += st_.get("matvecs", 0)
+                restarts += 1
+            st_["matvecs"] = n_mv
+            st_["restarts"] = restarts
             if stats is not None:
                 prev_mv = stats.get("matvecs", 0)
+                prev_conv = stats.get("converged", True)
                 stats.update(st_)
                 stats["matvecs"] = prev_mv + st_.get("matvecs", 0)
+                stats["converged"] = bool(prev_conv and st_.get("converged", True))
+            run.converged = run.converged and bool(st_.get("converged", True))
+            run.residual = max(run.residual, float(st_.get("true_residual_max", st_.get("residual_max", 0.0))))
             return r
 
+        run.converged, run.residual = True, 0.0
         lam, V, _ = topk_with_locking(run, nev, stats=stats)
         if fused is not None:
             fused.sync()
-            if validate:
-                fused.check()
+            fused.check()                                  # a peer that never reached a barrier is an error, validated or not
             if stats is not None:
                 stats["fused_matvec"] = True
+        if not run.converged:
+            msg = ("v3s eigen-solver: no convergence to %g within the Krylov cap after 3 restarts (largest residual %.3e); "
+                   "scipy's eigs would raise ArpackNoConvergence here" % (tol_, run.residual))
+            if validate:
+                raise Exception(msg)
+            import warnings
+            warnings.warn(msg)
         if stats is not None:
             stats["operator"] = "sparse-fp64" if sparse else "dense-fp32"
     else:
@@ -233,11 +252,20 @@ def run_pipeline(ops, plan, ed, rot9_local, rot_y_all, n_p, k, eps, polar_mode=0
     S2, Nbr = knn_stage(ops, plan, img, k)
     S2_out = S2.clone()                                      # pre-mutation copy for callers that want it
     P_rows, dis, scalars = markov_stage(ops, plan, S2, Nbr, eps, validate=validate)
+    knn_overflow = getattr(ops, "knn_overflow", None)
+    if validate and knn_overflow is not None:
+        # rows whose near-tie band did not fit the candidate buffers (dense ties: noisy or duplicate-heavy data):
+        # for those the exact-top-k containment proof does not hold (markov_stage has just synchronised anyway)
+        n_over = int(knn_overflow.item())
+        if n_over:
+            import warnings
+            warnings.warn("v3s kNN: %d candidate lists saturated (more near-ties around the k-th neighbour than the buffers "
+                          "hold); their neighbours are the best of an approximate ranking" % n_over)
     if on_lists is not None:
         on_lists(S2, Nbr)                                    # final (thresholded) kNN lists: their host transfer can start now
     Ps, lam = eigen_stage(ops, plan, P_rows, dis, validate=validate, stats=stats)
     fit = fit_stage(ops, plan, Ps, rot_y_all, polar_mode=polar_mode, check=check)
     out = {"Images_local": img, "S2": S2, "S2_unmutated": S2_out, "N": Nbr, "Ps": Ps, "Lambda": lam, "dinv_sqrt": dis,
-           "scalars": scalars}
+           "scalars": scalars, "knn_overflow": knn_overflow}
     out.update(fit)
     return out

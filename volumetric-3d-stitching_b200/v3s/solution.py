@@ -17,12 +17,16 @@ class OrientationRecoverySolver:
 
     @staticmethod
     def solve(parameters, rotations=None, N_p=None, polar_mode=0, stats=None, check_sigma=True,
-              photons_per_pattern=None, noise_seed=0):
+              photons_per_pattern=None, noise_seed=0, copy_results=None, validate=True):
         """solution.py:34-61 -> dict of numpy float64 arrays with the reference's 11 keys.
         Extensions that never change reference-mode results: `rotations` = explicit
         R (9,N) instead of the Hopf grid, `N_p` = free detector size, `check_sigma=False` = report
         Sigma_T > 60 instead of raising (diffusion.py:175-176), `photons_per_pattern` = Poisson photon
         noise on the patterns (BASELINE config 5; the reference has no noise model).
+        The large outputs ('Images', 'S2', 'N') are numpy views of reusable pinned host buffers (filled by
+        transfers that overlap stages 2-4).  `copy_results` None (default): results up to 256 MB are
+        copied into private arrays like the reference's, larger ones stay views that are valid until the next
+        call of solve; True / False force either.  `validate=False` skips the eigenvalue / convergence guards (compute.py:59-79).
         Under torch.distributed (one process per GPU, world > 1) the job is row-sharded: every rank calls
         solve with the same arguments and gets the same replicated results, except 'Images', which holds
         the rank's own pattern rows [rows[0], rows[1]) (key 'rows'; the full matrix never leaves the GPUs)."""
@@ -62,7 +66,7 @@ class OrientationRecoverySolver:
         out = run_pipeline(ops, plan, ed, rot9, rot_y, n_p, parameters['k'], parameters['Epsilon'],
                            polar_mode=polar_mode, check=check_sigma, stats=stats, on_images=start_images,
                            photons_per_pattern=photons_per_pattern, noise_seed=noise_seed,
-                           on_lists=start_lists if on_gpu else None)
+                           on_lists=start_lists if on_gpu else None, validate=validate)
         # the reference returns float64 everywhere: widen on the device, one staged transfer for all arrays
         f64 = lambda t: t.to(torch.float64)
         small = {'Ps': f64(out['Ps']), 'Lambda': f64(out['Lambda']), 'c': f64(out['c'])}
@@ -76,6 +80,9 @@ class OrientationRecoverySolver:
             _util.fetch_many({'Images': f64(out['Images_local'])})['Images']
         if 'S2' in xfer:
             host['S2'], host['N'] = xfer['S2'].result(), xfer['N'].result()
+        for key in ('Images', 'S2', 'N'):
+            if copy_results or (copy_results is None and host[key].nbytes <= (256 << 20)):
+                host[key] = np.array(host[key], copy=True)
         if not host['nonzero'][0]:
             raise Exception('Images is an all-zero array.')          # projection.py:47
         print('OrientationRecoverySolver.solve ended.')
