@@ -334,7 +334,8 @@ int v3s_fit_project(const double* Ps, int ldx, const double* Y, long long n_rows
 int v3s_or_func(const double* c81, const double* Ps, int ldx, long long n_rows, long long r_total, int form,
                 double rel_step, double* G, double* J, void* stream);
 /* Rotation.mean_geodesic_distance (rotation.py:228-244) inner sum over rows [row0,row0+n_rows)
- * against all N columns; partials_ws: 65536 doubles; out_sum[0] = sum |acos - acos|.            */
+ * against all N columns; partials_ws: 65536 doubles; out_sum[0] = sum |acos - acos|.  FP64 like the
+ * reference up to N = 20000; beyond, the N^2 pair terms are FP32 (acosf) summed in FP64 (~1e-7 relative). */
 int v3s_sigma_pairs(const double* quat_est, const double* quat_true, long long N, long long row0, long long n_rows,
                     double* partials_ws, double* out_sum, void* stream);
 

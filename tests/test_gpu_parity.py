@@ -780,20 +780,26 @@ def test_solve_connected_end_to_end(v3s_mod, golden_dir):
 
 
 def test_solve_default_parameters_shapes(v3s_mod, golden_dir):
-    """solution_test.py:12-56 (shapes) + the bit-reproducible stages of the default run."""
+    """solution_test.py:12-56 (shapes) + the bit-reproducible stages of the default run (BASELINE config 1)."""
     g = np.load(os.path.join(golden_dir, "default_cfg.npz"))
     p = v3s_mod.OrientationRecoverySolver.default_parameters()
     p["plot"] = False
-    try:
-        res = v3s_mod.OrientationRecoverySolver.solve(p)
-    except Exception as e:      # Sigma_T guard: the default graph has 182 components (SURVEY 0.3), the
-        assert "Sigma_T" in str(e)   # reference itself lands at 53-58 deg with an arbitrary eigenbasis
-        return
+    res = v3s_mod.OrientationRecoverySolver.solve(p, check_sigma=False)        # the assertions below always run
     assert res["Ps"].shape == (512, 10) and res["Lambda"].shape == (10,) and res["c"].shape == (9, 9)
     assert res["S2"].shape == (512, 24) and res["N"].shape == (512, 24) and res["Images"].shape == (512, 225)
     assert res["R"].shape == (9, 512) and res["Axis"].shape == (512, 3) and res["Quat"].shape == (512, 4)
     assert np.max(np.abs(res["Images"] - g["Images"])) < 2e-5 * g["Images"].max()
     assert np.allclose(res["Lambda"], 1.0, atol=1e-6)                              # lambda = 1 has multiplicity 182
+    assert np.array_equal(np.isinf(res["S2"]), np.isinf(g["S2_mutated"])) if "S2_mutated" in g.files else True
+    # the Sigma_T guard of diffusion.py:175-176: the default graph has 182 components (SURVEY 0.3), the reference
+    # itself lands at 53-58 deg with an arbitrary eigenbasis -- whichever side of 60 deg this run lands on, the
+    # guarded call must agree with it
+    if res["Sigma_T"][0] > 60:
+        with pytest.raises(Exception, match="Sigma_T"):
+            v3s_mod.OrientationRecoverySolver.solve(p)
+    else:
+        res2 = v3s_mod.OrientationRecoverySolver.solve(p)
+        assert abs(res2["Sigma_T"][0] - res["Sigma_T"][0]) < 1e-9
 
 
 @pytest.mark.parametrize("cfg", [(3, 3, 9), (3, 2, 12), (4, 5, 20), (5, 7, 124)])
@@ -826,31 +832,123 @@ def test_tiny_and_extreme_configurations(v3s_mod, cfg):
     assert Ps.shape == (N, 10)
 
 
-def test_full_size_invariants(ops):
-    """BASELINE config 2 size (N=10k, 64x64): size-independent properties of every stage."""
-    from v3s.pipeline import ShardPlan, knn_stage, markov_stage
-    N, n, n_p, k = 10000, 31, 64, 150
+def test_cfg2_size_connected_full_oracle_comparison(ops):
+    """BASELINE config 2 size (N = 10k patterns of 64 x 64, n = 31) through every stage against the oracle on the
+    same pattern matrix.  k = 300: with seed 0 the thresholded graph has 4 components at k = 150 and ONE at
+    k = 300 (oracle, scipy connected_components), so the eigen-subspace and the orientations are well defined.
+    Tolerances = BASELINE.json: distances 1e-5 (hybrid), eigenvalues 1e-6, principal angles 1e-4 rad,
+    orientations 0.1 deg median after one correct SO(3) projection on both sides."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    from scipy.sparse.csgraph import connected_components
+    from v3s.pipeline import ShardPlan, run_pipeline
+    N, n, n_p, k, eps = 10000, 31, 64, 300, 0.7
     R9, _ = orc.random_rotations(N, seed=0)
     ed = ops.to_device(orc.synthesize_3d(n)["ED"].astype(np.float32), torch.float32)
-    img = ops.synth_patterns(ed, ops.to_device(rot9_rowmajor(R9), torch.float64), n_p)
+    rot9 = ops.to_device(rot9_rowmajor(R9), torch.float64)
+    rot_y = ops.to_device(np.ascontiguousarray(R9.T), torch.float64)
+    stats = {}
+    out = run_pipeline(ops, ShardPlan(N), ed, rot9, rot_y, n_p, k, eps, polar_mode=2, check=False, stats=stats, validate=True)
+    assert stats["converged"] and stats["driver"].startswith("device")
+    assert int(out["knn_overflow"].item()) == 0
+    img = out["Images_local"]
+    # stage 1: sampled patterns against the oracle's synthesis
     sub = [0, 17, 4242, 9999]
     ref = orc.generate_from_rotations(R9[:, sub], n, n_p)
     assert np.max(np.abs(img[sub].cpu().numpy() - ref)) < 2e-5 * ref.max()
-    S2, Nbr = knn_stage(ops, ShardPlan(N), img, k)
-    S2h, Nh = S2.cpu().numpy(), Nbr.cpu().numpy()
-    assert np.all(np.diff(S2h, axis=1) >= 0) and np.all(S2h[:, 0] == 0) and np.array_equal(Nh[:, 0], np.arange(N))
-    assert all(len(set(r)) == k for r in Nh[::97])
-    # spot-check rows against a float64 recomputation of the whole distance row
-    A = orc.set_norm_to_one(orc.remove_offset(img.cpu().numpy().astype(np.float64)))
-    for r in (3, 5000, 9998):
-        d = np.arccos(np.clip(A @ A[r], -1, 1))
-        d[r] = 0
-        idx = np.argsort(d, kind="stable")[:k]
-        assert np.array_equal(idx, Nh[r]) and hybrid_frac_bad(S2h[r], d[idx], 1e-5) == 0
-    P_rows, dis, sc = markov_stage(ops, ShardPlan(N), S2, Nbr, 0.7)
-    # P = D^-1/2 W2 D^-1/2 with d = rowsum(W2): sqrt(d) is the lambda = 1 eigenvector; P is symmetric
-    v = (1.0 / dis).reshape(-1, 1).contiguous()
-    Pv = ops.block_matvec(P_rows, N, v)
-    assert float(torch.max(torch.abs(Pv - v)) / torch.max(v)) < 1e-5
-    Pd = P_rows[:, :N]
-    assert torch.equal(Pd, Pd.T)
+    # stage 2: the whole kNN table against the oracle on the same (FP32-valued) patterns
+    imgs = img.cpu().numpy().astype(np.float64)
+    S2o, No = orc.knn(imgs, k)
+    S2g, Ng = out["S2_unmutated"].cpu().numpy(), out["N"].cpu().numpy()
+    assert hybrid_frac_bad(S2g[:, 1:], S2o[:, 1:], 1e-5) == 0.0 and np.all(S2g[:, 0] == 0)
+    assert np.mean(Ng == No) > 0.9999 and np.array_equal(Ng[:, 0], np.arange(N))
+    # stage 3: the oracle's operator from its own lists; largest eigenpairs by ARPACK on the same matrix
+    W1 = orc.s2_to_w_matrix(S2o, No, eps)                      # mutates S2o like the reference
+    assert np.array_equal(np.isinf(S2o), np.isinf(out["S2"].cpu().numpy()))
+    P_ep, di = orc.dm_cov(orc.anisotropic_norm(W1), dense_D=False)
+    del W1
+    Psp = sp.csr_matrix(P_ep)
+    ncomp, _ = connected_components(Psp, directed=False)
+    assert ncomp == 1
+    w, V = spla.eigsh(Psp, 12, which="LA", tol=1e-13)
+    order = np.argsort(-w)
+    w, V = w[order], V[:, order]
+    assert w[9] - w[10] > 1e-5 * w[9]                          # the 10-dimensional invariant subspace is well defined
+    Lam_g = out["Lambda"].cpu().numpy()
+    print("cfg2-size: lambda", np.round(Lam_g, 6), "max rel err", np.max(np.abs(Lam_g - w[:10]) / w[:10]))
+    assert np.max(np.abs(Lam_g - w[:10]) / w[:10]) < 1e-6
+    Ps_o = di[:, None] * (V[:, :10] * w[:10][None, :])
+    Ps_g = out["Ps"].cpu().numpy()
+    ang = orc.principal_angles(Ps_g, Ps_o)
+    print("cfg2-size: principal angles max", np.max(ang))
+    assert np.max(ang) < 1e-4
+    Vg = Ps_g / (Lam_g[None, :] * out["dinv_sqrt"].cpu().numpy()[:, None])
+    resid = np.linalg.norm(P_ep @ Vg - Vg * Lam_g[None, :], axis=0)
+    assert np.max(resid) < 1e-6
+    # stage 4: fit of the oracle on ITS eigenvectors against ours (Recon is invariant to the eigenbasis)
+    ret = orc.dm_fit_all(Ps_o, R9, True, compat_polar=False, check=False, return_all=True)
+    recon_o = ret[3]
+    recon_g = out["recon_pre"].cpu().numpy()
+    dev = orc.geodesic_angle_deg(orc.project_so3(recon_g.reshape(-1, 3, 3)), orc.project_so3(recon_o.reshape(-1, 3, 3)))
+    print("cfg2-size: orientation parity median", np.median(dev), "max", dev.max(), "deg")
+    assert np.median(dev) < 0.1
+
+
+def test_cfg3_size_sampled_checks(ops):
+    """BASELINE config 3 size (N = 50k patterns of 128 x 128) on one GPU: properties that do not need the oracle to
+    finish -- sampled kNN rows against an FP64 recomputation of the whole distance row, P sqrt(d) = sqrt(d), the
+    eigen-residual ||P V - V Lambda|| with the FP64 operator, convergence, no saturated candidate list."""
+    from v3s.pipeline import ShardPlan, run_pipeline
+    N, n, n_p, k, eps = 50000, 31, 128, 150, 0.7
+    R9, _ = orc.random_rotations(N, seed=0)
+    ed = ops.to_device(orc.synthesize_3d(n)["ED"].astype(np.float32), torch.float32)
+    rot9 = ops.to_device(rot9_rowmajor(R9), torch.float64)
+    rot_y = ops.to_device(np.ascontiguousarray(R9.T), torch.float64)
+    stats = {}
+    prev = ops.operator
+    try:
+        ops.operator = "sparse"                                # FP64 operator: the residual below is then exact arithmetic
+        out = run_pipeline(ops, ShardPlan(N), ed, rot9, rot_y, n_p, k, eps, polar_mode=2, check=False, stats=stats, validate=True)
+        P_op, dis = out["P_rows"], out["dinv_sqrt"]
+        assert stats["converged"] and int(out["knn_overflow"].item()) == 0
+        img = out["Images_local"]
+        sub = [1, 31337]
+        ref = orc.generate_from_rotations(R9[:, sub], n, n_p)
+        assert np.max(np.abs(img[sub].cpu().numpy() - ref)) < 2e-5 * ref.max()
+        S2g, Ng = out["S2_unmutated"], out["N"]
+        assert bool(torch.all(S2g[:, 1:] >= S2g[:, :-1])) and bool(torch.all(S2g[:, 0] == 0))
+        assert torch.equal(Ng[:, 0].long(), torch.arange(N, device=Ng.device))
+        # FP64 reference of whole distance rows (centred unit rows in double, on the device, in chunks)
+        mean = torch.zeros((n_p * n_p,), dtype=torch.float64, device=img.device)
+        for c0 in range(0, N, 5000):
+            mean += img[c0:c0 + 5000].double().sum(dim=0)
+        mean /= N
+        rows = [3, 25000, 49998]
+        q = img[rows].double() - mean[None, :]
+        q = q / q.norm(dim=1, keepdim=True)
+        d_rows = []
+        for c0 in range(0, N, 5000):
+            blk = img[c0:c0 + 5000].double() - mean[None, :]
+            blk = blk / blk.norm(dim=1, keepdim=True)
+            d_rows.append(torch.arccos(torch.clamp(q @ blk.T, -1, 1)))
+        D = torch.cat(d_rows, dim=1).cpu().numpy()
+        for i, r in enumerate(rows):
+            d = D[i].copy()
+            d[r] = 0
+            idx = np.argsort(d, kind="stable")[:k]
+            assert np.array_equal(idx, Ng[r].cpu().numpy()) and hybrid_frac_bad(S2g[r].cpu().numpy()[1:], d[idx][1:], 1e-5) == 0
+        # operator properties
+        v = (1.0 / dis).reshape(-1, 1).contiguous()
+        v8 = torch.cat([v, torch.zeros((N, 7), dtype=torch.float64, device=v.device)], dim=1).contiguous()
+        Pv = ops.sparse_block_matvec(P_op, v8)[:, :1]
+        assert float(torch.max(torch.abs(Pv - v)) / torch.max(v)) < 1e-10
+        Lam = out["Lambda"]
+        V = out["Ps"] / (Lam[None, :] * dis[:, None])
+        Vp = torch.cat([V, torch.zeros((N, 6), dtype=torch.float64, device=V.device)], dim=1).contiguous()
+        PV = torch.cat([ops.sparse_block_matvec(P_op, Vp[:, :8].contiguous()), ops.sparse_block_matvec(P_op, Vp[:, 8:].contiguous())], dim=1)[:, :10]
+        resid = torch.linalg.norm(PV - V * Lam[None, :], dim=0)
+        print("cfg3-size: lambda", Lam.cpu().numpy().round(6), "max residual", float(resid.max()))
+        assert float(resid.max()) < 1e-6 and float(Lam[0]) > 1 - 1e-9 and float(Lam[1]) < 1 - 1e-4      # connected graph
+        assert float(torch.max(torch.abs(V.T @ V - torch.eye(10, dtype=torch.float64, device=V.device)))) < 1e-8
+    finally:
+        ops.operator = prev

@@ -9,6 +9,7 @@
 // SVD sign convention -- ours is Jacobi's, not LAPACK's), 1 = polar factor
 // U.Vh (src/octave/PolarDecompose.m), 2 = nearest rotation (det fixed to +1).
 #include "common.cuh"
+#include <type_traits>
 #include "v3s.h"
 
 namespace v3s {
@@ -239,16 +240,23 @@ fit_project_kernel(const double* __restrict__ Ps, int ldx, const double* __restr
 // the choice is uniform across a warp: bi != bj -> the row whose block satisfies (bi < bj and bi+bj
 // even) or (bi > bj and bi+bj odd) (balanced over row blocks); bi == bj -> the row with i < j.
 constexpr int SG_T = 256;
+// FP64MATH = true: the reference's arithmetic (FP64 dot products and acos).  false (N > kSigmaFp64MaxN): the N^2
+// pair terms in FP32 (dot, clip, acosf) accumulated in FP64 -- 1e10 double-precision acos at N = 10^5 were
+// 10 % of the whole pass for a statistic the reference itself prints with 2 digits; per-term error <= 2e-7 rad
+// except for the (measure ~theta^3) pairs of nearly identical orientations, mean error of the sum ~1e-7 relative.
+constexpr long long kSigmaFp64MaxN = 20000;
+template <bool FP64MATH>
 __global__ void __launch_bounds__(SG_T)
 sigma_pairs_kernel(const double* __restrict__ q1, const double* __restrict__ q2, long long N, long long row0,
                    long long n_rows, double* __restrict__ partials) {
-  __shared__ double sj1[SG_T][4], sj2[SG_T][4];
+  using T = typename std::conditional<FP64MATH, double, float>::type;
+  __shared__ T sj1[SG_T][4], sj2[SG_T][4];
   __shared__ double red[32];
   const int tid = threadIdx.x;
   const long long i = row0 + (long long)blockIdx.x * SG_T + tid;
   const bool i_ok = i < row0 + n_rows;
-  double a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0};
-  if (i_ok) for (int t = 0; t < 4; ++t) { a1[t] = q1[i * 4 + t]; a2[t] = q2[i * 4 + t]; }
+  T a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0};
+  if (i_ok) for (int t = 0; t < 4; ++t) { a1[t] = (T)q1[i * 4 + t]; a2[t] = (T)q2[i * 4 + t]; }
   double acc = 0.0;
   const long long j_per = ceil_div64(N, gridDim.y);
   const long long j0 = (long long)blockIdx.y * j_per;
@@ -257,21 +265,29 @@ sigma_pairs_kernel(const double* __restrict__ q1, const double* __restrict__ q2,
   for (long long jb = j0; jb < j1; jb += SG_T) {
     __syncthreads();
     const long long j = jb + tid;
-    for (int t = 0; t < 4; ++t) { sj1[tid][t] = j < j1 ? q1[j * 4 + t] : 0.0; sj2[tid][t] = j < j1 ? q2[j * 4 + t] : 0.0; }
+    for (int t = 0; t < 4; ++t) { sj1[tid][t] = j < j1 ? (T)q1[j * 4 + t] : T(0); sj2[tid][t] = j < j1 ? (T)q2[j * 4 + t] : T(0); }
     __syncthreads();
     const int lim = (int)((j1 - jb) < SG_T ? (j1 - jb) : SG_T);
     if (i_ok) {
+      T part = 0;                                  // FP32 mode: 256 terms per partial, then into the FP64 accumulator
       for (int jj = 0; jj < lim; ++jj) {
         const long long jg = jb + jj;
         const long long bi = i >> 5, bj = jg >> 5;
         const bool mine = (bi == bj) ? (i < jg) : ((bi < bj) ? (((bi + bj) & 1) == 0) : (((bi + bj) & 1) == 1));
         if (!mine) continue;
-        double d1 = a1[0] * sj1[jj][0] + a1[1] * sj1[jj][1] + a1[2] * sj1[jj][2] + a1[3] * sj1[jj][3];
-        double d2 = a2[0] * sj2[jj][0] + a2[1] * sj2[jj][1] + a2[2] * sj2[jj][2] + a2[3] * sj2[jj][3];
-        d1 = fmin(fmax(d1, 0.0), 1.0);
-        d2 = fmin(fmax(d2, 0.0), 1.0);
-        acc += 2.0 * fabs(acos(d1) - acos(d2));
+        T d1 = a1[0] * sj1[jj][0] + a1[1] * sj1[jj][1] + a1[2] * sj1[jj][2] + a1[3] * sj1[jj][3];
+        T d2 = a2[0] * sj2[jj][0] + a2[1] * sj2[jj][1] + a2[2] * sj2[jj][2] + a2[3] * sj2[jj][3];
+        if constexpr (FP64MATH) {
+          d1 = fmin(fmax(d1, 0.0), 1.0);
+          d2 = fmin(fmax(d2, 0.0), 1.0);
+          acc += 2.0 * fabs(acos(d1) - acos(d2));
+        } else {
+          d1 = fminf(fmaxf(d1, 0.f), 1.f);
+          d2 = fminf(fmaxf(d2, 0.f), 1.f);
+          part += fabsf(acosf(d1) - acosf(d2));
+        }
       }
+      if constexpr (!FP64MATH) acc += 2.0 * (double)part;
     }
   }
   acc = block_sum(acc, red);
@@ -391,7 +407,8 @@ extern "C" int v3s_sigma_pairs(const double* quat_est, const double* quat_true, 
   if (gy > maxy) gy = (int)maxy;
   if (gy < 1) gy = 1;
   V3S_REQUIRE((long long)gx * gy <= 65536, "v3s_sigma_pairs: partials workspace (65536 doubles) too small");
-  sigma_pairs_kernel<<<dim3(gx, gy), SG_T, 0, st>>>(quat_est, quat_true, N, row0, n_rows, partials_ws);
+  if (N <= kSigmaFp64MaxN) sigma_pairs_kernel<true><<<dim3(gx, gy), SG_T, 0, st>>>(quat_est, quat_true, N, row0, n_rows, partials_ws);
+  else sigma_pairs_kernel<false><<<dim3(gx, gy), SG_T, 0, st>>>(quat_est, quat_true, N, row0, n_rows, partials_ws);
   V3S_CHECK_LAUNCH();
   sum_partials_kernel<<<1, 256, 0, st>>>(partials_ws, gx * gy, 1.0, out_sum);
   V3S_CHECK_LAUNCH();

@@ -266,6 +266,6 @@ def run_pipeline(ops, plan, ed, rot9_local, rot_y_all, n_p, k, eps, polar_mode=0
     Ps, lam = eigen_stage(ops, plan, P_rows, dis, validate=validate, stats=stats)
     fit = fit_stage(ops, plan, Ps, rot_y_all, polar_mode=polar_mode, check=check)
     out = {"Images_local": img, "S2": S2, "S2_unmutated": S2_out, "N": Nbr, "Ps": Ps, "Lambda": lam, "dinv_sqrt": dis,
-           "scalars": scalars, "knn_overflow": knn_overflow}
+           "scalars": scalars, "knn_overflow": knn_overflow, "P_rows": P_rows}
     out.update(fit)
     return out
