@@ -178,10 +178,19 @@ int v3s_gram_topk(const void* a16_all, long long n_cols, const void* a16_rows, l
  * union -> cand_ws int [n_rows,cap], count_ws int [n_rows] (input of v3s_knn_refine).  Zero-norm
  * patterns (NaN -> distance 0, distance.py:58; zero_flag [n_cols] may be NULL): a zero query row
  * gets columns 0..cap-1, and the zero columns (compacted into zero_ws, int [cap + 1]) are appended to
- * every row.  *overflow counts rows cut at cap.                                                    */
+ * every row.  *overflow counts rows cut at cap.
+ * order_ws (may be NULL): int [2 n_rows + ceil(n_cols/anchor_stride) + ceil(n_rows/anchor_stride)]; its first
+ * n_rows ints receive a processing ORDER of the rows in which rows sharing their nearest anchor pattern
+ * (index a multiple of anchor_stride, nearest by g~ among the row's lists) are contiguous -- neighbouring
+ * patterns, whose candidate lists overlap (input of v3s_knn_refine_tiled); every candidate list is then also
+ * sorted by column index (v3s_knn_refine_tiled binary-searches them).  tiles_ws (may be NULL, with
+ * order_ws): int [1 + 2 max_tiles] = the table of row tiles for v3s_knn_refine_tiled: [0] = number of tiles,
+ * then (first position in `order`, rows <= tile_rows) per tile; a neighbourhood larger than tile_rows is cut,
+ * smaller consecutive ones are packed.  max_tiles >= (bins of order_ws) + n_rows / tile_rows + 2 suffices.  */
 int v3s_knn_merge_lists(const unsigned long long* lists, const int* counts, int S, int C, long long n_rows,
                         long long n_cols, long long row0, int k, float eps_g, int cap, const int* zero_flag,
-                        int* zero_ws, int* cand_ws, int* count_ws, int* overflow, void* stream);
+                        int* zero_ws, int* cand_ws, int* count_ws, int* overflow, int anchor_stride, int* order_ws,
+                        int tile_rows, int max_tiles, int* tiles_ws, void* stream);
 
 /* arccos epilogue (distance.py:56-59) + final ordering (distance.py:39-43) on selected candidates:
  * d = 2 asin(|a_r - a_c| / 2) from the FP32 rows, sorted by (d, index), first k kept -> S2 [n_rows,k]
@@ -190,6 +199,19 @@ int v3s_knn_merge_lists(const unsigned long long* lists, const int* counts, int 
 int v3s_knn_refine(const float* a_rows, const float* a_all, int P, long long row0, long long n_rows, long long n_cols,
                    int k, int cap, const int* zero_flag, const int* cand_ws, const int* count_ws, double* S2, int* Nbr,
                    double* dist_ws, const int* order, void* stream);
+
+/* v3s_knn_refine with the pair evaluation TILED over neighbouring rows: a tile of
+ * v3s_knn_refine_tile_rows(cap) rows (consecutive in `order`) keeps its rows in shared memory and reads every
+ * candidate row once for all the tile's rows that list it (the untiled form reads one candidate row per pair).
+ * Same distances up to FP32 summation order (the pixel axis is summed in chunks of 512).  P % 4 == 0.
+ * `tiles` / max_tiles: the tile table of v3s_knn_merge_lists.  Workspaces: dist_ws FP64 [n_rows,cap],
+ * pref_ws int [n_rows,cap], keys_ws 64-bit [max_tiles * 16384], np_ws int [max_tiles].  dedup != 0: a pair
+ * listed from both sides by rows of this call is evaluated once.                                    */
+int v3s_knn_refine_tile_rows(int cap);
+int v3s_knn_refine_tiled(const float* a_rows, const float* a_all, int P, long long row0, long long n_rows,
+                         long long n_cols, int k, int cap, const int* zero_flag, const int* cand_ws,
+                         const int* count_ws, double* S2, int* Nbr, double* dist_ws, const int* order, const int* tiles,
+                         int max_tiles, int* pref_ws, unsigned long long* keys_ws, int* np_ws, int dedup, void* stream);
 
 /* ---- stage 3: diffusion map ---------------------------------------------------------------- */
 

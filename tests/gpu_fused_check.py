@@ -70,13 +70,27 @@ def check(ops, N, P, k, r0, r1, seed, clustered=False):
     print("  N=%d P=%d k=%d rows[%d,%d) S=%d C=%d: %.2f ms, misses %d, max|g~-g| %.2e (bound %.2e), max union %d, overflow %d"
           % (N, P, k, r0, r1, S, Cc, dt * 1e3, miss, max_err, eps, max_union, int(ovf.item())))
     assert miss == 0 and max_err <= eps and int(ovf.item()) == 0
-    # end to end against the materialised path
-    ops.gram_impl = "fused"
-    S2f, Nf = ops.knn_rows(None, None, a32, zf, r0, r1, k)
-    ops.gram_impl = "tcgen05"
-    S2m, Nm = ops.knn_rows(None, None, a32, zf, r0, r1, k)
-    ops.gram_impl = "fused"
-    assert torch.equal(S2f, S2m) and torch.equal(Nf, Nm), "fused and materialised kNN differ"
+    # end to end against the materialised path (same untiled refinement kernel on both sides: bit for bit)
+    tiled = ops.tiled_refine
+    try:
+        ops.tiled_refine = False
+        ops.gram_impl = "fused"
+        S2f, Nf = ops.knn_rows(None, None, a32, zf, r0, r1, k)
+        ops.gram_impl = "tcgen05"
+        S2m, Nm = ops.knn_rows(None, None, a32, zf, r0, r1, k)
+        ops.gram_impl = "fused"
+        assert torch.equal(S2f, S2m) and torch.equal(Nf, Nm), "fused and materialised kNN differ"
+        # the tiled refinement sums the pixel axis in another order: same neighbours, distances to FP32 rounding
+        ops.tiled_refine = True
+        S2t, Nt = ops.knn_rows(None, None, a32, zf, r0, r1, k)
+        same = float((Nt == Nf).float().mean().item())
+        rel = float(((S2t - S2f).abs() / torch.clamp(S2f, min=1e-3)).max().item())
+        print("    tiled refinement vs untiled: same neighbours %.6f, max rel distance difference %.2e" % (same, rel))
+        assert same > 0.9995 and rel < 3e-6
+        assert bool(torch.all(S2t[:, 1:] >= S2t[:, :-1]))
+    finally:
+        ops.tiled_refine = tiled
+        ops.gram_impl = "fused"
     return dt
 
 

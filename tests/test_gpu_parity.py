@@ -316,6 +316,7 @@ def test_refinement_pair_dedup_bit_identical(ops):
     img = ops.to_device(A, torch.float32)
     a32, hi, lo, zf = ops.center_normalize(img, ops.column_sums(img) / N)
     out = {}
+    ops.tiled_refine = False                                   # (the tiled form sums in another order; see gpu_fused_check)
     for dedup in (True, False):
         ops.dedup_refine = dedup
         try:
@@ -330,6 +331,7 @@ def test_refinement_pair_dedup_bit_identical(ops):
         finally:
             ops.dedup_refine = True
         out[dedup] = [t.cpu().numpy() for pair in (whole, block, panels) for t in pair]
+    ops.tiled_refine = True
     for x, y in zip(out[True], out[False]):
         assert np.array_equal(x, y)
     S2w, Nw = out[True][0], out[True][1]

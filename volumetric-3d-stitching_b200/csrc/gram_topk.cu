@@ -501,7 +501,7 @@ __global__ void __launch_bounds__(kMergeThreads)
 knn_merge_kernel(const unsigned long long* __restrict__ lists, const int* __restrict__ counts, int S, int C, int n_rows,
                  int n_cols, long long row0, int k, float band, int cap, const int* __restrict__ zero_flag,
                  const int* __restrict__ zero_ws, int* __restrict__ cand, int* __restrict__ cand_count,
-                 int* __restrict__ overflow) {
+                 int* __restrict__ overflow, int anchor_stride, int* __restrict__ cluster_out) {
   // zero_ws (may be NULL): [0] = number of zero-norm patterns, [1 ...] = their indices (zero_cols_kernel)
   const int n_zero = zero_ws ? min(zero_ws[0], cap) : 0;
   const int* zero_cols = zero_ws ? zero_ws + 1 : nullptr;
@@ -510,16 +510,25 @@ knn_merge_kernel(const unsigned long long* __restrict__ lists, const int* __rest
   __shared__ int s_n, s_slot, s_eq;
   __shared__ uint32_t s_prefix;
   __shared__ int s_remaining;
+  __shared__ unsigned long long s_anchor;
   const int tid = threadIdx.x;
+  // cluster_out (optional): the row's nearest ANCHOR (a pattern whose index is a multiple of anchor_stride) among
+  // its listed columns -> rows that share an anchor are neighbours, so their candidate lists overlap; rows
+  // without a listed anchor go to per-position fallback bins behind the anchor bins (refine_tiled_kernel)
+  const int anchor_bins = cluster_out ? (n_cols + anchor_stride - 1) / anchor_stride : 0;
   for (int r = blockIdx.x; r < n_rows; r += gridDim.x) {
     __syncthreads();
     int* out = cand + (long long)r * cap;
     if (zero_flag && zero_flag[row0 + r]) {
       const int m = min(cap, n_cols);
       for (int s = tid; s < m; s += kMergeThreads) out[s] = s;
-      if (tid == 0) cand_count[r] = m;
+      if (tid == 0) {
+        cand_count[r] = m;
+        if (cluster_out) cluster_out[r] = anchor_bins + r / anchor_stride;
+      }
       continue;
     }
+    if (tid == 0) s_anchor = 0ull;
     if (tid == 0) s_n = 0;
     __syncthreads();
     for (int sgm = 0; sgm < S; ++sgm) {
@@ -565,6 +574,8 @@ knn_merge_kernel(const unsigned long long* __restrict__ lists, const int* __rest
     for (int i = tid; i < n; i += kMergeThreads) {
       const float g = __uint_as_float((uint32_t)(s_ent[i] >> 32));
       const int col = (int)(uint32_t)s_ent[i];
+      if (cluster_out && col % anchor_stride == 0)
+        atomicMax(&s_anchor, ((unsigned long long)float_to_key(g) << 32) | (unsigned)col);
       if (g >= lim && !(zero_flag && zero_flag[col])) {
         const int slot = atomicAdd(&s_slot, 1);
         if (slot < cap) out[slot] = col;
@@ -624,8 +635,98 @@ knn_merge_kernel(const unsigned long long* __restrict__ lists, const int* __rest
       if (total + n_zero > cap && tid == 0 && overflow) atomicAdd(overflow, 1);
       total = min(total + n_zero, cap);
     }
-    if (tid == 0) cand_count[r] = total;
+    if (cluster_out) {
+      // the tiled refinement looks rows up in each other's candidate lists (pairs listed from both sides are
+      // evaluated once): sort the list by column index so that the look-up is a binary search
+      __syncthreads();
+      int* sc = reinterpret_cast<int*>(s_ent);
+      int npad = 2;
+      while (npad < total) npad <<= 1;
+      for (int i = tid; i < npad; i += kMergeThreads) sc[i] = i < total ? out[i] : 0x7fffffff;
+      __syncthreads();
+      for (int size = 2; size <= npad; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+          for (int t = tid; t < npad / 2; t += kMergeThreads) {
+            const int lo = 2 * t - (t & (stride - 1));
+            const int hi = lo + stride;
+            const bool up = ((lo & size) == 0);
+            const int a = sc[lo], b = sc[hi];
+            if ((a > b) == up) { sc[lo] = b; sc[hi] = a; }
+          }
+          __syncthreads();
+        }
+      }
+      for (int i = tid; i < total; i += kMergeThreads) out[i] = sc[i];
+    }
+    if (tid == 0) {
+      cand_count[r] = total;
+      if (cluster_out) cluster_out[r] = s_anchor ? (int)((uint32_t)s_anchor / (uint32_t)anchor_stride) : anchor_bins + r / anchor_stride;
+    }
   }
+}
+
+// counting sort of the rows by cluster id -> order (rows of one cluster contiguous; order inside a cluster arbitrary)
+__global__ void cluster_hist_kernel(const int* __restrict__ cluster, int n, int* __restrict__ bins) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) atomicAdd(&bins[cluster[r]], 1);
+}
+__global__ void __launch_bounds__(1024)
+cluster_scan_kernel(int* __restrict__ bins, int n_bins) {      // exclusive scan in place, one block
+  __shared__ int s_part[1024];
+  __shared__ int s_carry;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (int b0 = 0; b0 < n_bins; b0 += 1024) {
+    const int i = b0 + tid;
+    const int v = i < n_bins ? bins[i] : 0;
+    s_part[tid] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      const int t = tid >= o ? s_part[tid - o] : 0;
+      __syncthreads();
+      s_part[tid] += t;
+      __syncthreads();
+    }
+    if (i < n_bins) bins[i] = s_carry + s_part[tid] - v;
+    __syncthreads();
+    if (tid == 1023) s_carry += s_part[1023];
+    __syncthreads();
+  }
+}
+__global__ void cluster_scatter_kernel(const int* __restrict__ cluster, int n, int* __restrict__ cursor, int* __restrict__ order) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x)
+    order[atomicAdd(&cursor[cluster[r]], 1)] = r;
+}
+// Tiles of at most qt consecutive rows of `order` that do not straddle clusters needlessly: a cluster larger than
+// qt is cut into pieces, smaller consecutive ones are packed while they fit.  ends[c] = end of cluster c in
+// `order` (the scatter's cursors).  tiles[0] = number of tiles, tiles[1 + 2 t] = first position, tiles[2 + 2 t] = rows.
+// (A serial pass over a few thousand clusters: one thread.)
+__global__ void cluster_tiles_kernel(const int* __restrict__ ends, int n_bins, int qt, int max_tiles, int* __restrict__ tiles) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  int nt = 0, start = 0, cur0 = 0, cur = 0;
+  for (int c = 0; c < n_bins; ++c) {
+    const int end = ends[c];
+    int sz = end - start;
+    if (sz > 0 && cur + sz > qt && cur > 0) {            // flush what is packed so far
+      if (nt < max_tiles) { tiles[1 + 2 * nt] = cur0; tiles[2 + 2 * nt] = cur; }
+      ++nt;
+      cur = 0;
+    }
+    if (cur == 0) cur0 = start;
+    while (sz > qt) {                                    // a big cluster: whole tiles of its own
+      if (nt < max_tiles) { tiles[1 + 2 * nt] = cur0; tiles[2 + 2 * nt] = qt; }
+      ++nt;
+      cur0 += qt;
+      sz -= qt;
+    }
+    cur += sz;
+    start = end;
+  }
+  if (cur > 0) {
+    if (nt < max_tiles) { tiles[1 + 2 * nt] = cur0; tiles[2 + 2 * nt] = cur; }
+    ++nt;
+  }
+  tiles[0] = nt < max_tiles ? nt : max_tiles;
 }
 
 // indices of the zero-norm patterns: ws[0] = count (may exceed cap), ws[1 + i] = index (first cap only)
@@ -813,7 +914,8 @@ extern "C" int v3s_gram_topk(const void* a16_all, long long n_cols, const void* 
 extern "C" int v3s_knn_merge_lists(const unsigned long long* lists, const int* counts, int S, int C, long long n_rows,
                                    long long n_cols, long long row0, int k, float eps_g, int cap, const int* zero_flag,
                                    int* zero_ws /* int [cap + 1], required with zero_flag */, int* cand_ws, int* count_ws,
-                                   int* overflow, void* stream) {
+                                   int* overflow, int anchor_stride, int* order_ws /* int [2 n_rows + bins], see header */,
+                                   int tile_rows, int max_tiles, int* tiles_ws /* int [1 + 2 max_tiles] */, void* stream) {
   V3S_REQUIRE((zero_flag == nullptr) || (zero_ws != nullptr), "v3s_knn_merge_lists: zero_flag needs zero_ws");
   V3S_REQUIRE(S >= 1 && C >= 32 && n_rows >= 0 && k >= 1 && cap >= 1, "v3s_knn_merge_lists: bad arguments");
   V3S_REQUIRE((size_t)S * C * 8 <= 200 * 1024, "v3s_knn_merge_lists: S*C = %d entries exceed shared memory", S * C);
@@ -830,9 +932,30 @@ extern "C" int v3s_knn_merge_lists(const unsigned long long* lists, const int* c
     V3S_CHECK_LAUNCH();
   }
   const int grid = (int)(n_rows < 16LL * kNumSMs ? n_rows : 16LL * kNumSMs);
+  V3S_REQUIRE(order_ws == nullptr || anchor_stride >= 1, "v3s_knn_merge_lists: anchor_stride >= 1 with order_ws");
+  // order_ws layout: [0, n_rows) order, [n_rows, 2 n_rows) cluster ids, then the bins
+  int* cluster = order_ws ? order_ws + n_rows : nullptr;
   knn_merge_kernel<<<grid, kMergeThreads, smem, (cudaStream_t)stream>>>(lists, counts, S, C, (int)n_rows, (int)n_cols, row0, k,
                                                                         2.0f * eps_g, cap, zero_flag, zero_flag ? zero_ws : nullptr,
-                                                                        cand_ws, count_ws, overflow);
+                                                                        cand_ws, count_ws, overflow, anchor_stride, cluster);
   V3S_CHECK_LAUNCH();
+  if (order_ws) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n_bins = (int)(ceil_div64(n_cols, anchor_stride) + ceil_div64(n_rows, anchor_stride));
+    int* bins = order_ws + 2 * n_rows;
+    V3S_CUDA(cudaMemsetAsync(bins, 0, sizeof(int) * (size_t)n_bins, st));
+    const int g = (int)(ceil_div64(n_rows, 256) < 4LL * kNumSMs ? ceil_div64(n_rows, 256) : 4LL * kNumSMs);
+    cluster_hist_kernel<<<g, 256, 0, st>>>(cluster, (int)n_rows, bins);
+    V3S_CHECK_LAUNCH();
+    cluster_scan_kernel<<<1, 1024, 0, st>>>(bins, n_bins);
+    V3S_CHECK_LAUNCH();
+    cluster_scatter_kernel<<<g, 256, 0, st>>>(cluster, (int)n_rows, bins, order_ws);
+    V3S_CHECK_LAUNCH();
+    if (tiles_ws) {
+      V3S_REQUIRE(tile_rows >= 1 && max_tiles >= 1, "v3s_knn_merge_lists: tile_rows / max_tiles with tiles_ws");
+      cluster_tiles_kernel<<<1, 32, 0, st>>>(bins, n_bins, tile_rows, max_tiles, tiles_ws);
+      V3S_CHECK_LAUNCH();
+    }
+  }
   return 0;
 }

@@ -140,7 +140,8 @@ refine_sort_kernel(const float* __restrict__ a_rows, const float* __restrict__ a
                    const int* __restrict__ cand, const int* __restrict__ cand_count, int cap, int kk_pad, int k,
                    const int* __restrict__ zero_flag,
                    int cache_row, const double* __restrict__ Bd, long long ldb, double* __restrict__ S2,
-                   int* __restrict__ Nbr, double* Dws, int phase, const int* __restrict__ order) {
+                   int* __restrict__ Nbr, double* Dws, int phase, const int* __restrict__ order,
+                   const int* __restrict__ pref = nullptr) {
   // phase 0: distances + sort in one launch.  phase 1: distances only, into Dws [n_rows, cap] in candidate
   // order; a pair whose partner row j < i of this call lists i too is skipped and stored as -(t + 1),
   // t = position of i in j's list.  phase 2: fetch the skipped values from the partner rows, sort, emit.
@@ -187,7 +188,22 @@ refine_sort_kernel(const float* __restrict__ a_rows, const float* __restrict__ a
         si[s] = j;
       }
     }
-    for (int s = warp; s < ((Bd || phase == 2) ? 0 : kk); s += kRefThreads / 32) {
+    if (phase == 3) {
+      // tiled refinement (refine_tiled_kernel): Dws holds |a_r - a_j|^2 of the pairs this row owns, pref the slot
+      // of the partner row that owns the others
+      for (int s = tid; s < kk; s += kRefThreads) {
+        const int j = cand[(long long)r * cap + s];
+        const int pr = pref[(long long)r * cap + s];
+        const double ss = pr >= 0 ? Dws[(long long)(j - row0) * cap + pr] : Dws[(long long)r * cap + s];
+        double half = 0.5 * sqrt(ss);
+        if (half > 1.0) half = 1.0;
+        double d = 2.0 * asin(half);
+        if (zero_flag && (rz || zero_flag[j])) d = 0.0;
+        sd[s] = d;
+        si[s] = j;
+      }
+    }
+    for (int s = warp; s < ((Bd || phase >= 2) ? 0 : kk); s += kRefThreads / 32) {
       const int j = cand[(long long)r * cap + s];
       if (phase == 1) {
         const long long lj = (long long)j - row0;
@@ -356,6 +372,251 @@ extern "C" int v3s_knn_refine(const float* a_rows, const float* a_all, int P, lo
   V3S_CHECK_LAUNCH();
   refine_sort_kernel<<<grid2, kRefThreads, base, st>>>(a_rows, a_all, P, row0, (int)n_rows, cand_ws, count_ws, cap, kk_pad, k,
                                                       zero_flag, 0, nullptr, 0, S2, Nbr, dist_ws, 2, order);
+  V3S_CHECK_LAUNCH();
+  return 0;
+}
+
+namespace v3s {
+// ---- tiled exact-distance refinement ---------------------------------------------------------------------
+// The refinement reads one candidate row (P floats) per (row, candidate) pair: ~N k P 4 bytes, and consecutive
+// rows have unrelated candidates when the patterns come in random order.  Here the rows are processed in TILES
+// of neighbouring patterns (rows that share their nearest anchor pattern, v3s_knn_merge_lists' `order`): the
+// tile's pairs are grouped by candidate, so a candidate row is read ONCE per tile and compared with every row
+// of the tile that lists it, from a shared-memory copy of the tile's rows, chunk by chunk of the pixel axis.
+//   refine_prepare_kernel : per tile, the pairs it owns (a pair listed from both sides by rows of this call is owned
+//                           by the row with the lower index; the other row records the owner's slot in `pref`),
+//                           sorted by candidate -> keys [tile][RT_KEYS] = candidate << 32 | row-in-tile << 16 | slot
+//   refine_tiled_kernel   : per tile and chunk of RT_CH pixels: the tile's rows -> shared memory; each warp walks
+//                           its share of the sorted pairs, keeps the current candidate's chunk in registers, adds
+//                           the chunk's |a_r - a_c|^2 (FP32, warp-shuffle sum) into Dss [n_rows, cap] (FP64 RED)
+//   refine_sort_kernel phase 3 : d = 2 asin(sqrt(ss)/2), sort by (d, index), emit the first k
+constexpr int RT_CH = 512;
+constexpr int RT_KEYS = 16384;
+constexpr int RT_QMAX = 48;
+constexpr int RT_THREADS = 256;      // prepare kernel
+constexpr int RT_MAIN_THREADS = 512; // main kernel: 16 warps x 2 CTAs per SM hide the candidate-row load latency
+
+__global__ void __launch_bounds__(RT_THREADS)
+refine_prepare_kernel(const int* __restrict__ order, const int* __restrict__ tiles, long long row0,
+                      const int* __restrict__ cand, const int* __restrict__ cand_count, int cap,
+                      unsigned long long* __restrict__ keys, int* __restrict__ np_out, int* __restrict__ pref, int dedup) {
+  extern __shared__ unsigned long long sk[];       // RT_KEYS
+  __shared__ int s_np;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tile = blockIdx.x;
+  if (tile >= tiles[0]) return;
+  const int q0 = tiles[1 + 2 * tile];
+  const int nq = tiles[2 + 2 * tile];
+  if (tid == 0) s_np = 0;
+  __syncthreads();
+  for (int qi = warp; qi < nq; qi += RT_THREADS / 32) {
+    const int r = order[q0 + qi];
+    const int cnt = cand_count[r];
+    const int me = (int)(row0 + r);
+    for (int s0 = 0; s0 < cnt; s0 += 32) {
+      const int s = s0 + lane;
+      const bool valid = s < cnt;
+      const int j = valid ? cand[(long long)r * cap + s] : -1;
+      bool owned = valid;
+      if (dedup && valid) {
+        const long long lj = (long long)j - row0;
+        if (lj >= 0 && lj < r) {                              // partner row of this call with a lower index
+          const int* cj = cand + lj * cap;
+          const int cntj = cand_count[lj];
+          int lo = 0, hi = cntj;                              // lists are sorted by column index (knn_merge_kernel)
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (cj[mid] < me) lo = mid + 1; else hi = mid;
+          }
+          if (lo < cntj && cj[lo] == me) { owned = false; pref[(long long)r * cap + s] = lo; }
+        }
+      }
+      const unsigned ob = __ballot_sync(0xffffffffu, owned);
+      int base = 0;
+      if (lane == 0 && ob) base = atomicAdd(&s_np, __popc(ob));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (owned) sk[base + __popc(ob & ((1u << lane) - 1u))] = ((unsigned long long)(unsigned)j << 32) | ((unsigned)qi << 16) | (unsigned)s;
+    }
+  }
+  __syncthreads();
+  const int np = s_np;
+  int npad = 2;
+  while (npad < np) npad <<= 1;
+  for (int i = np + tid; i < npad; i += RT_THREADS) sk[i] = ~0ull;
+  __syncthreads();
+  for (int size = 2; size <= npad; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = tid; t < npad / 2; t += RT_THREADS) {
+        const int lo = 2 * t - (t & (stride - 1));
+        const int hi = lo + stride;
+        const bool up = ((lo & size) == 0);
+        const unsigned long long a = sk[lo], b = sk[hi];
+        if ((a > b) == up) { sk[lo] = b; sk[hi] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  unsigned long long* out = keys + (long long)tile * RT_KEYS;
+  for (int i = tid; i < np; i += RT_THREADS) out[i] = sk[i];
+  if (tid == 0) np_out[tile] = np;
+}
+
+__global__ void __launch_bounds__(RT_MAIN_THREADS, 2)
+refine_tiled_kernel(const float* __restrict__ a_rows, const float* __restrict__ a_all, int P, const int* __restrict__ order,
+                    const int* __restrict__ tiles, const unsigned long long* __restrict__ keys,
+                    const int* __restrict__ np_arr, int cap, double* __restrict__ Dss) {
+  extern __shared__ __align__(16) float sq[];       // qt * RT_CH
+  __shared__ int s_rows[RT_QMAX];
+  constexpr int RT_THREADS = RT_MAIN_THREADS;       // (shadows the prepare kernel's block size inside this kernel)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n_tiles = tiles[0];
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int q0 = tiles[1 + 2 * tile];
+    const int nq = tiles[2 + 2 * tile];
+    const int np = np_arr[tile];
+    const unsigned long long* kb = keys + (long long)tile * RT_KEYS;
+    __syncthreads();
+    if (tid < nq) s_rows[tid] = order[q0 + tid];
+    const int i0 = (int)((long long)np * warp / (RT_THREADS / 32)), i1 = (int)((long long)np * (warp + 1) / (RT_THREADS / 32));
+    for (int c0 = 0; c0 < P; c0 += RT_CH) {
+      __syncthreads();
+      for (int idx = tid; idx < nq * (RT_CH / 4); idx += RT_THREADS) {
+        const int qi = idx / (RT_CH / 4), v = idx - qi * (RT_CH / 4);
+        const int col = c0 + 4 * v;
+        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col < P) val = *reinterpret_cast<const float4*>(a_rows + (long long)s_rows[qi] * P + col);
+        *reinterpret_cast<float4*>(sq + qi * RT_CH + 4 * v) = val;
+      }
+      __syncthreads();
+      // The warp walks its pairs in batches of 32 keys (one coalesced load, then shuffles): no memory latency per
+      // pair.  The candidate whose chunk the NEXT segment needs is fetched into the second register buffer
+      // while the current segment is being compared (the loads are what the kernel waits for: ~6 pairs of
+      // arithmetic per 2 kB row chunk).
+      int cur_u = -1;
+      float4 ua[RT_CH / 128], ub[RT_CH / 128];
+      const float* a_chunk = a_all + c0;
+      auto load_u = [&](float4 (&dst)[RT_CH / 128], int u) {
+        const float* up = a_chunk + (long long)u * P;
+#pragma unroll
+        for (int m = 0; m < RT_CH / 128; ++m) {
+          const int col = 4 * (lane + 32 * m);
+          dst[m] = (c0 + col < P) ? __ldg(reinterpret_cast<const float4*>(up + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      auto pair_sum = [&](const float4 (&uu)[RT_CH / 128], unsigned long long key) {
+        const int qi = (int)((key >> 16) & 0xffffu), s = (int)(key & 0xffffu);
+        const float* q = sq + qi * RT_CH;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int m = 0; m < RT_CH / 128; ++m) {
+          const float4 x = *reinterpret_cast<const float4*>(q + 4 * (lane + 32 * m));
+          float d;
+          d = x.x - uu[m].x; a0 = fmaf(d, d, a0);
+          d = x.y - uu[m].y; a1 = fmaf(d, d, a1);
+          d = x.z - uu[m].z; a2 = fmaf(d, d, a2);
+          d = x.w - uu[m].w; a3 = fmaf(d, d, a3);
+        }
+        float part = (a0 + a1) + (a2 + a3);
+        part = warp_sum(part);
+        if (lane == 0) atomicAdd(&Dss[(long long)s_rows[qi] * cap + s], (double)part);
+      };
+      for (int base = i0; base < i1; base += 32) {
+        const int nb = min(32, i1 - base);
+        const unsigned long long my_key = (lane < nb) ? __ldg(&kb[base + lane]) : ~0ull;
+        const int my_u = (int)(my_key >> 32);
+        const int prev_u = __shfl_up_sync(0xffffffffu, my_u, 1);
+        // segment starts of this batch: a key whose candidate differs from its predecessor's (lane 0: from the
+        // candidate still held in `ua` from the previous batch)
+        unsigned starts = __ballot_sync(0xffffffffu, lane < nb && (lane == 0 ? (my_u != cur_u) : (my_u != prev_u)));
+        int j = 0;
+        if (!(starts & 1u)) {
+          // the batch begins inside the segment whose chunk is already in `ua`
+          const int jn = starts ? (__ffs(starts) - 1) : nb;
+          if (starts) load_u(ub, __shfl_sync(0xffffffffu, my_u, jn));
+          for (; j < jn; ++j) pair_sum(ua, __shfl_sync(0xffffffffu, my_key, j));
+          if (starts) {
+#pragma unroll
+            for (int m = 0; m < RT_CH / 128; ++m) ua[m] = ub[m];
+            cur_u = __shfl_sync(0xffffffffu, my_u, jn);
+            starts &= starts - 1;
+          }
+        } else {
+          cur_u = __shfl_sync(0xffffffffu, my_u, 0);
+          load_u(ua, cur_u);
+          starts &= starts - 1;
+        }
+        while (j < nb) {
+          // `ua` holds the chunk of the segment starting at j; fetch the next segment's while comparing this one
+          const int jn = starts ? (__ffs(starts) - 1) : nb;
+          if (starts) load_u(ub, __shfl_sync(0xffffffffu, my_u, jn));
+          for (; j < jn; ++j) pair_sum(ua, __shfl_sync(0xffffffffu, my_key, j));
+          if (starts) {
+#pragma unroll
+            for (int m = 0; m < RT_CH / 128; ++m) ua[m] = ub[m];
+            cur_u = __shfl_sync(0xffffffffu, my_u, jn);
+            starts &= starts - 1;
+          }
+        }
+      }
+    }
+  }
+}
+
+}  // namespace v3s
+
+// rows per tile of the tiled refinement for a candidate capacity (0: capacity too large for it)
+extern "C" int v3s_knn_refine_tile_rows(int cap) {
+  if (cap < 1 || cap > v3s::RT_KEYS) return 0;
+  const int qt = v3s::RT_KEYS / cap;
+  return qt < v3s::RT_QMAX ? qt : v3s::RT_QMAX;
+}
+
+// v3s_knn_refine with the pair evaluation tiled over neighbouring rows (see above).  order int [n_rows] (rows of a
+// neighbourhood contiguous, from v3s_knn_merge_lists) is required; P must be a multiple of 4.  Workspaces:
+// dist_ws FP64 [n_rows,cap], pref_ws int [n_rows,cap], keys_ws 64-bit [max_tiles * 16384], np_ws int [max_tiles];
+// tiles (device, int [1 + 2 max_tiles]): the tile table written by v3s_knn_merge_lists.  dedup != 0: pairs listed
+// from both sides are evaluated once.
+extern "C" int v3s_knn_refine_tiled(const float* a_rows, const float* a_all, int P, long long row0, long long n_rows,
+                                    long long n_cols, int k, int cap, const int* zero_flag, const int* cand_ws,
+                                    const int* count_ws, double* S2, int* Nbr, double* dist_ws, const int* order,
+                                    const int* tiles, int max_tiles, int* pref_ws, unsigned long long* keys_ws, int* np_ws,
+                                    int dedup, void* stream) {
+  V3S_REQUIRE(k >= 1 && cap >= k && n_rows >= 0 && n_cols < (1LL << 31) && n_rows < (1LL << 31), "v3s_knn_refine_tiled: bad arguments");
+  V3S_REQUIRE(k <= n_cols, "Number of nearest neighbors to preserve is too high.");   // distance.py:33-34
+  V3S_REQUIRE(P > 0 && P % 4 == 0, "v3s_knn_refine_tiled: P = %d must be a multiple of 4", P);
+  V3S_REQUIRE(dist_ws && order && tiles && max_tiles >= 1 && pref_ws && keys_ws && np_ws,
+              "v3s_knn_refine_tiled: workspaces, order and the tile table are required");
+  const int qt = v3s_knn_refine_tile_rows(cap);
+  V3S_REQUIRE(qt >= 1, "v3s_knn_refine_tiled: candidate capacity %d too large", cap);
+  if (n_rows == 0) return 0;
+  using namespace v3s;
+  cudaStream_t st = (cudaStream_t)stream;
+  V3S_CUDA(cudaMemsetAsync(dist_ws, 0, sizeof(double) * (size_t)n_rows * cap, st));
+  V3S_CUDA(cudaMemsetAsync(pref_ws, 0xFF, sizeof(int) * (size_t)n_rows * cap, st));
+  static bool attr_set = false;
+  if (!attr_set) {
+    V3S_CUDA(cudaFuncSetAttribute(refine_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RT_KEYS * 8));
+    V3S_CUDA(cudaFuncSetAttribute(refine_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RT_QMAX * RT_CH * 4));
+    attr_set = true;
+  }
+  refine_prepare_kernel<<<max_tiles, RT_THREADS, RT_KEYS * 8, st>>>(order, tiles, row0, cand_ws, count_ws, cap, keys_ws, np_ws,
+                                                                   pref_ws, dedup);
+  V3S_CHECK_LAUNCH();
+  const int grid = max_tiles < 2 * kNumSMs ? max_tiles : 2 * kNumSMs;
+  refine_tiled_kernel<<<grid, RT_MAIN_THREADS, (size_t)qt * RT_CH * 4, st>>>(a_rows, a_all, P, order, tiles, keys_ws, np_ws, cap,
+                                                                            dist_ws);
+  V3S_CHECK_LAUNCH();
+  int kk_pad = 4;
+  while (kk_pad < cap) kk_pad <<= 1;
+  V3S_REQUIRE(kk_pad <= 4096, "v3s_knn_refine_tiled: candidate capacity %d too large (max 4096)", cap);
+  const size_t base = (size_t)kk_pad * (sizeof(double) + sizeof(int));
+  if (base > g_refine_smem_set) {
+    V3S_CUDA(cudaFuncSetAttribute(refine_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)base));
+    g_refine_smem_set = base;
+  }
+  const int grid2 = (int)(n_rows < 8LL * kNumSMs ? n_rows : 8LL * kNumSMs);
+  refine_sort_kernel<<<grid2, kRefThreads, base, st>>>(a_rows, a_all, P, row0, (int)n_rows, cand_ws, count_ws, cap, kk_pad, k,
+                                                      zero_flag, 0, nullptr, 0, S2, Nbr, dist_ws, 3, nullptr, pref_ws);
   V3S_CHECK_LAUNCH();
   return 0;
 }

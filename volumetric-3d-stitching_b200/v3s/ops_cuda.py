@@ -99,6 +99,7 @@ class CudaOps:
         self._snap_events = []
         self._symm_G = {}
         self.dedup_refine = True     # exact-distance refinement: mutual candidate pairs once (select.cu)
+        self.tiled_refine = True     # ... tiled over neighbouring rows for long rows (refine_tiled_kernel)
         self.use_fused_matvec = True # eigen-solver mat-vecs with the reduction / recurrence / exchange fused (FusedOperator)
         self.use_peer_gram = True    # sharded jobs: symmetric Gram with NVLink peer stores (else rectangular panels)
         self.operator = "auto"       # Markov operator of the eigen-solver: "dense" (FP32 rows), "sparse" (FP64 lists), "auto"
@@ -260,12 +261,32 @@ class CudaOps:
         cand = self.empty((nr, cap), torch.int32)
         cnt = self.empty((nr,), torch.int32)
         zws = self.empty((cap + 1,), torch.int32) if zero_flag is not None else None
-        dws = self.empty((nr, cap), torch.float64) if self.dedup_refine else None
+        # tiled refinement (a candidate row is read once per tile of neighbouring rows) where it pays: long rows
+        qt = int(_lib.lib.v3s_knn_refine_tile_rows(cap))
+        tiled = self.tiled_refine and qt >= 8 and P % 4 == 0 and P >= 1024 and nr >= 2048
+        order_ws = tiles_ws = None
+        max_tiles = 0
+        if tiled:
+            stride = qt                                    # one anchor per tile's worth of patterns
+            n_bins = (N + stride - 1) // stride + (nr + stride - 1) // stride
+            order_ws = self.empty((2 * nr + n_bins,), torch.int32)
+            max_tiles = n_bins + nr // qt + 2             # every neighbourhood: its whole tiles + at most one packed flush
+            tiles_ws = self.empty((1 + 2 * max_tiles,), torch.int32)
         h = self._tic("select_refine")
         call("v3s_knn_merge_lists", ptr(lists), ptr(counts), S, Cc, nr, N, r0, k, eps_g, cap, ptr(zero_flag), ptr(zws),
-             ptr(cand), ptr(cnt), ptr(self.knn_overflow), stream_ptr())
-        call("v3s_knn_refine", ptr(a32_all[r0:r1]), ptr(a32_all), P, r0, nr, N, k, cap, ptr(zero_flag), ptr(cand), ptr(cnt),
-             ptr(S2), ptr(Nbr), ptr(dws), ptr(order), stream_ptr())
+             ptr(cand), ptr(cnt), ptr(self.knn_overflow), qt if tiled else 1, ptr(order_ws), qt, max_tiles, ptr(tiles_ws),
+             stream_ptr())
+        dws = self.empty((nr, cap), torch.float64) if (self.dedup_refine or tiled) else None
+        if tiled:
+            pref = self.empty((nr, cap), torch.int32)
+            keys = self.empty((max_tiles * 16384,), torch.int64)
+            npw = self.empty((max_tiles,), torch.int32)
+            call("v3s_knn_refine_tiled", ptr(a32_all[r0:r1]), ptr(a32_all), P, r0, nr, N, k, cap, ptr(zero_flag), ptr(cand),
+                 ptr(cnt), ptr(S2), ptr(Nbr), ptr(dws), ptr(order_ws), ptr(tiles_ws), max_tiles, ptr(pref), ptr(keys),
+                 ptr(npw), 1 if self.dedup_refine else 0, stream_ptr())
+        else:
+            call("v3s_knn_refine", ptr(a32_all[r0:r1]), ptr(a32_all), P, r0, nr, N, k, cap, ptr(zero_flag), ptr(cand), ptr(cnt),
+                 ptr(S2), ptr(Nbr), ptr(dws), None, stream_ptr())
         self._toc(h)
         return S2, Nbr
 
