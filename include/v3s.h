@@ -330,6 +330,46 @@ int v3s_sparse_cheb_filter(const v3s_sparse_markov* op, long long n_rows, long l
                            int q_index, int degree, double c, double e, const unsigned long long* ybuf_ptrs,
                            const unsigned long long* flag_ptrs, int rank, int world, int epoch0, unsigned* ticket_dev,
                            int* status_dev, void* workspace, int* result_index, void* stream);
+/* ---- the whole eigen-solver behind one call -----------------------------------------------------
+ * DiffusionMapSolver.diffusion_coordinate's `eigs(P_ep, k)` (diffusion.py:61; ARPACK, 'LM'): the nev
+ * largest-magnitude eigenpairs of the symmetric P_ep by Chebyshev-filtered block Lanczos on the kernels
+ * above, driven from the library (no Python, no LAPACK).  UNLIKE every other entry point it synchronises
+ * the stream (a few small device-to-host copies per Ritz check) and allocates transient host memory.
+ * The operator is the rank's row block in either form plus the buffers the fused mat-vecs store into
+ * (one arena per job, as for v3s_cheb_filter): ybuf_ptrs [3*world] rotating [N,8] FP64 result blocks,
+ * xf_ptrs [2*world] FP32 strip operands (dense form only), flag_ptrs [world] (sharded only), ticket /
+ * status words, the mat-vec workspace (dense: v3s_block_matvec_workspace_bytes; sparse: 8 n_rows doubles);
+ * `epoch` is the arena's barrier counter, advanced by the call.  Host struct, device pointers inside.   */
+typedef struct v3s_eig_problem {
+  const float* P_rows;                  /* dense FP32 rows [n_rows, ldp], or NULL                     */
+  long long ldp;
+  const v3s_sparse_markov* sparse;      /* or the sparse operator (host descriptor), or NULL          */
+  long long n_rows, N, row0;
+  int rank, world;
+  const unsigned long long* ybuf_ptrs;  /* host [3*world]                                             */
+  const unsigned long long* xf_ptrs;    /* host [2*world], dense form                                 */
+  const unsigned long long* flag_ptrs;  /* host [world], world > 1                                    */
+  unsigned* ticket_dev;
+  int* status_dev;
+  void* mv_workspace;
+  int epoch;                            /* in / out                                                   */
+} v3s_eig_problem;
+/* ws: v3s_eig_topk_workspace_doubles(N, max_dim) doubles (device).  max_dim = Krylov cap (multiple of 8,
+ * e.g. 320), degree = Chebyshev degree (6; 0 = plain Lanczos; the filter is used from N = 2048 on),
+ * probe_steps = plain steps before the filter (10), seed = start block.  Outputs: lambda_host [nev]
+ * (host, by decreasing magnitude), Y_dev [N,nev] FP64 row-major orthonormal eigenvectors (device, complete
+ * on every rank), resid_host [nev] (may be NULL) residual norms, info_host [8] = {converged, mat-vecs,
+ * Krylov dimension, 1 if filtered, Ritz checks, 1 if an eigenvalue cluster of multiplicity >= 8 may hide
+ * further copies (disconnected graph: deflate and rerun, as v3s/eig.py's topk_with_locking does), 0, 0}.
+ * Fails with the reference's "No spare-matrix for eigs-calculation" when nev >= N - 1.                  */
+long long v3s_eig_topk_workspace_doubles(long long N, int max_dim);
+int v3s_eig_topk(v3s_eig_problem* problem /* host */, int nev, double tol, int max_dim, int degree, int probe_steps,
+                 unsigned long long seed, double* ws, double* lambda_host, double* Y_dev, double* resid_host,
+                 int* info_host, void* stream);
+/* the host eigen-solver of the small projected matrices (Householder tridiagonalisation + implicit QL): a [n,n]
+ * symmetric row-major, overwritten with the eigenvectors in its columns; w [n] ascending.  Host pointers.    */
+int v3s_sym_eig_host(double* a, int n, double* w);
+
 /* per-launch device time of the mat-vec kernel, dense or sparse (CUDA events owned by the library, recorded on the
  * launching stream): enable/reset, then read the elapsed milliseconds (returns the launch count). */
 int v3s_profile_matvec(int enable);

@@ -42,6 +42,16 @@ for (N, n, n_p, k) in ((3001, 15, 31, 250), (5000, 15, 48, 200)):
     st_s, st_1 = {}, {}
     sp_s = run_pipeline(ops, plan, ed, rot9_all[plan.lo:plan.hi].contiguous(), rot_y, n_p, k, 0.7, check=False, stats=st_s)
     sp_1 = run_pipeline(ops, one, ed, rot9_all, rot_y, n_p, k, 0.7, check=False, stats=st_1)
+    # the same sharded job with the whole eigen-solver behind one C-ABI call (v3s_eig_topk, peer stores + barriers inside)
+    ops.eig_driver = "cabi"
+    st_c = {}
+    sp_c = run_pipeline(ops, plan, ed, rot9_all[plan.lo:plan.hi].contiguous(), rot_y, n_p, k, 0.7, check=False, stats=st_c)
+    ops.eig_driver = "python"
+    lam_c = float((sp_c["Lambda"] - sp_1["Lambda"]).abs().max().item())
+    ang_c = float(np.max(orc.principal_angles(sp_c["Ps"].cpu().numpy(), sp_1["Ps"].cpu().numpy())))
+    print(f"rank {rank} N={N}: v3s_eig_topk sharded vs Python driver on one GPU: |dLambda| {lam_c:.2e}, subspace angle {ang_c:.2e}, "
+          f"driver {st_c.get('driver')} matvecs {st_c.get('matvecs')}", flush=True)
+    ok &= str(st_c.get("driver", "")).startswith("cabi") and bool(st_c.get("converged")) and lam_c < 1e-8 and ang_c < 1e-6
     ops.operator = "auto"
     lam_sp = float((sp_s["Lambda"] - sp_1["Lambda"]).abs().max().item())
     ang_sp = float(np.max(orc.principal_angles(sp_s["Ps"].cpu().numpy(), sp_1["Ps"].cpu().numpy())))

@@ -622,6 +622,35 @@ def test_sparse_operator_eigenpairs(v3s_mod, ops, hub):
         assert cosang > 1 - 1e-9
 
 
+@pytest.mark.parametrize("N,k", [(3000, 60), (1200, 80)])
+def test_eig_topk_cabi_against_dense_eigh(v3s_mod, ops, N, k):
+    """v3s_eig_topk -- the whole eigen-solver behind ONE C-ABI call (library-driven block Lanczos + Chebyshev
+    filter + its own QL Ritz extraction; replaces eigs() of diffusion.py:61) -- against a dense FP64
+    eigendecomposition of the oracle's P_ep, for both forms of the operator, on the filtered (N >= 2048) and the
+    plain path; and through the stage API with ops.eig_driver = "cabi"."""
+    S2, Nbr = _so3_knn_lists(N, k, seed=21)
+    _, _, _, _, Po, dio = orc.diffusion_coordinate(S2.copy(), Nbr, 0.7, validate=False, return_all=True)
+    w, V = np.linalg.eigh(0.5 * (Po + Po.T))
+    idx = np.argsort(-np.abs(w))[:10]
+    lam_ref, V_ref = w[idx], V[:, idx]
+    assert abs(lam_ref[9]) - np.sort(np.abs(w))[::-1][10] > 1e-6              # the 10-dimensional subspace is unique
+    prev_op, prev_drv = ops.operator, ops.eig_driver
+    try:
+        ops.eig_driver = "cabi"
+        for mode, tol_l in (("sparse", 1e-9), ("dense", 1e-6)):
+            ops.operator = mode
+            stats = {}
+            Ps, Lam = v3s_mod.DiffusionMapSolver.diffusion_coordinate(S2.copy(), Nbr, 0.7, validate=False, stats=stats)
+            print("eig_topk (C-ABI)", mode, stats.get("driver"), "matvecs", stats.get("matvecs"), "krylov", stats.get("krylov_dim"),
+                  "max |dlambda|", np.max(np.abs(Lam - lam_ref)))
+            assert stats["driver"] == ("cabi-chebyshev" if N >= 2048 else "cabi-plain") and stats["converged"]
+            assert np.max(np.abs(Lam - lam_ref)) < tol_l
+            Ps_ref = dio[:, None] * (V_ref * lam_ref[None, :])
+            assert np.max(orc.principal_angles(Ps, Ps_ref)) < (1e-6 if mode == "sparse" else 1e-4)
+    finally:
+        ops.operator, ops.eig_driver = prev_op, prev_drv
+
+
 def test_eigen_connected_sparse_operator(v3s_mod, ops, golden_dir):
     g = np.load(os.path.join(golden_dir, "connected_n15.npz"))
     prev = ops.operator

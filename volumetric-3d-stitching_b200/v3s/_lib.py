@@ -23,6 +23,14 @@ class Geometry(C.Structure):
     _fields_ = [("pixel", f64), ("zd", f64), ("lambda_", f64), ("n_p_nobin", i32), ("grid_scale", f64)]
 
 
+class EigProblem(C.Structure):
+    """v3s_eig_problem (include/v3s.h)."""
+    _fields_ = [("P_rows", C.c_void_p), ("ldp", C.c_longlong), ("sparse", C.c_void_p), ("n_rows", C.c_longlong),
+                ("N", C.c_longlong), ("row0", C.c_longlong), ("rank", C.c_int), ("world", C.c_int),
+                ("ybuf_ptrs", C.c_void_p), ("xf_ptrs", C.c_void_p), ("flag_ptrs", C.c_void_p), ("ticket_dev", C.c_void_p),
+                ("status_dev", C.c_void_p), ("mv_workspace", C.c_void_p), ("epoch", C.c_int)]
+
+
 class SparseMarkovDesc(C.Structure):
     """v3s_sparse_markov (include/v3s.h): device pointers of the sparse operator's arrays."""
     _fields_ = [("nbr", p), ("a_val", p), ("t_ptr", p), ("t_col", p), ("t_val", p), ("k", i32)]
@@ -87,6 +95,10 @@ SIGNATURES = {
     "v3s_sparse_cheb_filter": (i32, [C.POINTER(SparseMarkovDesc), i64, i64, i64, p, i32, i32, f64, f64,
                                      C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), i32, i32, i32, p, p, p,
                                      C.POINTER(i32), p]),
+    "v3s_eig_topk_workspace_doubles": (i64, [i64, i32]),
+    "v3s_eig_topk": (i32, [C.POINTER(EigProblem), i32, f64, i32, i32, i32, C.c_ulonglong, p, C.POINTER(f64), p, C.POINTER(f64),
+                           C.POINTER(i32), p]),
+    "v3s_sym_eig_host": (i32, [C.POINTER(f64), i32, C.POINTER(f64)]),
     "v3s_profile_matvec": (i32, [i32]),
     "v3s_profile_matvec_read": (i32, [C.POINTER(C.c_float), i32]),
     "v3s_fit_gram": (i32, [p, i32, p, i64, p, p]),

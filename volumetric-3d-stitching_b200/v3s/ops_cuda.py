@@ -103,6 +103,7 @@ class CudaOps:
         self.use_fused_matvec = True # eigen-solver mat-vecs with the reduction / recurrence / exchange fused (FusedOperator)
         self.use_peer_gram = True    # sharded jobs: symmetric Gram with NVLink peer stores (else rectangular panels)
         self.operator = "auto"       # Markov operator of the eigen-solver: "dense" (FP32 rows), "sparse" (FP64 lists), "auto"
+        self.eig_driver = "python"   # "cabi": the whole eigen-solver through v3s_eig_topk (library-driven, no LAPACK)
         self.symm_error = None
         self._pin = None
 
@@ -759,6 +760,43 @@ class FusedOperator:
             a["epoch"] += int(degree)
         self.n_matvec += int(degree)
         return a["ybufs"][res.value]
+
+    def eig_topk(self, nev, tol=1e-8, max_dim=320, degree=6, probe_steps=10, seed=0):
+        """The whole eigen-solver through ONE C-ABI call (v3s_eig_topk: block Lanczos + Chebyshev filter + Ritz
+        extraction driven from the library, no Python / LAPACK in the loop).
+        -> lambda [nev] numpy (by decreasing magnitude), Y [N,nev] f64 tensor, residual norms [nev], info dict."""
+        a = self.a
+        pb = _lib.EigProblem()
+        if self.sparse:
+            pb.P_rows, pb.ldp, pb.sparse = None, 0, C.cast(C.pointer(self.P_rows.desc), C.c_void_p)
+            pb.n_rows = self.P_rows.n_rows
+            ws_mv = self._sp_ws
+        else:
+            pb.P_rows, pb.ldp, pb.sparse = self.P_rows.data_ptr(), self.P_rows.shape[1], None
+            pb.n_rows = self.P_rows.shape[0]
+            ws_mv = self.ops._mv_workspace(self.P_rows.shape[0], self.N)
+        pb.N, pb.row0, pb.rank, pb.world = self.N, self.row0, self.rank, self.world
+        pb.ybuf_ptrs = C.cast(a["yptrs"], C.c_void_p)
+        pb.xf_ptrs = C.cast(a["xptrs"], C.c_void_p)
+        pb.flag_ptrs = C.cast(a["fptrs"], C.c_void_p)
+        pb.ticket_dev, pb.status_dev = a["ticket"].data_ptr(), a["status"].data_ptr()
+        pb.mv_workspace = ws_mv.data_ptr()
+        pb.epoch = a["epoch"]
+        md = max(16, (min(int(max_dim), self.N) // 8) * 8)
+        ws = self.ops.empty((int(_lib.lib.v3s_eig_topk_workspace_doubles(self.N, md)),), torch.float64)
+        Y = self.ops.empty((self.N, nev), torch.float64)
+        lam = (C.c_double * nev)()
+        res = (C.c_double * nev)()
+        info = (C.c_int * 8)()
+        call("v3s_eig_topk", C.byref(pb), int(nev), float(tol), md, int(degree), int(probe_steps), int(seed), ptr(ws), lam, ptr(Y),
+             res, info, stream_ptr())
+        a["epoch"] = int(pb.epoch)
+        self.n_matvec += int(info[1])
+        import numpy as _np
+        return (_np.array(lam[:nev]), Y, _np.array(res[:nev]),
+                {"converged": bool(info[0]), "matvecs": int(info[1]), "krylov_dim": int(info[2]),
+                 "driver": "cabi-chebyshev" if info[3] else "cabi-plain", "ritz_checks": int(info[4]),
+                 "saturated_cluster": bool(info[5])})
 
     def check(self):
         """Raise if a peer barrier timed out (one small D2H; called once after every solve).  The status word
