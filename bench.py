@@ -492,7 +492,29 @@ def main():
         d2h = sum(v.nbytes for kk_, v in res.items() if kk_ not in ("R", "Axis", "Quat", "rows", "c0"))
         e2e = {"value": round(e2e_s, 5), "unit": "s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "host_ms": host_e2e,
-               "note": "OrientationRecoverySolver.solve with numpy inputs/outputs on each rank; max over ranks; bytes per rank"}
+               "note": "OrientationRecoverySolver.solve with numpy inputs/outputs on each rank; max over ranks; bytes per rank; "
+                       "every output float64 like the reference's (the pattern matrix is %.1f GB of it: the transfer overlaps "
+                       "stages 2-4 and is what bounds this number when it is slower than they are)" % (res["Images"].nbytes / 1e9)}
+        # the same call returning the pattern matrix in the FP32 it is computed in (half the PCIe bytes)
+        del res
+        import numpy as _np
+
+        def call32():
+            with contextlib.redirect_stdout(io.StringIO()):
+                return OrientationRecoverySolver.solve(params, rotations=R9, N_p=n_p, check_sigma=False,
+                                                       photons_per_pattern=wl.get("photons"), images_dtype=_np.float32)
+        res = call32()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            res = call32()
+        barrier()
+        t32 = torch.tensor([(time.perf_counter() - t0) / 2], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t32, op=dist.ReduceOp.MAX)
+        e2e["with_float32_images"] = {"value": round(float(t32.item()), 5), "unit": "s",
+                                      "d2h_bytes_per_step": int(sum(v.nbytes for kk_, v in res.items() if kk_ not in ("R", "Axis", "Quat", "rows", "c0")))}
+        del res
 
     if rank != 0:
         if world > 1:

@@ -36,3 +36,25 @@ def test_error_plumbing_without_gpu():
     assert rc != 0 and "operator descriptor" in _lib.last_error()
     assert _lib.lib.v3s_xf_floats(130) == 2048
     assert _lib.lib.v3s_synth_workspace_bytes(64) == 64 * 64 * 16
+
+
+def test_sym_eig_host_against_numpy():
+    """v3s_sym_eig_host (Householder + QL, the Ritz extraction of v3s_eig_topk and the N <= 600 eigen path): a host
+    routine, so it is checked here on the CPU box."""
+    import ctypes as C
+
+    import numpy as np
+    from v3s import _lib
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 3, 8, 33, 128, 200):
+        A = rng.standard_normal((n, n))
+        A = (A + A.T) / 2
+        if n == 33:                                   # a degenerate cluster (lambda = 1 eleven times) plus a spread
+            A = np.diag(np.r_[np.ones(11), rng.random(22)]) + 1e-9 * A
+        a, w = np.ascontiguousarray(A.copy()), np.zeros(n)
+        rc = _lib.lib.v3s_sym_eig_host(a.ctypes.data_as(C.POINTER(C.c_double)), n, w.ctypes.data_as(C.POINTER(C.c_double)))
+        assert rc == 0
+        assert np.max(np.abs(w - np.linalg.eigvalsh(A))) < 1e-12 * max(1.0, np.abs(A).max())
+        assert np.max(np.abs(A @ a - a * w[None, :])) < 1e-12 * max(1.0, np.abs(A).max())
+        assert np.max(np.abs(a.T @ a - np.eye(n))) < 1e-12
+    assert _lib.lib.v3s_sym_eig_host(None, 3, None) != 0 and "bad arguments" in _lib.last_error()

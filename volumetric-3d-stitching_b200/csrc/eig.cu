@@ -23,8 +23,8 @@ namespace v3s {
 
 // ---- small dense symmetric eigen-solver (host): Householder tridiagonalisation + implicit QL ----------------
 // A (n x n, row-major, symmetric) -> eigenvalues w ascending, eigenvectors in the COLUMNS of A.
-static void sym_tridiagonalise(std::vector<double>& a, int n, std::vector<double>& d, std::vector<double>& e) {
-  auto A = [&](int i, int j) -> double& { return a[(size_t)i * n + j]; };
+static void sym_tridiagonalise(std::vector<double>& a, int n, int ld, std::vector<double>& d, std::vector<double>& e) {
+  auto A = [&](int i, int j) -> double& { return a[(size_t)i * ld + j]; };
   for (int i = n - 1; i > 0; --i) {
     const int l = i - 1;
     double h = 0.0, scale = 0.0;
@@ -77,8 +77,9 @@ static void sym_tridiagonalise(std::vector<double>& a, int n, std::vector<double
     for (int j = 0; j <= l; ++j) A(j, i) = A(i, j) = 0.0;
   }
 }
-static int tridiagonal_ql(std::vector<double>& d, std::vector<double>& e, int n, std::vector<double>& z) {
-  auto Z = [&](int i, int j) -> double& { return z[(size_t)i * n + j]; };
+// z is stored TRANSPOSED here (row i = vector i): the plane rotations then update two contiguous rows
+static int tridiagonal_ql(std::vector<double>& d, std::vector<double>& e, int n, int ld, std::vector<double>& z) {
+  auto Z = [&](int i, int j) -> double& { return z[(size_t)j * ld + i]; };
   for (int i = 1; i < n; ++i) e[i - 1] = e[i];
   e[n - 1] = 0.0;
   for (int l = 0; l < n; ++l) {
@@ -130,8 +131,19 @@ static int sym_eig(std::vector<double>& a, int n, std::vector<double>& w) {
   std::vector<double> e((size_t)n);
   w.assign((size_t)n, 0.0);
   if (n == 1) { w[0] = a[0]; a[0] = 1.0; return 0; }
-  sym_tridiagonalise(a, n, w, e);
-  if (tridiagonal_ql(w, e, n, a)) return 1;
+  // row stride padded away from multiples of 256 B: the column walks of the reduction would otherwise hit one cache set
+  const int ld = (n >= 64 && n % 32 == 0) ? n + 8 : n;
+  {
+    std::vector<double> ap((size_t)n * ld, 0.0), zt((size_t)n * ld);
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) ap[(size_t)i * ld + j] = a[(size_t)i * n + j];
+    sym_tridiagonalise(ap, n, ld, w, e);
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) zt[(size_t)j * ld + i] = ap[(size_t)i * ld + j];
+    if (tridiagonal_ql(w, e, n, ld, zt)) return 1;
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) a[(size_t)i * n + j] = zt[(size_t)j * ld + i];
+  }
   std::vector<int> idx((size_t)n);
   for (int i = 0; i < n; ++i) idx[i] = i;
   std::sort(idx.begin(), idx.end(), [&](int x, int y) { return w[x] < w[y]; });

@@ -605,6 +605,15 @@ class CudaOps:
         call("v3s_cheb_combine", ptr(PY), ptr(Yk), ptr(Ykm1), float(alpha), float(beta), float(gamma), ptr(Y_out),
              ptr(Xf_out), PY.numel(), stream_ptr())
 
+    def sym_eig_host(self, A):
+        """Eigenpairs of a small symmetric matrix (numpy, host) by v3s_sym_eig_host: w ascending, vectors in columns."""
+        import numpy as np
+        a = np.ascontiguousarray(np.asarray(A, dtype=np.float64)).copy()
+        n = a.shape[0]
+        w = np.empty((n,), dtype=np.float64)
+        call("v3s_sym_eig_host", a.ctypes.data_as(C.POINTER(C.c_double)), n, w.ctypes.data_as(C.POINTER(C.c_double)))
+        return w, a
+
     # ---- stage 4 -----------------------------------------------------------------------------
     def fit_gram(self, Ps, Y):
         out = self.empty((162,), torch.float64)

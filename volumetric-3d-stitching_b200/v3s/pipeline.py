@@ -135,11 +135,15 @@ def eigen_stage(ops, plan, P_rows, dis, nev=NEV, validate=True, tol=None, stats=
         cols = [matvec(eye[:, j:j + 8].contiguous()) for j in range(0, N, 8)]
         Pd = torch.cat(cols, dim=1)
         Pd = 0.5 * (Pd + Pd.T)
-        w_all, V_all = torch.linalg.eigh(Pd)
-        w_np = w_all.cpu().numpy()
+        # full eigendecomposition of the small matrix by the library's own Householder + QL solver (host; the
+        # same routine that extracts Ritz pairs inside v3s_eig_topk) -- no LAPACK / cuSOLVER on the path
+        if hasattr(ops, "sym_eig_host"):
+            w_np, V_np = ops.sym_eig_host(Pd.cpu().numpy())
+        else:                                                 # CPU stand-in of the tests
+            w_np, V_np = np.linalg.eigh(Pd.cpu().numpy())
         idx = np.argsort(-np.abs(w_np), kind="stable")[:nev]
         lam = w_np[idx]
-        V = V_all[:, torch.as_tensor(idx, device=dev)]
+        V = torch.as_tensor(np.ascontiguousarray(V_np[:, idx]), dtype=torch.float64, device=dev)
         if stats is not None:
             stats.update({"matvecs": len(cols), "dense": True})
     elif hasattr(ops, "lanczos_step") and N >= 64:

@@ -17,7 +17,7 @@ class OrientationRecoverySolver:
 
     @staticmethod
     def solve(parameters, rotations=None, N_p=None, polar_mode=0, stats=None, check_sigma=True,
-              photons_per_pattern=None, noise_seed=0, copy_results=None, validate=True):
+              photons_per_pattern=None, noise_seed=0, copy_results=None, validate=True, images_dtype=np.float64):
         """solution.py:34-61 -> dict of numpy float64 arrays with the reference's 11 keys.
         Extensions that never change reference-mode results: `rotations` = explicit
         R (9,N) instead of the Hopf grid, `N_p` = free detector size, `check_sigma=False` = report
@@ -26,7 +26,8 @@ class OrientationRecoverySolver:
         The large outputs ('Images', 'S2', 'N') are numpy views of reusable pinned host buffers (filled by
         transfers that overlap stages 2-4).  `copy_results` None (default): results up to 256 MB are
         copied into private arrays like the reference's, larger ones stay views that are valid until the next
-        call of solve; True / False force either.  `validate=False` skips the eigenvalue / convergence guards (compute.py:59-79).
+        call of solve; True / False force either.  `images_dtype=np.float32` returns the pattern matrix in the precision
+        it is computed in (half the bytes over PCIe; the float64 default only widens the same values).  `validate=False` skips the eigenvalue / convergence guards (compute.py:59-79).
         Under torch.distributed (one process per GPU, world > 1) the job is row-sharded: every rank calls
         solve with the same arguments and gets the same replicated results, except 'Images', which holds
         the rank's own pattern rows [rows[0], rows[1]) (key 'rows'; the full matrix never leaves the GPUs)."""
@@ -54,7 +55,7 @@ class OrientationRecoverySolver:
         # the pattern matrix is by far the largest output: its host transfer starts as soon as stage 1
         # is done and overlaps stages 2-4 (side stream + worker thread)
         on_gpu = ops.device.type == 'cuda'
-        start_images = (lambda img: xfer.setdefault('Images', _util.AsyncFetch(img))) if on_gpu else None
+        start_images = (lambda img: xfer.setdefault('Images', _util.AsyncFetch(img, out_dtype=images_dtype))) if on_gpu else None
         # so are the kNN lists (final once the Markov matrix is built): they travel during the eigen-solver
 
         def start_lists(S2_dev, N_dev):
