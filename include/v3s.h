@@ -174,6 +174,29 @@ int v3s_gram_topk_plan(long long n_rows, long long n_cols, int k, int* out /* ho
 int v3s_gram_topk(const void* a16_all, long long n_cols, const void* a16_rows, long long n_rows, int Ppad, int k,
                   float eps_g, unsigned long long* lists, int* counts, int* overflow, int* ws, void* stream);
 
+/* The same selection with HALF the tensor-core work (G is symmetric: a tile on / above the diagonal serves its rows
+ * and, mirrored, its columns).  Two calls:
+ *  v3s_gram_topk_limits -- pass 1: v3s_gram_topk for the rank's rows against every `sample_stride`-th pattern only;
+ *    lim_rows [n_rows] = (k-th largest g~ of that sample) - 2 eps_g, a valid lower limit of the row's candidate band
+ *    (the k-th largest over a subset never exceeds the one over all patterns).  lists / counts / ws as for
+ *    v3s_gram_topk with n_cols = ceil(n_cols / sample_stride) in v3s_gram_topk_plan.
+ *  v3s_gram_topk_sym -- pass 2: the tiles with column tile >= row block of the n x n problem (this rank's share of
+ *    them), one list per pattern: element (r, c), c >= r, is appended to list r when g~ >= lim[r] and to list c when
+ *    c > r and g~ >= lim[c] (atomic slot counters; about sample_stride * k entries per list, capacity C; a counter
+ *    past C is reported by v3s_knn_merge_lists as overflow).  lim [n] must be complete on every rank.  peer_lists /
+ *    peer_counts (host arrays [world]): rank o's lists [cnt_o, C] and zero-initialised counters [cnt_o] as mapped in
+ *    THIS process (NVLink peer memory for o != rank): compute and exchange are one kernel; the caller synchronises the
+ *    ranks before v3s_knn_merge_lists (S = 1).  Rank o owns cnt_base + (o < rem) consecutive patterns.
+ *    step_ws: int [v3s_gram_topk_sym_steps(n, world)].                                                          */
+int v3s_gram_topk_limits(const void* a16_all, long long n_cols, const void* a16_rows, long long n_rows, int Ppad, int k,
+                         float eps_g, int sample_stride, unsigned long long* lists, int* counts, int* overflow, int* ws,
+                         float* lim_rows, void* stream);
+int v3s_gram_topk_sym_steps(long long n, int world);
+int v3s_gram_topk_sym(const void* a16_all, long long n, int Ppad, const float* lim, int C,
+                      const unsigned long long* peer_lists /* host [world] */,
+                      const unsigned long long* peer_counts /* host [world] */, int world, int rank, long long cnt_base,
+                      int rem, int* step_ws, void* stream);
+
 /* unite the S lists of every row: candidates = entries within 2 eps_g of the k-th largest g~ of the
  * union -> cand_ws int [n_rows,cap], count_ws int [n_rows] (input of v3s_knn_refine).  Zero-norm
  * patterns (NaN -> distance 0, distance.py:58; zero_flag [n_cols] may be NULL): a zero query row

@@ -94,6 +94,38 @@ def check(ops, N, P, k, r0, r1, seed, clustered=False):
     return dt
 
 
+def check_sym(ops, N, P, k, seed, clustered=False):
+    """Symmetric form (pass 1: limits from every 8th pattern; pass 2: tiles on / above the diagonal, both directions)
+    against the rectangular fused kernel: identical S2 / N (same refinement kernel on both sides)."""
+    rng = np.random.default_rng(seed)
+    if clustered:
+        base = rng.standard_normal((200, P)).astype(np.float32)
+        A = (base[rng.integers(0, 200, N)] + 0.5 * rng.standard_normal((N, P))).astype(np.float32)
+    else:
+        A = rng.random((N, P)).astype(np.float32) ** 3
+    img = ops.to_device(A, torch.float32)
+    a32, _, _, zf = ops.center_normalize(img, ops.column_sums(img) / N, want_split=False)
+    tiled, sym = ops.tiled_refine, ops.symmetric_gram
+    try:
+        ops.tiled_refine = False
+        ops.symmetric_gram = False
+        S2r, Nr = ops.knn_rows(None, None, a32, zf, 0, N, k)
+        ovr = int(ops.knn_overflow.item())
+        ops.symmetric_gram = True
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        S2s, Ns = ops.knn_rows(None, None, a32, zf, 0, N, k)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        ovs = int(ops.knn_overflow.item())
+        same = float((Ns == Nr).float().mean().item())
+        print("  symmetric N=%d P=%d k=%d: %.1f ms (whole kNN), identical S2 %s, same neighbours %.6f, overflow %d / %d"
+              % (N, P, k, dt * 1e3, bool(torch.equal(S2s, S2r)), same, ovs, ovr))
+        assert torch.equal(S2s, S2r) and torch.equal(Ns, Nr) and ovs == 0 and ovr == 0
+    finally:
+        ops.tiled_refine, ops.symmetric_gram = tiled, sym
+
+
 def perf(ops, N, P, k, nr, cg):
     """Throughput of the fused kernel alone on random unit rows (device-generated)."""
     from v3s import _lib
@@ -136,6 +168,11 @@ def main():
         cg, N, P, nr = (int(a) for a in sys.argv[2:6])
         perf(ops, N, P, 150, nr, cg)
         _lib.call("v3s_set_gram_topk_cta_group", 0)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "sym":
+        check_sym(ops, 20000, 1024, 150, 31)
+        check_sym(ops, 17001, 640, 100, 32, clustered=True)
+        print("symmetric check ok")
         return
     if len(sys.argv) > 1 and sys.argv[1] == "perf":
         for cg in (1, 2):

@@ -478,6 +478,262 @@ gram_topk_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_const
   }
 }
 
+// ---- symmetric form: half the tensor-core work -----------------------------------------------------------------
+// G is symmetric, so a tile on or above the diagonal serves both its rows AND (mirrored) its columns.  With one
+// list per pattern, appended to from any tile, the running threshold of the rectangular kernel has no single owner;
+// instead every pattern's lower limit is FIXED beforehand: pass 1 runs the rectangular kernel above against every
+// `sample_stride`-th pattern only (1/8 of the work) and the k-th largest g~ of that sample -- a valid lower bound
+// of the k-th largest over all patterns -- minus the band becomes lim[i].  Pass 2 (this kernel) computes the tiles
+// with col-tile >= row-block, and for every element (r, c), c >= r:
+//     g~ >= lim[r]  ->  list r gets (g~, c);      c > r and g~ >= lim[c]  ->  list c gets (g~, r)
+// (atomic slot counters; ~sample_stride * k entries per list).  Sharded jobs split the tile list over the ranks and
+// append into the owner rank's lists through NVLink peer mappings -- compute and exchange in one kernel.
+struct SymPeers {
+  unsigned long long* lists[8];      // rank o's lists [cnt_o, C]
+  int* counts[8];                    // rank o's slot counters [cnt_o]
+  int world, rem;
+  long long cnt_base;                // rank o owns cnt_base + (o < rem) consecutive patterns
+};
+__device__ __forceinline__ void sym_owner(const SymPeers& pr, long long x, int& o, long long& lo) {
+  const long long big = pr.cnt_base + 1, split = big * pr.rem;
+  if (x < split) { o = (int)(x / big); lo = o * big; }
+  else { o = pr.rem + (int)((x - split) / pr.cnt_base); lo = split + (long long)(o - pr.rem) * pr.cnt_base; }
+}
+struct SymPlan {
+  int n_rb, n_cb;      // row blocks of 128*CG patterns, column tiles of 256 patterns
+  int PR, PC;          // a step = a patch of PR x PC tiles shared by all workers of all ranks
+  int steps;           // patches that touch the upper triangle
+  int rank, world, workers;
+};
+// patch `step` (in the order both sides enumerate) -> (pr, pc); returns false past the end
+__host__ __device__ inline int sym_count_steps(const SymPlan& p, int rows_per_block) {
+  int n = 0;
+  const int gr = (p.n_rb + p.PR - 1) / p.PR, gc = (p.n_cb + p.PC - 1) / p.PC;
+  for (int pr = 0; pr < gr; ++pr)
+    for (int pc = 0; pc < gc; ++pc)
+      if ((long long)(pc * p.PC + p.PC) * TK_BN - 1 >= (long long)pr * p.PR * rows_per_block) ++n;
+  return n;
+}
+
+template <int CG>
+__global__ void __launch_bounds__(TK_THREADS, 1)
+gram_sym_topk_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constant__ CUtensorMap tm_cols, int n,
+                     int num_kb, const SymPlan plan, const float* __restrict__ lim, int C, const SymPeers peers,
+                     int* __restrict__ step_sync) {
+  using Cfg = TopkCfg<CG>;
+  constexpr int STAGES = Cfg::STAGES, A_BYTES = Cfg::A_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES;
+  constexpr int RB = TK_BM * CG;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tfull = bars + 2 * STAGES;
+  uint64_t* tempty = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  __shared__ float s_clim[2][TK_BN];          // lower limits of the tile's columns, per accumulator stage
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  const int worker = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int slot = plan.rank * plan.workers + worker;           // this worker's tile of every patch
+  const int dr = slot / plan.PC, dc = slot % plan.PC;
+  const int gr = (plan.n_rb + plan.PR - 1) / plan.PR, gc = (plan.n_cb + plan.PC - 1) / plan.PC;
+
+  if (warp == 4 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_rows) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_cols) : "memory");
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], CG); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4 * CG); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (CG == 2) cluster_sync_all();
+  if (warp == 5) {
+    if constexpr (CG == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+  }
+  tk_fence_before();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  tk_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // every role walks the same patch sequence; `valid` = this worker has a tile (on or above the diagonal) in it
+#define SYM_FOR_EACH_STEP(BODY)                                                                                      \
+  {                                                                                                                  \
+    int step = 0;                                                                                                    \
+    for (int pr = 0; pr < gr; ++pr)                                                                                  \
+      for (int pc = 0; pc < gc; ++pc) {                                                                              \
+        if ((long long)(pc * plan.PC + plan.PC) * TK_BN - 1 < (long long)pr * plan.PR * RB) continue;                \
+        const int rb = pr * plan.PR + dr, cb = pc * plan.PC + dc;                                                    \
+        const bool valid = dr < plan.PR && rb < plan.n_rb && cb < plan.n_cb &&                                       \
+                           (long long)cb * TK_BN + TK_BN - 1 >= (long long)rb * RB;                                  \
+        BODY                                                                                                         \
+        ++step;                                                                                                      \
+      }                                                                                                              \
+  }
+
+  if (warp == 4) {
+    int stage = 0;
+    uint32_t phase = 0;
+    const int target = (int)(gridDim.x);                       // every CTA of this rank arrives at every step
+    SYM_FOR_EACH_STEP({
+      int* ctr = step_sync + step;
+      if (lane == 0) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(ctr) : "memory");
+      if (valid) {
+        int seen;
+        long long t_start = 0;
+        do {
+          asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
+          if (seen < target) {
+            __nanosleep(64);
+            const long long now = clock64();
+            if (t_start == 0) t_start = now;
+            else if (now - t_start > 2000000000LL) break;
+          }
+        } while (seen < target);
+        __syncwarp();
+        const int row0 = rb * RB + (int)cta_rank * TK_BM;
+        const int col0 = cb * TK_BN + (int)cta_rank * (TK_BN / CG);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          if (elect_one()) {
+            const uint32_t s = smem_u32(smem + stage * STAGE_BYTES);
+            if constexpr (CG == 1) {
+              mbar_expect_tx(&full[stage], STAGE_BYTES);
+            } else {
+              if (leader) mbar_expect_tx(&full[stage], 2 * STAGE_BYTES);
+              else mbar_arrive_remote(&full[stage], 0);
+            }
+            tk_tma_load<CG>(s, &tm_rows, kb * TK_BK, row0, &full[stage]);
+            tk_tma_load<CG>(s + A_BYTES, &tm_cols, kb * TK_BK, col0, &full[stage]);
+          }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    })
+  } else if (warp == 5) {
+    if (leader) {
+      constexpr uint32_t idesc = tk_idesc<CG>();
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      SYM_FOR_EACH_STEP({
+        if (valid) {
+          mbar_wait(&tempty[acc], acc_phase ^ 1);
+          tk_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TK_BN);
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(&full[stage], phase);
+            tk_fence_after();
+            const uint32_t s = smem_u32(smem + stage * STAGE_BYTES);
+            const uint64_t a_desc = tk_kmajor_desc(s);
+            const uint64_t b_desc = tk_kmajor_desc(s + A_BYTES);
+            if (elect_one()) {
+              tk_umma_kblock<CG>(d_tmem, a_desc, b_desc, idesc, kb > 0 ? 1u : 0u);
+              tk_commit<CG>(&empty[stage]);
+              if (kb == num_kb - 1) tk_commit<CG>(&tfull[acc]);
+            }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
+        }
+      })
+    }
+  } else {
+    // ---------------- epilogue: one pattern row per thread, both directions of every element on / above the diagonal ----
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    SYM_FOR_EACH_STEP({
+      if (valid) {
+        const int row = rb * RB + (int)cta_rank * TK_BM + warp * 32 + lane;        // global pattern index
+        const bool row_ok = row < n;
+        const float rlim = row_ok ? lim[row] : 3.0e38f;
+        int ro = 0;
+        long long rlo = 0;
+        if (row_ok) sym_owner(peers, row, ro, rlo);
+        unsigned long long* Lr = peers.lists[ro] + (long long)(row - rlo) * C;
+        int* Cr = peers.counts[ro] + (row - rlo);
+        // the column limits of this tile -> shared memory (stage `acc`); all four epilogue warps, then a named barrier
+        for (int j = threadIdx.x; j < TK_BN; j += 128) {
+          const int c = cb * TK_BN + j;
+          s_clim[acc][j] = c < n ? lim[c] : 3.0e38f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        mbar_wait(&tfull[acc], acc_phase);
+        tk_fence_after();
+        const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * TK_BN);
+        // A slot counter's atomicAdd takes an L2 round trip.  The entry of a hit is therefore stored only when the
+        // thread's NEXT hit (or the end of the tile) comes: the round trip overlaps the compares in between
+        // (stored right away, ~6 hits per thread and tile kept the epilogue as long as the tile's MMAs).
+        int rpos = -1;
+        int cpos = -1;
+        unsigned long long rent = 0ull;
+        unsigned long long cent = 0ull;
+        unsigned long long* cL = nullptr;
+#pragma unroll 1
+        for (int ch = 0; ch < TK_BN / 32; ++ch) {
+          uint32_t v[32];
+          tk_tmem_ld32(t_row + (uint32_t)(ch * 32), v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          const int col0 = cb * TK_BN + ch * 32;
+          if (col0 + 31 < row || !row_ok) continue;                   // this chunk lies entirely below the diagonal (per thread)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int c = col0 + j;
+            const float g = __uint_as_float(v[j]) * TK_ACC_SCALE;
+            if (c >= row && c < n) {
+              if (g >= rlim) {
+                if (rpos >= 0 && rpos < C) Lr[rpos] = rent;
+                rpos = atomicAdd(Cr, 1);
+                rent = ((unsigned long long)__float_as_uint(g) << 32) | (unsigned)c;
+              }
+              if (c > row && g >= s_clim[acc][ch * 32 + j]) {
+                if (cpos >= 0 && cpos < C) cL[cpos] = cent;
+                int co;
+                long long clo;
+                sym_owner(peers, c, co, clo);
+                cpos = atomicAdd(peers.counts[co] + (c - clo), 1);
+                cL = peers.lists[co] + (long long)(c - clo) * C;
+                cent = ((unsigned long long)__float_as_uint(g) << 32) | (unsigned)row;
+              }
+            }
+          }
+        }
+        if (rpos >= 0 && rpos < C) Lr[rpos] = rent;
+        if (cpos >= 0 && cpos < C) cL[cpos] = cent;
+        tk_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CG == 1) mbar_arrive(&tempty[acc]);
+          else mbar_arrive_remote(&tempty[acc], 0);
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    })
+  }
+#undef SYM_FOR_EACH_STEP
+  tk_fence_before();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 5) {
+    tk_fence_after();
+    if constexpr (CG == 1)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
 // FP16 Gram operand of centred unit rows: fl16(2^8 a), zero padded to Ppad columns
 __global__ void split_f16_kernel(const float* __restrict__ a, long long n_rows, int P, int Ppad, __half* __restrict__ out) {
   const long long total = n_rows * (long long)(Ppad / 2);
@@ -532,7 +788,11 @@ knn_merge_kernel(const unsigned long long* __restrict__ lists, const int* __rest
     if (tid == 0) s_n = 0;
     __syncthreads();
     for (int sgm = 0; sgm < S; ++sgm) {
-      const int c = counts[(long long)r * S + sgm];
+      int c = counts[(long long)r * S + sgm];
+      if (c > C) {                                           // symmetric form: a slot counter ran past its list
+        if (tid == 0 && overflow) atomicAdd(overflow, 1);
+        c = C;
+      }
       const unsigned long long* L = lists + ((long long)r * S + sgm) * C;
       __shared__ int s_base;
       if (tid == 0) { s_base = s_n; s_n += c; }
@@ -727,6 +987,63 @@ __global__ void cluster_tiles_kernel(const int* __restrict__ ends, int n_bins, i
     ++nt;
   }
   tiles[0] = nt < max_tiles ? nt : max_tiles;
+}
+
+// lower limit of every row's candidate band from the lists of a SAMPLE of the columns (pass 1 of the symmetric
+// form): lim = (k-th largest g~ of the union of the row's lists) - band, or -inf while fewer than k were seen
+__global__ void __launch_bounds__(kMergeThreads)
+knn_limits_kernel(const unsigned long long* __restrict__ lists, const int* __restrict__ counts, int S, int C, int n_rows,
+                  int k, float band, float* __restrict__ lim_out) {
+  extern __shared__ unsigned long long s_ent[];
+  __shared__ int hist[256];
+  __shared__ int s_n, s_base;
+  __shared__ uint32_t s_prefix;
+  __shared__ int s_remaining;
+  const int tid = threadIdx.x;
+  for (int r = blockIdx.x; r < n_rows; r += gridDim.x) {
+    __syncthreads();
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    for (int sgm = 0; sgm < S; ++sgm) {
+      const int c = min(counts[(long long)r * S + sgm], C);
+      const unsigned long long* L = lists + ((long long)r * S + sgm) * C;
+      if (tid == 0) { s_base = s_n; s_n += c; }
+      __syncthreads();
+      for (int i = tid; i < c; i += kMergeThreads) s_ent[s_base + i] = L[i];
+      __syncthreads();
+    }
+    const int n = s_n;
+    if (n < k) {
+      if (tid == 0) lim_out[r] = -3.0e38f;
+      continue;
+    }
+    uint32_t prefix = 0, mask = 0;
+    int remaining = k;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+      for (int i = tid; i < 256; i += kMergeThreads) hist[i] = 0;
+      __syncthreads();
+      for (int i = tid; i < n; i += kMergeThreads) {
+        const uint32_t key = float_to_key(__uint_as_float((uint32_t)(s_ent[i] >> 32)));
+        if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int cum = 0, d = 255;
+        for (; d > 0; --d) {
+          if (cum + hist[d] >= remaining) break;
+          cum += hist[d];
+        }
+        s_prefix = prefix | ((uint32_t)d << shift);
+        s_remaining = remaining - cum;
+      }
+      __syncthreads();
+      prefix = s_prefix;
+      remaining = s_remaining;
+      mask |= 255u << shift;
+      __syncthreads();
+    }
+    if (tid == 0) lim_out[r] = key_to_float(prefix) - band;
+  }
 }
 
 // indices of the zero-norm patterns: ws[0] = count (may exceed cap), ws[1 + i] = index (first cap only)
@@ -957,5 +1274,150 @@ extern "C" int v3s_knn_merge_lists(const unsigned long long* lists, const int* c
       V3S_CHECK_LAUNCH();
     }
   }
+  return 0;
+}
+
+
+// ---- symmetric form, host side ---------------------------------------------------------------------------------
+static int g_sym_cg = 2;
+
+// Pass 1: lower limits lim [n_rows] of the rows' candidate bands from every `sample_stride`-th pattern (the
+// rectangular fused kernel on a strided view of a16_all; lists / counts / ws sized by v3s_gram_topk_plan for
+// (n_rows, ceil(n_cols / sample_stride), k)).
+extern "C" int v3s_gram_topk_limits(const void* a16_all, long long n_cols, const void* a16_rows, long long n_rows, int Ppad,
+                                    int k, float eps_g, int sample_stride, unsigned long long* lists, int* counts, int* overflow,
+                                    int* ws, float* lim_rows, void* stream) {
+  V3S_REQUIRE(sample_stride >= 1 && lim_rows, "v3s_gram_topk_limits: bad arguments");
+  const long long ns = ceil_div64(n_cols, sample_stride);
+  V3S_REQUIRE(k <= ns, "v3s_gram_topk_limits: the column sample (%lld) is smaller than k", ns);
+  if (n_rows == 0) return 0;
+  const int cg = topk_cta_group(n_rows, ns);
+  int pl[4];
+  if (v3s_gram_topk_plan(n_rows, ns, k, pl)) return 1;
+  V3S_CUDA(cudaMemsetAsync(ws, 0, sizeof(int) * (size_t)pl[3], (cudaStream_t)stream));
+  const int workers = topk_workers(cg);
+  const TopkPlan plan = make_topk_plan(n_rows, ns, cg, workers);
+  const int C = pl[1];
+  CUtensorMap mr, ma;
+  if (make_tmap_2d(&mr, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a16_rows, n_rows, Ppad, (long long)Ppad * 2, TK_BK, TK_BM,
+                   CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  if (make_tmap_2d(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a16_all, ns, Ppad, (long long)Ppad * 2 * sample_stride, TK_BK, TK_BN / cg,
+                   CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  const float band = 2.0f * eps_g;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int num_kb = Ppad / TK_BK;
+  unsigned int* tau_keys = reinterpret_cast<unsigned int*>(ws);
+  int* step_sync = ws + pl[2];
+  int rc;
+#define V3S_TOPK_LAUNCH(CGV, EPLV) rc = launch_topk<CGV, EPLV>(mr, ma, n_rows, ns, num_kb, plan, workers, k, band, lists, counts, overflow, tau_keys, step_sync, st)
+  if (cg == 1) {
+    if (C == 256) V3S_TOPK_LAUNCH(1, 8); else if (C == 512) V3S_TOPK_LAUNCH(1, 16); else V3S_TOPK_LAUNCH(1, 32);
+  } else {
+    if (C == 256) V3S_TOPK_LAUNCH(2, 8); else if (C == 512) V3S_TOPK_LAUNCH(2, 16); else V3S_TOPK_LAUNCH(2, 32);
+  }
+#undef V3S_TOPK_LAUNCH
+  if (rc) return rc;
+  const size_t smem = (size_t)pl[0] * C * 8;
+  V3S_REQUIRE(smem <= 200 * 1024, "v3s_gram_topk_limits: S*C = %d entries exceed shared memory", pl[0] * C);
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    V3S_CUDA(cudaFuncSetAttribute(knn_limits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  const int grid = (int)(n_rows < 16LL * kNumSMs ? n_rows : 16LL * kNumSMs);
+  knn_limits_kernel<<<grid, kMergeThreads, smem, st>>>(lists, counts, pl[0], C, (int)n_rows, k, band, lim_rows);
+  V3S_CHECK_LAUNCH();
+  return 0;
+}
+
+template <int CG>
+static int sym_workers() {
+  auto kern = gram_sym_topk_kernel<CG>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TopkCfg<CG>::SMEM) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return kNumSMs / CG;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)kNumSMs);
+  cfg.blockDim = dim3(TK_THREADS);
+  cfg.dynamicSmemBytes = TopkCfg<CG>::SMEM;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int nc = 0;
+  if (cudaOccupancyMaxActiveClusters(&nc, kern, &cfg) != cudaSuccess || nc < 1) { (void)cudaGetLastError(); nc = kNumSMs / CG; }
+  return nc < kNumSMs / CG ? nc : kNumSMs / CG;
+}
+static SymPlan make_sym_plan(long long n, int cg, int workers, int rank, int world) {
+  SymPlan p{};
+  p.n_rb = (int)ceil_div64(n, TK_BM * cg);
+  p.n_cb = (int)ceil_div64(n, TK_BN);
+  const int total = workers * world;
+  int pc = 1;
+  while ((pc + 1) * (pc + 1) <= total) ++pc;               // floor(sqrt(total))
+  if (pc * (pc + 1) <= total) ++pc;                         // a slightly wide patch wastes fewer workers
+  p.PC = pc;
+  p.PR = total / pc;
+  p.rank = rank; p.world = world; p.workers = workers;
+  p.steps = sym_count_steps(p, TK_BM * cg);
+  return p;
+}
+// ints of the step-counter workspace of v3s_gram_topk_sym for n patterns on `world` ranks
+extern "C" int v3s_gram_topk_sym_steps(long long n, int world) {
+  if (n < 1 || world < 1 || world > 8) return 0;
+  static int w2 = 0;
+  if (!w2) w2 = sym_workers<2>();
+  return make_sym_plan(n, g_sym_cg, w2, 0, world).steps + 1;
+}
+
+// Pass 2: the tiles on / above the diagonal of the n x n Gram matrix, this rank's share; appends (g~, index) to the
+// lists of BOTH patterns of every element that reaches their limit lim [n] (complete on every rank).  peer_lists /
+// peer_counts (host arrays [world]): rank o's lists [cnt_o, C] (64-bit entries) and slot counters [cnt_o] (zeroed by
+// the caller) as mapped in THIS process; rank o owns cnt_base + (o < rem) consecutive patterns.  step_ws: int
+// [v3s_gram_topk_sym_steps(n, world)] (zeroed here).  The caller synchronises the ranks before reading its lists.
+extern "C" int v3s_gram_topk_sym(const void* a16_all, long long n, int Ppad, const float* lim, int C,
+                                 const unsigned long long* peer_lists /* host [world] */,
+                                 const unsigned long long* peer_counts /* host [world] */, int world, int rank,
+                                 long long cnt_base, int rem, int* step_ws, void* stream) {
+  V3S_REQUIRE(Ppad > 0 && Ppad % 64 == 0 && n >= 1 && n < (1LL << 31), "v3s_gram_topk_sym: bad shape");
+  V3S_REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world && cnt_base >= 1 && rem >= 0 && rem < world &&
+                  cnt_base * world + rem == n, "v3s_gram_topk_sym: bad sharding");
+  V3S_REQUIRE(lim && peer_lists && peer_counts && step_ws && C >= 32, "v3s_gram_topk_sym: null argument");
+  static int w2 = 0;
+  if (!w2) w2 = sym_workers<2>();
+  const int workers = w2;
+  const SymPlan plan = make_sym_plan(n, 2, workers, rank, world);
+  cudaStream_t st = (cudaStream_t)stream;
+  V3S_CUDA(cudaMemsetAsync(step_ws, 0, sizeof(int) * (size_t)(plan.steps + 1), st));
+  SymPeers pr{};
+  for (int i = 0; i < world; ++i) {
+    pr.lists[i] = reinterpret_cast<unsigned long long*>(peer_lists[i]);
+    pr.counts[i] = reinterpret_cast<int*>(peer_counts[i]);
+  }
+  pr.world = world; pr.rem = rem; pr.cnt_base = cnt_base;
+  CUtensorMap mr, mc;
+  if (make_tmap_2d(&mr, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a16_all, n, Ppad, (long long)Ppad * 2, TK_BK, TK_BM,
+                   CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  if (make_tmap_2d(&mc, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a16_all, n, Ppad, (long long)Ppad * 2, TK_BK, TK_BN / 2,
+                   CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  auto kern = gram_sym_topk_kernel<2>;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(TK_THREADS);
+  cfg.dynamicSmemBytes = TopkCfg<2>::SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cfg.gridDim = dim3((unsigned)(workers * 2));
+  V3S_CUDA(cudaLaunchKernelEx(&cfg, kern, mr, mc, (int)n, Ppad / TK_BK, plan, lim, C, pr, step_ws));
+  ++v3s::g_kernel_launches;
   return 0;
 }

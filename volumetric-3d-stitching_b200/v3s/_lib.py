@@ -63,6 +63,9 @@ SIGNATURES = {
     "v3s_set_gram_topk_cta_group": (i32, [i32]),
     "v3s_gram_topk_plan": (i32, [i64, i64, i32, C.POINTER(i32)]),
     "v3s_gram_topk": (i32, [p, i64, p, i64, i32, i32, C.c_float, p, p, p, p, p]),
+    "v3s_gram_topk_limits": (i32, [p, i64, p, i64, i32, i32, C.c_float, i32, p, p, p, p, p, p]),
+    "v3s_gram_topk_sym_steps": (i32, [i64, i32]),
+    "v3s_gram_topk_sym": (i32, [p, i64, i32, p, i32, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), i32, i32, i64, i32, p, p]),
     "v3s_knn_merge_lists": (i32, [p, p, i32, i32, i64, i64, i64, i32, C.c_float, i32, p, p, p, p, p, i32, p, i32, i32, p, p]),
     "v3s_knn_refine_tile_rows": (i32, [i32]),
     "v3s_knn_refine_tiled": (i32, [p, p, i32, i64, i64, i64, i32, i32, p, p, p, p, p, p, p, p, i32, p, p, p, i32, p]),

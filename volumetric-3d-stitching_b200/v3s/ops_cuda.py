@@ -30,6 +30,7 @@ def fused_gram_error_bound(P):
     return 2.0 ** -10 * (1.0 + 2.0 ** -11) + 1.2e-7 * (P / 16.0) + 2e-6
 
 
+SYM_SAMPLE_STRIDE = 8   # symmetric fused Gram: pass 1 looks at every 8th pattern to fix the rows' lower limits
 PANEL_BYTES = 4 << 30   # Gram row panel budget when G is streamed in panels
 SYM_BYTES = 48 << 30    # the whole symmetric G is materialised (half the MMA work) up to this size
 
@@ -100,6 +101,7 @@ class CudaOps:
         self._symm_G = {}
         self.dedup_refine = True     # exact-distance refinement: mutual candidate pairs once (select.cu)
         self.tiled_refine = True     # ... tiled over neighbouring rows for long rows (refine_tiled_kernel)
+        self.symmetric_gram = True   # fused Gram / top-k on the upper-triangle tiles only (gram_sym_topk_kernel) for large N
         self.use_fused_matvec = True # eigen-solver mat-vecs with the reduction / recurrence / exchange fused (FusedOperator)
         self.use_peer_gram = True    # sharded jobs: symmetric Gram with NVLink peer stores (else rectangular panels)
         self.operator = "auto"       # Markov operator of the eigen-solver: "dense" (FP32 rows), "sparse" (FP64 lists), "auto"
@@ -246,17 +248,42 @@ class CudaOps:
         Nbr = self.empty((nr, k), torch.int32)
         if nr == 0:
             return S2, Nbr
-        pl = (C.c_int * 4)()
-        call("v3s_gram_topk_plan", nr, N, k, pl)
-        S, Cc, rows_pad = int(pl[0]), int(pl[1]), int(pl[2])
-        lists = self.empty((rows_pad * S * Cc,), torch.int64)
-        counts = self.empty((rows_pad * S,), torch.int32)
-        tws = self.empty((int(pl[3]),), torch.int32)
         self.knn_overflow = self.zeros((1,), torch.int32)
         eps_g = fused_gram_error_bound(P)
+        stride = SYM_SAMPLE_STRIDE
+        # symmetric form (half the MMA work + a 1/stride sampling pass) for whole, large problems
+        sym = self.symmetric_gram and r0 == 0 and nr == N and N >= 16384 and (N + stride - 1) // stride >= 4 * k
+        pl = (C.c_int * 4)()
         h = self._tic("gram")
-        call("v3s_gram_topk", ptr(a16_all), N, ptr(a16_all[r0:r1]), nr, a16_all.shape[1], k, eps_g, ptr(lists), ptr(counts),
-             ptr(self.knn_overflow), ptr(tws), stream_ptr())
+        if sym:
+            ns = (N + stride - 1) // stride
+            call("v3s_gram_topk_plan", nr, ns, k, pl)
+            S1, C1, rows_pad1 = int(pl[0]), int(pl[1]), int(pl[2])
+            lists1 = self.empty((rows_pad1 * S1 * C1,), torch.int64)
+            counts1 = self.empty((rows_pad1 * S1,), torch.int32)
+            tws1 = self.empty((int(pl[3]),), torch.int32)
+            lim = self.empty((N,), torch.float32)
+            h1 = self._tic("gram_limits_pass")
+            call("v3s_gram_topk_limits", ptr(a16_all), N, ptr(a16_all[r0:r1]), nr, a16_all.shape[1], k, eps_g, stride, ptr(lists1),
+                 ptr(counts1), ptr(self.knn_overflow), ptr(tws1), ptr(lim), stream_ptr())
+            self._toc(h1)
+            S, Cc = 1, 2048
+            while Cc < 1.5 * stride * k + 256:
+                Cc *= 2
+            lists = self.empty((N * Cc,), torch.int64)
+            counts = self.zeros((N,), torch.int32)
+            step_ws = self.empty((int(_lib.lib.v3s_gram_topk_sym_steps(N, 1)),), torch.int32)
+            pls = (C.c_ulonglong * 1)(lists.data_ptr())
+            pcs = (C.c_ulonglong * 1)(counts.data_ptr())
+            call("v3s_gram_topk_sym", ptr(a16_all), N, a16_all.shape[1], ptr(lim), Cc, pls, pcs, 1, 0, N, 0, ptr(step_ws), stream_ptr())
+        else:
+            call("v3s_gram_topk_plan", nr, N, k, pl)
+            S, Cc, rows_pad = int(pl[0]), int(pl[1]), int(pl[2])
+            lists = self.empty((rows_pad * S * Cc,), torch.int64)
+            counts = self.empty((rows_pad * S,), torch.int32)
+            tws = self.empty((int(pl[3]),), torch.int32)
+            call("v3s_gram_topk", ptr(a16_all), N, ptr(a16_all[r0:r1]), nr, a16_all.shape[1], k, eps_g, ptr(lists), ptr(counts),
+                 ptr(self.knn_overflow), ptr(tws), stream_ptr())
         self._toc(h)
         cap = min(k + KNN_MARGIN + KNN_EXTRA_CAP, N)
         cand = self.empty((nr, cap), torch.int32)
