@@ -306,6 +306,8 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the v3s path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # the all-gather of the FP32 rows runs beside the persistent Gram kernel on the SMs it leaves free
+        os.environ.setdefault("NCCL_MAX_CTAS", "16")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from v3s import _lib, _util
     from v3s.pipeline import ShardPlan, run_pipeline

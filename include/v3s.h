@@ -156,6 +156,10 @@ int v3s_split_f16(const float* a_f32, long long n_rows, int P, int Ppad, void* a
  * staging half of the shared column tile; 1 = one CTA per SM, M=128 N=256; 0 (default) = by size.   */
 int v3s_set_gram_topk_cta_group(int cg);
 
+/* SMs the persistent fused Gram kernels leave free (default 0): a collective running beside them (the all-gather of
+ * the FP32 rows in a sharded job) needs a few, and the kernels' workers must all be resident at once.             */
+int v3s_set_gram_reserved_sms(int sms);
+
 /* buffer sizes of v3s_gram_topk for a problem: out[0] = S lists per row (column segments),
  * out[1] = C entries per list, out[2] = padded row count of `lists` / `counts`, out[3] = ints of `ws`. */
 int v3s_gram_topk_plan(long long n_rows, long long n_cols, int k, int* out /* host [4] */);

@@ -103,6 +103,20 @@ for (N, n, n_p, k) in ((3001, 15, 31, 250), (5000, 15, 48, 200)):
     ok &= ang_fn < 1e-6
     if not ok:
         print(f"rank {rank} N={N}: CHECK FAILED (connected={connected})", flush=True)
+# --- sharded SYMMETRIC fused Gram / top-k (N >= 16384: each rank computes its share of the upper-triangle tiles and
+#     appends candidates into the owners' lists over NVLink) against the same kNN on one GPU
+N, n, n_p, k = 20000, 7, 40, 100
+R9, _ = orc.random_rotations(N, seed=5)
+ed = ops.to_device(orc.synthesize_3d(n)["ED"].astype(np.float32), torch.float32)
+img_all = ops.synth_patterns(ed, Projector.rot9_rowmajor(R9, ops), n_p)
+plan, one = ShardPlan.from_env(N), ShardPlan(N)
+S2s, Ns_ = knn_stage(ops, plan, img_all[plan.lo:plan.hi].contiguous(), k)
+ov_s = int(ops.knn_overflow.item())
+S21, N1_ = knn_stage(ops, one, img_all, k)
+same = float((Ns_ == N1_).float().mean().item())
+dmax = float((S2s - S21).abs().max().item())
+print(f"rank {rank} N={N}: sharded symmetric kNN vs one GPU: max |dS2| {dmax:.2e}, same neighbours {same:.6f}, overflow {ov_s}", flush=True)
+ok &= dmax == 0.0 and same == 1.0 and ov_s == 0
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:

@@ -1083,10 +1083,19 @@ static int topk_query_workers() {
   if (cudaOccupancyMaxActiveClusters(&nc, kern, &cfg) != cudaSuccess || nc < 1) { (void)cudaGetLastError(); nc = kNumSMs / CG; }
   return nc < kNumSMs / CG ? nc : kNumSMs / CG;
 }
+static int g_reserved_sms = 0;
 static int topk_workers(int cg) {
   static int w[3] = {0, 0, 0};
   if (w[cg] == 0) w[cg] = (cg == 1) ? topk_query_workers<1>() : topk_query_workers<2>();
-  return w[cg];
+  const int r = w[cg] - (g_reserved_sms + cg - 1) / cg;
+  return r < 1 ? 1 : r;
+}
+// SMs the persistent Gram kernels leave free (0 = none): a collective that runs BESIDE the kernel needs a few, and
+// the kernel's workers must all be resident at once (they start every tile together)
+extern "C" int v3s_set_gram_reserved_sms(int sms) {
+  V3S_REQUIRE(sms >= 0 && sms <= 64, "v3s_set_gram_reserved_sms: 0..64");
+  g_reserved_sms = sms;
+  return 0;
 }
 
 static TopkPlan make_topk_plan(long long n_rows, long long n_cols, int cg, int workers) {

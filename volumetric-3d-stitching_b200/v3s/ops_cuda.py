@@ -102,6 +102,11 @@ class CudaOps:
         self.dedup_refine = True     # exact-distance refinement: mutual candidate pairs once (select.cu)
         self.tiled_refine = True     # ... tiled over neighbouring rows for long rows (refine_tiled_kernel)
         self.symmetric_gram = True   # fused Gram / top-k on the upper-triangle tiles only (gram_sym_topk_kernel) for large N
+        # ... in a sharded job too (each rank a share of the tiles, appends into the owners' lists over NVLink).  Correct
+        # (tests/multi_gpu_check.py) but off by default: the remote slot-counter atomics cost more than the halved MMA
+        # work saves (cfg 4 on 2 GPUs: 281 ms against ~250 ms with the rectangular kernel per rank)
+        self.symmetric_gram_sharded = False
+        self.overlap_reserved_sms = 16   # SMs left to NCCL while the all-gather of the FP32 rows overlaps the Gram kernel
         self.use_fused_matvec = True # eigen-solver mat-vecs with the reduction / recurrence / exchange fused (FusedOperator)
         self.use_peer_gram = True    # sharded jobs: symmetric Gram with NVLink peer stores (else rectangular panels)
         self.operator = "auto"       # Markov operator of the eigen-solver: "dense" (FP32 rows), "sparse" (FP64 lists), "auto"
@@ -238,7 +243,7 @@ class CudaOps:
         call("v3s_split_f16", ptr(a32), n, P, Ppad, ptr(a16), stream_ptr())
         return a16
 
-    def knn_rows_fused(self, a16_all, a32_all, zero_flag, r0, r1, k, order=None):
+    def knn_rows_fused(self, a16_all, a32_all, zero_flag, r0, r1, k, order=None, plan=None, a32_ready=None):
         """k nearest neighbours of rows [r0,r1) with the selection fused into the Gram kernel's epilogue:
         v3s_gram_topk (candidate lists per row and column segment) -> v3s_knn_merge_lists (value band around
         the k-th largest) -> v3s_knn_refine (exact distances from the FP32 rows, sort)."""
@@ -250,9 +255,23 @@ class CudaOps:
             return S2, Nbr
         self.knn_overflow = self.zeros((1,), torch.int32)
         eps_g = fused_gram_error_bound(P)
-        stride = SYM_SAMPLE_STRIDE
-        # symmetric form (half the MMA work + a 1/stride sampling pass) for whole, large problems
-        sym = self.symmetric_gram and r0 == 0 and nr == N and N >= 16384 and (N + stride - 1) // stride >= 4 * k
+        if a32_ready is not None:                      # leave room for the collective that runs beside the Gram kernel
+            call("v3s_set_gram_reserved_sms", self.overlap_reserved_sms)
+        import os as _os
+        stride = int(_os.environ.get('V3S_SYM_STRIDE', SYM_SAMPLE_STRIDE))
+        # symmetric form (half the MMA work + a 1/stride sampling pass) for large problems: the whole matrix on one
+        # GPU, or the rank's share of the upper-triangle tiles with appends into the owners' lists over NVLink
+        world = 1 if plan is None else plan.world
+        whole = (r0 == 0 and nr == N) if world == 1 else (r0 == plan.lo and r1 == plan.hi)
+        sym = (self.symmetric_gram and whole and N >= 16384 and (N + stride - 1) // stride >= 4 * k and world <= 8
+               and (world == 1 or (self.symmetric_gram_sharded and self.use_peer_gram and min(plan.counts) >= 1)))
+        Csym = 2048
+        while Csym < 1.5 * stride * k + 256:
+            Csym *= 2
+        peer = None
+        if sym and world > 1:
+            peer = self._sym_lists_arena(plan, Csym)
+            sym = peer is not None
         pl = (C.c_int * 4)()
         h = self._tic("gram")
         if sym:
@@ -262,20 +281,31 @@ class CudaOps:
             lists1 = self.empty((rows_pad1 * S1 * C1,), torch.int64)
             counts1 = self.empty((rows_pad1 * S1,), torch.int32)
             tws1 = self.empty((int(pl[3]),), torch.int32)
-            lim = self.empty((N,), torch.float32)
+            lim_loc = self.empty((nr,), torch.float32)
             h1 = self._tic("gram_limits_pass")
             call("v3s_gram_topk_limits", ptr(a16_all), N, ptr(a16_all[r0:r1]), nr, a16_all.shape[1], k, eps_g, stride, ptr(lists1),
-                 ptr(counts1), ptr(self.knn_overflow), ptr(tws1), ptr(lim), stream_ptr())
+                 ptr(counts1), ptr(self.knn_overflow), ptr(tws1), ptr(lim_loc), stream_ptr())
             self._toc(h1)
-            S, Cc = 1, 2048
-            while Cc < 1.5 * stride * k + 256:
-                Cc *= 2
-            lists = self.empty((N * Cc,), torch.int64)
-            counts = self.zeros((N,), torch.int32)
-            step_ws = self.empty((int(_lib.lib.v3s_gram_topk_sym_steps(N, 1)),), torch.int32)
-            pls = (C.c_ulonglong * 1)(lists.data_ptr())
-            pcs = (C.c_ulonglong * 1)(counts.data_ptr())
-            call("v3s_gram_topk_sym", ptr(a16_all), N, a16_all.shape[1], ptr(lim), Cc, pls, pcs, 1, 0, N, 0, ptr(step_ws), stream_ptr())
+            S, Cc = 1, Csym
+            step_ws = self.empty((int(_lib.lib.v3s_gram_topk_sym_steps(N, world)),), torch.int32)
+            if world == 1:
+                lists = self.empty((N * Cc,), torch.int64)
+                counts = self.zeros((N,), torch.int32)
+                pls = (C.c_ulonglong * 1)(lists.data_ptr())
+                pcs = (C.c_ulonglong * 1)(counts.data_ptr())
+                call("v3s_gram_topk_sym", ptr(a16_all), N, a16_all.shape[1], ptr(lim_loc), Cc, pls, pcs, 1, 0, N, 0, ptr(step_ws),
+                     stream_ptr())
+            else:
+                import torch.distributed as dist
+                lim = plan.all_gather_rows(lim_loc)
+                lists_full, counts_full, pls, pcs = peer
+                counts_full.zero_()
+                dist.barrier(group=plan.group)           # every rank's counters are zero before anybody appends
+                base, rem = divmod(N, world)
+                call("v3s_gram_topk_sym", ptr(a16_all), N, a16_all.shape[1], ptr(lim), Cc, pls, pcs, world, plan.rank, base, rem,
+                     ptr(step_ws), stream_ptr())
+                dist.barrier(group=plan.group)           # all appends (incl. the peers' into this rank's lists) are done
+                lists, counts = lists_full[: nr * Cc], counts_full[:nr]
         else:
             call("v3s_gram_topk_plan", nr, N, k, pl)
             S, Cc, rows_pad = int(pl[0]), int(pl[1]), int(pl[2])
@@ -285,6 +315,9 @@ class CudaOps:
             call("v3s_gram_topk", ptr(a16_all), N, ptr(a16_all[r0:r1]), nr, a16_all.shape[1], k, eps_g, ptr(lists), ptr(counts),
                  ptr(self.knn_overflow), ptr(tws), stream_ptr())
         self._toc(h)
+        if a32_ready is not None:
+            call("v3s_set_gram_reserved_sms", 0)
+            a32_ready.wait()                           # the all-gather of the FP32 rows ran beside the Gram kernel
         cap = min(k + KNN_MARGIN + KNN_EXTRA_CAP, N)
         cand = self.empty((nr, cap), torch.int32)
         cnt = self.empty((nr,), torch.int32)
@@ -317,6 +350,29 @@ class CudaOps:
                  ptr(S2), ptr(Nbr), ptr(dws), None, stream_ptr())
         self._toc(h)
         return S2, Nbr
+
+    def _sym_lists_arena(self, plan, Cc):
+        """Per-rank candidate lists + slot counters of the sharded symmetric Gram in torch symmetric memory (peers append
+        into them over NVLink).  -> (lists int64 [cmax*Cc], counts int32 [cmax], peer list ptrs, peer counter ptrs) or None."""
+        import torch.distributed as dist
+        key = ("symlists", plan.N, plan.world, plan.rank, Cc)
+        ent = self._symm_G.get(key)
+        if ent is None:
+            try:
+                import torch.distributed._symmetric_memory as symm
+                cmax = max(plan.counts)
+                lbytes = cmax * Cc * 8
+                buf = symm.empty((lbytes + cmax * 4 + 256,), dtype=torch.uint8, device=self.device)
+                hdl = symm.rendezvous(buf, plan.group if plan.group is not None else dist.group.WORLD)
+                bases = [int(x) for x in hdl.buffer_ptrs]
+                lists = buf[:lbytes].view(torch.int64)
+                counts = buf[lbytes: lbytes + cmax * 4].view(torch.int32)
+                ent = (lists, counts, (C.c_ulonglong * plan.world)(*bases), (C.c_ulonglong * plan.world)(*[b + lbytes for b in bases]), buf)
+            except Exception as e:                      # no peer access / API missing: rectangular kernel instead
+                ent = False
+                self.symm_error = repr(e)
+            self._symm_G[key] = ent
+        return None if ent is False else ent[:4]
 
     def gram_rows(self, hi_all, lo_all, a32_all, r0, r1, out=None):
         """G[r0:r1, :] as f32 [r1-r0, ldg]."""
@@ -408,7 +464,7 @@ class CudaOps:
             raise Exception("Number of nearest neighbors to preserve is too high.")   # distance.py:33-34
         nr = r1 - r0
         if self.gram_impl == "fused":
-            return self.knn_rows_fused(self.split_f16(a32_all), a32_all, zero_flag, r0, r1, k)
+            return self.knn_rows_fused(self.split_f16(a32_all), a32_all, zero_flag, r0, r1, k, plan=plan)
         if hi_all is None:
             hi_all, lo_all = self.split_bf16(a32_all)
         S2 = self.empty((nr, k), torch.float64)

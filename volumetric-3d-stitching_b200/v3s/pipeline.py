@@ -79,10 +79,19 @@ def knn_stage(ops, plan, img_local, k):
     if plan.world == 1:
         a32_all, hi_all, lo_all, zf_all = ops.center_normalize(img_local, mean, want_split=not fused)
     else:
-        # ship the FP32 unit rows only (4 B/element) and split them locally: half the all-gather volume
         a32, _, _, zf = ops.center_normalize(img_local, mean, want_split=False)
-        a32_all = plan.all_gather_rows(a32)
         zf_all = plan.all_gather_rows(zf)
+        if fused and hasattr(ops, "knn_rows_fused") and len(set(plan.counts)) == 1:
+            # the Gram kernel needs the FP16 operand of every pattern (2 B/element): gather that first, and let the
+            # all-gather of the FP32 rows (4 B/element, needed by the exact-distance refinement only) run beside it
+            import torch.distributed as dist
+            a16_all = plan.all_gather_rows(ops.split_f16(a32))
+            a32_all = torch.empty((plan.N,) + tuple(a32.shape[1:]), dtype=a32.dtype, device=a32.device)
+            work = dist.all_gather_into_tensor(a32_all, a32.contiguous(), group=plan.group, async_op=True)
+            S2_loc, Nbr_loc = ops.knn_rows_fused(a16_all, a32_all, zf_all, plan.lo, plan.hi, k, plan=plan, a32_ready=work)
+            return plan.all_gather_rows(S2_loc), plan.all_gather_rows(Nbr_loc)
+        # ship the FP32 unit rows only (4 B/element) and split them locally: half the all-gather volume
+        a32_all = plan.all_gather_rows(a32)
         hi_all, lo_all = (None, None) if fused else ops.split_bf16(a32_all)
     S2_loc, Nbr_loc = ops.knn_rows(hi_all, lo_all, a32_all, zf_all, plan.lo, plan.hi, k, plan=plan)
     S2_all = plan.all_gather_rows(S2_loc)
