@@ -572,6 +572,10 @@ def main():
         "operator": stats.get("operator"),
         "alt_operator": alt,
     }
+    sym_run = "gram_limits_pass" in kt
+    # MMAs really issued: rectangular = every tile of the row block; symmetric = 1/stride sample pass + tiles on/above the diagonal
+    from v3s import ops_cuda as _oc
+    gram_issued = gram_flop * ((1.0 / _oc.SYM_SAMPLE_STRIDE + 0.5 * (1.0 + 256.0 / N)) if sym_run else 1.0)
     long_kernel = gram_per_pass > 20.0                    # timed inside a long step: the sustained (power-capped) peak applies
     gram_peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]) if long_kernel else peaks["bf16_tflops"]
     gram_roof = {"kernel": "gram_topk_kernel (tcgen05 cta_group::2 / TMEM / TMA, top-k selection in the epilogue)", "bound": "tensor",
@@ -581,9 +585,13 @@ def main():
                  "traffic": None, "ms_per_pass": round(gram_per_pass, 3),
                  "peak_source": peak_src + (" bf16_tflops_sustained (the kernel runs %.0f ms inside a long step)" % gram_per_pass if long_kernel
                                             else " bf16_tflops (burst: the kernel runs %.1f ms)" % gram_per_pass),
-                 "note": "algorithmic 2*rows*N*P flop per launch = the MMAs issued (one FP16 product per element, every tile of the "
-                         "rank's row block; G is never written: the epilogue keeps per-row candidate lists)",
-                 "issued_mma_frac": (round(achieved / gram_peak, 4) if achieved else None)}
+                 "note": "algorithmic 2*rows*N*P flop per pass (SURVEY 8(d): no symmetry discount) over the time of the Gram kernels of the "
+                         "pass; one FP16 product per element; G is never written (the epilogue keeps per-pattern candidate lists). "
+                         "On one GPU from N = 16384 the kernels are the symmetric pair: a 1/8-sample pass fixing every pattern's "
+                         "lower limit + the upper-triangle tiles serving rows and columns (0.625 of the rectangular MMA work), so "
+                         "the algorithmic rate can exceed the pipe's peak; issued_mma_frac is what the tensor pipe really does",
+                 "issued_mma_frac": (round((gram_issued / (gram_per_pass * 1e-3) / 1e12) / gram_peak, 4) if gram_ms else None),
+                 "symmetric": bool(sym_run)}
     mv_roof = {"kernel": "block_matvec_kernel (TMA-fed, warp-shuffle-reduced)", "bound": "hbm", "achieved": (round(mv_gbs, 1) if mv_gbs else None),
                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": (round(mv_gbs / peaks["hbm_gbs"], 4) if mv_gbs else None),
                "traffic": None, "ms_per_pass": round(sum(mv) / args.steps, 3) if mv else None, "launches_per_pass": len(mv) // args.steps,
@@ -603,7 +611,7 @@ def main():
     if world == 1 and pipes:
         line["ncu_pipe_utilisation"] = pipes          # committed ncu capture of this workload (not measured in this run)
     if world == 1:
-        mv_roof["traffic"] = None if sparse_run else traffic.get("block_matvec_kernel")
+        mv_roof["traffic"] = traffic.get("sparse_block_matvec_kernel" if sparse_run else "block_matvec_kernel")
         gram_roof["traffic"] = traffic.get("gram_topk_kernel")
         mv_roof["traffic_source"] = gram_roof["traffic_source"] = "profiles/r02_traffic.json (ncu --set full, bytes per launch)"
     dominant_is_mv = bool(mv) and (not gram_ms or sum(mv) >= sum(gram_ms))
