@@ -188,9 +188,11 @@ int v3s_gram_topk(const void* a16_all, long long n_cols, const void* a16_rows, l
  *    them), one list per pattern: element (r, c), c >= r, is appended to list r when g~ >= lim[r] and to list c when
  *    c > r and g~ >= lim[c] (atomic slot counters; about sample_stride * k entries per list, capacity C; a counter
  *    past C is reported by v3s_knn_merge_lists as overflow).  lim [n] must be complete on every rank.  peer_lists /
- *    peer_counts (host arrays [world]): rank o's lists [cnt_o, C] and zero-initialised counters [cnt_o] as mapped in
- *    THIS process (NVLink peer memory for o != rank): compute and exchange are one kernel; the caller synchronises the
- *    ranks before v3s_knn_merge_lists (S = 1).  Rank o owns cnt_base + (o < rem) consecutive patterns.
+ *    peer_counts (host arrays [world]): the lists [cnt_o, C] and zero-initialised counters [cnt_o] that receive the
+ *    entries of rank o's patterns -- either rank o's own buffers as mapped in THIS process (NVLink peer memory for
+ *    o != rank: compute and exchange are one kernel, then v3s_knn_merge_lists with S = 1), or LOCAL per-owner buffers
+ *    (no remote atomics; every owner then reads its segments from the peers: v3s_knn_merge_segment_lists, the
+ *    default); the caller synchronises the ranks in between.  Rank o owns cnt_base + (o < rem) consecutive patterns.
  *    step_ws: int [v3s_gram_topk_sym_steps(n, world)].                                                          */
 int v3s_gram_topk_limits(const void* a16_all, long long n_cols, const void* a16_rows, long long n_rows, int Ppad, int k,
                          float eps_g, int sample_stride, unsigned long long* lists, int* counts, int* overflow, int* ws,
@@ -218,6 +220,18 @@ int v3s_knn_merge_lists(const unsigned long long* lists, const int* counts, int 
                         long long n_cols, long long row0, int k, float eps_g, int cap, const int* zero_flag,
                         int* zero_ws, int* cand_ws, int* count_ws, int* overflow, int anchor_stride, int* order_ws,
                         int tile_rows, int max_tiles, int* tiles_ws, void* stream);
+
+/* v3s_knn_merge_lists with the S (<= 8) lists of a row given by a table instead of one contiguous array:
+ * seg_lists[s] -> [n_rows, C] entries, seg_counts[s] -> [n_rows] counters (host arrays of device addresses).  The
+ * sharded symmetric Gram (v3s_gram_topk_sym with peer_lists / peer_counts pointing at LOCAL per-owner buffers) leaves
+ * one segment per SOURCE rank in that rank's memory; the owner of the rows merges them straight from the peers'
+ * memory over NVLink (the only exchange of that stage, a few kB per row).  The union of a row's segments is held in
+ * min(C, 24576) entries; more counts as overflow.                                                              */
+int v3s_knn_merge_segment_lists(const unsigned long long* seg_lists /* host [S] */,
+                                const unsigned long long* seg_counts /* host [S] */, int S, int C, long long n_rows,
+                                long long n_cols, long long row0, int k, float eps_g, int cap, const int* zero_flag,
+                                int* zero_ws, int* cand_ws, int* count_ws, int* overflow, int anchor_stride, int* order_ws,
+                                int tile_rows, int max_tiles, int* tiles_ws, void* stream);
 
 /* arccos epilogue (distance.py:56-59) + final ordering (distance.py:39-43) on selected candidates:
  * d = 2 asin(|a_r - a_c| / 2) from the FP32 rows, sorted by (d, index), first k kept -> S2 [n_rows,k]

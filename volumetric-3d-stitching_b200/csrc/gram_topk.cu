@@ -753,8 +753,17 @@ __global__ void split_f16_kernel(const float* __restrict__ a, long long n_rows, 
 // g~ = 0 here: a zero QUERY row gets the first columns (all its distances are 0, ties by index), and
 // zero COLUMNS (listed in zero_cols) are appended to every row's candidates.
 constexpr int kMergeThreads = 128;
+// Segment table (n > 0): segment s of row r is lists[s] + r * C with its count at counts[s][r] -- the per-source-rank
+// lists of the sharded symmetric Gram, read where they were written (the peers' memory, over NVLink).  n = 0: the
+// segments of a row are contiguous in `lists` / `counts` (one GPU, rectangular kernel).
+struct MergeSegs {
+  const unsigned long long* lists[8];
+  const int* counts[8];
+  int n;
+};
 __global__ void __launch_bounds__(kMergeThreads)
-knn_merge_kernel(const unsigned long long* __restrict__ lists, const int* __restrict__ counts, int S, int C, int n_rows,
+knn_merge_kernel(const unsigned long long* __restrict__ lists, const int* __restrict__ counts, const MergeSegs segs, int S,
+                 int C, int ent_cap, int n_rows,
                  int n_cols, long long row0, int k, float band, int cap, const int* __restrict__ zero_flag,
                  const int* __restrict__ zero_ws, int* __restrict__ cand, int* __restrict__ cand_count,
                  int* __restrict__ overflow, int anchor_stride, int* __restrict__ cluster_out) {
@@ -788,15 +797,20 @@ knn_merge_kernel(const unsigned long long* __restrict__ lists, const int* __rest
     if (tid == 0) s_n = 0;
     __syncthreads();
     for (int sgm = 0; sgm < S; ++sgm) {
-      int c = counts[(long long)r * S + sgm];
+      int c = segs.n ? segs.counts[sgm][r] : counts[(long long)r * S + sgm];
       if (c > C) {                                           // symmetric form: a slot counter ran past its list
         if (tid == 0 && overflow) atomicAdd(overflow, 1);
         c = C;
       }
-      const unsigned long long* L = lists + ((long long)r * S + sgm) * C;
+      const unsigned long long* L = segs.n ? segs.lists[sgm] + (long long)r * C : lists + ((long long)r * S + sgm) * C;
       __shared__ int s_base;
-      if (tid == 0) { s_base = s_n; s_n += c; }
+      if (tid == 0) {
+        s_base = s_n;
+        if (c > ent_cap - s_n && overflow) atomicAdd(overflow, 1);   // (segment table: the union is held in ent_cap entries)
+        s_n += min(c, ent_cap - s_n);
+      }
       __syncthreads();
+      c = min(c, ent_cap - s_base);
       for (int i = tid; i < c; i += kMergeThreads) s_ent[s_base + i] = L[i];
       __syncthreads();
     }
@@ -1236,17 +1250,18 @@ extern "C" int v3s_gram_topk(const void* a16_all, long long n_cols, const void* 
 #undef V3S_TOPK_LAUNCH
 }
 
-// Candidate index lists from the per-segment lists of v3s_gram_topk (see knn_merge_kernel).
-extern "C" int v3s_knn_merge_lists(const unsigned long long* lists, const int* counts, int S, int C, long long n_rows,
-                                   long long n_cols, long long row0, int k, float eps_g, int cap, const int* zero_flag,
-                                   int* zero_ws /* int [cap + 1], required with zero_flag */, int* cand_ws, int* count_ws,
-                                   int* overflow, int anchor_stride, int* order_ws /* int [2 n_rows + bins], see header */,
-                                   int tile_rows, int max_tiles, int* tiles_ws /* int [1 + 2 max_tiles] */, void* stream) {
+static int merge_lists_impl(const unsigned long long* lists, const int* counts, const MergeSegs& segs, int S, int C,
+                            long long n_rows, long long n_cols, long long row0, int k, float eps_g, int cap,
+                            const int* zero_flag, int* zero_ws, int* cand_ws, int* count_ws, int* overflow, int anchor_stride,
+                            int* order_ws, int tile_rows, int max_tiles, int* tiles_ws, void* stream) {
   V3S_REQUIRE((zero_flag == nullptr) || (zero_ws != nullptr), "v3s_knn_merge_lists: zero_flag needs zero_ws");
   V3S_REQUIRE(S >= 1 && C >= 32 && n_rows >= 0 && k >= 1 && cap >= 1, "v3s_knn_merge_lists: bad arguments");
-  V3S_REQUIRE((size_t)S * C * 8 <= 200 * 1024, "v3s_knn_merge_lists: S*C = %d entries exceed shared memory", S * C);
+  // segment table: the S lists of a row hold ONE pattern's candidates split by source rank -- their union is sized
+  // like one list (C entries, at most 24576); contiguous segments: every segment can be full
+  const int ent_cap = segs.n ? (C < 24576 ? C : 24576) : S * C;
+  V3S_REQUIRE((size_t)ent_cap * 8 <= 200 * 1024, "v3s_knn_merge_lists: S*C = %d entries exceed shared memory", ent_cap);
   if (n_rows == 0) return 0;
-  const size_t smem = (size_t)S * C * 8;
+  const size_t smem = (size_t)ent_cap * 8;
   static size_t smem_set = 0;
   if (smem > smem_set) {
     V3S_CUDA(cudaFuncSetAttribute(knn_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1261,9 +1276,10 @@ extern "C" int v3s_knn_merge_lists(const unsigned long long* lists, const int* c
   V3S_REQUIRE(order_ws == nullptr || anchor_stride >= 1, "v3s_knn_merge_lists: anchor_stride >= 1 with order_ws");
   // order_ws layout: [0, n_rows) order, [n_rows, 2 n_rows) cluster ids, then the bins
   int* cluster = order_ws ? order_ws + n_rows : nullptr;
-  knn_merge_kernel<<<grid, kMergeThreads, smem, (cudaStream_t)stream>>>(lists, counts, S, C, (int)n_rows, (int)n_cols, row0, k,
-                                                                        2.0f * eps_g, cap, zero_flag, zero_flag ? zero_ws : nullptr,
-                                                                        cand_ws, count_ws, overflow, anchor_stride, cluster);
+  knn_merge_kernel<<<grid, kMergeThreads, smem, (cudaStream_t)stream>>>(lists, counts, segs, S, C, ent_cap, (int)n_rows,
+                                                                        (int)n_cols, row0, k, 2.0f * eps_g, cap, zero_flag,
+                                                                        zero_flag ? zero_ws : nullptr, cand_ws, count_ws, overflow,
+                                                                        anchor_stride, cluster);
   V3S_CHECK_LAUNCH();
   if (order_ws) {
     cudaStream_t st = (cudaStream_t)stream;
@@ -1284,6 +1300,38 @@ extern "C" int v3s_knn_merge_lists(const unsigned long long* lists, const int* c
     }
   }
   return 0;
+}
+
+// Candidate index lists from the per-segment lists of v3s_gram_topk (see knn_merge_kernel).
+extern "C" int v3s_knn_merge_lists(const unsigned long long* lists, const int* counts, int S, int C, long long n_rows,
+                                   long long n_cols, long long row0, int k, float eps_g, int cap, const int* zero_flag,
+                                   int* zero_ws /* int [cap + 1], required with zero_flag */, int* cand_ws, int* count_ws,
+                                   int* overflow, int anchor_stride, int* order_ws /* int [2 n_rows + bins], see header */,
+                                   int tile_rows, int max_tiles, int* tiles_ws /* int [1 + 2 max_tiles] */, void* stream) {
+  V3S_REQUIRE(lists && counts, "v3s_knn_merge_lists: null lists");
+  MergeSegs segs{};
+  return merge_lists_impl(lists, counts, segs, S, C, n_rows, n_cols, row0, k, eps_g, cap, zero_flag, zero_ws, cand_ws, count_ws,
+                          overflow, anchor_stride, order_ws, tile_rows, max_tiles, tiles_ws, stream);
+}
+
+// The same with the S segments of a row given by a table: seg_lists[s] -> [n_rows, C] entries, seg_counts[s] ->
+// [n_rows] counters (host arrays of device addresses, S <= 8) -- the sharded symmetric Gram keeps one segment per
+// SOURCE rank in that rank's memory; the owner of the rows reads them over the NVLink peer mappings.
+extern "C" int v3s_knn_merge_segment_lists(const unsigned long long* seg_lists /* host [S] */,
+                                           const unsigned long long* seg_counts /* host [S] */, int S, int C, long long n_rows,
+                                           long long n_cols, long long row0, int k, float eps_g, int cap, const int* zero_flag,
+                                           int* zero_ws, int* cand_ws, int* count_ws, int* overflow, int anchor_stride,
+                                           int* order_ws, int tile_rows, int max_tiles, int* tiles_ws, void* stream) {
+  V3S_REQUIRE(seg_lists && seg_counts && S >= 1 && S <= 8, "v3s_knn_merge_segment_lists: 1..8 segments");
+  MergeSegs segs{};
+  for (int i = 0; i < S; ++i) {
+    segs.lists[i] = reinterpret_cast<const unsigned long long*>(seg_lists[i]);
+    segs.counts[i] = reinterpret_cast<const int*>(seg_counts[i]);
+    V3S_REQUIRE(segs.lists[i] && segs.counts[i], "v3s_knn_merge_segment_lists: null segment %d", i);
+  }
+  segs.n = S;
+  return merge_lists_impl(nullptr, nullptr, segs, S, C, n_rows, n_cols, row0, k, eps_g, cap, zero_flag, zero_ws, cand_ws,
+                          count_ws, overflow, anchor_stride, order_ws, tile_rows, max_tiles, tiles_ws, stream);
 }
 
 
@@ -1376,11 +1424,25 @@ static SymPlan make_sym_plan(long long n, int cg, int workers, int rank, int wor
   return p;
 }
 // ints of the step-counter workspace of v3s_gram_topk_sym for n patterns on `world` ranks
-extern "C" int v3s_gram_topk_sym_steps(long long n, int world) {
-  if (n < 1 || world < 1 || world > 8) return 0;
+// CTA pairs of the symmetric kernel: all that fit, minus the SMs reserved for a collective running beside it (every
+// worker must be resident: they start each patch together)
+static int sym_workers_now() {
   static int w2 = 0;
   if (!w2) w2 = sym_workers<2>();
-  return make_sym_plan(n, g_sym_cg, w2, 0, world).steps + 1;
+  const int r = w2 - (g_reserved_sms + 1) / 2;
+  return r < 1 ? 1 : r;
+}
+extern "C" int v3s_gram_topk_sym_steps(long long n, int world) {
+  if (n < 1 || world < 1 || world > 8) return 0;
+  // (largest over the worker counts a reservation can leave: fewer workers -> smaller patches -> more steps)
+  int most = 0;
+  static int w2 = 0;
+  if (!w2) w2 = sym_workers<2>();
+  for (int w = w2 > 32 ? w2 - 32 : 1; w <= w2; ++w) {
+    const int st = make_sym_plan(n, g_sym_cg, w, 0, world).steps + 1;
+    most = st > most ? st : most;
+  }
+  return most;
 }
 
 // Pass 2: the tiles on / above the diagonal of the n x n Gram matrix, this rank's share; appends (g~, index) to the
@@ -1396,9 +1458,7 @@ extern "C" int v3s_gram_topk_sym(const void* a16_all, long long n, int Ppad, con
   V3S_REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world && cnt_base >= 1 && rem >= 0 && rem < world &&
                   cnt_base * world + rem == n, "v3s_gram_topk_sym: bad sharding");
   V3S_REQUIRE(lim && peer_lists && peer_counts && step_ws && C >= 32, "v3s_gram_topk_sym: null argument");
-  static int w2 = 0;
-  if (!w2) w2 = sym_workers<2>();
-  const int workers = w2;
+  const int workers = sym_workers_now();
   const SymPlan plan = make_sym_plan(n, 2, workers, rank, world);
   cudaStream_t st = (cudaStream_t)stream;
   V3S_CUDA(cudaMemsetAsync(step_ws, 0, sizeof(int) * (size_t)(plan.steps + 1), st));

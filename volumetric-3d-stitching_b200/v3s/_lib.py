@@ -68,6 +68,8 @@ SIGNATURES = {
     "v3s_gram_topk_sym_steps": (i32, [i64, i32]),
     "v3s_gram_topk_sym": (i32, [p, i64, i32, p, i32, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), i32, i32, i64, i32, p, p]),
     "v3s_knn_merge_lists": (i32, [p, p, i32, i32, i64, i64, i64, i32, C.c_float, i32, p, p, p, p, p, i32, p, i32, i32, p, p]),
+    "v3s_knn_merge_segment_lists": (i32, [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), i32, i32, i64, i64, i64, i32, C.c_float,
+                                          i32, p, p, p, p, p, i32, p, i32, i32, p, p]),
     "v3s_knn_refine_tile_rows": (i32, [i32]),
     "v3s_knn_refine_tiled": (i32, [p, p, i32, i64, i64, i64, i32, i32, p, p, p, p, p, p, p, p, i32, p, p, p, i32, p]),
     "v3s_knn_refine": (i32, [p, p, i32, i64, i64, i64, i32, i32, p, p, p, p, p, p, p, p]),

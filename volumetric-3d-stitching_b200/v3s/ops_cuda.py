@@ -102,10 +102,10 @@ class CudaOps:
         self.dedup_refine = True     # exact-distance refinement: mutual candidate pairs once (select.cu)
         self.tiled_refine = True     # ... tiled over neighbouring rows for long rows (refine_tiled_kernel)
         self.symmetric_gram = True   # fused Gram / top-k on the upper-triangle tiles only (gram_sym_topk_kernel) for large N
-        # ... in a sharded job too (each rank a share of the tiles, appends into the owners' lists over NVLink).  Correct
-        # (tests/multi_gpu_check.py) but off by default: the remote slot-counter atomics cost more than the halved MMA
-        # work saves (cfg 4 on 2 GPUs: 281 ms against ~250 ms with the rectangular kernel per rank)
-        self.symmetric_gram_sharded = False
+        # ... in a sharded job too: each rank a share of the tiles, appends into LOCAL per-owner lists, every owner merges
+        # its patterns' segments from the peers' memory over NVLink (remote slot-counter atomics from inside the
+        # kernel's epilogue cost more than the halved MMA work saved)
+        self.symmetric_gram_sharded = True
         self.overlap_reserved_sms = 16   # SMs left to NCCL while the all-gather of the FP32 rows overlaps the Gram kernel
         self.use_fused_matvec = True # eigen-solver mat-vecs with the reduction / recurrence / exchange fused (FusedOperator)
         self.use_peer_gram = True    # sharded jobs: symmetric Gram with NVLink peer stores (else rectangular panels)
@@ -298,14 +298,17 @@ class CudaOps:
             else:
                 import torch.distributed as dist
                 lim = plan.all_gather_rows(lim_loc)
-                lists_full, counts_full, pls, pcs = peer
-                counts_full.zero_()
-                dist.barrier(group=plan.group)           # every rank's counters are zero before anybody appends
+                counts_loc, pls, pcs, seg_lists, seg_counts = peer
+                # (the all-gather above is also the barrier that orders the peers' merge of the previous pass's
+                # segments before the counters are cleared)
+                counts_loc.zero_()
                 base, rem = divmod(N, world)
+                # appends go into LOCAL per-owner buffers (no remote atomics); each owner then merges its patterns'
+                # segments straight from the ranks that produced them
                 call("v3s_gram_topk_sym", ptr(a16_all), N, a16_all.shape[1], ptr(lim), Cc, pls, pcs, world, plan.rank, base, rem,
                      ptr(step_ws), stream_ptr())
-                dist.barrier(group=plan.group)           # all appends (incl. the peers' into this rank's lists) are done
-                lists, counts = lists_full[: nr * Cc], counts_full[:nr]
+                dist.barrier(group=plan.group)           # every rank's segments are complete
+                lists = counts = None
         else:
             call("v3s_gram_topk_plan", nr, N, k, pl)
             S, Cc, rows_pad = int(pl[0]), int(pl[1]), int(pl[2])
@@ -334,9 +337,14 @@ class CudaOps:
             max_tiles = n_bins + nr // qt + 2             # every neighbourhood: its whole tiles + at most one packed flush
             tiles_ws = self.empty((1 + 2 * max_tiles,), torch.int32)
         h = self._tic("select_refine")
-        call("v3s_knn_merge_lists", ptr(lists), ptr(counts), S, Cc, nr, N, r0, k, eps_g, cap, ptr(zero_flag), ptr(zws),
-             ptr(cand), ptr(cnt), ptr(self.knn_overflow), qt if tiled else 1, ptr(order_ws), qt, max_tiles, ptr(tiles_ws),
-             stream_ptr())
+        if sym and world > 1:
+            call("v3s_knn_merge_segment_lists", seg_lists, seg_counts, world, Cc, nr, N, r0, k, eps_g, cap, ptr(zero_flag),
+                 ptr(zws), ptr(cand), ptr(cnt), ptr(self.knn_overflow), qt if tiled else 1, ptr(order_ws), qt, max_tiles,
+                 ptr(tiles_ws), stream_ptr())
+        else:
+            call("v3s_knn_merge_lists", ptr(lists), ptr(counts), S, Cc, nr, N, r0, k, eps_g, cap, ptr(zero_flag), ptr(zws),
+                 ptr(cand), ptr(cnt), ptr(self.knn_overflow), qt if tiled else 1, ptr(order_ws), qt, max_tiles, ptr(tiles_ws),
+                 stream_ptr())
         dws = self.empty((nr, cap), torch.float64) if (self.dedup_refine or tiled) else None
         if tiled:
             pref = self.empty((nr, cap), torch.int32)
@@ -352,8 +360,11 @@ class CudaOps:
         return S2, Nbr
 
     def _sym_lists_arena(self, plan, Cc):
-        """Per-rank candidate lists + slot counters of the sharded symmetric Gram in torch symmetric memory (peers append
-        into them over NVLink).  -> (lists int64 [cmax*Cc], counts int32 [cmax], peer list ptrs, peer counter ptrs) or None."""
+        """Buffers of the sharded symmetric Gram in torch symmetric memory: on every rank, one (lists [cmax, Cc] int64,
+        counters [cmax] int32) region PER OWNER rank, filled by the local kernel with local atomics; region `o` of rank
+        q holds what q found for o's patterns, and o reads it over NVLink when it merges.
+        -> (local counters [world * cmax] int32, append tables (lists, counters: local, per owner), merge tables
+        (lists, counters: this rank's region on every source rank)) or None."""
         import torch.distributed as dist
         key = ("symlists", plan.N, plan.world, plan.rank, Cc)
         ent = self._symm_G.get(key)
@@ -361,18 +372,23 @@ class CudaOps:
             try:
                 import torch.distributed._symmetric_memory as symm
                 cmax = max(plan.counts)
-                lbytes = cmax * Cc * 8
-                buf = symm.empty((lbytes + cmax * 4 + 256,), dtype=torch.uint8, device=self.device)
+                w = plan.world
+                seg = cmax * Cc * 8                          # one owner's lists
+                lbytes = w * seg
+                buf = symm.empty((lbytes + w * cmax * 4 + 256,), dtype=torch.uint8, device=self.device)
                 hdl = symm.rendezvous(buf, plan.group if plan.group is not None else dist.group.WORLD)
                 bases = [int(x) for x in hdl.buffer_ptrs]
-                lists = buf[:lbytes].view(torch.int64)
-                counts = buf[lbytes: lbytes + cmax * 4].view(torch.int32)
-                ent = (lists, counts, (C.c_ulonglong * plan.world)(*bases), (C.c_ulonglong * plan.world)(*[b + lbytes for b in bases]), buf)
+                mine = bases[plan.rank]
+                counts = buf[lbytes: lbytes + w * cmax * 4].view(torch.int32)
+                u64 = C.c_ulonglong * w
+                ent = (counts,
+                       u64(*[mine + o * seg for o in range(w)]), u64(*[mine + lbytes + o * cmax * 4 for o in range(w)]),
+                       u64(*[b + plan.rank * seg for b in bases]), u64(*[b + lbytes + plan.rank * cmax * 4 for b in bases]), buf)
             except Exception as e:                      # no peer access / API missing: rectangular kernel instead
                 ent = False
                 self.symm_error = repr(e)
             self._symm_G[key] = ent
-        return None if ent is False else ent[:4]
+        return None if ent is False else ent[:5]
 
     def gram_rows(self, hi_all, lo_all, a32_all, r0, r1, out=None):
         """G[r0:r1, :] as f32 [r1-r0, ldg]."""

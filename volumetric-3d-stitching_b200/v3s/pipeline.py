@@ -41,6 +41,20 @@ class ShardPlan:
             return ShardPlan(N, dist.get_rank(), dist.get_world_size(), dist.group.WORLD)
         return ShardPlan(N)
 
+    _side_groups = {}
+
+    def side_group(self):
+        """A second communicator over the same ranks: a long transfer issued on it (the all-gather of the FP32 rows,
+        which runs beside the Gram kernels) does not hold up the short collectives of the main group -- operations of
+        one NCCL communicator execute in issue order."""
+        import torch.distributed as dist
+        key = (id(self.group), self.world)
+        g = ShardPlan._side_groups.get(key)
+        if g is None:
+            ranks = dist.get_process_group_ranks(self.group) if self.group is not None else list(range(self.world))
+            g = ShardPlan._side_groups[key] = dist.new_group(ranks=ranks)
+        return g
+
     # ---- collectives (no-ops for a single process) ---------------------------------------
     def all_reduce_sum(self, t):
         if self.world > 1:
@@ -87,7 +101,7 @@ def knn_stage(ops, plan, img_local, k):
             import torch.distributed as dist
             a16_all = plan.all_gather_rows(ops.split_f16(a32))
             a32_all = torch.empty((plan.N,) + tuple(a32.shape[1:]), dtype=a32.dtype, device=a32.device)
-            work = dist.all_gather_into_tensor(a32_all, a32.contiguous(), group=plan.group, async_op=True)
+            work = dist.all_gather_into_tensor(a32_all, a32.contiguous(), group=plan.side_group(), async_op=True)
             S2_loc, Nbr_loc = ops.knn_rows_fused(a16_all, a32_all, zf_all, plan.lo, plan.hi, k, plan=plan, a32_ready=work)
             return plan.all_gather_rows(S2_loc), plan.all_gather_rows(Nbr_loc)
         # ship the FP32 unit rows only (4 B/element) and split them locally: half the all-gather volume
