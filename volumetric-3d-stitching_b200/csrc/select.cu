@@ -480,6 +480,15 @@ refine_tiled_kernel(const float* __restrict__ a_rows, const float* __restrict__ 
     const int i0 = (int)((long long)np * warp / (RT_THREADS / 32)), i1 = (int)((long long)np * (warp + 1) / (RT_THREADS / 32));
     for (int c0 = 0; c0 < P; c0 += RT_CH) {
       __syncthreads();
+      // the NEXT chunk of the tile's rows -> L2 now (one 128-byte line per request): its load phase, which all warps
+      // of the CTA wait for, then finds the lines on chip
+      if (c0 + RT_CH < P) {
+        for (int idx = tid; idx < nq * (RT_CH / 32); idx += RT_THREADS) {
+          const int qi = idx / (RT_CH / 32), l = idx - qi * (RT_CH / 32);
+          const int col = c0 + RT_CH + 32 * l;
+          if (col < P) asm volatile("prefetch.global.L2 [%0];" ::"l"(a_rows + (long long)s_rows[qi] * P + col));
+        }
+      }
       for (int idx = tid; idx < nq * (RT_CH / 4); idx += RT_THREADS) {
         const int qi = idx / (RT_CH / 4), v = idx - qi * (RT_CH / 4);
         const int col = c0 + 4 * v;
@@ -503,37 +512,78 @@ refine_tiled_kernel(const float* __restrict__ a_rows, const float* __restrict__ 
           dst[m] = (c0 + col < P) ? __ldg(reinterpret_cast<const float4*>(up + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       };
-      auto pair_sum = [&](const float4 (&uu)[RT_CH / 128], unsigned long long key) {
-        const int qi = (int)((key >> 16) & 0xffffu), s = (int)(key & 0xffffu);
+      // |q - u|^2 of one pair over this lane's 16 pixels of the chunk: packed FP32 (FFMA2: two lanes per
+      // instruction -- d = fma(u, -1, q) is the exactly rounded difference, then fma(d, d, acc)); four running sums
+      // in the same element order as four scalar accumulators
+      auto pair_partial = [&](const float4 (&uu)[RT_CH / 128], int qi) -> float {
         const float* q = sq + qi * RT_CH;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        float2 a01 = make_float2(0.f, 0.f), a23 = make_float2(0.f, 0.f);
+        const float2 neg1 = make_float2(-1.f, -1.f);
 #pragma unroll
         for (int m = 0; m < RT_CH / 128; ++m) {
           const float4 x = *reinterpret_cast<const float4*>(q + 4 * (lane + 32 * m));
-          float d;
-          d = x.x - uu[m].x; a0 = fmaf(d, d, a0);
-          d = x.y - uu[m].y; a1 = fmaf(d, d, a1);
-          d = x.z - uu[m].z; a2 = fmaf(d, d, a2);
-          d = x.w - uu[m].w; a3 = fmaf(d, d, a3);
+          const float2 d01 = __ffma2_rn(make_float2(uu[m].x, uu[m].y), neg1, make_float2(x.x, x.y));
+          const float2 d23 = __ffma2_rn(make_float2(uu[m].z, uu[m].w), neg1, make_float2(x.z, x.w));
+          a01 = __ffma2_rn(d01, d01, a01);
+          a23 = __ffma2_rn(d23, d23, a23);
         }
-        float part = (a0 + a1) + (a2 + a3);
-        part = warp_sum(part);
-        if (lane == 0) atomicAdd(&Dss[(long long)s_rows[qi] * cap + s], (double)part);
+        return (a01.x + a01.y) + (a23.x + a23.y);
+      };
+      // pairs j0 .. j1-1 of the current batch (all with the candidate chunk `uu`), four at a time: the four per-lane
+      // partial sums are reduced across the warp together -- 6 shuffles for 4 pairs instead of 5 per pair, every
+      // step adding the same two operands as the xor butterfly of warp_sum (bit-identical totals) -- and end up in
+      // lanes 0 / 8 / 16 / 24, which add them to the pairs' FP64 sums in parallel
+      auto seg_pairs = [&](const float4 (&uu)[RT_CH / 128], unsigned my_lo, int j0, int j1) {
+        const bool b4 = lane & 16, b3 = lane & 8;
+        for (int j = j0; j < j1; j += 4) {
+          float p[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            p[t] = 0.f;
+            if (j + t < j1) {                                    // warp-uniform
+              const unsigned lo = __shfl_sync(0xffffffffu, my_lo, j + t);
+              p[t] = pair_partial(uu, (int)(lo >> 16));
+            }
+          }
+          const float r0 = __shfl_xor_sync(0xffffffffu, b4 ? p[0] : p[2], 16);
+          const float r1 = __shfl_xor_sync(0xffffffffu, b4 ? p[1] : p[3], 16);
+          const float k0 = (b4 ? p[2] : p[0]) + r0;              // pairs 0 / 2 (lanes 0-15 / 16-31)
+          const float k1 = (b4 ? p[3] : p[1]) + r1;              // pairs 1 / 3
+          float v = (b3 ? k1 : k0) + __shfl_xor_sync(0xffffffffu, b3 ? k0 : k1, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          v += __shfl_xor_sync(0xffffffffu, v, 2);
+          v += __shfl_xor_sync(0xffffffffu, v, 1);
+          const int t = ((lane >> 4) << 1) | ((lane >> 3) & 1);  // the pair whose total this lane holds
+          const unsigned lo = __shfl_sync(0xffffffffu, my_lo, min(j + t, 31));
+          if ((lane & 7) == 0 && j + t < j1)
+            atomicAdd(&Dss[(long long)s_rows[lo >> 16] * cap + (int)(lo & 0xffffu)], (double)v);
+        }
       };
       for (int base = i0; base < i1; base += 32) {
         const int nb = min(32, i1 - base);
         const unsigned long long my_key = (lane < nb) ? __ldg(&kb[base + lane]) : ~0ull;
         const int my_u = (int)(my_key >> 32);
+        const unsigned my_lo = (unsigned)my_key;                 // row in tile << 16 | slot
         const int prev_u = __shfl_up_sync(0xffffffffu, my_u, 1);
         // segment starts of this batch: a key whose candidate differs from its predecessor's (lane 0: from the
         // candidate still held in `ua` from the previous batch)
         unsigned starts = __ballot_sync(0xffffffffu, lane < nb && (lane == 0 ? (my_u != cur_u) : (my_u != prev_u)));
+        // every candidate chunk this batch will need -> L2 now: the register double buffer below covers one segment
+        // (a few pairs) of latency, not a DRAM access; the batch's later segments then hit in L2
+        for (unsigned rest = starts; rest;) {
+          const int js = __ffs(rest) - 1;
+          rest &= rest - 1;
+          const int u = __shfl_sync(0xffffffffu, my_u, js);
+          if (lane < RT_CH / 32 && c0 + 32 * lane < P)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a_chunk + (long long)u * P + 32 * lane));
+        }
         int j = 0;
         if (!(starts & 1u)) {
           // the batch begins inside the segment whose chunk is already in `ua`
           const int jn = starts ? (__ffs(starts) - 1) : nb;
           if (starts) load_u(ub, __shfl_sync(0xffffffffu, my_u, jn));
-          for (; j < jn; ++j) pair_sum(ua, __shfl_sync(0xffffffffu, my_key, j));
+          seg_pairs(ua, my_lo, j, jn);
+          j = jn;
           if (starts) {
 #pragma unroll
             for (int m = 0; m < RT_CH / 128; ++m) ua[m] = ub[m];
@@ -549,7 +599,8 @@ refine_tiled_kernel(const float* __restrict__ a_rows, const float* __restrict__ 
           // `ua` holds the chunk of the segment starting at j; fetch the next segment's while comparing this one
           const int jn = starts ? (__ffs(starts) - 1) : nb;
           if (starts) load_u(ub, __shfl_sync(0xffffffffu, my_u, jn));
-          for (; j < jn; ++j) pair_sum(ua, __shfl_sync(0xffffffffu, my_key, j));
+          seg_pairs(ua, my_lo, j, jn);
+          j = jn;
           if (starts) {
 #pragma unroll
             for (int m = 0; m < RT_CH / 128; ++m) ua[m] = ub[m];

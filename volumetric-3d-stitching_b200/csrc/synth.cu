@@ -22,6 +22,21 @@ struct PixelTap {   // 16 bytes
 
 constexpr int kSynthThreads = 512;
 constexpr int kMaxPlanes = 4;
+constexpr int kSynthMaxN = 256;       // voxels per side (the cell index travels in 8 bits of PixelTap::idx)
+
+// f in [0, n-1] (FP64 grid coordinate) -> cell index i in [0, n-2] and weight t = f - i as FP32 (t = 1 at the upper
+// edge, like the reference's clipped searchsorted cell).  The nearest integer of f comes from the magic-number add
+// (its low word), the remainder is exact in FP64 and rounded to FP32 once; a negative remainder moves one cell down.
+__device__ __forceinline__ void split_cell(double f, int n, int& i, float& t) {
+  const double magic = 6755399441055744.0;             // 2^52 + 2^51
+  const double fr = f + magic;
+  i = __double2loint(fr);
+  double rem = f - (fr - magic);                        // in [-0.5, 0.5], exact
+  if (rem < 0.0) { rem += 1.0; --i; }
+  t = (float)rem;
+  if (i < 0) { i = 0; t = 0.f; }                        // (f = -0 / rounding at the lower edge)
+  if (i > n - 2) { t += (float)(i - (n - 2)); i = n - 2; }
+}
 
 struct SynthParams {
   int n;            // voxels per side
@@ -42,6 +57,7 @@ synth_kernel(const float* __restrict__ ed, const double* __restrict__ rot, const
   float*  gmag = reinterpret_cast<float*>(tmp + nz * n2);                     // nz*n^2
   float2* tw   = reinterpret_cast<float2*>(gmag + ((nz * n2 + 1) & ~1));      // n
   __shared__ double Rm[9];
+  __shared__ double Uax[kSynthMaxN];                                          // U_i, rotation.py:146
 
   const int tid = threadIdx.x;
   for (int i = tid; i < n3; i += kSynthThreads) F[i] = ed[i];
@@ -58,6 +74,8 @@ synth_kernel(const float* __restrict__ ed, const double* __restrict__ rot, const
   const double half_n = 0.5 * (double)n;
   const double U0 = (1.0 - (n + 1) * 0.5) / half_n;   // U_i = (i + 1 - (n+1)/2) / (n/2), rotation.py:146
   const double Ulast = ((double)n - (n + 1) * 0.5) / half_n;
+  const double mU0h = -U0 * half_n;
+  for (int i = tid; i < n; i += kSynthThreads) Uax[i] = (i + 1 - (n + 1) * 0.5) / half_n;
 
   for (long long pat = blockIdx.x; pat < prm.N; pat += gridDim.x) {
     __syncthreads();
@@ -70,7 +88,7 @@ synth_kernel(const float* __restrict__ ed, const double* __restrict__ rot, const
     for (int col = tid; col < n2; col += kSynthThreads) {
       const int i = col / n, j = col - i * n;
       // p = (x, y, z) = (U_j, U_k, U_i): array axes are (z, x, y), projection.py:79
-      const double px = (j + 1 - (n + 1) * 0.5) / half_n, pz = (i + 1 - (n + 1) * 0.5) / half_n;
+      const double px = Uax[j], pz = Uax[i];
       const double b0 = r00 * px + r02 * pz, b1 = r10 * px + r12 * pz, b2 = r20 * px + r22 * pz;
       float2 acc[kMaxPlanes];
 #pragma unroll
@@ -79,14 +97,18 @@ synth_kernel(const float* __restrict__ ed, const double* __restrict__ rot, const
 #pragma unroll
       for (int z = 0; z < kMaxPlanes; ++z) ph[z] = 0;
       for (int k = 0; k < n; ++k) {
-        const double py = (k + 1 - (n + 1) * 0.5) / half_n;
+        const double py = Uax[k];                      // (warp-wide broadcast from shared memory)
         const double q0 = b0 + r01 * py, q1 = b1 + r11 * py, q2 = b2 + r21 * py;
         float v = 0.f;
         const bool inb = !(q0 < U0 || q0 > Ulast || q1 < U0 || q1 > Ulast || q2 < U0 || q2 > Ulast);
         if (inb) {
-          const double f0 = (q0 - U0) * half_n, f1 = (q1 - U0) * half_n, f2 = (q2 - U0) * half_n;
-          int i0 = min(max((int)f0, 0), n - 2), i1 = min(max((int)f1, 0), n - 2), i2 = min(max((int)f2, 0), n - 2);
-          const float t0 = (float)(f0 - i0), t1 = (float)(f1 - i1), t2 = (float)(f2 - i2);
+          // grid coordinate f = (q - U0) n/2 in [0, n-1]; cell index and FP32 weight without double <-> int
+          // conversions (quarter-rate pipe): adding 2^52 + 2^51 rounds f to the nearest integer in the low word
+          int i0, i1, i2;
+          float t0, t1, t2;
+          split_cell(fma(q0, half_n, mU0h), n, i0, t0);
+          split_cell(fma(q1, half_n, mU0h), n, i1, t1);
+          split_cell(fma(q2, half_n, mU0h), n, i2, t2);
           const float* b = F + (i0 * n + i1) * n + i2;
           const float c000 = b[0], c001 = b[1], c010 = b[n], c011 = b[n + 1];
           const float c100 = b[n2], c101 = b[n2 + 1], c110 = b[n2 + n], c111 = b[n2 + n + 1];

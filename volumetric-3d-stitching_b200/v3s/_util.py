@@ -109,7 +109,10 @@ class AsyncFetch:
     SINGLE_BUFFER_BYTES = 1 << 30
     CHUNK_BYTES = 256 << 20
 
-    def __init__(self, t, out_dtype=np.float64, slot="images"):
+    def __init__(self, t, out_dtype=np.float64, slot="images", private=False):
+        """private=True: `result()` returns a freshly allocated array the caller owns (copied out of the pinned
+        buffer by a worker thread as soon as the transfer is complete, i.e. while the GPU is still busy with the
+        later stages) instead of a view of the reusable buffer."""
         cls = AsyncFetch
         if cls._stream is None:
             cls._stream = torch.cuda.Stream()
@@ -147,11 +150,28 @@ class AsyncFetch:
             self._done = torch.cuda.Event()
             self._done.record()
         self._out = view.numpy()
+        self._future = None
+        if private:
+            global _pool
+            if _pool is None:
+                import concurrent.futures as cf
+                _pool = cf.ThreadPoolExecutor(max_workers=_host_threads())
+            self._future = _pool.submit(self._copy_out)
+
+    def _copy_out(self):
+        self._done.synchronize()
+        dst = np.empty(self._out.shape, dtype=self._out.dtype)
+        np.copyto(dst, self._out)                      # (numpy releases the GIL for the copy)
+        return dst
 
     def result(self):
         import time
         t0 = time.perf_counter()
-        self._done.synchronize()
+        if self._future is not None:
+            out = self._future.result()
+        else:
+            self._done.synchronize()
+            out = self._out
         TIMERS["result_wait_s"] += time.perf_counter() - t0
         self._keep = None
-        return self._out
+        return out

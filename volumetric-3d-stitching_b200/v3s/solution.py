@@ -32,6 +32,13 @@ class OrientationRecoverySolver:
         solve with the same arguments and gets the same replicated results, except 'Images', which holds
         the rank's own pattern rows [rows[0], rows[1]) (key 'rows'; the full matrix never leaves the GPUs)."""
         print('OrientationRecoverySolver.solve started.')
+        import time
+        t_mark = [time.perf_counter()]
+
+        def lap(name):                                               # host-side diagnostics (bench.py's e2e.host_ms)
+            now = time.perf_counter()
+            _util.TIMERS[name] = _util.TIMERS.get(name, 0.0) + now - t_mark[0]
+            t_mark[0] = now
         if not OrientationRecoverySolver.validate_parameters(parameters):
             parameters = OrientationRecoverySolver.default_parameters()
         if not OrientationRecoverySolver.validate_parameters(parameters):
@@ -55,19 +62,25 @@ class OrientationRecoverySolver:
         # the pattern matrix is by far the largest output: its host transfer starts as soon as stage 1
         # is done and overlaps stages 2-4 (side stream + worker thread)
         on_gpu = ops.device.type == 'cuda'
-        start_images = (lambda img: xfer.setdefault('Images', _util.AsyncFetch(img, out_dtype=images_dtype))) if on_gpu else None
+        def private(t, itemsize=8):          # results the caller gets as private arrays (see `copy_results`)
+            return bool(copy_results or (copy_results is None and t.numel() * itemsize <= (256 << 20)))
+        start_images = (lambda img: xfer.setdefault('Images', _util.AsyncFetch(
+            img, out_dtype=images_dtype, private=private(img, np.dtype(images_dtype).itemsize)))) if on_gpu else None
         # so are the kNN lists (final once the Markov matrix is built): they travel during the eigen-solver
 
         def start_lists(S2_dev, N_dev):
-            xfer['S2'] = _util.AsyncFetch(S2_dev, slot='S2')
-            xfer['N'] = _util.AsyncFetch(N_dev, slot='N')            # int32 on the wire, float64 (distance.py:37) on the host
+            # (private copies are made by worker threads while the eigen-solver runs)
+            xfer['S2'] = _util.AsyncFetch(S2_dev, slot='S2', private=private(S2_dev))
+            xfer['N'] = _util.AsyncFetch(N_dev, slot='N', private=private(N_dev))   # int32 on the wire, float64 (distance.py:37) on the host
         plan = ShardPlan.from_env(Nn)
         if plan.world > 1:
             rot9 = rot9[plan.lo:plan.hi].contiguous()
+        lap('setup_s')
         out = run_pipeline(ops, plan, ed, rot9, rot_y, n_p, parameters['k'], parameters['Epsilon'],
                            polar_mode=polar_mode, check=check_sigma, stats=stats, on_images=start_images,
                            photons_per_pattern=photons_per_pattern, noise_seed=noise_seed,
                            on_lists=start_lists if on_gpu else None, validate=validate)
+        lap('pipeline_host_s')
         # the reference returns float64 everywhere: widen on the device, one staged transfer for all arrays
         f64 = lambda t: t.to(torch.float64)
         small = {'Ps': f64(out['Ps']), 'Lambda': f64(out['Lambda']), 'c': f64(out['c'])}
@@ -77,13 +90,16 @@ class OrientationRecoverySolver:
             **small,
             'nonzero': plan.all_reduce_sum(torch.any(out['Images_local'] != 0).reshape(1).to(torch.int32)).to(torch.uint8),
             'Sigma_T': out['sigma_T'].reshape(1).to(torch.float64)})
+        lap('small_results_s')
         host['Images'] = xfer['Images'].result() if 'Images' in xfer else \
             _util.fetch_many({'Images': f64(out['Images_local'])})['Images']
         if 'S2' in xfer:
             host['S2'], host['N'] = xfer['S2'].result(), xfer['N'].result()
+        lap('large_results_wait_s')
         for key in ('Images', 'S2', 'N'):
-            if copy_results or (copy_results is None and host[key].nbytes <= (256 << 20)):
+            if key not in xfer and (copy_results or (copy_results is None and host[key].nbytes <= (256 << 20))):
                 host[key] = np.array(host[key], copy=True)
+        lap('private_copies_s')
         if not host['nonzero'][0]:
             raise Exception('Images is an all-zero array.')          # projection.py:47
         print('OrientationRecoverySolver.solve ended.')
