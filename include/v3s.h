@@ -249,6 +249,23 @@ int v3s_knn_refine(const float* a_rows, const float* a_all, int P, long long row
  * pref_ws int [n_rows,cap], keys_ws 64-bit [max_tiles * 16384], np_ws int [max_tiles].  dedup != 0: a pair
  * listed from both sides by rows of this call is evaluated once.                                    */
 int v3s_knn_refine_tile_rows(int cap);
+/* The two halves of v3s_knn_refine_tiled, for sharded jobs (the ranks synchronise in between):
+ *  _pairs: |a_r - a_c|^2 of every pair THIS rank owns -> dist_ws (FP64 sums), pref_ws = slot of the partner row's
+ *    list for pairs the partner owns.  cand_all [n_cols,cap] / count_all [n_cols] (may be NULL): the candidate lists
+ *    of all patterns (all-gathered) -- a pair listed from both sides is then evaluated once even when its two rows
+ *    belong to different ranks (owner: the lower index for indices of equal parity, else the higher).
+ *  _emit: distances, ordering, first k -> S2 / Nbr; a sum owned by a partner row is read from that row's dist_ws:
+ *    peer_dss (host array [world], may be NULL for one rank) = the ranks' dist_ws as mapped in this process
+ *    (NVLink peer memory); rank o owns cnt_base + (o < rem) consecutive patterns.                              */
+int v3s_knn_refine_tiled_pairs(const float* a_rows, const float* a_all, int P, long long row0, long long n_rows,
+                               long long n_cols, int cap, const int* cand_ws, const int* count_ws, double* dist_ws,
+                               const int* order, const int* tiles, int max_tiles, int* pref_ws,
+                               unsigned long long* keys_ws, int* np_ws, int dedup, const int* cand_all,
+                               const int* count_all, void* stream);
+int v3s_knn_refine_tiled_emit(long long row0, long long n_rows, long long n_cols, int k, int cap, const int* zero_flag,
+                              const int* cand_ws, const int* count_ws, double* S2, int* Nbr, double* dist_ws,
+                              const int* pref_ws, const unsigned long long* peer_dss /* host [world] */, int world,
+                              long long cnt_base, int rem, void* stream);
 int v3s_knn_refine_tiled(const float* a_rows, const float* a_all, int P, long long row0, long long n_rows,
                          long long n_cols, int k, int cap, const int* zero_flag, const int* cand_ws,
                          const int* count_ws, double* S2, int* Nbr, double* dist_ws, const int* order, const int* tiles,
@@ -415,6 +432,9 @@ int v3s_sym_eig_host(double* a, int n, double* w);
  * launching stream): enable/reset, then read the elapsed milliseconds (returns the launch count). */
 int v3s_profile_matvec(int enable);
 int v3s_profile_matvec_read(float* ms_out, int cap);
+/* milliseconds between the end of recorded launch i and the start of launch i+1 (the fused reduction / exchange kernel
+ * with its cross-rank barrier, Lanczos steps, host gaps); call before v3s_profile_matvec_read; returns the gap count. */
+int v3s_profile_matvec_gaps(float* ms_out, int cap);
 
 /* ---- stage 4: orientation retrieval ---------------------------------------------------------- */
 

@@ -678,6 +678,20 @@ extern "C" int v3s_profile_matvec(int enable) {
   return 0;
 }
 
+// Milliseconds between the END of recorded mat-vec launch i and the START of launch i+1 (what follows a mat-vec on
+// the stream: the fused reduction / recurrence / exchange kernel with its cross-rank barrier, Lanczos steps, host
+// gaps).  Call before v3s_profile_matvec_read (which resets the record); returns the number of gaps.
+extern "C" int v3s_profile_matvec_gaps(float* ms_out, int cap) {
+  const int n = (int)(g_prof_used / 2);
+  if (n > 0) cudaEventSynchronize(g_prof_ev[g_prof_used - 1]);
+  for (int i = 0; i + 1 < n && i < cap; ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, g_prof_ev[2 * i + 1], g_prof_ev[2 * i + 2]) != cudaSuccess) ms = -1.f;
+    ms_out[i] = ms;
+  }
+  return n > 0 ? n - 1 : 0;
+}
+
 // Elapsed milliseconds of the block_matvec_kernel launches recorded since v3s_profile_matvec(1)
 // (synchronises on the last event); returns the number of launches, writes min(count, cap) values.
 extern "C" int v3s_profile_matvec_read(float* ms_out, int cap) {

@@ -135,13 +135,29 @@ select_kernel(const float* __restrict__ G, long long ldg, int n_rows, int n_cols
 
 constexpr int kRefThreads = 256;
 
+// Sharded tiled refinement: the pair sums of rank o's rows live in dss[o] ([cnt_o, cap] FP64, NVLink peer mappings);
+// rank o owns cnt_base + (o < rem) consecutive patterns.  world = 0: one rank, everything in the local workspace.
+struct RefPeers {
+  const double* dss[8];
+  int world, rem;
+  long long cnt_base;
+};
+__device__ __forceinline__ const double* ref_peer_row(const RefPeers& pr, long long x, int cap) {
+  const long long big = pr.cnt_base + 1, split = big * pr.rem;
+  int o;
+  long long lo;
+  if (x < split) { o = (int)(x / big); lo = o * big; }
+  else { o = pr.rem + (int)((x - split) / pr.cnt_base); lo = split + (long long)(o - pr.rem) * pr.cnt_base; }
+  return pr.dss[o] + (x - lo) * cap;
+}
+
 __global__ void __launch_bounds__(kRefThreads)
 refine_sort_kernel(const float* __restrict__ a_rows, const float* __restrict__ a_all, int P, long long row0, int n_rows,
                    const int* __restrict__ cand, const int* __restrict__ cand_count, int cap, int kk_pad, int k,
                    const int* __restrict__ zero_flag,
                    int cache_row, const double* __restrict__ Bd, long long ldb, double* __restrict__ S2,
                    int* __restrict__ Nbr, double* Dws, int phase, const int* __restrict__ order,
-                   const int* __restrict__ pref = nullptr) {
+                   const int* __restrict__ pref = nullptr, const RefPeers peers = RefPeers{}) {
   // phase 0: distances + sort in one launch.  phase 1: distances only, into Dws [n_rows, cap] in candidate
   // order; a pair whose partner row j < i of this call lists i too is skipped and stored as -(t + 1),
   // t = position of i in j's list.  phase 2: fetch the skipped values from the partner rows, sort, emit.
@@ -194,7 +210,10 @@ refine_sort_kernel(const float* __restrict__ a_rows, const float* __restrict__ a
       for (int s = tid; s < kk; s += kRefThreads) {
         const int j = cand[(long long)r * cap + s];
         const int pr = pref[(long long)r * cap + s];
-        const double ss = pr >= 0 ? Dws[(long long)(j - row0) * cap + pr] : Dws[(long long)r * cap + s];
+        // (a pair owned by the partner row: its sum is in that row's workspace -- on this rank, or read from the
+        // owner rank's memory over NVLink in a sharded job)
+        const double ss = pr < 0 ? Dws[(long long)r * cap + s]
+                                 : (peers.world > 0 ? ref_peer_row(peers, j, cap)[pr] : Dws[(long long)(j - row0) * cap + pr]);
         double half = 0.5 * sqrt(ss);
         if (half > 1.0) half = 1.0;
         double d = 2.0 * asin(half);
@@ -399,7 +418,11 @@ constexpr int RT_MAIN_THREADS = 512; // main kernel: 16 warps x 2 CTAs per SM hi
 __global__ void __launch_bounds__(RT_THREADS)
 refine_prepare_kernel(const int* __restrict__ order, const int* __restrict__ tiles, long long row0,
                       const int* __restrict__ cand, const int* __restrict__ cand_count, int cap,
-                      unsigned long long* __restrict__ keys, int* __restrict__ np_out, int* __restrict__ pref, int dedup) {
+                      unsigned long long* __restrict__ keys, int* __restrict__ np_out, int* __restrict__ pref, int dedup,
+                      const int* __restrict__ cand_all, const int* __restrict__ count_all) {
+  // cand_all / count_all (sharded job, else NULL): the candidate lists of ALL patterns (all-gathered) -- a pair listed
+  // from both sides is then evaluated once whichever ranks own its two rows: by the lower index when the indices
+  // have equal parity, else by the higher (both directions carry about half of every row's mutual pairs)
   extern __shared__ unsigned long long sk[];       // RT_KEYS
   __shared__ int s_np;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -420,9 +443,11 @@ refine_prepare_kernel(const int* __restrict__ order, const int* __restrict__ til
       bool owned = valid;
       if (dedup && valid) {
         const long long lj = (long long)j - row0;
-        if (lj >= 0 && lj < r) {                              // partner row of this call with a lower index
-          const int* cj = cand + lj * cap;
-          const int cntj = cand_count[lj];
+        const bool partner_first = cand_all ? (j != me && ((((me ^ j) & 1) == 0) == (j < me)))   // the partner would own it
+                                            : (lj >= 0 && lj < r);                                // partner row of this call with a lower index
+        if (partner_first) {
+          const int* cj = cand_all ? cand_all + (long long)j * cap : cand + lj * cap;
+          const int cntj = cand_all ? count_all[j] : cand_count[lj];
           int lo = 0, hi = cntj;                              // lists are sorted by column index (knn_merge_kernel)
           while (lo < hi) {
             const int mid = (lo + hi) >> 1;
@@ -622,21 +647,24 @@ extern "C" int v3s_knn_refine_tile_rows(int cap) {
   return qt < v3s::RT_QMAX ? qt : v3s::RT_QMAX;
 }
 
-// v3s_knn_refine with the pair evaluation tiled over neighbouring rows (see above).  order int [n_rows] (rows of a
-// neighbourhood contiguous, from v3s_knn_merge_lists) is required; P must be a multiple of 4.  Workspaces:
-// dist_ws FP64 [n_rows,cap], pref_ws int [n_rows,cap], keys_ws 64-bit [max_tiles * 16384], np_ws int [max_tiles];
-// tiles (device, int [1 + 2 max_tiles]): the tile table written by v3s_knn_merge_lists.  dedup != 0: pairs listed
-// from both sides are evaluated once.
-extern "C" int v3s_knn_refine_tiled(const float* a_rows, const float* a_all, int P, long long row0, long long n_rows,
-                                    long long n_cols, int k, int cap, const int* zero_flag, const int* cand_ws,
-                                    const int* count_ws, double* S2, int* Nbr, double* dist_ws, const int* order,
-                                    const int* tiles, int max_tiles, int* pref_ws, unsigned long long* keys_ws, int* np_ws,
-                                    int dedup, void* stream) {
-  V3S_REQUIRE(k >= 1 && cap >= k && n_rows >= 0 && n_cols < (1LL << 31) && n_rows < (1LL << 31), "v3s_knn_refine_tiled: bad arguments");
-  V3S_REQUIRE(k <= n_cols, "Number of nearest neighbors to preserve is too high.");   // distance.py:33-34
+// The tiled refinement in two halves (a sharded job synchronises its ranks in between):
+//   v3s_knn_refine_tiled_pairs : |a_r - a_c|^2 of every pair this rank owns -> dist_ws (FP64 sums, [n_rows, cap]),
+//                                pref_ws = slot of the partner row for pairs the partner owns.  cand_all / count_all
+//                                (may be NULL): the candidate lists of ALL n_cols patterns, all-gathered -- pairs listed
+//                                from both sides are then shared ACROSS ranks too (see refine_prepare_kernel).
+//   v3s_knn_refine_tiled_emit  : d = 2 asin(sqrt(ss)/2), sort by (d, index), first k -> S2, Nbr; sums owned by a partner
+//                                row are read from peer_dss[o] (host array [world] of the ranks' dist_ws as mapped in
+//                                this process; NULL / world <= 1: the local dist_ws).
+extern "C" int v3s_knn_refine_tiled_pairs(const float* a_rows, const float* a_all, int P, long long row0, long long n_rows,
+                                          long long n_cols, int cap, const int* cand_ws, const int* count_ws,
+                                          double* dist_ws, const int* order, const int* tiles, int max_tiles, int* pref_ws,
+                                          unsigned long long* keys_ws, int* np_ws, int dedup, const int* cand_all,
+                                          const int* count_all, void* stream) {
+  V3S_REQUIRE(cap >= 1 && n_rows >= 0 && n_cols < (1LL << 31) && n_rows < (1LL << 31), "v3s_knn_refine_tiled: bad arguments");
   V3S_REQUIRE(P > 0 && P % 4 == 0, "v3s_knn_refine_tiled: P = %d must be a multiple of 4", P);
   V3S_REQUIRE(dist_ws && order && tiles && max_tiles >= 1 && pref_ws && keys_ws && np_ws,
               "v3s_knn_refine_tiled: workspaces, order and the tile table are required");
+  V3S_REQUIRE((cand_all == nullptr) == (count_all == nullptr), "v3s_knn_refine_tiled: cand_all and count_all go together");
   const int qt = v3s_knn_refine_tile_rows(cap);
   V3S_REQUIRE(qt >= 1, "v3s_knn_refine_tiled: candidate capacity %d too large", cap);
   if (n_rows == 0) return 0;
@@ -651,12 +679,32 @@ extern "C" int v3s_knn_refine_tiled(const float* a_rows, const float* a_all, int
     attr_set = true;
   }
   refine_prepare_kernel<<<max_tiles, RT_THREADS, RT_KEYS * 8, st>>>(order, tiles, row0, cand_ws, count_ws, cap, keys_ws, np_ws,
-                                                                   pref_ws, dedup);
+                                                                   pref_ws, dedup, cand_all, count_all);
   V3S_CHECK_LAUNCH();
   const int grid = max_tiles < 2 * kNumSMs ? max_tiles : 2 * kNumSMs;
   refine_tiled_kernel<<<grid, RT_MAIN_THREADS, (size_t)qt * RT_CH * 4, st>>>(a_rows, a_all, P, order, tiles, keys_ws, np_ws, cap,
                                                                             dist_ws);
   V3S_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int v3s_knn_refine_tiled_emit(long long row0, long long n_rows, long long n_cols, int k, int cap,
+                                         const int* zero_flag, const int* cand_ws, const int* count_ws, double* S2, int* Nbr,
+                                         double* dist_ws, const int* pref_ws, const unsigned long long* peer_dss /* host [world] */,
+                                         int world, long long cnt_base, int rem, void* stream) {
+  V3S_REQUIRE(k >= 1 && cap >= k && n_rows >= 0 && n_rows < (1LL << 31), "v3s_knn_refine_tiled: bad arguments");
+  V3S_REQUIRE(k <= n_cols, "Number of nearest neighbors to preserve is too high.");   // distance.py:33-34
+  V3S_REQUIRE(dist_ws && pref_ws, "v3s_knn_refine_tiled_emit: workspaces are required");
+  if (n_rows == 0) return 0;
+  using namespace v3s;
+  cudaStream_t st = (cudaStream_t)stream;
+  RefPeers peers{};
+  if (peer_dss && world > 1) {
+    V3S_REQUIRE(world <= 8 && cnt_base >= 1 && rem >= 0 && rem < world && cnt_base * world + rem == n_cols,
+                "v3s_knn_refine_tiled_emit: bad sharding");
+    for (int i = 0; i < world; ++i) peers.dss[i] = reinterpret_cast<const double*>(peer_dss[i]);
+    peers.world = world; peers.rem = rem; peers.cnt_base = cnt_base;
+  }
   int kk_pad = 4;
   while (kk_pad < cap) kk_pad <<= 1;
   V3S_REQUIRE(kk_pad <= 4096, "v3s_knn_refine_tiled: candidate capacity %d too large (max 4096)", cap);
@@ -666,10 +714,28 @@ extern "C" int v3s_knn_refine_tiled(const float* a_rows, const float* a_all, int
     g_refine_smem_set = base;
   }
   const int grid2 = (int)(n_rows < 8LL * kNumSMs ? n_rows : 8LL * kNumSMs);
-  refine_sort_kernel<<<grid2, kRefThreads, base, st>>>(a_rows, a_all, P, row0, (int)n_rows, cand_ws, count_ws, cap, kk_pad, k,
-                                                      zero_flag, 0, nullptr, 0, S2, Nbr, dist_ws, 3, nullptr, pref_ws);
+  refine_sort_kernel<<<grid2, kRefThreads, base, st>>>(nullptr, nullptr, 0, row0, (int)n_rows, cand_ws, count_ws, cap, kk_pad, k,
+                                                      zero_flag, 0, nullptr, 0, S2, Nbr, dist_ws, 3, nullptr, pref_ws, peers);
   V3S_CHECK_LAUNCH();
   return 0;
+}
+
+// v3s_knn_refine with the pair evaluation tiled over neighbouring rows (see above): both halves in one call (one
+// rank).  order int [n_rows] (rows of a neighbourhood contiguous, from v3s_knn_merge_lists) is required; P must be a
+// multiple of 4.  Workspaces: dist_ws FP64 [n_rows,cap], pref_ws int [n_rows,cap], keys_ws 64-bit [max_tiles * 16384],
+// np_ws int [max_tiles]; tiles (device, int [1 + 2 max_tiles]): the tile table written by v3s_knn_merge_lists.
+// dedup != 0: pairs listed from both sides are evaluated once.
+extern "C" int v3s_knn_refine_tiled(const float* a_rows, const float* a_all, int P, long long row0, long long n_rows,
+                                    long long n_cols, int k, int cap, const int* zero_flag, const int* cand_ws,
+                                    const int* count_ws, double* S2, int* Nbr, double* dist_ws, const int* order,
+                                    const int* tiles, int max_tiles, int* pref_ws, unsigned long long* keys_ws, int* np_ws,
+                                    int dedup, void* stream) {
+  V3S_REQUIRE(k >= 1 && cap >= k, "v3s_knn_refine_tiled: bad arguments");
+  V3S_REQUIRE(k <= n_cols, "Number of nearest neighbors to preserve is too high.");   // distance.py:33-34
+  if (int rc = v3s_knn_refine_tiled_pairs(a_rows, a_all, P, row0, n_rows, n_cols, cap, cand_ws, count_ws, dist_ws, order, tiles,
+                                          max_tiles, pref_ws, keys_ws, np_ws, dedup, nullptr, nullptr, stream)) return rc;
+  return v3s_knn_refine_tiled_emit(row0, n_rows, n_cols, k, cap, zero_flag, cand_ws, count_ws, S2, Nbr, dist_ws, pref_ws,
+                                   nullptr, 1, n_cols, 0, stream);
 }
 
 namespace v3s {

@@ -72,6 +72,8 @@ SIGNATURES = {
                                           i32, p, p, p, p, p, i32, p, i32, i32, p, p]),
     "v3s_knn_refine_tile_rows": (i32, [i32]),
     "v3s_knn_refine_tiled": (i32, [p, p, i32, i64, i64, i64, i32, i32, p, p, p, p, p, p, p, p, i32, p, p, p, i32, p]),
+    "v3s_knn_refine_tiled_pairs": (i32, [p, p, i32, i64, i64, i64, i32, p, p, p, p, p, i32, p, p, p, i32, p, p, p]),
+    "v3s_knn_refine_tiled_emit": (i32, [i64, i64, i64, i32, i32, p, p, p, p, p, p, p, C.POINTER(C.c_ulonglong), i32, i64, i32, p]),
     "v3s_knn_refine": (i32, [p, p, i32, i64, i64, i64, i32, i32, p, p, p, p, p, p, p, p]),
     "v3s_knn_from_dense": (i32, [p, i64, i32, i32, p, p, p, p, p, p]),
     "v3s_s2_scalars": (i32, [p, i64, i32, f64, i32, i32, p, p]),
@@ -107,6 +109,7 @@ SIGNATURES = {
     "v3s_sym_eig_host": (i32, [C.POINTER(f64), i32, C.POINTER(f64)]),
     "v3s_profile_matvec": (i32, [i32]),
     "v3s_profile_matvec_read": (i32, [C.POINTER(C.c_float), i32]),
+    "v3s_profile_matvec_gaps": (i32, [C.POINTER(C.c_float), i32]),
     "v3s_fit_gram": (i32, [p, i32, p, i64, p, p]),
     "v3s_fit_solve": (i32, [p, p, p]),
     "v3s_fit_project": (i32, [p, i32, p, i64, p, i32, p, p, p, p, p]),

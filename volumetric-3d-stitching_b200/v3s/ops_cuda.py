@@ -106,6 +106,7 @@ class CudaOps:
         # its patterns' segments from the peers' memory over NVLink (remote slot-counter atomics from inside the
         # kernel's epilogue cost more than the halved MMA work saved)
         self.symmetric_gram_sharded = True
+        self.share_pairs_across_ranks = True   # sharded tiled refinement: mutual pairs once per JOB, not once per rank
         self.overlap_reserved_sms = 16   # SMs left to NCCL while the all-gather of the FP32 rows overlaps the Gram kernel
         self.use_fused_matvec = True # eigen-solver mat-vecs with the reduction / recurrence / exchange fused (FusedOperator)
         self.use_peer_gram = True    # sharded jobs: symmetric Gram with NVLink peer stores (else rectangular panels)
@@ -148,6 +149,9 @@ class CudaOps:
         if self._profile:
             cap = 1 << 16
             buf = (C.c_float * cap)()
+            ng = min(int(_lib.lib.v3s_profile_matvec_gaps(buf, cap)), cap)
+            if ng:
+                out["matvec_gap"] = [float(buf[i]) for i in range(ng)]
             n = min(int(_lib.lib.v3s_profile_matvec_read(buf, cap)), cap)
             if n:
                 out["matvec"] = [float(buf[i]) for i in range(n)]
@@ -243,7 +247,19 @@ class CudaOps:
         call("v3s_split_f16", ptr(a32), n, P, Ppad, ptr(a16), stream_ptr())
         return a16
 
-    def knn_rows_fused(self, a16_all, a32_all, zero_flag, r0, r1, k, order=None, plan=None, a32_ready=None):
+    def sym_stride(self):
+        import os as _os
+        return int(_os.environ.get('V3S_SYM_STRIDE', SYM_SAMPLE_STRIDE))
+
+    def wants_symmetric_gram(self, N, nr, k, plan=None, whole=True):
+        """Whether knn_rows_fused takes the symmetric form (half the MMA work + a sampling pass) for this problem."""
+        stride = self.sym_stride()
+        world = 1 if plan is None else plan.world
+        return bool(self.symmetric_gram and whole and N >= 16384 and (N + stride - 1) // stride >= 4 * k and world <= 8
+                    and (world == 1 or (self.symmetric_gram_sharded and self.use_peer_gram and min(plan.counts) >= 1)))
+
+    def knn_rows_fused(self, a16_all, a32_all, zero_flag, r0, r1, k, order=None, plan=None, a32_ready=None,
+                       a16_ready=None, a16_rows=None, a16_sample=None):
         """k nearest neighbours of rows [r0,r1) with the selection fused into the Gram kernel's epilogue:
         v3s_gram_topk (candidate lists per row and column segment) -> v3s_knn_merge_lists (value band around
         the k-th largest) -> v3s_knn_refine (exact distances from the FP32 rows, sort)."""
@@ -257,14 +273,17 @@ class CudaOps:
         eps_g = fused_gram_error_bound(P)
         if a32_ready is not None:                      # leave room for the collective that runs beside the Gram kernel
             call("v3s_set_gram_reserved_sms", self.overlap_reserved_sms)
-        import os as _os
-        stride = int(_os.environ.get('V3S_SYM_STRIDE', SYM_SAMPLE_STRIDE))
+        stride = self.sym_stride()
         # symmetric form (half the MMA work + a 1/stride sampling pass) for large problems: the whole matrix on one
-        # GPU, or the rank's share of the upper-triangle tiles with appends into the owners' lists over NVLink
+        # GPU, or the rank's share of the upper-triangle tiles with per-owner lists merged over NVLink
         world = 1 if plan is None else plan.world
         whole = (r0 == 0 and nr == N) if world == 1 else (r0 == plan.lo and r1 == plan.hi)
-        sym = (self.symmetric_gram and whole and N >= 16384 and (N + stride - 1) // stride >= 4 * k and world <= 8
-               and (world == 1 or (self.symmetric_gram_sharded and self.use_peer_gram and min(plan.counts) >= 1)))
+        sym = self.wants_symmetric_gram(N, nr, k, plan, whole)
+        if a16_rows is None:
+            a16_rows = a16_all[r0:r1]
+        if a16_ready is not None and not (sym and a16_sample is not None):
+            a16_ready.wait()
+            a16_ready = None
         Csym = 2048
         while Csym < 1.5 * stride * k + 256:
             Csym *= 2
@@ -272,10 +291,15 @@ class CudaOps:
         if sym and world > 1:
             peer = self._sym_lists_arena(plan, Csym)
             sym = peer is not None
+            if not sym and a16_ready is not None:      # rectangular kernel after all: it needs the whole operand now
+                a16_ready.wait()
+                a16_ready = None
         pl = (C.c_int * 4)()
         h = self._tic("gram")
         if sym:
-            ns = (N + stride - 1) // stride
+            # pass 1 against a sample of the patterns: every stride-th row of a16_all, or (sharded) the already gathered
+            # compact sample a16_sample while the all-gather of the full operand is still running
+            ns = (N + stride - 1) // stride if a16_sample is None else int(a16_sample.shape[0])
             call("v3s_gram_topk_plan", nr, ns, k, pl)
             S1, C1, rows_pad1 = int(pl[0]), int(pl[1]), int(pl[2])
             lists1 = self.empty((rows_pad1 * S1 * C1,), torch.int64)
@@ -283,9 +307,15 @@ class CudaOps:
             tws1 = self.empty((int(pl[3]),), torch.int32)
             lim_loc = self.empty((nr,), torch.float32)
             h1 = self._tic("gram_limits_pass")
-            call("v3s_gram_topk_limits", ptr(a16_all), N, ptr(a16_all[r0:r1]), nr, a16_all.shape[1], k, eps_g, stride, ptr(lists1),
-                 ptr(counts1), ptr(self.knn_overflow), ptr(tws1), ptr(lim_loc), stream_ptr())
+            if a16_sample is None:
+                call("v3s_gram_topk_limits", ptr(a16_all), N, ptr(a16_rows), nr, a16_all.shape[1], k, eps_g, stride, ptr(lists1),
+                     ptr(counts1), ptr(self.knn_overflow), ptr(tws1), ptr(lim_loc), stream_ptr())
+            else:
+                call("v3s_gram_topk_limits", ptr(a16_sample), ns, ptr(a16_rows), nr, a16_sample.shape[1], k, eps_g, 1, ptr(lists1),
+                     ptr(counts1), ptr(self.knn_overflow), ptr(tws1), ptr(lim_loc), stream_ptr())
             self._toc(h1)
+            if a16_ready is not None:
+                a16_ready.wait()                       # the full FP16 operand (gathered beside pass 1) is needed from here on
             S, Cc = 1, Csym
             step_ws = self.empty((int(_lib.lib.v3s_gram_topk_sym_steps(N, world)),), torch.int32)
             if world == 1:
@@ -315,7 +345,7 @@ class CudaOps:
             lists = self.empty((rows_pad * S * Cc,), torch.int64)
             counts = self.empty((rows_pad * S,), torch.int32)
             tws = self.empty((int(pl[3]),), torch.int32)
-            call("v3s_gram_topk", ptr(a16_all), N, ptr(a16_all[r0:r1]), nr, a16_all.shape[1], k, eps_g, ptr(lists), ptr(counts),
+            call("v3s_gram_topk", ptr(a16_all), N, ptr(a16_rows), nr, a16_all.shape[1], k, eps_g, ptr(lists), ptr(counts),
                  ptr(self.knn_overflow), ptr(tws), stream_ptr())
         self._toc(h)
         if a32_ready is not None:
@@ -345,19 +375,60 @@ class CudaOps:
             call("v3s_knn_merge_lists", ptr(lists), ptr(counts), S, Cc, nr, N, r0, k, eps_g, cap, ptr(zero_flag), ptr(zws),
                  ptr(cand), ptr(cnt), ptr(self.knn_overflow), qt if tiled else 1, ptr(order_ws), qt, max_tiles, ptr(tiles_ws),
                  stream_ptr())
-        dws = self.empty((nr, cap), torch.float64) if (self.dedup_refine or tiled) else None
+        # sharded job: pairs listed from both sides are shared ACROSS ranks too -- the candidate lists of all patterns
+        # are all-gathered, every rank evaluates the pairs it owns, and the other side reads the sum from the owner's
+        # workspace over NVLink (without this 7/8 of an 8-rank job's mutual pairs are evaluated twice)
+        share = None
+        if (tiled and self.dedup_refine and self.share_pairs_across_ranks and world > 1 and plan is not None
+                and r0 == plan.lo and r1 == plan.hi and len(set(plan.counts)) == 1):
+            share = self._sym_dss_arena(plan, cap)
+        dws = None
+        if share is None and (self.dedup_refine or tiled):
+            dws = self.empty((nr, cap), torch.float64)
         if tiled:
             pref = self.empty((nr, cap), torch.int32)
             keys = self.empty((max_tiles * 16384,), torch.int64)
             npw = self.empty((max_tiles,), torch.int32)
-            call("v3s_knn_refine_tiled", ptr(a32_all[r0:r1]), ptr(a32_all), P, r0, nr, N, k, cap, ptr(zero_flag), ptr(cand),
-                 ptr(cnt), ptr(S2), ptr(Nbr), ptr(dws), ptr(order_ws), ptr(tiles_ws), max_tiles, ptr(pref), ptr(keys),
-                 ptr(npw), 1 if self.dedup_refine else 0, stream_ptr())
+            if share is None:
+                call("v3s_knn_refine_tiled", ptr(a32_all[r0:r1]), ptr(a32_all), P, r0, nr, N, k, cap, ptr(zero_flag), ptr(cand),
+                     ptr(cnt), ptr(S2), ptr(Nbr), ptr(dws), ptr(order_ws), ptr(tiles_ws), max_tiles, ptr(pref), ptr(keys),
+                     ptr(npw), 1 if self.dedup_refine else 0, stream_ptr())
+            else:
+                import torch.distributed as dist
+                dws, peer_dss = share
+                cand_all = plan.all_gather_rows(cand)
+                cnt_all = plan.all_gather_rows(cnt)        # (also orders the peers' reads of the previous pass before the memset)
+                call("v3s_knn_refine_tiled_pairs", ptr(a32_all[r0:r1]), ptr(a32_all), P, r0, nr, N, cap, ptr(cand), ptr(cnt),
+                     ptr(dws), ptr(order_ws), ptr(tiles_ws), max_tiles, ptr(pref), ptr(keys), ptr(npw), 1, ptr(cand_all),
+                     ptr(cnt_all), stream_ptr())
+                dist.barrier(group=plan.group)             # every rank's pair sums are complete
+                base, rem = divmod(N, world)
+                call("v3s_knn_refine_tiled_emit", r0, nr, N, k, cap, ptr(zero_flag), ptr(cand), ptr(cnt), ptr(S2), ptr(Nbr),
+                     ptr(dws), ptr(pref), peer_dss, world, base, rem, stream_ptr())
         else:
             call("v3s_knn_refine", ptr(a32_all[r0:r1]), ptr(a32_all), P, r0, nr, N, k, cap, ptr(zero_flag), ptr(cand), ptr(cnt),
                  ptr(S2), ptr(Nbr), ptr(dws), None, stream_ptr())
         self._toc(h)
         return S2, Nbr
+
+    def _sym_dss_arena(self, plan, cap):
+        """The rank's pair-sum workspace [cmax, cap] FP64 of the tiled refinement in torch symmetric memory (peers read
+        the sums of pairs this rank owns).  -> (local tensor, table of every rank's workspace) or None."""
+        import torch.distributed as dist
+        key = ("dss", plan.N, plan.world, plan.rank, cap)
+        ent = self._symm_G.get(key)
+        if ent is None:
+            try:
+                import torch.distributed._symmetric_memory as symm
+                cmax = max(plan.counts)
+                buf = symm.empty((cmax, cap), dtype=torch.float64, device=self.device)
+                hdl = symm.rendezvous(buf, plan.group if plan.group is not None else dist.group.WORLD)
+                ent = (buf, (C.c_ulonglong * plan.world)(*[int(x) for x in hdl.buffer_ptrs]))
+            except Exception as e:                      # no peer access / API missing: every rank evaluates its own pairs
+                ent = False
+                self.symm_error = repr(e)
+            self._symm_G[key] = ent
+        return None if ent is False else ent
 
     def _sym_lists_arena(self, plan, Cc):
         """Buffers of the sharded symmetric Gram in torch symmetric memory: on every rank, one (lists [cmax, Cc] int64,

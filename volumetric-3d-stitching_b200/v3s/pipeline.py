@@ -99,10 +99,25 @@ def knn_stage(ops, plan, img_local, k):
             # the Gram kernel needs the FP16 operand of every pattern (2 B/element): gather that first, and let the
             # all-gather of the FP32 rows (4 B/element, needed by the exact-distance refinement only) run beside it
             import torch.distributed as dist
-            a16_all = plan.all_gather_rows(ops.split_f16(a32))
+            a16 = ops.split_f16(a32)
             a32_all = torch.empty((plan.N,) + tuple(a32.shape[1:]), dtype=a32.dtype, device=a32.device)
-            work = dist.all_gather_into_tensor(a32_all, a32.contiguous(), group=plan.side_group(), async_op=True)
-            S2_loc, Nbr_loc = ops.knn_rows_fused(a16_all, a32_all, zf_all, plan.lo, plan.hi, k, plan=plan, a32_ready=work)
+            side = plan.side_group()
+            if getattr(ops, "wants_symmetric_gram", None) and ops.wants_symmetric_gram(plan.N, plan.hi - plan.lo, k, plan):
+                # the sampling pass of the symmetric form needs a SAMPLE of the patterns only (any subset gives valid
+                # limits): gather every stride-th local row first (1/stride of the volume) and let both full
+                # all-gathers run beside the Gram kernels on the side communicator
+                smp = a16[::ops.sym_stride()].contiguous()           # (equal row counts: checked above)
+                sample = torch.empty((plan.world * smp.shape[0],) + tuple(smp.shape[1:]), dtype=smp.dtype, device=smp.device)
+                dist.all_gather_into_tensor(sample, smp, group=plan.group)
+                a16_all = torch.empty((plan.N,) + tuple(a16.shape[1:]), dtype=a16.dtype, device=a16.device)
+                w16 = dist.all_gather_into_tensor(a16_all, a16, group=side, async_op=True)
+                w32 = dist.all_gather_into_tensor(a32_all, a32.contiguous(), group=side, async_op=True)
+                S2_loc, Nbr_loc = ops.knn_rows_fused(a16_all, a32_all, zf_all, plan.lo, plan.hi, k, plan=plan, a32_ready=w32,
+                                                     a16_ready=w16, a16_rows=a16, a16_sample=sample)
+            else:
+                a16_all = plan.all_gather_rows(a16)
+                work = dist.all_gather_into_tensor(a32_all, a32.contiguous(), group=side, async_op=True)
+                S2_loc, Nbr_loc = ops.knn_rows_fused(a16_all, a32_all, zf_all, plan.lo, plan.hi, k, plan=plan, a32_ready=work)
             return plan.all_gather_rows(S2_loc), plan.all_gather_rows(Nbr_loc)
         # ship the FP32 unit rows only (4 B/element) and split them locally: half the all-gather volume
         a32_all = plan.all_gather_rows(a32)
@@ -285,13 +300,21 @@ def run_pipeline(ops, plan, ed, rot9_local, rot_y_all, n_p, k, eps, polar_mode=0
                  validate=True, on_images=None, photons_per_pattern=None, noise_seed=0, on_lists=None):
     """Full path on device.  ed [n,n,n] f32; rot9_local [hi-lo,9] f64 row-major Rm of the rank's
     patterns; rot_y_all [N,9] f64 = Rotation_R.T (the reference's column-major unfold, transposed)."""
+    # stage boundaries on the stream (bench.py: stage time minus the stage's kernels = exchanges + host gaps)
+    tic = getattr(ops, "_tic", lambda name: None)
+    toc = getattr(ops, "_toc", lambda h: None)
+    h = tic("stage1_patterns")
     img = ops.synth_patterns(ed, rot9_local, n_p)
     if photons_per_pattern is not None:                      # BASELINE config 5: Poisson photon noise
         ops.poisson_noise_(img, photons_per_pattern, noise_seed, plan.lo)
+    toc(h)
     if on_images is not None:
         on_images(img)                                       # e.g. start the host transfer of the patterns now
+    h = tic("stage2_knn")
     S2, Nbr = knn_stage(ops, plan, img, k)
+    toc(h)
     S2_out = S2.clone()                                      # pre-mutation copy for callers that want it
+    h = tic("stage3_markov_eigen")
     P_rows, dis, scalars = markov_stage(ops, plan, S2, Nbr, eps, validate=validate)
     knn_overflow = getattr(ops, "knn_overflow", None)
     if validate and knn_overflow is not None:
@@ -305,7 +328,10 @@ def run_pipeline(ops, plan, ed, rot9_local, rot_y_all, n_p, k, eps, polar_mode=0
     if on_lists is not None:
         on_lists(S2, Nbr)                                    # final (thresholded) kNN lists: their host transfer can start now
     Ps, lam = eigen_stage(ops, plan, P_rows, dis, validate=validate, stats=stats)
+    toc(h)
+    h = tic("stage4_fit")
     fit = fit_stage(ops, plan, Ps, rot_y_all, polar_mode=polar_mode, check=check)
+    toc(h)
     out = {"Images_local": img, "S2": S2, "S2_unmutated": S2_out, "N": Nbr, "Ps": Ps, "Lambda": lam, "dinv_sqrt": dis,
            "scalars": scalars, "knn_overflow": knn_overflow, "P_rows": P_rows}
     out.update(fit)
