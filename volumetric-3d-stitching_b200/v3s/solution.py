@@ -8,6 +8,12 @@ from .projection import Projector
 from .rotation import Rotation
 
 
+# results up to this size are handed out as private arrays (copied by worker threads while the GPU is busy); larger
+# ones stay views of the reusable pinned transfer buffers -- in a sharded job every rank of the box would otherwise
+# copy the replicated kNN lists at the same time, on the cores that have to keep eight GPUs fed with launches
+PRIVATE_COPY_BYTES = 64 << 20
+
+
 class OrientationRecoverySolver:
 
     @staticmethod
@@ -24,7 +30,7 @@ class OrientationRecoverySolver:
         Sigma_T > 60 instead of raising (diffusion.py:175-176), `photons_per_pattern` = Poisson photon
         noise on the patterns (BASELINE config 5; the reference has no noise model).
         The large outputs ('Images', 'S2', 'N') are numpy views of reusable pinned host buffers (filled by
-        transfers that overlap stages 2-4).  `copy_results` None (default): results up to 256 MB are
+        transfers that overlap stages 2-4).  `copy_results` None (default): results up to 64 MB are
         copied into private arrays like the reference's, larger ones stay views that are valid until the next
         call of solve; True / False force either.  `images_dtype=np.float32` returns the pattern matrix in the precision
         it is computed in (half the bytes over PCIe; the float64 default only widens the same values).  `validate=False` skips the eigenvalue / convergence guards (compute.py:59-79).
@@ -63,7 +69,7 @@ class OrientationRecoverySolver:
         # is done and overlaps stages 2-4 (side stream + worker thread)
         on_gpu = ops.device.type == 'cuda'
         def private(t, itemsize=8):          # results the caller gets as private arrays (see `copy_results`)
-            return bool(copy_results or (copy_results is None and t.numel() * itemsize <= (256 << 20)))
+            return bool(copy_results or (copy_results is None and t.numel() * itemsize <= PRIVATE_COPY_BYTES))
         start_images = (lambda img: xfer.setdefault('Images', _util.AsyncFetch(
             img, out_dtype=images_dtype, private=private(img, np.dtype(images_dtype).itemsize)))) if on_gpu else None
         # so are the kNN lists (final once the Markov matrix is built): they travel during the eigen-solver
@@ -97,7 +103,7 @@ class OrientationRecoverySolver:
             host['S2'], host['N'] = xfer['S2'].result(), xfer['N'].result()
         lap('large_results_wait_s')
         for key in ('Images', 'S2', 'N'):
-            if key not in xfer and (copy_results or (copy_results is None and host[key].nbytes <= (256 << 20))):
+            if key not in xfer and (copy_results or (copy_results is None and host[key].nbytes <= PRIVATE_COPY_BYTES)):
                 host[key] = np.array(host[key], copy=True)
         lap('private_copies_s')
         if not host['nonzero'][0]:
