@@ -286,6 +286,8 @@ def main():
                     help="Markov operator of the eigen-solver (auto: the form a cost model predicts to be faster -- "
                          "dense FP32 rows for small N, the FP64 kNN-list form otherwise)")
     ap.add_argument("--no-alt-operator", action="store_true", help="skip the extra passes with the other operator form")
+    ap.add_argument("--eig-driver", default=None, choices=["python", "cabi"],
+                    help="eigen-solver driver: the Python host loop or the whole solver behind v3s_eig_topk (default: the backend's)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -316,6 +318,8 @@ def main():
     from v3s.solution import OrientationRecoverySolver
     ops = _util.get_ops()
     ops.operator = args.operator
+    if args.eig_driver:
+        ops.eig_driver = args.eig_driver
     N, n, n_p, k, eps = wl["N"], wl["n"], wl["n_p"], wl["k"], wl["eps"]
     plan = ShardPlan.from_env(N)
     R9, _ = Rotation.random_rotations(N, seed=0)

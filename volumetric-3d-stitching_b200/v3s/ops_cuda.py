@@ -111,7 +111,10 @@ class CudaOps:
         self.use_fused_matvec = True # eigen-solver mat-vecs with the reduction / recurrence / exchange fused (FusedOperator)
         self.use_peer_gram = True    # sharded jobs: symmetric Gram with NVLink peer stores (else rectangular panels)
         self.operator = "auto"       # Markov operator of the eigen-solver: "dense" (FP32 rows), "sparse" (FP64 lists), "auto"
-        self.eig_driver = "python"   # "cabi": the whole eigen-solver through v3s_eig_topk (library-driven, no LAPACK)
+        # "cabi" (default): the whole eigen-solver through ONE C-ABI call, v3s_eig_topk (library-driven: no Python, no
+        # LAPACK in the loop); "python": the host-driven loop of v3s/eig.py (also the fallback when the C-ABI solver
+        # reaches its Krylov cap, and the driver of the deflation rounds of disconnected graphs)
+        self.eig_driver = "cabi"
         self.symm_error = None
         self._pin = None
 

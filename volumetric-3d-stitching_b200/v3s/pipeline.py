@@ -198,21 +198,31 @@ def eigen_stage(ops, plan, P_rows, dis, nev=NEV, validate=True, tol=None, stats=
                                                         and min(plan.counts) >= 1
                                                         and getattr(ops, "use_fused_matvec", True)) else None
 
-        def run_cabi(lock):
-            # the whole solver behind one C-ABI call (v3s_eig_topk); a saturated eigenvalue cluster (disconnected
-            # graph) needs the deflation rounds below, which go through the Python driver
+        def run_cabi():
+            # the whole solver behind one C-ABI call (v3s_eig_topk: block Lanczos + Chebyshev filter + Ritz extraction
+            # driven by the library, no Python / LAPACK in the loop).  -> result, or None when it did not converge
+            # within its Krylov cap (the host-driven solver below then takes over: it restarts and deflates)
             lam_, Y_, res_, info = fused.eig_topk(nev, tol=tol_, seed=seed)
             if stats is not None:
-                prev_mv = stats.get("matvecs", 0)
+                stats["matvecs"] = stats.get("matvecs", 0) + info["matvecs"]
+            if not info["converged"]:
+                if stats is not None:
+                    stats["cabi_not_converged"] = True
+                return None
+            if stats is not None:
+                n_mv = stats["matvecs"]
                 stats.update(info)
-                stats["matvecs"] = prev_mv + info["matvecs"]
-            run.converged = run.converged and info["converged"]
+                stats["matvecs"] = n_mv
+                stats["residual_max"] = float(np.max(res_))
             run.residual = max(run.residual, float(np.max(res_)))
             return lam_, Y_, res_
 
         def run(lock):
+            # (a saturated eigenvalue cluster -- disconnected graph -- needs deflation rounds: host-driven solver)
             if lock is None and fused is not None and getattr(ops, "eig_driver", "python") == "cabi":
-                return run_cabi(lock)
+                r_ = run_cabi()
+                if r_ is not None:
+                    return r_
             st_ = {}
             plain_op = fused.plain if fused is not None else ((lambda Xf, Q: matvec(Q)) if sparse else (lambda Xf, Q: matvec_f32(Xf)))
             pre = fused.sync if fused is not None else None
