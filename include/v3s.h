@@ -367,6 +367,13 @@ typedef struct v3s_sparse_markov {
   const int* t_col;      /* [nnz]   source rows, ascending inside a row                             */
   const double* t_val;   /* [nnz]                                                                   */
   int k;
+  /* optional locality hint (NULL / 0: natural order): a permutation of the rows order_row0 .. order_row0 +
+   * order_rows - 1 (as offsets 0 .. order_rows-1) in which neighbouring patterns are contiguous (the `order` of
+   * v3s_knn_merge_lists).  A mat-vec over exactly that row block walks its rows in this order, one contiguous
+   * chunk per CTA, so that rows processed together gather the same rows of X (their neighbour lists overlap) and
+   * hit in L1.  Results do not depend on it (fixed summation order per row).                                */
+  const int* row_order;
+  long long order_row0, order_rows;
 } v3s_sparse_markov;
 /* s2_to_w_matrix + anisotropic_norm + dm_cov on the lists (as v3s_build_markov) -> the arrays of the
  * descriptor (caller-allocated: a_val [N k], t_ptr [N+1], t_col / t_val [N k]) and dinv_sqrt [N].

@@ -755,6 +755,34 @@ def test_fit_connected(v3s_mod, golden_dir):
         v3s_mod.DiffusionMapSolver.dm_fit_all(g["Ps"], g["R9"], False)
 
 
+@pytest.mark.parametrize("blocks", [[(0, 25000)], [(0, 6250), (6250, 18757), (18757, 25000)]])
+def test_sigma_pairs_fp32_form_large_n(ops, blocks):
+    """rotation.py:214-244 at sizes beyond 20000 patterns: the packed-FP32 pair kernel (32 x 32 ownership blocks,
+    sqrt(1-x) p7(x) arc cosine) against a plain torch FP64 evaluation of the same sum -- in one call, and as the row
+    blocks of a sharded job with unaligned starts (every unordered pair is evaluated by exactly one block; only the
+    total over the blocks is the statistic).  Tolerance: 2e-7 rad mean error per term."""
+    import torch
+    N = 25000
+    g = torch.Generator(device="cpu").manual_seed(3)
+    qe = torch.randn((N, 4), generator=g, dtype=torch.float64)
+    qt = torch.randn((N, 4), generator=g, dtype=torch.float64)
+    qt[: N // 3] = qe[: N // 3] + 1e-3 * qt[: N // 3]                  # a third of the estimates nearly right
+    qe, qt = (x / x.norm(dim=1, keepdim=True) for x in (qe, qt))
+    qe, qt = qe.cuda().contiguous(), qt.cuda().contiguous()
+    got = sum(float(ops.sigma_pairs(qe, qt, r0, r1).item()) for r0, r1 in blocks)
+    ref = 0.0
+    for a in range(0, N, 2500):
+        b = min(a + 2500, N)
+        d1 = torch.acos((qe[a:b] @ qe.T).clamp(0, 1))
+        d2 = torch.acos((qt[a:b] @ qt.T).clamp(0, 1))
+        t = (d1 - d2).abs()
+        idx = torch.arange(a, b, device="cuda")
+        t[idx - a, idx] = 0.0                                           # i == j is not a pair
+        ref += float(t.sum().item())
+    pairs = N * (N - 1)
+    assert abs(got - ref) / pairs < 2e-7, (got, ref, abs(got - ref) / pairs)
+
+
 def test_or_func_and_fit_without_prior(v3s_mod, ops, golden_dir):
     """the constraint residuals of the fit without known orientations against the
     oracle's restatement (both the Python and the Octave expression), the kernel's forward-difference

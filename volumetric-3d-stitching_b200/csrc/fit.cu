@@ -294,6 +294,99 @@ sigma_pairs_kernel(const double* __restrict__ q1, const double* __restrict__ q2,
   if (tid == 0) partials[(long long)blockIdx.y * gridDim.x + blockIdx.x] = acc;
 }
 
+// The FP32 form for large N, restructured: (1) ownership of a pair is decided once per 32 x 32 block of (i, j) -- rows
+// are mapped to threads from a 32-aligned base, so the decision is uniform across a warp and a block that belongs to
+// the transposed side is skipped without touching its elements; (2) two columns per instruction: the j-side
+// quaternions sit in shared memory as float2 pairs (j, j+1) and dots, clip-free polynomial and products run as packed
+// FP32 (FFMA2 / FADD2 / FMUL2); (3) acos(x) on [0,1] as sqrt(1-x) * p7(x) (Abramowitz & Stegun 4.4.46, |error| <= 2e-8)
+// with the approximate square root (1 ulp) instead of the library acosf.  Per-term error ~1e-7 rad like the form above.
+__device__ __forceinline__ float2 sg_acos01_2(float2 x) {
+  const float2 one = make_float2(1.f, 1.f);
+  float2 p = make_float2(-0.0012624911f, -0.0012624911f);
+  p = __ffma2_rn(p, x, make_float2(0.0066700901f, 0.0066700901f));
+  p = __ffma2_rn(p, x, make_float2(-0.0170881256f, -0.0170881256f));
+  p = __ffma2_rn(p, x, make_float2(0.0308918810f, 0.0308918810f));
+  p = __ffma2_rn(p, x, make_float2(-0.0501743046f, -0.0501743046f));
+  p = __ffma2_rn(p, x, make_float2(0.0889789874f, 0.0889789874f));
+  p = __ffma2_rn(p, x, make_float2(-0.2145988016f, -0.2145988016f));
+  p = __ffma2_rn(p, x, make_float2(1.5707963050f, 1.5707963050f));
+  const float2 y = __ffma2_rn(x, make_float2(-1.f, -1.f), one);      // 1 - x >= 0 after the clip
+  float sx, sy;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sx) : "f"(y.x));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sy) : "f"(y.y));
+  return __fmul2_rn(make_float2(sx, sy), p);
+}
+__global__ void __launch_bounds__(SG_T)
+sigma_pairs_f32_kernel(const double* __restrict__ q1, const double* __restrict__ q2, long long N, long long row0,
+                       long long n_rows, long long i_base, long long j_per, double* __restrict__ partials) {
+  // sj[q][pair][t] = (component t of quaternion j = 2 pair, of j = 2 pair + 1); q = 0: estimated, 1: true
+  __shared__ __align__(16) float2 sj[2][SG_T / 2][4];
+  __shared__ double red[32];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const long long i = i_base + (long long)blockIdx.x * SG_T + tid;       // i_base is a multiple of 32
+  const bool i_ok = i >= row0 && i < row0 + n_rows;
+  float a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0};
+  if (i_ok) for (int t = 0; t < 4; ++t) { a1[t] = (float)q1[i * 4 + t]; a2[t] = (float)q2[i * 4 + t]; }
+  const long long bi = i >> 5;                                           // uniform across the warp
+  double acc = 0.0;
+  const long long j0 = (long long)blockIdx.y * j_per;                    // j_per is a multiple of SG_T
+  long long j1 = j0 + j_per;
+  if (j1 > N) j1 = N;
+  for (long long jb = j0; jb < j1; jb += SG_T) {
+    __syncthreads();
+    {
+      const long long j = jb + tid;
+      float* dst1 = reinterpret_cast<float*>(&sj[0][tid >> 1][0]) + (tid & 1);
+      float* dst2 = reinterpret_cast<float*>(&sj[1][tid >> 1][0]) + (tid & 1);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        dst1[2 * t] = j < j1 ? (float)q1[j * 4 + t] : 0.f;
+        dst2[2 * t] = j < j1 ? (float)q2[j * 4 + t] : 0.f;
+      }
+    }
+    __syncthreads();
+    float2 part = make_float2(0.f, 0.f);           // <= 256 terms per partial, then into the FP64 accumulator
+    for (int blk = 0; blk < SG_T / 32; ++blk) {
+      const long long jblk = jb + 32 * blk;
+      if (jblk >= j1) break;
+      const long long bj = jblk >> 5;
+      const bool diag = bi == bj;
+      if (!diag && !((bi < bj) ? (((bi + bj) & 1) == 0) : (((bi + bj) & 1) == 1))) continue;   // the other side's block
+      const int n_in = (int)((j1 - jblk) < 32 ? (j1 - jblk) : 32);
+#pragma unroll 4
+      for (int pp = 0; pp < 16; ++pp) {
+        const int pr = blk * 16 + pp;
+        const float4 u01 = *reinterpret_cast<const float4*>(&sj[0][pr][0]);   // (t0.j, t0.j+1, t1.j, t1.j+1)
+        const float4 u23 = *reinterpret_cast<const float4*>(&sj[0][pr][2]);
+        const float4 v01 = *reinterpret_cast<const float4*>(&sj[1][pr][0]);
+        const float4 v23 = *reinterpret_cast<const float4*>(&sj[1][pr][2]);
+        float2 d1 = __fmul2_rn(make_float2(a1[0], a1[0]), make_float2(u01.x, u01.y));
+        d1 = __ffma2_rn(make_float2(a1[1], a1[1]), make_float2(u01.z, u01.w), d1);
+        d1 = __ffma2_rn(make_float2(a1[2], a1[2]), make_float2(u23.x, u23.y), d1);
+        d1 = __ffma2_rn(make_float2(a1[3], a1[3]), make_float2(u23.z, u23.w), d1);
+        float2 d2 = __fmul2_rn(make_float2(a2[0], a2[0]), make_float2(v01.x, v01.y));
+        d2 = __ffma2_rn(make_float2(a2[1], a2[1]), make_float2(v01.z, v01.w), d2);
+        d2 = __ffma2_rn(make_float2(a2[2], a2[2]), make_float2(v23.x, v23.y), d2);
+        d2 = __ffma2_rn(make_float2(a2[3], a2[3]), make_float2(v23.z, v23.w), d2);
+        d1.x = fminf(fmaxf(d1.x, 0.f), 1.f); d1.y = fminf(fmaxf(d1.y, 0.f), 1.f);      // rotation.py:220 (clip to [0,1])
+        d2.x = fminf(fmaxf(d2.x, 0.f), 1.f); d2.y = fminf(fmaxf(d2.y, 0.f), 1.f);
+        const float2 g1 = sg_acos01_2(d1), g2 = sg_acos01_2(d2);
+        float tx = fabsf(g1.x - g2.x), ty = fabsf(g1.y - g2.y);
+        // columns past the end, and on the diagonal block the pairs with j <= i, do not count
+        const int jx = 2 * pp, jy = 2 * pp + 1;
+        if (jx >= n_in || (diag && jblk + jx <= i)) tx = 0.f;
+        if (jy >= n_in || (diag && jblk + jy <= i)) ty = 0.f;
+        part.x += tx;
+        part.y += ty;
+      }
+    }
+    if (i_ok) acc += 2.0 * ((double)part.x + (double)part.y);
+  }
+  (void)lane;
+  acc = block_sum(acc, red);
+  if (tid == 0) partials[(long long)blockIdx.y * gridDim.x + blockIdx.x] = acc;
+}
+
 __global__ void sum_partials_kernel(const double* __restrict__ partials, int n, double scale, double* __restrict__ out) {
   __shared__ double red[32];
   double acc = 0.0;
@@ -401,14 +494,29 @@ extern "C" int v3s_sigma_pairs(const double* quat_est, const double* quat_true, 
   V3S_REQUIRE(N >= 1 && row0 >= 0 && n_rows >= 0 && row0 + n_rows <= N, "v3s_sigma_pairs: bad shape");
   cudaStream_t st = (cudaStream_t)stream;
   if (n_rows == 0) { V3S_CUDA(cudaMemsetAsync(out_sum, 0, sizeof(double), st)); return 0; }
-  const int gx = (int)ceil_div64(n_rows, SG_T);
-  int gy = (int)ceil_div64(8LL * kNumSMs, gx);
   const long long maxy = ceil_div64(N, SG_T);
+  if (N <= kSigmaFp64MaxN) {
+    const int gx = (int)ceil_div64(n_rows, SG_T);
+    int gy = (int)ceil_div64(8LL * kNumSMs, gx);
+    if (gy > maxy) gy = (int)maxy;
+    if (gy < 1) gy = 1;
+    V3S_REQUIRE((long long)gx * gy <= 65536, "v3s_sigma_pairs: partials workspace (65536 doubles) too small");
+    sigma_pairs_kernel<true><<<dim3(gx, gy), SG_T, 0, st>>>(quat_est, quat_true, N, row0, n_rows, partials_ws);
+    V3S_CHECK_LAUNCH();
+    sum_partials_kernel<<<1, 256, 0, st>>>(partials_ws, gx * gy, 1.0, out_sum);
+    V3S_CHECK_LAUNCH();
+    return 0;
+  }
+  // FP32 form: threads <-> rows from a 32-aligned base, column ranges in multiples of the 256-column chunk
+  const long long i_base = row0 & ~31LL;
+  const int gx = (int)ceil_div64(row0 + n_rows - i_base, SG_T);
+  int gy = (int)ceil_div64(16LL * kNumSMs, gx);
   if (gy > maxy) gy = (int)maxy;
   if (gy < 1) gy = 1;
+  const long long j_per = ceil_div64(ceil_div64(N, gy), SG_T) * SG_T;
+  gy = (int)ceil_div64(N, j_per);
   V3S_REQUIRE((long long)gx * gy <= 65536, "v3s_sigma_pairs: partials workspace (65536 doubles) too small");
-  if (N <= kSigmaFp64MaxN) sigma_pairs_kernel<true><<<dim3(gx, gy), SG_T, 0, st>>>(quat_est, quat_true, N, row0, n_rows, partials_ws);
-  else sigma_pairs_kernel<false><<<dim3(gx, gy), SG_T, 0, st>>>(quat_est, quat_true, N, row0, n_rows, partials_ws);
+  sigma_pairs_f32_kernel<<<dim3(gx, gy), SG_T, 0, st>>>(quat_est, quat_true, N, row0, n_rows, i_base, j_per, partials_ws);
   V3S_CHECK_LAUNCH();
   sum_partials_kernel<<<1, 256, 0, st>>>(partials_ws, gx * gy, 1.0, out_sum);
   V3S_CHECK_LAUNCH();

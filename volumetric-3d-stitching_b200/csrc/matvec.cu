@@ -175,7 +175,8 @@ __global__ void reduce_segments_kernel(const double* __restrict__ Ypart, long lo
 // throughput 12 %, warps active 34 % (profiles/r01_ncu_full_summary.txt) -- latency-bound; fetching
 // the next 32 entries ahead of the gathers and one row per warp without a grid-stride tail were tried
 // and changed nothing (36 -> 38 us), so the simple form stays.
-constexpr int SP_THREADS = 256;
+constexpr int SP_THREADS = 1024;   // 32 warps work on 32 consecutive rows of the processing order: with the neighbourhood order
+                                   // of the kNN stage these share most of their gathers (L1 hits); two CTAs per SM
 
 __device__ __forceinline__ double sp_segment(const int* __restrict__ cols, const double* __restrict__ vals, int len,
                                              const double* __restrict__ X, int ldx, int j, int g, int lane, double acc) {
@@ -227,12 +228,14 @@ __global__ void __launch_bounds__(SP_THREADS)
 sparse_block_matvec_kernel(const int* __restrict__ nbr, const double* __restrict__ a_val, int k,
                            const int* __restrict__ t_ptr, const int* __restrict__ t_col, const double* __restrict__ t_val,
                            long long row0, long long n_rows, const double* __restrict__ X, int ldx,
-                           double* __restrict__ Y, int ldy) {
+                           double* __restrict__ Y, int ldy, const int* __restrict__ order) {
   const int lane = threadIdx.x & 31, j = lane & 7, g = lane >> 3, w = threadIdx.x >> 5;
-  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  // phase 1: one warp per row
-  for (long long r = warp; r < n_rows; r += nwarps) {
+  // phase 1: one warp per row; every CTA walks one contiguous chunk of the processing order
+  const long long per_cta = ceil_div64(n_rows, gridDim.x);
+  const long long c0 = blockIdx.x * per_cta;
+  const long long c1 = c0 + per_cta < n_rows ? c0 + per_cta : n_rows;
+  for (long long idx = c0 + w; idx < c1; idx += SP_THREADS / 32) {
+    const long long r = order ? order[idx] : idx;
     const long long i = row0 + r;
     const int p0 = t_ptr[i];
     const int d = t_ptr[i + 1] - p0;
@@ -347,11 +350,12 @@ static int mv_launch(const float* P_rows, long long ldp, long long n_rows, long 
 static int sp_launch(const v3s_sparse_markov& op, long long row0, long long n_rows, const double* X, int ldx, double* Y,
                      int ldy, cudaStream_t st) {
   long long g = ceil_div64(n_rows, SP_THREADS / 32);
-  if (g > 8LL * kNumSMs) g = 8LL * kNumSMs;
+  if (g > 2LL * kNumSMs) g = 2LL * kNumSMs;
+  const int* order = (op.row_order && op.order_row0 == row0 && op.order_rows == n_rows) ? op.row_order : nullptr;
   cudaEvent_t e1 = nullptr;
   if (int rc = prof_begin(st, &e1)) return rc;
   sparse_block_matvec_kernel<<<(int)g, SP_THREADS, 0, st>>>(op.nbr, op.a_val, op.k, op.t_ptr, op.t_col, op.t_val, row0, n_rows,
-                                                          X, ldx, Y, ldy);
+                                                          X, ldx, Y, ldy, order);
   V3S_CHECK_LAUNCH();
   if (e1) V3S_CUDA(cudaEventRecord(e1, st));
   return 0;

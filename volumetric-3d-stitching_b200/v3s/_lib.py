@@ -33,7 +33,8 @@ class EigProblem(C.Structure):
 
 class SparseMarkovDesc(C.Structure):
     """v3s_sparse_markov (include/v3s.h): device pointers of the sparse operator's arrays."""
-    _fields_ = [("nbr", p), ("a_val", p), ("t_ptr", p), ("t_col", p), ("t_val", p), ("k", i32)]
+    _fields_ = [("nbr", p), ("a_val", p), ("t_ptr", p), ("t_col", p), ("t_val", p), ("k", i32),
+                ("row_order", p), ("order_row0", i64), ("order_rows", i64)]
 
 
 # name -> (restype, argtypes); mirrors include/v3s.h one to one

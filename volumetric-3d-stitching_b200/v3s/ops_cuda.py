@@ -46,13 +46,18 @@ class SparseMarkov:
     """Sparse form of P_ep (v3s_sparse_markov): P = A + A^T on the kNN lists, FP64.  Holds every
     rank's copy of the whole operator (O(N k)); a rank multiplies its own rows [r0, r1)."""
 
-    def __init__(self, nbr, a_val, t_ptr, t_col, t_val, r0, r1):
+    def __init__(self, nbr, a_val, t_ptr, t_col, t_val, r0, r1, row_order=None):
         self.nbr, self.a_val, self.t_ptr, self.t_col, self.t_val = nbr, a_val, t_ptr, t_col, t_val
         self.N, self.k = int(nbr.shape[0]), int(nbr.shape[1])
         self.r0, self.r1 = int(r0), int(r1)
         self.device = nbr.device
+        # row_order (optional): (row0, rows, int32 permutation) -- the neighbourhood order of the kNN stage for this
+        # rank's row block; a locality hint of the mat-vec kernel, never part of the result
+        self.row_order = row_order
+        ro = row_order if (row_order is not None and row_order[0] == self.r0 and row_order[1] == self.r1 - self.r0) else None
         self.desc = _lib.SparseMarkovDesc(nbr.data_ptr(), a_val.data_ptr(), t_ptr.data_ptr(), t_col.data_ptr(),
-                                          t_val.data_ptr(), self.k)
+                                          t_val.data_ptr(), self.k, ro[2].data_ptr() if ro else None,
+                                          ro[0] if ro else 0, ro[1] if ro else 0)
 
     @property
     def n_rows(self):
@@ -65,7 +70,7 @@ class SparseMarkov:
 
     def rows(self, r0, r1):
         """The same operator restricted to another row block (shares the arrays)."""
-        return SparseMarkov(self.nbr, self.a_val, self.t_ptr, self.t_col, self.t_val, r0, r1)
+        return SparseMarkov(self.nbr, self.a_val, self.t_ptr, self.t_col, self.t_val, r0, r1, self.row_order)
 
     def to_dense(self):
         """[n_rows, N] FP64 (tests / tiny problems)."""
@@ -106,6 +111,8 @@ class CudaOps:
         # its patterns' segments from the peers' memory over NVLink (remote slot-counter atomics from inside the
         # kernel's epilogue cost more than the halved MMA work saved)
         self.symmetric_gram_sharded = True
+        self._row_order = None       # (row0, rows, order int32 [rows], N) of the last fused kNN call with a tile order
+        self.sparse_row_order = True # sparse mat-vec: walk the rows in the kNN stage's neighbourhood order (L1 reuse)
         self.share_pairs_across_ranks = True   # sharded tiled refinement: mutual pairs once per JOB, not once per rank
         self.overlap_reserved_sms = 16   # SMs left to NCCL while the all-gather of the FP32 rows overlaps the Gram kernel
         self.use_fused_matvec = True # eigen-solver mat-vecs with the reduction / recurrence / exchange fused (FusedOperator)
@@ -369,6 +376,7 @@ class CudaOps:
             order_ws = self.empty((2 * nr + n_bins,), torch.int32)
             max_tiles = n_bins + nr // qt + 2             # every neighbourhood: its whole tiles + at most one packed flush
             tiles_ws = self.empty((1 + 2 * max_tiles,), torch.int32)
+        self._row_order = None
         h = self._tic("select_refine")
         if sym and world > 1:
             call("v3s_knn_merge_segment_lists", seg_lists, seg_counts, world, Cc, nr, N, r0, k, eps_g, cap, ptr(zero_flag),
@@ -412,6 +420,8 @@ class CudaOps:
             call("v3s_knn_refine", ptr(a32_all[r0:r1]), ptr(a32_all), P, r0, nr, N, k, cap, ptr(zero_flag), ptr(cand), ptr(cnt),
                  ptr(S2), ptr(Nbr), ptr(dws), None, stream_ptr())
         self._toc(h)
+        if order_ws is not None:
+            self._row_order = (r0, nr, order_ws[:nr], N)
         return S2, Nbr
 
     def _sym_dss_arena(self, plan, cap):
@@ -668,7 +678,10 @@ class CudaOps:
         call("v3s_build_markov_sparse", ptr(S2t), ptr(Nbr), N, k, ptr(scalars), ptr(a_val), ptr(t_ptr), ptr(t_col), ptr(t_val),
              ptr(dis), ptr(ws), ptr(iws), stream_ptr())
         self._toc(h)
-        return SparseMarkov(Nbr, a_val, t_ptr, t_col, t_val, r0, r1), dis
+        # the neighbourhood order the kNN stage found for exactly these rows (if it ran in this process for this N)
+        ro = self._row_order if (self._row_order is not None and self._row_order[0] == r0 and self._row_order[1] == r1 - r0
+                                 and self._row_order[3] == N and self.sparse_row_order) else None
+        return SparseMarkov(Nbr, a_val, t_ptr, t_col, t_val, r0, r1, ro[:3] if ro else None), dis
 
     def sparse_block_matvec(self, sp, X, out=None):
         """Y_rows [n_rows,b] f64 = P[r0:r1, :] @ X [N,b] (f64), sparse operator."""
