@@ -15,7 +15,7 @@
 
 namespace v3s {
 
-struct PixelTap {   // 16 bytes
+struct __align__(16) PixelTap {   // 16 bytes, one 128-bit load
   int   idx;        // i0 | i1<<8 | zrel<<16 | valid<<24
   float t0, t1, t2;
 };
@@ -56,6 +56,7 @@ synth_kernel(const float* __restrict__ ed, const double* __restrict__ rot, const
   float2* tmp  = slab + nz * n2;                                              // nz*n^2
   float*  gmag = reinterpret_cast<float*>(tmp + nz * n2);                     // nz*n^2
   float2* tw   = reinterpret_cast<float2*>(gmag + ((nz * n2 + 1) & ~1));      // n
+  float2* twk  = tw + n;                                                       // kMaxPlanes * n: twiddles of the axis-2 DFT
   __shared__ double Rm[9];
   __shared__ double Uax[kSynthMaxN];                                          // U_i, rotation.py:146
 
@@ -71,6 +72,13 @@ synth_kernel(const float* __restrict__ ed, const double* __restrict__ rot, const
 #pragma unroll
   for (int z = 0; z < kMaxPlanes; ++z) fz[z] = (((prm.z0 + z) - n / 2) % n + n) % n;
 
+  __syncthreads();
+  // axis-2 DFT of plane z at position k: exp(-2 pi i k f_z / n) = tw[(k f_z) mod n] -- the same for every column, so
+  // tabulated once per CTA instead of a running phase per thread
+  for (int i = tid; i < kMaxPlanes * n; i += kSynthThreads) {
+    const int z = i / n, k = i - z * n;
+    twk[i] = tw[(k * fz[z]) % n];
+  }
   const double half_n = 0.5 * (double)n;
   const double U0 = (1.0 - (n + 1) * 0.5) / half_n;   // U_i = (i + 1 - (n+1)/2) / (n/2), rotation.py:146
   const double Ulast = ((double)n - (n + 1) * 0.5) / half_n;
@@ -93,38 +101,50 @@ synth_kernel(const float* __restrict__ ed, const double* __restrict__ rot, const
       float2 acc[kMaxPlanes];
 #pragma unroll
       for (int z = 0; z < kMaxPlanes; ++z) acc[z] = make_float2(0.f, 0.f);
-      int ph[kMaxPlanes];
-#pragma unroll
-      for (int z = 0; z < kMaxPlanes; ++z) ph[z] = 0;
-      for (int k = 0; k < n; ++k) {
+      // one voxel of the rotated object: trilinear sample of F at R p, p = (U_j, U_k, U_i); 0 outside the grid
+      // (rotation.py:152-160).  Branch-free (clamped cell, value selected at the end) so that two voxels per
+      // iteration interleave their dependent chains: FP64 coordinates -> cell split -> 8 gathers -> 7 lerps.
+      auto sample = [&](int k) -> float {
         const double py = Uax[k];                      // (warp-wide broadcast from shared memory)
         const double q0 = b0 + r01 * py, q1 = b1 + r11 * py, q2 = b2 + r21 * py;
-        float v = 0.f;
         const bool inb = !(q0 < U0 || q0 > Ulast || q1 < U0 || q1 > Ulast || q2 < U0 || q2 > Ulast);
-        if (inb) {
-          // grid coordinate f = (q - U0) n/2 in [0, n-1]; cell index and FP32 weight without double <-> int
-          // conversions (quarter-rate pipe): adding 2^52 + 2^51 rounds f to the nearest integer in the low word
-          int i0, i1, i2;
-          float t0, t1, t2;
-          split_cell(fma(q0, half_n, mU0h), n, i0, t0);
-          split_cell(fma(q1, half_n, mU0h), n, i1, t1);
-          split_cell(fma(q2, half_n, mU0h), n, i2, t2);
-          const float* b = F + (i0 * n + i1) * n + i2;
-          const float c000 = b[0], c001 = b[1], c010 = b[n], c011 = b[n + 1];
-          const float c100 = b[n2], c101 = b[n2 + 1], c110 = b[n2 + n], c111 = b[n2 + n + 1];
-          const float c00 = c000 + t2 * (c001 - c000), c01 = c010 + t2 * (c011 - c010);
-          const float c10 = c100 + t2 * (c101 - c100), c11 = c110 + t2 * (c111 - c110);
-          const float c0 = c00 + t1 * (c01 - c00), c1 = c10 + t1 * (c11 - c10);
-          v = c0 + t0 * (c1 - c0);
-        }
+        // grid coordinate f = (q - U0) n/2 in [0, n-1]; cell index and FP32 weight without double <-> int
+        // conversions (quarter-rate pipe): adding 2^52 + 2^51 rounds f to the nearest integer in the low word
+        int i0, i1, i2;
+        float t0, t1, t2;
+        split_cell(inb ? fma(q0, half_n, mU0h) : 0.0, n, i0, t0);
+        split_cell(inb ? fma(q1, half_n, mU0h) : 0.0, n, i1, t1);
+        split_cell(inb ? fma(q2, half_n, mU0h) : 0.0, n, i2, t2);
+        const float* b = F + (i0 * n + i1) * n + i2;
+        const float c000 = b[0], c001 = b[1], c010 = b[n], c011 = b[n + 1];
+        const float c100 = b[n2], c101 = b[n2 + 1], c110 = b[n2 + n], c111 = b[n2 + n + 1];
+        const float c00 = c000 + t2 * (c001 - c000), c01 = c010 + t2 * (c011 - c010);
+        const float c10 = c100 + t2 * (c101 - c100), c11 = c110 + t2 * (c111 - c110);
+        const float c0 = c00 + t1 * (c01 - c00), c1 = c10 + t1 * (c11 - c10);
+        return inb ? c0 + t0 * (c1 - c0) : 0.f;
+      };
+      int k = 0;
+      for (; k + 1 < n; k += 2) {
+        const float v0 = sample(k), v1 = sample(k + 1);
 #pragma unroll
         for (int z = 0; z < kMaxPlanes; ++z) {
           if (z < nz) {
-            const float2 w = tw[ph[z]];
-            acc[z].x = fmaf(v, w.x, acc[z].x);
-            acc[z].y = fmaf(v, w.y, acc[z].y);
-            ph[z] += fz[z];
-            if (ph[z] >= n) ph[z] -= n;
+            const float2 w0 = twk[z * n + k], w1 = twk[z * n + k + 1];
+            acc[z].x = fmaf(v0, w0.x, acc[z].x);
+            acc[z].y = fmaf(v0, w0.y, acc[z].y);
+            acc[z].x = fmaf(v1, w1.x, acc[z].x);
+            acc[z].y = fmaf(v1, w1.y, acc[z].y);
+          }
+        }
+      }
+      if (k < n) {
+        const float v0 = sample(k);
+#pragma unroll
+        for (int z = 0; z < kMaxPlanes; ++z) {
+          if (z < nz) {
+            const float2 w0 = twk[z * n + k];
+            acc[z].x = fmaf(v0, w0.x, acc[z].x);
+            acc[z].y = fmaf(v0, w0.y, acc[z].y);
           }
         }
       }
@@ -169,21 +189,32 @@ synth_kernel(const float* __restrict__ ed, const double* __restrict__ rot, const
 
     // ---- phase C: sample on the detector grid -----------------------------------------
     float* dst = out + pat * out_stride;
-    for (int p = tid; p < prm.P; p += kSynthThreads) {
-      const PixelTap t = taps[p];
-      float v = 0.f;
-      if (t.idx >> 24) {
-        const int i0 = t.idx & 0xff, i1 = (t.idx >> 8) & 0xff, z = (t.idx >> 16) & 0xff;
-        const float* g0 = gmag + z * n2 + i0 * n + i1;
-        const float* g1 = g0 + n2;
-        const float a00 = g0[0] + t.t2 * (g1[0] - g0[0]);
-        const float a01 = g0[1] + t.t2 * (g1[1] - g0[1]);
-        const float a10 = g0[n] + t.t2 * (g1[n] - g0[n]);
-        const float a11 = g0[n + 1] + t.t2 * (g1[n + 1] - g0[n + 1]);
-        const float a0 = a00 + t.t1 * (a01 - a00), a1 = a10 + t.t1 * (a11 - a10);
-        v = a0 + t.t0 * (a1 - a0);
+    // four pixels per iteration: their tap records (global / L2) are requested together, so one memory latency
+    // covers four interpolations instead of one
+    for (int p0 = tid; p0 < prm.P; p0 += 4 * kSynthThreads) {
+      PixelTap t[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int p = p0 + u * kSynthThreads;
+        t[u] = p < prm.P ? taps[p] : PixelTap{0, 0.f, 0.f, 0.f};
       }
-      dst[p] = v;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int p = p0 + u * kSynthThreads;
+        float v = 0.f;
+        if (t[u].idx >> 24) {
+          const int i0 = t[u].idx & 0xff, i1 = (t[u].idx >> 8) & 0xff, z = (t[u].idx >> 16) & 0xff;
+          const float* g0 = gmag + z * n2 + i0 * n + i1;
+          const float* g1 = g0 + n2;
+          const float a00 = g0[0] + t[u].t2 * (g1[0] - g0[0]);
+          const float a01 = g0[1] + t[u].t2 * (g1[1] - g0[1]);
+          const float a10 = g0[n] + t[u].t2 * (g1[n] - g0[n]);
+          const float a11 = g0[n + 1] + t[u].t2 * (g1[n + 1] - g0[n + 1]);
+          const float a0 = a00 + t[u].t1 * (a01 - a00), a1 = a10 + t[u].t1 * (a11 - a10);
+          v = a0 + t[u].t0 * (a1 - a0);
+        }
+        if (p < prm.P) dst[p] = v;
+      }
     }
   }
 }
@@ -377,7 +408,7 @@ extern "C" int v3s_synth_patterns(const float* ed, int n, const double* rot9, lo
   const int P = n_p * n_p;
   const int n2 = n * n, n3 = n2 * n;
   size_t smem = sizeof(float) * ((n3 + 3) & ~3) + 2 * sizeof(float2) * nz * n2 + sizeof(float) * ((nz * n2 + 1) & ~1) +
-                sizeof(float2) * n;
+                sizeof(float2) * n + sizeof(float2) * kMaxPlanes * n;
   V3S_REQUIRE(smem <= 227 * 1024, "v3s_synth_patterns: object n=%d needs %zu B shared memory (max 232448)", n, smem);
   static size_t smem_set = 0;
   if (smem > smem_set) {
