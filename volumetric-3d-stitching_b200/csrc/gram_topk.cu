@@ -747,6 +747,35 @@ __global__ void split_f16_kernel(const float* __restrict__ a, long long n_rows, 
   }
 }
 
+// One digit of the radix select, by warp 0: the largest digit d whose suffix count sum(hist[d .. 255]) reaches
+// `remaining` (d = 0 if none does), and the count above it.  Lane l owns bins 8l .. 8l+7; the suffix sums over lanes
+// come from five shuffles, only the lane that contains the crossing walks its eight bins.
+__device__ __forceinline__ void radix_pick_digit(const int* __restrict__ hist, int remaining, int* d_out, int* above_out) {
+  const int lane = threadIdx.x & 31;
+  int t = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t += hist[8 * lane + i];
+  int sfx = t;                                            // inclusive suffix sum over lanes >= lane
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_down_sync(0xffffffffu, sfx, o);
+    if (lane + o < 32) sfx += v;
+  }
+  const unsigned reach = __ballot_sync(0xffffffffu, sfx >= remaining);
+  const int owner = reach ? 31 - __clz(reach) : 0;
+  if (lane == owner) {
+    int cum = sfx - t, d = 8 * lane + 7;
+    for (; d > 8 * lane; --d) {
+      if (cum + hist[d] >= remaining) break;
+      cum += hist[d];
+    }
+    // (no break: d = 8 lane, which reaches `remaining` by the choice of the owner -- or, without any crossing,
+    // owner = 0 and d = 0 with everything above it counted, like a serial scan from 255 down to 1)
+    *d_out = d;
+    *above_out = cum;
+  }
+}
+
 // Unite the S per-segment lists of every row: k-th largest g~ over the union (4-pass radix select in
 // shared memory), candidates = every entry within `band` of it (at most cap, the largest first on
 // overflow).  Zero-norm patterns (0/0 -> NaN -> distance 0 in the reference, distance.py:58) have
@@ -826,14 +855,14 @@ knn_merge_kernel(const unsigned long long* __restrict__ lists, const int* __rest
         if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1);
       }
       __syncthreads();
-      if (tid == 0) {
-        int cum = 0, d = 255;
-        for (; d > 0; --d) {
-          if (cum + hist[d] >= remaining) break;
-          cum += hist[d];
+      if (tid < 32) {
+        __shared__ int s_d, s_above;
+        radix_pick_digit(hist, remaining, &s_d, &s_above);
+        __syncwarp();
+        if (tid == 0) {
+          s_prefix = prefix | ((uint32_t)s_d << shift);
+          s_remaining = remaining - s_above;
         }
-        s_prefix = prefix | ((uint32_t)d << shift);
-        s_remaining = remaining - cum;
       }
       __syncthreads();
       prefix = s_prefix;
@@ -871,14 +900,14 @@ knn_merge_kernel(const unsigned long long* __restrict__ lists, const int* __rest
           if ((key & m2) == p2) atomicAdd(&hist[(key >> shift) & 255u], 1);
         }
         __syncthreads();
-        if (tid == 0) {
-          int cum = 0, d = 255;
-          for (; d > 0; --d) {
-            if (cum + hist[d] >= rem2) break;
-            cum += hist[d];
+        if (tid < 32) {
+          __shared__ int s_d2, s_above2;
+          radix_pick_digit(hist, rem2, &s_d2, &s_above2);
+          __syncwarp();
+          if (tid == 0) {
+            s_prefix = p2 | ((uint32_t)s_d2 << shift);
+            s_remaining = rem2 - s_above2;
           }
-          s_prefix = p2 | ((uint32_t)d << shift);
-          s_remaining = rem2 - cum;
         }
         __syncthreads();
         p2 = s_prefix;
@@ -1041,14 +1070,14 @@ knn_limits_kernel(const unsigned long long* __restrict__ lists, const int* __res
         if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1);
       }
       __syncthreads();
-      if (tid == 0) {
-        int cum = 0, d = 255;
-        for (; d > 0; --d) {
-          if (cum + hist[d] >= remaining) break;
-          cum += hist[d];
+      if (tid < 32) {
+        __shared__ int s_d, s_above;
+        radix_pick_digit(hist, remaining, &s_d, &s_above);
+        __syncwarp();
+        if (tid == 0) {
+          s_prefix = prefix | ((uint32_t)s_d << shift);
+          s_remaining = remaining - s_above;
         }
-        s_prefix = prefix | ((uint32_t)d << shift);
-        s_remaining = remaining - cum;
       }
       __syncthreads();
       prefix = s_prefix;
