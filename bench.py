@@ -227,6 +227,17 @@ def cpu_baseline_block(wl, sample_n):
                           t["diffusion"], t["fit"], " (each x (N/Ns)^2)" if extrap else ""))}
 
 
+def workload_config(wl, world):
+    """The `config` object of the JSON line -- the same for both arms (it names the workload, not the implementation)."""
+    N, P = wl["N"], wl["n_p"] ** 2
+    cfg = {"workload": wl["desc"], "N": N, "pixels": P, "object_voxels_1d": wl["n"], "k": wl["k"], "epsilon": wl["eps"],
+           "rotations": "uniform random SO(3), seed 0", "parallelism": "rows%d" % world,
+           "l2": "inputs larger than L2 (pattern matrix %.0f MB)" % (N * P * 4 / 1e6)}
+    if wl.get("photons"):
+        cfg["photons_per_pattern"] = wl["photons"]
+    return cfg
+
+
 def run_reference_arm(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -252,8 +263,7 @@ def run_reference_arm(args, wl):
     line = {"impl": "reference", "metric": METRIC, "value": round(v, 3), "unit": "s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(v * 1e3, 1), "higher_is_better": False, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl["desc"], "N": wl["N"], "pixels": wl["n_p"] ** 2, "object_voxels_1d": wl["n"], "k": wl["k"],
-                       "epsilon": wl["eps"], "rotations": "uniform random SO(3), seed 0"},
+            "config": workload_config(wl, int(os.environ.get("WORLD_SIZE", "1"))),
             "steps_run": done, "extrapolated": extrap,
             "wall_seconds_of_each_pass_run": [round(w, 2) for w in walls],
             "cpu_baseline": {"value": round(v, 3), "unit": "s", "cores": cores, "kind": "port", "extrapolated": extrap,
@@ -277,7 +287,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="v3s", choices=["v3s", "reference"])
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-sample", type=int, default=4000,
+    ap.add_argument("--cpu-sample", type=int, default=8000,
                     help="patterns of the CPU arm when the workload is too large to run whole (N > %d)" % FULL_N_LIMIT)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-baseline-only", action="store_true", help=argparse.SUPPRESS)
@@ -559,12 +569,10 @@ def main():
         "metric": METRIC, "value": round(ms / 1e3, 5), "unit": "s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms, 3), "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["desc"], "N": N, "pixels": P, "object_voxels_1d": n, "k": k, "epsilon": eps,
-                   "rotations": "uniform random SO(3), seed 0", "parallelism": "rows%d" % world,
-                   "untimed_passes_before_the_timed_region": args.warmup + extra_warmup,
-                   "l2": "inputs larger than L2 (pattern matrix %.0f MB, Markov matrix %.0f MB)" % (N * P * 4 / 1e6, rows_local * N * 4 / 1e6),
-                   "arithmetic": "FP16 tcgen05 Gram (one product, FP32 accumulate; ranks kNN candidates only), FP32 exact "
-                                 "distances / synthesis, FP64 Markov operator, reductions and eigen-solver"},
+        "config": workload_config(wl, world),
+        "untimed_passes_before_the_timed_region": args.warmup + extra_warmup,
+        "arithmetic": "FP16 tcgen05 Gram (one product, FP32 accumulate; ranks kNN candidates only), FP32 exact "
+                      "distances / synthesis, FP64 Markov operator, reductions and eigen-solver",
         "clocks": clocks,
         "e2e": e2e,
         "gpu_launches": int(launches),

@@ -1,11 +1,12 @@
 #!/bin/bash
 # ncu evidence of round 2 (run on the GPU box through gpurun; one GPU).  Every profiled command line first runs
-# plain (&&) as B200_PROFILING.md asks.  Outputs go to gpurun_out/; the summaries are copied to profiles/ by hand.
+# plain (&&) as B200_PROFILING.md asks.  Outputs go to gpurun_out/; the summaries are copied to profiles/ by
+# profiles/summarize_ncu.py r02.
 set -x
 B="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-alt-operator --no-e2e"
 $B > gpurun_out/r02_plain_cfg4.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02_launches_cfg4.csv $B > gpurun_out/r02_ncu_launches.log 2>&1
-for K in gram_sym_topk_kernel refine_tiled_kernel synth_kernel; do
+for K in gram_sym_topk_kernel refine_tiled_kernel synth_kernel sigma_pairs_f32_kernel knn_merge_kernel; do
   ncu --set full --clock-control none --import-source on -k regex:$K -s 1 -c 1 -o gpurun_out/r02_prof_$K $B > gpurun_out/r02_ncu_$K.log 2>&1
 done
 ncu --set full --clock-control none --import-source on -k regex:sparse_block_matvec -s 130 -c 2 -o gpurun_out/r02_prof_sparse_matvec $B > gpurun_out/r02_ncu_spmv.log 2>&1

@@ -236,6 +236,59 @@ def test_fused_gram_topk_saturated_lists_are_reported(ops):
     assert np.all(np.diff(S2, axis=1) >= 0) and np.all(np.isfinite(S2))
 
 
+def test_integration_md_raw_ctypes_binding_of_stage_2(golden_dir):
+    """INTEGRATION.md, option B: DistanceMatrix.knn (distance.py:17-22) bound straight to the C-ABI with ctypes and
+    torch as the allocator only -- the fused entry points in the order the document shows them -- against the
+    reference's own output on the connected fixture."""
+    import ctypes as C
+    ROOT_ = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = C.CDLL(os.path.join(ROOT_, "volumetric-3d-stitching_b200", "v3s", "libv3s.so"))
+    lib.v3s_last_error.restype = C.c_char_p
+    P = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+    ST = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    LL = C.c_longlong
+
+    def ok(rc):
+        if rc:
+            raise Exception(lib.v3s_last_error().decode())
+
+    g = np.load(os.path.join(golden_dir, "connected_n15.npz"))
+    k = int(g["k"])
+    img = torch.as_tensor(g["Images_f32"], dtype=torch.float32).cuda()
+    N, Pp = img.shape
+    Ppad = (Pp + 63) // 64 * 64
+    sums = torch.empty(Pp, dtype=torch.float64, device="cuda")
+    ok(lib.v3s_column_sums(P(img), LL(N), Pp, LL(Pp), P(sums), ST()))
+    mean = sums / N
+    a32 = torch.empty((N, Pp), dtype=torch.float32, device="cuda")
+    zf = torch.empty(N, dtype=torch.int32, device="cuda")
+    ok(lib.v3s_center_normalize(P(img), LL(N), Pp, LL(Pp), P(mean), P(a32), None, None, Ppad, None, P(zf), ST()))
+    a16 = torch.empty((N, Ppad), dtype=torch.float16, device="cuda")
+    ok(lib.v3s_split_f16(P(a32), LL(N), Pp, Ppad, P(a16), ST()))
+    pl = (C.c_int * 4)()
+    ok(lib.v3s_gram_topk_plan(LL(N), LL(N), k, pl))
+    lists = torch.empty(pl[2] * pl[0] * pl[1], dtype=torch.int64, device="cuda")
+    counts = torch.empty(pl[2] * pl[0], dtype=torch.int32, device="cuda")
+    ws = torch.empty(pl[3], dtype=torch.int32, device="cuda")
+    ovf = torch.zeros(1, dtype=torch.int32, device="cuda")
+    eps_g = 2.0 ** -10 * (1 + 2.0 ** -11) + 1.2e-7 * Pp / 16 + 2e-6
+    ok(lib.v3s_gram_topk(P(a16), LL(N), P(a16), LL(N), Ppad, k, C.c_float(eps_g), P(lists), P(counts), P(ovf), P(ws), ST()))
+    cap = min(k + 8 + 160, N)
+    cand = torch.empty((N, cap), dtype=torch.int32, device="cuda")
+    cnt = torch.empty(N, dtype=torch.int32, device="cuda")
+    zws = torch.empty(cap + 1, dtype=torch.int32, device="cuda")
+    ok(lib.v3s_knn_merge_lists(P(lists), P(counts), pl[0], pl[1], LL(N), LL(N), LL(0), k, C.c_float(eps_g), cap, P(zf), P(zws),
+                               P(cand), P(cnt), P(ovf), 1, None, 1, 0, None, ST()))
+    S2 = torch.empty((N, k), dtype=torch.float64, device="cuda")
+    Nbr = torch.empty((N, k), dtype=torch.int32, device="cuda")
+    ok(lib.v3s_knn_refine(P(a32), P(a32), Pp, LL(0), LL(N), LL(N), k, cap, P(zf), P(cand), P(cnt), P(S2), P(Nbr), None, None, ST()))
+    torch.cuda.synchronize()
+    assert int(ovf.item()) == 0
+    S2h, Nh = S2.cpu().numpy(), Nbr.cpu().numpy().astype(float)
+    assert hybrid_frac_bad(S2h, g["S2"], 1e-5) == 0.0
+    assert np.mean(Nh == g["N"]) > 0.9999
+
+
 def test_knn_connected_fixture(v3s_mod, golden_dir):
     g = np.load(os.path.join(golden_dir, "connected_n15.npz"))
     S2, N = v3s_mod.DistanceMatrix.knn(g["Images_f32"].astype(np.float64), int(g["k"]))

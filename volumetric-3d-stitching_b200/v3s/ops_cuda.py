@@ -85,6 +85,19 @@ class SparseMarkov:
         return P[self.r0:self.r1]
 
 
+class _StreamEvents:
+    """wait(): the current stream waits for the recorded events (transfers issued on side streams)."""
+    uses_sms = False
+
+    def __init__(self, events):
+        self.events = events
+
+    def wait(self):
+        cur = torch.cuda.current_stream()
+        for ev in self.events:
+            cur.wait_event(ev)
+
+
 class CudaOps:
     name = "cuda-sm100a"
 
@@ -111,6 +124,7 @@ class CudaOps:
         # its patterns' segments from the peers' memory over NVLink (remote slot-counter atomics from inside the
         # kernel's epilogue cost more than the halved MMA work saved)
         self.symmetric_gram_sharded = True
+        self.copy_engine_gather = True   # sharded jobs: operand all-gathers as copy-engine pulls from symmetric memory
         self._row_order = None       # (row0, rows, order int32 [rows], N) of the last fused kNN call with a tile order
         self.sparse_row_order = True # sparse mat-vec: walk the rows in the kNN stage's neighbourhood order (L1 reuse)
         self.share_pairs_across_ranks = True   # sharded tiled refinement: mutual pairs once per JOB, not once per rank
@@ -226,11 +240,11 @@ class CudaOps:
         call("v3s_column_sums", ptr(img), img.shape[0], img.shape[1], img.stride(0), ptr(sums), stream_ptr())
         return sums
 
-    def center_normalize(self, img, mean, want_split=True):
+    def center_normalize(self, img, mean, want_split=True, out_a32=None):
         """-> a32 [n,P] f32, hi, lo [n,Ppad] bf16 (or None), zero_flag [n] i32."""
         n, P = img.shape
         Ppad = round_up(P, GRAM_KPAD)
-        a32 = self.empty((n, P), torch.float32)
+        a32 = out_a32 if out_a32 is not None else self.empty((n, P), torch.float32)
         hi = self.empty((n, Ppad), torch.bfloat16) if want_split else None
         lo = self.empty((n, Ppad), torch.bfloat16) if want_split else None
         zf = self.empty((n,), torch.int32)
@@ -249,11 +263,11 @@ class CudaOps:
         call("v3s_split_bf16", ptr(a32), n, P, Ppad, ptr(hi), ptr(lo), stream_ptr())
         return hi, lo
 
-    def split_f16(self, a32):
+    def split_f16(self, a32, out=None):
         """FP16 operand fl16(2^8 a) [n,Ppad] of the fused Gram / top-k kernel."""
         n, P = a32.shape
         Ppad = round_up(P, GRAM_KPAD)
-        a16 = self.empty((n, Ppad), torch.float16)
+        a16 = out if out is not None else self.empty((n, Ppad), torch.float16)
         call("v3s_split_f16", ptr(a32), n, P, Ppad, ptr(a16), stream_ptr())
         return a16
 
@@ -281,8 +295,8 @@ class CudaOps:
             return S2, Nbr
         self.knn_overflow = self.zeros((1,), torch.int32)
         eps_g = fused_gram_error_bound(P)
-        if a32_ready is not None:                      # leave room for the collective that runs beside the Gram kernel
-            call("v3s_set_gram_reserved_sms", self.overlap_reserved_sms)
+        if a32_ready is not None and getattr(a32_ready, "uses_sms", True):
+            call("v3s_set_gram_reserved_sms", self.overlap_reserved_sms)   # room for the NCCL kernels running beside the Gram kernel
         stride = self.sym_stride()
         # symmetric form (half the MMA work + a 1/stride sampling pass) for large problems: the whole matrix on one
         # GPU, or the rank's share of the upper-triangle tiles with per-owner lists merged over NVLink
@@ -338,7 +352,7 @@ class CudaOps:
             else:
                 import torch.distributed as dist
                 lim = plan.all_gather_rows(lim_loc)
-                counts_loc, pls, pcs, seg_lists, seg_counts = peer
+                counts_loc, pls, pcs, seg_lists, seg_counts, hdl_lists = peer
                 # (the all-gather above is also the barrier that orders the peers' merge of the previous pass's
                 # segments before the counters are cleared)
                 counts_loc.zero_()
@@ -347,7 +361,7 @@ class CudaOps:
                 # segments straight from the ranks that produced them
                 call("v3s_gram_topk_sym", ptr(a16_all), N, a16_all.shape[1], ptr(lim), Cc, pls, pcs, world, plan.rank, base, rem,
                      ptr(step_ws), stream_ptr())
-                dist.barrier(group=plan.group)           # every rank's segments are complete
+                hdl_lists.barrier()                      # every rank's segments are complete (device-side, stream-ordered)
                 lists = counts = None
         else:
             call("v3s_gram_topk_plan", nr, N, k, pl)
@@ -406,13 +420,13 @@ class CudaOps:
                      ptr(npw), 1 if self.dedup_refine else 0, stream_ptr())
             else:
                 import torch.distributed as dist
-                dws, peer_dss = share
+                dws, peer_dss, hdl_dss = share
                 cand_all = plan.all_gather_rows(cand)
                 cnt_all = plan.all_gather_rows(cnt)        # (also orders the peers' reads of the previous pass before the memset)
                 call("v3s_knn_refine_tiled_pairs", ptr(a32_all[r0:r1]), ptr(a32_all), P, r0, nr, N, cap, ptr(cand), ptr(cnt),
                      ptr(dws), ptr(order_ws), ptr(tiles_ws), max_tiles, ptr(pref), ptr(keys), ptr(npw), 1, ptr(cand_all),
                      ptr(cnt_all), stream_ptr())
-                dist.barrier(group=plan.group)             # every rank's pair sums are complete
+                hdl_dss.barrier()                          # every rank's pair sums are complete (device-side, stream-ordered)
                 base, rem = divmod(N, world)
                 call("v3s_knn_refine_tiled_emit", r0, nr, N, k, cap, ptr(zero_flag), ptr(cand), ptr(cnt), ptr(S2), ptr(Nbr),
                      ptr(dws), ptr(pref), peer_dss, world, base, rem, stream_ptr())
@@ -423,6 +437,57 @@ class CudaOps:
         if order_ws is not None:
             self._row_order = (r0, nr, order_ws[:nr], N)
         return S2, Nbr
+
+    def rows_arena(self, plan, P):
+        """The rank's centred unit rows (FP32 [cmax, P]) and Gram operand (FP16 [cmax, Ppad]) in torch symmetric memory,
+        so that the peers can PULL them with copy-engine transfers (`gather_rows_by_copy_engines`) instead of an NCCL
+        all-gather whose kernels would take SMs from the Gram kernels running beside it.
+        -> dict(a32, a16: local tensors; a32_peer, a16_peer: every rank's buffer as mapped here; hdl) or None."""
+        import torch.distributed as dist
+        if not self.copy_engine_gather:
+            return None
+        Ppad = round_up(P, GRAM_KPAD)
+        key = ("rows", plan.N, plan.world, plan.rank, P)
+        ent = self._symm_G.get(key)
+        if ent is None:
+            try:
+                import torch.distributed._symmetric_memory as symm
+                cmax = max(plan.counts)
+                b32 = round_up(cmax * P * 4, 256)
+                buf = symm.empty((b32 + cmax * Ppad * 2,), dtype=torch.uint8, device=self.device)
+                hdl = symm.rendezvous(buf, plan.group if plan.group is not None else dist.group.WORLD)
+                ent = {"buf": buf, "hdl": hdl,
+                       "a32": buf[: cmax * P * 4].view(torch.float32).view(cmax, P),
+                       "a16": buf[b32: b32 + cmax * Ppad * 2].view(torch.float16).view(cmax, Ppad),
+                       "a32_peer": [hdl.get_buffer(r, (cmax, P), torch.float32, 0) for r in range(plan.world)],
+                       "a16_peer": [hdl.get_buffer(r, (cmax, Ppad), torch.float16, b32 // 2) for r in range(plan.world)],
+                       "streams": [torch.cuda.Stream() for _ in range(min(4, max(1, plan.world - 1)))]}
+            except Exception as e:                      # no peer access / API missing: NCCL all-gathers instead
+                ent = False
+                self.symm_error = repr(e)
+            self._symm_G[key] = ent
+        return None if ent is False else ent
+
+    def gather_rows_by_copy_engines(self, arena, plan, which, out):
+        """out [N, ...] <- every rank's block of arena[which] ("a16" / "a32"), pulled over NVLink by the copy engines on
+        side streams (no SMs).  The caller has made sure every rank's block is complete (a collective after the kernels
+        that wrote it).  -> an object whose wait() makes the current stream wait for the transfers."""
+        ready = torch.cuda.Event()
+        ready.record()
+        events = []
+        streams = arena["streams"]
+        for i in range(plan.world):
+            q = (plan.rank + i) % plan.world                   # own block first, then the peers in rotating order
+            st = streams[i % len(streams)]
+            st.wait_event(ready)
+            with torch.cuda.stream(st):
+                out[plan.offsets[q]: plan.offsets[q] + plan.counts[q]].copy_(arena[which + "_peer"][q][: plan.counts[q]],
+                                                                              non_blocking=True)
+        for st in streams:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            events.append(ev)
+        return _StreamEvents(events)
 
     def _sym_dss_arena(self, plan, cap):
         """The rank's pair-sum workspace [cmax, cap] FP64 of the tiled refinement in torch symmetric memory (peers read
@@ -436,7 +501,7 @@ class CudaOps:
                 cmax = max(plan.counts)
                 buf = symm.empty((cmax, cap), dtype=torch.float64, device=self.device)
                 hdl = symm.rendezvous(buf, plan.group if plan.group is not None else dist.group.WORLD)
-                ent = (buf, (C.c_ulonglong * plan.world)(*[int(x) for x in hdl.buffer_ptrs]))
+                ent = (buf, (C.c_ulonglong * plan.world)(*[int(x) for x in hdl.buffer_ptrs]), hdl)
             except Exception as e:                      # no peer access / API missing: every rank evaluates its own pairs
                 ent = False
                 self.symm_error = repr(e)
@@ -467,12 +532,12 @@ class CudaOps:
                 u64 = C.c_ulonglong * w
                 ent = (counts,
                        u64(*[mine + o * seg for o in range(w)]), u64(*[mine + lbytes + o * cmax * 4 for o in range(w)]),
-                       u64(*[b + plan.rank * seg for b in bases]), u64(*[b + lbytes + plan.rank * cmax * 4 for b in bases]), buf)
+                       u64(*[b + plan.rank * seg for b in bases]), u64(*[b + lbytes + plan.rank * cmax * 4 for b in bases]), hdl, buf)
             except Exception as e:                      # no peer access / API missing: rectangular kernel instead
                 ent = False
                 self.symm_error = repr(e)
             self._symm_G[key] = ent
-        return None if ent is False else ent[:5]
+        return None if ent is False else ent[:6]
 
     def gram_rows(self, hi_all, lo_all, a32_all, r0, r1, out=None):
         """G[r0:r1, :] as f32 [r1-r0, ldg]."""

@@ -93,31 +93,44 @@ def knn_stage(ops, plan, img_local, k):
     if plan.world == 1:
         a32_all, hi_all, lo_all, zf_all = ops.center_normalize(img_local, mean, want_split=not fused)
     else:
-        a32, _, _, zf = ops.center_normalize(img_local, mean, want_split=False)
+        fused_sharded = fused and hasattr(ops, "knn_rows_fused") and len(set(plan.counts)) == 1
+        arena = ops.rows_arena(plan, int(img_local.shape[1])) if (fused_sharded and hasattr(ops, "rows_arena")) else None
+        nr = plan.hi - plan.lo
+        a32, _, _, zf = ops.center_normalize(img_local, mean, want_split=False,
+                                             **({"out_a32": arena["a32"][:nr]} if arena is not None else {}))
         zf_all = plan.all_gather_rows(zf)
-        if fused and hasattr(ops, "knn_rows_fused") and len(set(plan.counts)) == 1:
-            # the Gram kernel needs the FP16 operand of every pattern (2 B/element): gather that first, and let the
-            # all-gather of the FP32 rows (4 B/element, needed by the exact-distance refinement only) run beside it
+        if fused_sharded:
+            # the Gram kernel needs the FP16 operand of every pattern (2 B/element), the exact-distance refinement the
+            # FP32 rows (4 B/element): both are gathered BESIDE the Gram kernels
             import torch.distributed as dist
-            a16 = ops.split_f16(a32)
+            a16 = ops.split_f16(a32, **({"out": arena["a16"][:nr]} if arena is not None else {}))
             a32_all = torch.empty((plan.N,) + tuple(a32.shape[1:]), dtype=a32.dtype, device=a32.device)
-            side = plan.side_group()
-            if getattr(ops, "wants_symmetric_gram", None) and ops.wants_symmetric_gram(plan.N, plan.hi - plan.lo, k, plan):
+            a16_all = torch.empty((plan.N,) + tuple(a16.shape[1:]), dtype=a16.dtype, device=a16.device)
+            sym = bool(getattr(ops, "wants_symmetric_gram", None) and ops.wants_symmetric_gram(plan.N, nr, k, plan))
+            sample = None
+            if sym:
                 # the sampling pass of the symmetric form needs a SAMPLE of the patterns only (any subset gives valid
-                # limits): gather every stride-th local row first (1/stride of the volume) and let both full
-                # all-gathers run beside the Gram kernels on the side communicator
+                # limits): gather every stride-th local row first (1/stride of the volume)
                 smp = a16[::ops.sym_stride()].contiguous()           # (equal row counts: checked above)
                 sample = torch.empty((plan.world * smp.shape[0],) + tuple(smp.shape[1:]), dtype=smp.dtype, device=smp.device)
                 dist.all_gather_into_tensor(sample, smp, group=plan.group)
-                a16_all = torch.empty((plan.N,) + tuple(a16.shape[1:]), dtype=a16.dtype, device=a16.device)
+            if arena is not None:
+                # copy engines pull the blocks from the peers' symmetric memory: no SMs taken from the Gram kernels
+                arena["hdl"].barrier()                   # (device-side, stream-ordered) every rank's rows are complete
+                w16 = ops.gather_rows_by_copy_engines(arena, plan, "a16", a16_all)
+                w32 = ops.gather_rows_by_copy_engines(arena, plan, "a32", a32_all)
+            else:
+                # NCCL all-gathers on a second communicator (operations of one communicator execute in issue order:
+                # the short collectives of the main group must not queue behind 6.5 GB)
+                side = plan.side_group()
                 w16 = dist.all_gather_into_tensor(a16_all, a16, group=side, async_op=True)
                 w32 = dist.all_gather_into_tensor(a32_all, a32.contiguous(), group=side, async_op=True)
+            if sym:
                 S2_loc, Nbr_loc = ops.knn_rows_fused(a16_all, a32_all, zf_all, plan.lo, plan.hi, k, plan=plan, a32_ready=w32,
                                                      a16_ready=w16, a16_rows=a16, a16_sample=sample)
             else:
-                a16_all = plan.all_gather_rows(a16)
-                work = dist.all_gather_into_tensor(a32_all, a32.contiguous(), group=side, async_op=True)
-                S2_loc, Nbr_loc = ops.knn_rows_fused(a16_all, a32_all, zf_all, plan.lo, plan.hi, k, plan=plan, a32_ready=work)
+                w16.wait()
+                S2_loc, Nbr_loc = ops.knn_rows_fused(a16_all, a32_all, zf_all, plan.lo, plan.hi, k, plan=plan, a32_ready=w32)
             return plan.all_gather_rows(S2_loc), plan.all_gather_rows(Nbr_loc)
         # ship the FP32 unit rows only (4 B/element) and split them locally: half the all-gather volume
         a32_all = plan.all_gather_rows(a32)
