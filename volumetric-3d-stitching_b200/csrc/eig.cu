@@ -344,6 +344,14 @@ static int lanczos_run(EigCtx& c, double* W0, int run_dim, int first_check, int 
       V3S_CUDA(cudaStreamSynchronize(c.st));
       copied = steps;
       V3S_REQUIRE(hstatus == 0, "block Lanczos broke down (Cholesky-QR of a rank-deficient block)");
+      // The host now spends ~1 ms on the Ritz values: keep the GPU busy with the NEXT step meanwhile.  It is
+      // speculative -- discarded when this check finds convergence (its basis rows / T block lie beyond m / steps,
+      // nothing reads them) and adopted otherwise; every rank takes the same decisions from the same numbers.
+      double* Wspec = nullptr;
+      if (!last && m + 2 * b <= run_dim) {                      // (not when it would be the run's last step: that one ends with a check)
+        if (int rc = degree > 0 ? apply_cheb(c, Q, degree, cc, ee, &Wspec) : apply_plain(c, Q, &Wspec)) return rc;
+        if (int rc = v3s_lanczos_step(c.V, N, N, m + b, run_dim, Wspec, c.Xf, c.T + (size_t)steps * 128, c.lzws, c.status, c.st)) return rc;
+      }
       // projected block-tridiagonal matrix: A_j on the diagonal, B_j (upper triangular) below it
       std::vector<double> Tm((size_t)m * m, 0.0), w;
       for (int j = 0; j < steps; ++j) {
@@ -413,8 +421,16 @@ static int lanczos_run(EigCtx& c, double* W0, int run_dim, int first_check, int 
           for (int i = 0; i < m; ++i) out.S[(size_t)i * want + jv] = Tfull[(size_t)i * m + col];
         }
       }
-      if (out.converged || last) break;
+      if (out.converged || last) {
+        if (Wspec) c.matvecs -= degree > 0 ? degree : 1;      // (the discarded step is not part of the solve's count)
+        break;
+      }
       next_check = steps + gap;
+      if (Wspec) {                                            // the speculative step becomes a regular one
+        m += b;
+        Q = Wspec;
+        ++steps;
+      }
     }
     m += b;
   }
@@ -472,13 +488,21 @@ extern "C" int v3s_eig_topk(v3s_eig_problem* pb, int nev, double tol, int max_di
   V3S_CUDA(cudaMemsetAsync(c.Xf, 0, sizeof(float) * (size_t)v3s_xf_floats(N), st));      // strip padding columns stay zero
   // seeded start block (host xorshift + Box-Muller; the reference starts ARPACK from an unseeded random vector)
   {
-    std::vector<double> h((size_t)N * 8);
-    unsigned long long s = seed * 0x9E3779B97F4A7C15ull + 0xD1B54A32D192ED03ull;
-    auto next = [&]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return (double)((s >> 11) + 1) / 9007199254740993.0; };
-    for (size_t i = 0; i + 1 < h.size(); i += 2) {
-      const double r = sqrt(-2.0 * log(next())), a = 6.283185307179586 * next();
-      h[i] = r * cos(a);
-      h[i + 1] = r * sin(a);
+    // (kept between calls: 8 N normal deviates are ~16 ms of host time at N = 10^5, the same block every pass)
+    static std::vector<double> h;
+    static long long h_n = -1;
+    static unsigned long long h_seed = 0;
+    if (h_n != N || h_seed != seed) {
+      h.assign((size_t)N * 8, 0.0);
+      unsigned long long s = seed * 0x9E3779B97F4A7C15ull + 0xD1B54A32D192ED03ull;
+      auto next = [&]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return (double)((s >> 11) + 1) / 9007199254740993.0; };
+      for (size_t i = 0; i + 1 < h.size(); i += 2) {
+        const double r = sqrt(-2.0 * log(next())), a = 6.283185307179586 * next();
+        h[i] = r * cos(a);
+        h[i + 1] = r * sin(a);
+      }
+      h_n = N;
+      h_seed = seed;
     }
     V3S_CUDA(cudaMemcpyAsync(c.blk, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice, st));
     V3S_CUDA(cudaStreamSynchronize(st));
