@@ -126,20 +126,22 @@ def orientation_errors_deg(Recon, R_true):
     is removed (orthogonal Procrustes), then angle_i = acos((tr(R_est_i^T R_true_i A) - 1)/2).
     Device arithmetic (batched 3x3 in FP64); returns numpy (N,)."""
     ops = _util.get_ops()
-    M = _util.to_dev(Recon, torch.float64).reshape(-1, 3, 3)
-    Rt = _util.to_dev(R_true, torch.float64).T.reshape(-1, 3, 3)      # same (transposed) convention as the fit target
-    U, _, Vh = torch.linalg.svd(M)
-    det = torch.linalg.det(U @ Vh)
-    U = U.clone()
-    U[:, :, 2] *= det[:, None]
-    Re = U @ Vh
-    # global alignment: A = argmin sum ||Re_i - Rt_i A||  ->  polar factor of sum Rt_i^T Re_i
-    C = (Rt.transpose(1, 2) @ Re).sum(0)
-    Uc, _, Vc = torch.linalg.svd(C)
-    d = torch.linalg.det(Uc @ Vc)
-    Uc = Uc.clone()
-    Uc[:, 2] *= d
-    A = Uc @ Vc
+    Rd = _util.to_dev(Recon, torch.float64).reshape(-1, 9)
+    Y = _util.to_dev(R_true, torch.float64).T.contiguous()            # same (transposed) convention as the fit target
+    Rt = Y.reshape(-1, 3, 3)
+    # nearest rotation of every fitted matrix by the library's own projection kernel (fit.cu, polar mode 2: SVD through
+    # a 3x3 Jacobi eigen-solver, det fixed): Recon = [0 | Recon] @ I in the kernel's terms
+    Psf = torch.cat([torch.zeros((Rd.shape[0], 1), dtype=torch.float64, device=Rd.device), Rd], dim=1).contiguous()
+    eye = torch.eye(9, dtype=torch.float64, device=Rd.device)
+    _, rproj, _, _ = ops.fit_project(Psf, Y, eye, 2)
+    Re = rproj.reshape(-1, 3, 3)
+    # global alignment: A = argmin sum ||Re_i - Rt_i A||  ->  polar factor of sum Rt_i^T Re_i (one 3x3, on the host)
+    C = torch.einsum('nji,njk->ik', Rt, Re).cpu().numpy()
+    Uc, _, Vc = np.linalg.svd(C)
+    if np.linalg.det(Uc @ Vc) < 0:
+        Uc = Uc.copy()
+        Uc[:, 2] *= -1.0
+    A = torch.as_tensor(Uc @ Vc, dtype=torch.float64, device=Rd.device)
     tr = torch.einsum('nij,nij->n', Re, Rt @ A)
     ang = torch.rad2deg(torch.arccos(torch.clamp((tr - 1) / 2, -1, 1)))
     return ang.cpu().numpy()
