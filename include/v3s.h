@@ -435,6 +435,12 @@ int v3s_eig_topk(v3s_eig_problem* problem /* host */, int nev, double tol, int m
  * symmetric row-major, overwritten with the eigenvectors in its columns; w [n] ascending.  Host pointers.    */
 int v3s_sym_eig_host(double* a, int n, double* w);
 
+/* Small device -> host read (<= 256 kB) that uses no copy engine: a one-block kernel stores the bytes into a pinned,
+ * device-mapped mailbox, the stream is synchronised, the bytes are copied to host_dst.  A cudaMemcpy D2H would queue
+ * behind any bulk transfer running on the device-to-host engine (solve() ships 13 GB of patterns while stages 2-4
+ * run); the eigen-solver's Ritz checks and the stage API's validation scalars read through this instead.        */
+int v3s_read_small(const void* dev_src, void* host_dst, long long bytes, void* stream);
+
 /* per-launch device time of the mat-vec kernel, dense or sparse (CUDA events owned by the library, recorded on the
  * launching stream): enable/reset, then read the elapsed milliseconds (returns the launch count). */
 int v3s_profile_matvec(int enable);

@@ -1,5 +1,6 @@
 // C-ABI plumbing: thread-local error message, version, device probe.
 #include "common.cuh"
+#include <cstring>
 #include "v3s.h"
 #include <stdarg.h>
 
@@ -52,4 +53,35 @@ extern "C" int v3s_peer_fill(float* dst, float value, long long n, void* stream)
   v3s::peer_fill_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(dst, value, n);
   V3S_CHECK_LAUNCH();
   return 0;
+}
+
+// ---- small device -> host reads that bypass the copy engines --------------------------------------------------
+// A cudaMemcpy D2H of a few bytes queues on the device-to-host copy engine BEHIND whatever bulk transfer is running
+// there (the 13 GB pattern matrix of OrientationRecoverySolver.solve travels while stages 2-4 run): every Ritz check
+// of the eigen-solver, every validation scalar then waits for hundreds of megabytes.  These reads go through a
+// pinned, device-mapped mailbox instead: a one-block kernel stores the bytes over PCIe, the stream is synchronised,
+// the host copies them out.
+namespace v3s {
+constexpr size_t kMailboxBytes = 256 * 1024;
+static unsigned char* g_mailbox = nullptr;
+__global__ void store_to_host_kernel(const unsigned char* __restrict__ src, unsigned char* __restrict__ dst, long long bytes) {
+  const long long n16 = ((((uintptr_t)src | (uintptr_t)dst) & 15) == 0) ? bytes / 16 : 0;
+  for (long long i = threadIdx.x; i < n16; i += blockDim.x)
+    reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
+  for (long long i = n16 * 16 + threadIdx.x; i < bytes; i += blockDim.x) dst[i] = src[i];
+}
+int read_back(void* host_dst, const void* dev_src, size_t bytes, cudaStream_t st) {
+  V3S_REQUIRE(bytes <= kMailboxBytes, "v3s read_back: %zu bytes exceed the mailbox", bytes);
+  if (!g_mailbox) V3S_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g_mailbox), kMailboxBytes, cudaHostAllocMapped | cudaHostAllocPortable));
+  if (bytes == 0) return 0;
+  store_to_host_kernel<<<1, 256, 0, st>>>(reinterpret_cast<const unsigned char*>(dev_src), g_mailbox, (long long)bytes);
+  V3S_CHECK_LAUNCH();
+  V3S_CUDA(cudaStreamSynchronize(st));
+  memcpy(host_dst, g_mailbox, bytes);
+  return 0;
+}
+}  // namespace v3s
+extern "C" int v3s_read_small(const void* dev_src, void* host_dst, long long bytes, void* stream) {
+  V3S_REQUIRE(dev_src && host_dst && bytes >= 0, "v3s_read_small: bad arguments");
+  return v3s::read_back(host_dst, dev_src, (size_t)bytes, (cudaStream_t)stream);
 }

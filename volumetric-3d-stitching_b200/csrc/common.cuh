@@ -84,6 +84,9 @@ __host__ __device__ inline long long xf_strip_index(long long col, int j) {
 }
 __host__ __device__ inline long long xf_strip_floats(long long N) { return ((N + 127) >> 7) * 1024; }
 
+// small device -> host read through a pinned mapped mailbox (api.cu): synchronises the stream, uses no copy engine
+int read_back(void* host_dst, const void* dev_src, size_t bytes, cudaStream_t st);
+
 // order-preserving float <-> uint key (larger float => larger key)
 __device__ __forceinline__ uint32_t float_to_key(float f) {
   uint32_t u = __float_as_uint(f);

@@ -338,10 +338,9 @@ static int lanczos_run(EigCtx& c, double* W0, int run_dim, int first_check, int 
     const bool last = (m + b > run_dim);
     if (steps >= next_check || last) {
       int hstatus = 0;
-      V3S_CUDA(cudaMemcpyAsync(Th.data() + (size_t)copied * 128, c.T + (size_t)copied * 128, sizeof(double) * 128 * (steps - copied),
-                               cudaMemcpyDeviceToHost, c.st));
-      V3S_CUDA(cudaMemcpyAsync(&hstatus, c.status, sizeof(int), cudaMemcpyDeviceToHost, c.st));
-      V3S_CUDA(cudaStreamSynchronize(c.st));
+      // (through the pinned mailbox, not the copy engine: a D2H memcpy would queue behind a bulk transfer of the caller)
+      if (int rc = read_back(&hstatus, c.status, sizeof(int), c.st)) return rc;
+      if (int rc = read_back(Th.data() + (size_t)copied * 128, c.T + (size_t)copied * 128, sizeof(double) * 128 * (steps - copied), c.st)) return rc;
       copied = steps;
       V3S_REQUIRE(hstatus == 0, "block Lanczos broke down (Cholesky-QR of a rank-deficient block)");
       // The host now spends ~1 ms on the Ritz values: keep the GPU busy with the NEXT step meanwhile.  It is
@@ -560,8 +559,7 @@ extern "C" int v3s_eig_topk(v3s_eig_problem* pb, int nev, double tol, int max_di
       small_gram_kernel<<<64, 256, 0, st>>>(c.Y, 16, c.PY, 16, nev, N, c.small);
       V3S_CHECK_LAUNCH();
       std::vector<double> H(256), Hn((size_t)nev * nev), wz;
-      V3S_CUDA(cudaMemcpyAsync(H.data(), c.small, sizeof(double) * 256, cudaMemcpyDeviceToHost, st));
-      V3S_CUDA(cudaStreamSynchronize(st));
+      if (int rc = read_back(H.data(), c.small, sizeof(double) * 256, st)) return rc;
       for (int i = 0; i < nev; ++i)
         for (int j = 0; j < nev; ++j) Hn[(size_t)i * nev + j] = 0.5 * (H[i * 16 + j] + H[j * 16 + i]);
       V3S_REQUIRE(sym_eig(Hn, nev, wz) == 0, "v3s_eig_topk: Rayleigh-Ritz eigenproblem did not converge");
@@ -580,8 +578,7 @@ extern "C" int v3s_eig_topk(v3s_eig_problem* pb, int nev, double tol, int max_di
       small_gram_kernel<<<64, 256, 0, st>>>(c.YZ, 16, c.YZ, 16, nev, N, c.small + 768);
       V3S_CHECK_LAUNCH();
       std::vector<double> G(768);
-      V3S_CUDA(cudaMemcpyAsync(G.data(), c.small + 256, sizeof(double) * 768, cudaMemcpyDeviceToHost, st));
-      V3S_CUDA(cudaStreamSynchronize(st));
+      if (int rc = read_back(G.data(), c.small + 256, sizeof(double) * 768, st)) return rc;
       lam.assign((size_t)nev, 0.0);
       res.assign((size_t)nev, 0.0);
       std::vector<int> idx((size_t)nev);

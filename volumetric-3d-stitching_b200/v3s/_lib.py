@@ -110,6 +110,7 @@ SIGNATURES = {
     "v3s_sym_eig_host": (i32, [C.POINTER(f64), i32, C.POINTER(f64)]),
     "v3s_profile_matvec": (i32, [i32]),
     "v3s_profile_matvec_read": (i32, [C.POINTER(C.c_float), i32]),
+    "v3s_read_small": (i32, [p, p, i64, p]),
     "v3s_profile_matvec_gaps": (i32, [C.POINTER(C.c_float), i32]),
     "v3s_fit_gram": (i32, [p, i32, p, i64, p, p]),
     "v3s_fit_solve": (i32, [p, p, p]),

@@ -107,7 +107,8 @@ class AsyncFetch:
     _pins = {}                      # slot -> [buffers], [next index]
     _chunk = {}                     # slot -> cached device staging buffer (uint8)
     SINGLE_BUFFER_BYTES = 1 << 30
-    CHUNK_BYTES = 256 << 20
+    import os as _os
+    CHUNK_BYTES = int(_os.environ.get("V3S_FETCH_CHUNK_MB", "256")) << 20
 
     def __init__(self, t, out_dtype=np.float64, slot="images", private=False):
         """private=True: `result()` returns a freshly allocated array the caller owns (copied out of the pinned

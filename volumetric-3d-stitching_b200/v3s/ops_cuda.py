@@ -124,7 +124,9 @@ class CudaOps:
         # its patterns' segments from the peers' memory over NVLink (remote slot-counter atomics from inside the
         # kernel's epilogue cost more than the halved MMA work saved)
         self.symmetric_gram_sharded = True
-        self.copy_engine_gather = True   # sharded jobs: operand all-gathers as copy-engine pulls from symmetric memory
+        import os as _os
+        # sharded jobs: operand all-gathers as copy-engine pulls from symmetric memory (V3S_CE_GATHER=0: NCCL all-gathers)
+        self.copy_engine_gather = _os.environ.get("V3S_CE_GATHER", "1") != "0"
         self._row_order = None       # (row0, rows, order int32 [rows], N) of the last fused kNN call with a tile order
         self.sparse_row_order = True # sparse mat-vec: walk the rows in the kNN stage's neighbourhood order (L1 reuse)
         self.share_pairs_across_ranks = True   # sharded tiled refinement: mutual pairs once per JOB, not once per rank
@@ -179,6 +181,16 @@ class CudaOps:
             n = min(int(_lib.lib.v3s_profile_matvec_read(buf, cap)), cap)
             if n:
                 out["matvec"] = [float(buf[i]) for i in range(n)]
+        return out
+
+    def read_small(self, t):
+        """Small device tensor -> numpy WITHOUT the device-to-host copy engine (v3s_read_small: pinned mapped mailbox).
+        `.cpu()` / `.item()` would queue behind a bulk D2H transfer in flight (solve() ships the pattern matrix while
+        the later stages run) and stall the launching thread for its whole remainder."""
+        import numpy as np
+        t = t.contiguous()
+        out = np.empty(tuple(t.shape), dtype=torch.empty(0, dtype=t.dtype).numpy().dtype)
+        call("v3s_read_small", ptr(t), C.c_void_p(out.ctypes.data), t.numel() * t.element_size(), stream_ptr())
         return out
 
     # ---- allocation helpers ---------------------------------------------------------------
@@ -1062,7 +1074,7 @@ class FusedOperator:
         """Raise if a peer barrier timed out (one small D2H; called once after every solve).  The status word
         lives in the cached arena: it is cleared once reported, so one failed solve does not poison the next."""
         if self.world > 1:
-            st = int(self.a["status"].item())
+            st = int(self.ops.read_small(self.a["status"])[0])
             if st != 0:
                 self.a["status"].zero_()
                 raise Exception("v3s: a peer rank never reached the mat-vec barrier (status %d): the result blocks of "

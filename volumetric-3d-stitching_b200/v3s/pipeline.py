@@ -157,7 +157,7 @@ def markov_stage(ops, plan, S2_all, Nbr_all, eps, med_row=4, idx_off=1, validate
     DENSE_OPERATOR_BYTES per rank -- the FP64 list form (`SparseMarkov`), which never forms N x N."""
     scalars = ops.s2_scalars(S2_all, eps, med_row, idx_off)
     if validate:
-        check_scalars(scalars.cpu().numpy())
+        check_scalars(ops.read_small(scalars) if hasattr(ops, "read_small") else scalars.cpu().numpy())
     ops.s2_threshold_(S2_all, scalars)
     if hasattr(ops, "wants_sparse_operator") and ops.wants_sparse_operator(plan.hi - plan.lo, plan.N, int(S2_all.shape[1])):
         P_rows, dis = ops.build_markov_sparse(S2_all, Nbr_all, scalars, plan.lo, plan.hi)
@@ -312,7 +312,7 @@ def fit_stage(ops, plan, Ps, Y, polar_mode=0, check=True):
     sigma_t = (180.0 / math.pi) * 2.0 * part / (N * (N - 1))
     out = {"c": c, "recon_pre": recon, "rproj": rproj, "quat_est": qe, "quat_true": qt, "sigma_T": sigma_t}
     if check:
-        s = float(sigma_t.item())
+        s = float(ops.read_small(sigma_t.reshape(1))[0]) if hasattr(ops, "read_small") else float(sigma_t.item())
         out["sigma_T_host"] = s
         if s > 60:
             raise Exception("Sigma_T = " + str(s))           # diffusion.py:175-176
@@ -343,7 +343,7 @@ def run_pipeline(ops, plan, ed, rot9_local, rot_y_all, n_p, k, eps, polar_mode=0
     if validate and knn_overflow is not None:
         # rows whose near-tie band did not fit the candidate buffers (dense ties: noisy or duplicate-heavy data):
         # for those the exact-top-k containment proof does not hold (markov_stage has just synchronised anyway)
-        n_over = int(knn_overflow.item())
+        n_over = int(ops.read_small(knn_overflow)[0]) if hasattr(ops, "read_small") else int(knn_overflow.item())
         if n_over:
             import warnings
             warnings.warn("v3s kNN: %d candidate lists saturated (more near-ties around the k-th neighbour than the buffers "
