@@ -57,4 +57,26 @@ def test_sym_eig_host_against_numpy():
         assert np.max(np.abs(w - np.linalg.eigvalsh(A))) < 1e-12 * max(1.0, np.abs(A).max())
         assert np.max(np.abs(A @ a - a * w[None, :])) < 1e-12 * max(1.0, np.abs(A).max())
         assert np.max(np.abs(a.T @ a - np.eye(n))) < 1e-12
+    # the operator of a disconnected kNN graph (the reference's default run has 182 components): a permuted block-diagonal
+    # normalised Markov matrix -- eigenvalue 1 once per component, rank-deficient blocks with zero clusters
+    def markov_blocks(nb, bs):
+        n = nb * bs
+        M = np.zeros((n, n))
+        for i in range(nb):
+            W = rng.random((bs, bs))
+            W = W + W.T
+            if i % 3 == 0:
+                W[:] = 1.0                              # rank one: eigenvalue 0 with multiplicity bs - 1
+            d = W.sum(1)
+            M[i * bs:(i + 1) * bs, i * bs:(i + 1) * bs] = W / np.sqrt(np.outer(d, d))
+        p = rng.permutation(n)
+        return M[np.ix_(p, p)]
+    for A in (markov_blocks(64, 8), markov_blocks(182, 3), np.zeros((40, 40)), np.ones((64, 64)), np.eye(50)):
+        n = A.shape[0]
+        a, w = np.ascontiguousarray(A.copy()), np.zeros(n)
+        rc = _lib.lib.v3s_sym_eig_host(a.ctypes.data_as(C.POINTER(C.c_double)), n, w.ctypes.data_as(C.POINTER(C.c_double)))
+        assert rc == 0, _lib.last_error()
+        assert np.max(np.abs(w - np.linalg.eigvalsh(A))) < 1e-12 * max(1.0, np.abs(A).max())
+        assert np.max(np.abs(A @ a - a * w[None, :])) < 1e-12 * max(1.0, np.abs(A).max())
+        assert np.max(np.abs(a.T @ a - np.eye(n))) < 1e-12
     assert _lib.lib.v3s_sym_eig_host(None, 3, None) != 0 and "bad arguments" in _lib.last_error()

@@ -22,61 +22,6 @@
 namespace v3s {
 
 // ---- small dense symmetric eigen-solver (host): Householder tridiagonalisation + implicit QL ----------------
-// A (n x n, row-major, symmetric) -> eigenvalues w ascending, eigenvectors in the COLUMNS of A.
-static void sym_tridiagonalise(std::vector<double>& a, int n, int ld, std::vector<double>& d, std::vector<double>& e) {
-  auto A = [&](int i, int j) -> double& { return a[(size_t)i * ld + j]; };
-  for (int i = n - 1; i > 0; --i) {
-    const int l = i - 1;
-    double h = 0.0, scale = 0.0;
-    if (l > 0) {
-      for (int k = 0; k <= l; ++k) scale += fabs(A(i, k));
-      if (scale == 0.0) {
-        e[i] = A(i, l);
-      } else {
-        for (int k = 0; k <= l; ++k) { A(i, k) /= scale; h += A(i, k) * A(i, k); }
-        double f = A(i, l);
-        const double g = f >= 0.0 ? -sqrt(h) : sqrt(h);
-        e[i] = scale * g;
-        h -= f * g;
-        A(i, l) = f - g;
-        f = 0.0;
-        for (int j = 0; j <= l; ++j) {
-          A(j, i) = A(i, j) / h;
-          double gg = 0.0;
-          for (int k = 0; k <= j; ++k) gg += A(j, k) * A(i, k);
-          for (int k = j + 1; k <= l; ++k) gg += A(k, j) * A(i, k);
-          e[j] = gg / h;
-          f += e[j] * A(i, j);
-        }
-        const double hh = f / (h + h);
-        for (int j = 0; j <= l; ++j) {
-          f = A(i, j);
-          const double gg = e[j] - hh * f;
-          e[j] = gg;
-          for (int k = 0; k <= j; ++k) A(j, k) -= f * e[k] + gg * A(i, k);
-        }
-      }
-    } else {
-      e[i] = A(i, l);
-    }
-    d[i] = h;
-  }
-  d[0] = 0.0;
-  e[0] = 0.0;
-  for (int i = 0; i < n; ++i) {
-    const int l = i - 1;
-    if (d[i] != 0.0) {
-      for (int j = 0; j <= l; ++j) {
-        double g = 0.0;
-        for (int k = 0; k <= l; ++k) g += A(i, k) * A(k, j);
-        for (int k = 0; k <= l; ++k) A(k, j) -= g * A(k, i);
-      }
-    }
-    d[i] = A(i, i);
-    A(i, i) = 1.0;
-    for (int j = 0; j <= l; ++j) A(j, i) = A(i, j) = 0.0;
-  }
-}
 // One plane rotation of the QL iteration applied to two contiguous vectors (6 n^3 flops of the whole solve are here):
 // an AVX2 + FMA build of the loop is used where the host CPU has it (checked once at run time).
 __attribute__((target("avx2,fma"))) static void ql_rotate_avx2(double* __restrict__ zi, double* __restrict__ zi1, int len,
@@ -106,24 +51,32 @@ static int tridiagonal_ql(std::vector<double>& d, std::vector<double>& e, int n,
   auto Z = [&](int i, int j) -> double& { return z[(size_t)j * ld + i]; };
   for (int i = 1; i < n; ++i) e[i - 1] = e[i];
   e[n - 1] = 0.0;
+  // deflation threshold relative to the matrix norm as well as to the neighbouring diagonal entries: a cluster of
+  // (numerically) zero eigenvalues -- rank-deficient blocks of a disconnected graph's operator -- leaves off-diagonal
+  // noise of the size of its diagonal noise, which a purely relative test never accepts
+  double anorm = 0.0;
+  for (int i = 0; i < n; ++i) anorm = fmax(anorm, fabs(d[i]) + fabs(e[i]));
   for (int l = 0; l < n; ++l) {
     int iter = 0, m;
     do {
       for (m = l; m < n - 1; ++m) {
         const double dd = fabs(d[m]) + fabs(d[m + 1]);
-        if (fabs(e[m]) <= 2.3e-16 * dd) break;
+        if (fabs(e[m]) <= 2.3e-16 * (dd + anorm)) break;
       }
       if (m != l) {
         if (iter++ == 60) return 1;
         double g = (d[l + 1] - d[l]) / (2.0 * e[l]);
-        double r = hypot(g, 1.0);
+        double r = sqrt(g * g + 1.0);
+        if (!(r < 1e150)) r = hypot(g, 1.0);
         g = d[m] - d[l] + e[l] / (g + (g >= 0.0 ? fabs(r) : -fabs(r)));
         double s = 1.0, c = 1.0, p = 0.0;
         int i;
         for (i = m - 1; i >= l; --i) {
           double f = s * e[i];
           const double b = c * e[i];
-          e[i + 1] = (r = hypot(f, g));
+          r = sqrt(f * f + g * g);                         // (the scalar recurrence is the critical path of the iteration:
+          if (!(r > 1e-150 && r < 1e150)) r = hypot(f, g); //  plain sqrt unless the squares could over- / underflow)
+          e[i + 1] = r;
           if (r == 0.0) {
             d[i + 1] -= p;
             e[m] = 0.0;
@@ -146,21 +99,101 @@ static int tridiagonal_ql(std::vector<double>& d, std::vector<double>& e, int n,
   }
   return 0;
 }
+// Householder tridiagonalisation on the FULL symmetric matrix with row-contiguous inner loops (symmetric mat-vec +
+// rank-2 update per step, backward accumulation of Q), so that the compiler vectorises them; the body is compiled
+// twice, for AVX2 + FMA and for the baseline ISA, and picked at run time.
+//   a [n, ld] row-major symmetric (destroyed) -> d [n] diagonal, e [n] with e[i] = T[i][i-1] (e[0] = 0),
+//   qt [n, ld]: Q TRANSPOSED (row i = column i of Q, the layout tridiagonal_ql rotates), A = Q T Q^T.
+#define V3S_TRIDIAG_BODY                                                                                              \
+  std::vector<double> beta((size_t)n, 0.0), p((size_t)n), t((size_t)n);                                               \
+  for (int k = 0; k + 2 < n; ++k) {                                                                                    \
+    double* x = &a[(size_t)k * ld + k + 1];                                                                            \
+    const int len = n - k - 1;                                                                                         \
+    double sigma = 0.0;                                                                                                \
+    for (int i = 1; i < len; ++i) sigma += x[i] * x[i];                                                                \
+    const double x0 = x[0];                                                                                            \
+    d[k] = a[(size_t)k * ld + k];                                                                                      \
+    if (sigma == 0.0) { e[k + 1] = x0; beta[k] = 0.0; continue; }                                                      \
+    const double mu = sqrt(x0 * x0 + sigma);                                                                           \
+    const double v0 = x0 <= 0.0 ? x0 - mu : -sigma / (x0 + mu);                                                        \
+    const double b = 2.0 * v0 * v0 / (sigma + v0 * v0);                                                                \
+    const double inv = 1.0 / v0;                                                                                       \
+    x[0] = 1.0;                                                                                                        \
+    for (int i = 1; i < len; ++i) x[i] *= inv;               /* x is now v (v[0] = 1), kept in row k for Q */          \
+    beta[k] = b;                                                                                                       \
+    e[k + 1] = mu;                                                                                                     \
+    /* p = b A_sub v */                                                                                                \
+    double pv = 0.0;                                                                                                   \
+    for (int i = 0; i < len; ++i) {                                                                                    \
+      const double* row = &a[(size_t)(k + 1 + i) * ld + k + 1];                                                        \
+      double acc = 0.0;                                                                                                \
+      for (int j = 0; j < len; ++j) acc += row[j] * x[j];                                                              \
+      p[i] = b * acc;                                                                                                  \
+      pv += p[i] * x[i];                                                                                               \
+    }                                                                                                                  \
+    const double K = 0.5 * b * pv;                                                                                     \
+    for (int i = 0; i < len; ++i) p[i] -= K * x[i];          /* w */                                                   \
+    for (int i = 0; i < len; ++i) {                          /* A_sub -= v w^T + w v^T */                              \
+      double* row = &a[(size_t)(k + 1 + i) * ld + k + 1];                                                              \
+      const double vi = x[i], wi = p[i];                                                                               \
+      for (int j = 0; j < len; ++j) row[j] -= vi * p[j] + wi * x[j];                                                   \
+    }                                                                                                                  \
+  }                                                                                                                    \
+  e[0] = 0.0;                                                                                                          \
+  if (n >= 2) {                                                                                                        \
+    d[n - 2] = a[(size_t)(n - 2) * ld + n - 2];                                                                        \
+    e[n - 1] = a[(size_t)(n - 2) * ld + n - 1];                                                                        \
+  }                                                                                                                    \
+  d[n - 1] = a[(size_t)(n - 1) * ld + n - 1];                                                                          \
+  /* Q = H_0 H_1 ... by backward accumulation, row-major in q; then transposed into qt */                             \
+  std::vector<double> q((size_t)n * ld, 0.0);                                                                          \
+  for (int i = 0; i < n; ++i) q[(size_t)i * ld + i] = 1.0;                                                             \
+  for (int k = n - 3; k >= 0; --k) {                                                                                   \
+    const double b = beta[k];                                                                                          \
+    if (b == 0.0) continue;                                                                                            \
+    const double* v = &a[(size_t)k * ld + k + 1];                                                                      \
+    const int len = n - k - 1;                                                                                         \
+    for (int j = 0; j < len; ++j) t[j] = 0.0;                                                                          \
+    for (int i = 0; i < len; ++i) {                                                                                    \
+      const double* row = &q[(size_t)(k + 1 + i) * ld + k + 1];                                                        \
+      const double vi = v[i];                                                                                          \
+      for (int j = 0; j < len; ++j) t[j] += vi * row[j];                                                               \
+    }                                                                                                                  \
+    for (int i = 0; i < len; ++i) {                                                                                    \
+      double* row = &q[(size_t)(k + 1 + i) * ld + k + 1];                                                              \
+      const double bv = b * v[i];                                                                                      \
+      for (int j = 0; j < len; ++j) row[j] -= bv * t[j];                                                               \
+    }                                                                                                                  \
+  }                                                                                                                    \
+  for (int i = 0; i < n; ++i)                                                                                          \
+    for (int j = 0; j < n; ++j) qt[(size_t)j * ld + i] = q[(size_t)i * ld + j];
+
+__attribute__((target("avx2,fma"))) static void tridiag_full_avx2(std::vector<double>& a, int n, int ld, std::vector<double>& d,
+                                                                   std::vector<double>& e, std::vector<double>& qt) {
+  V3S_TRIDIAG_BODY
+}
+static void tridiag_full_generic(std::vector<double>& a, int n, int ld, std::vector<double>& d, std::vector<double>& e,
+                                 std::vector<double>& qt) {
+  V3S_TRIDIAG_BODY
+}
+#undef V3S_TRIDIAG_BODY
+
 // eigenpairs of the symmetric n x n matrix a (row-major; destroyed): w ascending, vectors = columns of a
-// rows_from > 0: only rows rows_from .. n-1 of the eigenvector matrix are valid on return (60 % less work)
+// rows_from > 0: only rows rows_from .. n-1 of the eigenvector matrix are valid on return (the QL rotations carry
+// those components only)
 static int sym_eig(std::vector<double>& a, int n, std::vector<double>& w, int rows_from = 0) {
-  std::vector<double> e((size_t)n);
+  std::vector<double> e((size_t)n, 0.0);
   w.assign((size_t)n, 0.0);
   if (n == 1) { w[0] = a[0]; a[0] = 1.0; return 0; }
-  // row stride padded away from multiples of 256 B: the column walks of the reduction would otherwise hit one cache set
+  // row stride padded away from multiples of 256 B (cache sets)
   const int ld = (n >= 64 && n % 32 == 0) ? n + 8 : n;
   {
     std::vector<double> ap((size_t)n * ld, 0.0), zt((size_t)n * ld);
     for (int i = 0; i < n; ++i)
       for (int j = 0; j < n; ++j) ap[(size_t)i * ld + j] = a[(size_t)i * n + j];
-    sym_tridiagonalise(ap, n, ld, w, e);
-    for (int i = 0; i < n; ++i)
-      for (int j = 0; j < n; ++j) zt[(size_t)j * ld + i] = ap[(size_t)i * ld + j];
+    static const bool avx2 = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("fma");
+    if (avx2) tridiag_full_avx2(ap, n, ld, w, e, zt);
+    else tridiag_full_generic(ap, n, ld, w, e, zt);
     if (tridiagonal_ql(w, e, n, ld, zt, rows_from)) return 1;
     for (int i = 0; i < n; ++i)
       for (int j = 0; j < n; ++j) a[(size_t)i * n + j] = zt[(size_t)j * ld + i];
