@@ -83,6 +83,11 @@ int v3s_column_sums(const float* img, long long n_rows, int P, long long stride,
 int v3s_center_normalize(const float* img, long long n_rows, int P, long long stride, const double* mean /* [P] */,
                          float* a_f32, void* a_hi, void* a_lo, int Ppad, double* norms, int* zero_flag, void* stream);
 
+/* v3s_center_normalize that also writes the FP16 operand of the fused Gram / top-k kernel (what v3s_split_f16
+ * makes of a_f32: fl16(2^8 a), zero padded to Ppad columns, Ppad a multiple of 64 for the kernel) in the same pass. */
+int v3s_center_normalize_f16(const float* img, long long n_rows, int P, long long stride, const double* mean,
+                             float* a_f32, void* a_f16, int Ppad, int* zero_flag, void* stream);
+
 /* BF16 hi/lo split of already centred unit rows a_f32 [n_rows,P] -> a_hi, a_lo [n_rows,Ppad]
  * (identical to what v3s_center_normalize emits; used on the all-gathered rows of a sharded job). */
 int v3s_split_bf16(const float* a_f32, long long n_rows, int P, int Ppad, void* a_hi, void* a_lo, void* stream);

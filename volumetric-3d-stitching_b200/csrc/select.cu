@@ -287,10 +287,14 @@ refine_sort_kernel(const float* __restrict__ a_rows, const float* __restrict__ a
     }
     if (phase == 1) continue;
     __syncthreads();
-    // bitonic sort of kk_pad (d, idx) pairs, ascending by d then idx
-    for (int size = 2; size <= kk_pad; size <<= 1) {
+    // bitonic sort of (d, idx) pairs, ascending by d then idx, over the smallest power of two that holds this row's
+    // kk candidates (the padding up to kk_pad sorts last and is never read: kk >= k)
+    int kp = 4;
+    while (kp < kk) kp <<= 1;
+    if (kp > kk_pad) kp = kk_pad;
+    for (int size = 2; size <= kp; size <<= 1) {
       for (int stride = size >> 1; stride > 0; stride >>= 1) {
-        for (int t = tid; t < kk_pad / 2; t += kRefThreads) {
+        for (int t = tid; t < kp / 2; t += kRefThreads) {
           const int lo = 2 * t - (t & (stride - 1));
           const int hi = lo + stride;
           const bool up = ((lo & size) == 0);

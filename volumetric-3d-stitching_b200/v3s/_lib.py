@@ -52,6 +52,7 @@ SIGNATURES = {
     "v3s_poisson_noise": (i32, [p, i64, i32, i64, i64, f64, C.c_ulonglong, p]),
     "v3s_column_sums": (i32, [p, i64, i32, i64, p, p]),
     "v3s_center_normalize": (i32, [p, i64, i32, i64, p, p, p, p, i32, p, p, p]),
+    "v3s_center_normalize_f16": (i32, [p, i64, i32, i64, p, p, p, i32, p, p]),
     "v3s_split_bf16": (i32, [p, i64, i32, i32, p, p, p]),
     "v3s_gram_rows": (i32, [p, p, i64, p, p, i64, i32, p, i64, p]),
     "v3s_set_gram_kblock": (i32, [i32]),

@@ -266,6 +266,18 @@ class CudaOps:
         self._toc(h)
         return a32, hi, lo, zf
 
+    def center_normalize_f16(self, img, mean, out_a32=None, out_a16=None):
+        """center_normalize + split_f16 in one pass over the patterns -> a32 [n,P] f32, a16 [n,Ppad] f16, zero_flag [n]."""
+        n, P = img.shape
+        Ppad = round_up(P, GRAM_KPAD)
+        a32 = out_a32 if out_a32 is not None else self.empty((n, P), torch.float32)
+        a16 = out_a16 if out_a16 is not None else self.empty((n, Ppad), torch.float16)
+        zf = self.empty((n,), torch.int32)
+        h = self._tic("center_normalize")
+        call("v3s_center_normalize_f16", ptr(img), n, P, img.stride(0), ptr(mean), ptr(a32), ptr(a16), Ppad, ptr(zf), stream_ptr())
+        self._toc(h)
+        return a32, a16, zf
+
     def split_bf16(self, a32):
         """BF16 hi/lo Gram operands of centred unit rows a32 [n,P] (same values as center_normalize's)."""
         n, P = a32.shape
@@ -633,7 +645,7 @@ class CudaOps:
         dist.barrier(group=plan.group)                   # every rank's tiles (incl. peer stores into this block) are done
         return buf[: plan.hi - plan.lo]
 
-    def knn_rows(self, hi_all, lo_all, a32_all, zero_flag, r0, r1, k, plan=None):
+    def knn_rows(self, hi_all, lo_all, a32_all, zero_flag, r0, r1, k, plan=None, a16_all=None):
         """k nearest neighbours (round distance) of rows [r0,r1) against all rows.
         -> S2 [r1-r0,k] f64 ascending, Nbr [r1-r0,k] i32.  Gram panels are streamed."""
         N, P = a32_all.shape
@@ -641,7 +653,8 @@ class CudaOps:
             raise Exception("Number of nearest neighbors to preserve is too high.")   # distance.py:33-34
         nr = r1 - r0
         if self.gram_impl == "fused":
-            return self.knn_rows_fused(self.split_f16(a32_all), a32_all, zero_flag, r0, r1, k, plan=plan)
+            return self.knn_rows_fused(a16_all if a16_all is not None else self.split_f16(a32_all), a32_all, zero_flag, r0, r1, k,
+                                       plan=plan)
         if hi_all is None:
             hi_all, lo_all = self.split_bf16(a32_all)
         S2 = self.empty((nr, k), torch.float64)

@@ -90,20 +90,30 @@ def knn_stage(ops, plan, img_local, k):
     plan.all_reduce_sum(sums)
     mean = sums / N
     fused = getattr(ops, "gram_impl", None) == "fused"       # the Gram operand (FP16) is derived from a32 inside knn_rows
-    if plan.world == 1:
+    a16_all = None
+    if plan.world == 1 and fused and hasattr(ops, "center_normalize_f16"):
+        a32_all, a16_all, zf_all = ops.center_normalize_f16(img_local, mean)    # centred rows + Gram operand in one pass
+        hi_all = lo_all = None
+    elif plan.world == 1:
         a32_all, hi_all, lo_all, zf_all = ops.center_normalize(img_local, mean, want_split=not fused)
     else:
         fused_sharded = fused and hasattr(ops, "knn_rows_fused") and len(set(plan.counts)) == 1
         arena = ops.rows_arena(plan, int(img_local.shape[1])) if (fused_sharded and hasattr(ops, "rows_arena")) else None
         nr = plan.hi - plan.lo
-        a32, _, _, zf = ops.center_normalize(img_local, mean, want_split=False,
-                                             **({"out_a32": arena["a32"][:nr]} if arena is not None else {}))
+        a16 = None
+        if fused_sharded and hasattr(ops, "center_normalize_f16"):
+            a32, a16, zf = ops.center_normalize_f16(img_local, mean,
+                                                    **({"out_a32": arena["a32"][:nr], "out_a16": arena["a16"][:nr]} if arena is not None else {}))
+        else:
+            a32, _, _, zf = ops.center_normalize(img_local, mean, want_split=False,
+                                                 **({"out_a32": arena["a32"][:nr]} if arena is not None else {}))
         zf_all = plan.all_gather_rows(zf)
         if fused_sharded:
             # the Gram kernel needs the FP16 operand of every pattern (2 B/element), the exact-distance refinement the
             # FP32 rows (4 B/element): both are gathered BESIDE the Gram kernels
             import torch.distributed as dist
-            a16 = ops.split_f16(a32, **({"out": arena["a16"][:nr]} if arena is not None else {}))
+            if a16 is None:
+                a16 = ops.split_f16(a32, **({"out": arena["a16"][:nr]} if arena is not None else {}))
             a32_all = torch.empty((plan.N,) + tuple(a32.shape[1:]), dtype=a32.dtype, device=a32.device)
             a16_all = torch.empty((plan.N,) + tuple(a16.shape[1:]), dtype=a16.dtype, device=a16.device)
             sym = bool(getattr(ops, "wants_symmetric_gram", None) and ops.wants_symmetric_gram(plan.N, nr, k, plan))
@@ -135,7 +145,8 @@ def knn_stage(ops, plan, img_local, k):
         # ship the FP32 unit rows only (4 B/element) and split them locally: half the all-gather volume
         a32_all = plan.all_gather_rows(a32)
         hi_all, lo_all = (None, None) if fused else ops.split_bf16(a32_all)
-    S2_loc, Nbr_loc = ops.knn_rows(hi_all, lo_all, a32_all, zf_all, plan.lo, plan.hi, k, plan=plan)
+    S2_loc, Nbr_loc = ops.knn_rows(hi_all, lo_all, a32_all, zf_all, plan.lo, plan.hi, k, plan=plan,
+                                   **({"a16_all": a16_all} if a16_all is not None else {}))
     S2_all = plan.all_gather_rows(S2_loc)
     Nbr_all = plan.all_gather_rows(Nbr_loc)
     return S2_all, Nbr_all
