@@ -632,6 +632,10 @@ def main():
         pipes = None
     if world == 1 and pipes:
         line["ncu_pipe_utilisation"] = pipes          # committed ncu capture of this workload (not measured in this run)
+    try:     # north-star kernel 1 (direct analytical synthesis, an optional mode): its committed FP32-pipe capture (cfg-2 size)
+        line["ncu_direct_synthesis_fp32_pipe"] = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))["cfg2_ncu_pipes"]["synth_direct_kernel"]
+    except Exception:
+        pass
     if world == 1:
         mv_roof["traffic"] = traffic.get("sparse_block_matvec_kernel" if sparse_run else "block_matvec_kernel")
         gram_roof["traffic"] = traffic.get("gram_topk_kernel")
