@@ -165,6 +165,10 @@ int v3s_set_gram_topk_cta_group(int cg);
  * the FP32 rows in a sharded job) needs a few, and the kernels' workers must all be resident at once.             */
 int v3s_set_gram_reserved_sms(int sms);
 
+/* Slack of the persistent Gram workers' per-tile lockstep (default 0: all workers start every tile together, so
+ * that every K slice is read from HBM once; lag > 0: a worker may run up to `lag` tiles ahead of the slowest).   */
+int v3s_set_gram_sync_lag(int lag);
+
 /* buffer sizes of v3s_gram_topk for a problem: out[0] = S lists per row (column segments),
  * out[1] = C entries per list, out[2] = padded row count of `lists` / `counts`, out[3] = ints of `ws`. */
 int v3s_gram_topk_plan(long long n_rows, long long n_cols, int k, int* out /* host [4] */);

@@ -172,6 +172,7 @@ struct TopkPlan {
   int rg;          // row blocks per group: units of a group are ordered segment-major, so the workers
                    // running together cover ~rg row blocks x S segments
   int units;
+  int sync_lag;    // a worker starts tile step s once every worker has ARRIVED at step s - sync_lag (0: strict lockstep)
 };
 __host__ __device__ inline void topk_decode_unit(const TopkPlan& p, int u, int& rb, int& seg) {
   const int per_group = p.rg * p.S;
@@ -332,10 +333,14 @@ gram_topk_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_const
           if (lane == 0) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(ctr) : "memory");
           const int t = t0 + j;
           if (t >= t1) continue;                              // nothing to do at this step: arrive only
-          int seen;
+          // (sync_lag > 0: wait for the arrivals at an EARLIER step -- the streams stay within sync_lag tiles of each
+          // other, which L2 still bridges, while one worker's slow epilogue no longer holds up every other worker)
+          const int widx = wave * plan.tps + j - plan.sync_lag;
+          const int* wctr = step_sync + (widx > 0 ? widx : 0);
+          int seen = widx < 0 ? target : 0;
           long long t_start = 0;
-          do {
-            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
+          if (widx >= 0) do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(wctr) : "memory");
             if (seen < target) {
               __nanosleep(64);
               // the barrier only aligns the workers' memory streams: after ~1 s (a worker that is not resident
@@ -504,6 +509,7 @@ struct SymPlan {
   int PR, PC;          // a step = a patch of PR x PC tiles shared by all workers of all ranks
   int steps;           // patches that touch the upper triangle
   int rank, world, workers;
+  int sync_lag;        // as TopkPlan::sync_lag
 };
 // patch `step` (in the order both sides enumerate) -> (pr, pc); returns false past the end
 __host__ __device__ inline int sym_count_steps(const SymPlan& p, int rows_per_block) {
@@ -586,10 +592,12 @@ gram_sym_topk_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_c
       int* ctr = step_sync + step;
       if (lane == 0) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(ctr) : "memory");
       if (valid) {
-        int seen;
+        const int widx = step - plan.sync_lag;
+        const int* wctr = step_sync + (widx > 0 ? widx : 0);
+        int seen = widx < 0 ? target : 0;
         long long t_start = 0;
-        do {
-          asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
+        if (widx >= 0) do {
+          asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(wctr) : "memory");
           if (seen < target) {
             __nanosleep(64);
             const long long now = clock64();
@@ -1127,11 +1135,18 @@ static int topk_query_workers() {
   return nc < kNumSMs / CG ? nc : kNumSMs / CG;
 }
 static int g_reserved_sms = 0;
+static int g_sync_lag = 0;
 static int topk_workers(int cg) {
   static int w[3] = {0, 0, 0};
   if (w[cg] == 0) w[cg] = (cg == 1) ? topk_query_workers<1>() : topk_query_workers<2>();
   const int r = w[cg] - (g_reserved_sms + cg - 1) / cg;
   return r < 1 ? 1 : r;
+}
+// Slack of the workers' per-tile lockstep (TopkPlan::sync_lag): 0 = every worker starts every tile together.
+extern "C" int v3s_set_gram_sync_lag(int lag) {
+  V3S_REQUIRE(lag >= 0 && lag <= 8, "v3s_set_gram_sync_lag: 0..8");
+  g_sync_lag = lag;
+  return 0;
 }
 // SMs the persistent Gram kernels leave free (0 = none): a collective that runs BESIDE the kernel needs a few, and
 // the kernel's workers must all be resident at once (they start every tile together)
@@ -1162,6 +1177,7 @@ static TopkPlan make_topk_plan(long long n_rows, long long n_cols, int cg, int w
   p.rg = workers / p.S;
   if (p.rg < 1) p.rg = 1;
   p.units = p.n_rb * p.S;
+  p.sync_lag = g_sync_lag;
   return p;
 }
 
@@ -1449,6 +1465,7 @@ static SymPlan make_sym_plan(long long n, int cg, int workers, int rank, int wor
   p.PC = pc;
   p.PR = total / pc;
   p.rank = rank; p.world = world; p.workers = workers;
+  p.sync_lag = g_sync_lag;
   p.steps = sym_count_steps(p, TK_BM * cg);
   return p;
 }

@@ -64,6 +64,7 @@ SIGNATURES = {
     "v3s_split_f16": (i32, [p, i64, i32, i32, p, p]),
     "v3s_set_gram_topk_cta_group": (i32, [i32]),
     "v3s_set_gram_reserved_sms": (i32, [i32]),
+    "v3s_set_gram_sync_lag": (i32, [i32]),
     "v3s_gram_topk_plan": (i32, [i64, i64, i32, C.POINTER(i32)]),
     "v3s_gram_topk": (i32, [p, i64, p, i64, i32, i32, C.c_float, p, p, p, p, p]),
     "v3s_gram_topk_limits": (i32, [p, i64, p, i64, i32, i32, C.c_float, i32, p, p, p, p, p, p]),

@@ -30,6 +30,7 @@ def fused_gram_error_bound(P):
     return 2.0 ** -10 * (1.0 + 2.0 ** -11) + 1.2e-7 * (P / 16.0) + 2e-6
 
 
+GRAM_SYNC_LAG = 0       # slack (in tiles) of the persistent Gram workers' lockstep (v3s_set_gram_sync_lag)
 SYM_SAMPLE_STRIDE = 8   # symmetric fused Gram: pass 1 looks at every 8th pattern to fix the rows' lower limits
 PANEL_BYTES = 4 << 30   # Gram row panel budget when G is streamed in panels
 SYM_BYTES = 48 << 30    # the whole symmetric G is materialised (half the MMA work) up to this size
@@ -127,6 +128,9 @@ class CudaOps:
         import os as _os
         # sharded jobs: operand all-gathers as copy-engine pulls from symmetric memory (V3S_CE_GATHER=0: NCCL all-gathers)
         self.copy_engine_gather = _os.environ.get("V3S_CE_GATHER", "1") != "0"
+        lag = int(_os.environ.get("V3S_GRAM_SYNC_LAG", str(GRAM_SYNC_LAG)))
+        if lag:
+            call("v3s_set_gram_sync_lag", lag)
         self._row_order = None       # (row0, rows, order int32 [rows], N) of the last fused kNN call with a tile order
         self.sparse_row_order = True # sparse mat-vec: walk the rows in the kNN stage's neighbourhood order (L1 reuse)
         self.share_pairs_across_ranks = True   # sharded tiled refinement: mutual pairs once per JOB, not once per rank
