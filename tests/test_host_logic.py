@@ -260,6 +260,17 @@ def _worker(rank, world, port, q, operator="dense"):
         ops.operator = operator
         stats = {}
         out = run_pipeline(ops, plan, ed, rot9[plan.lo:plan.hi], rot_y, 2 * n + 1, k, eps, check=False, stats=stats)
+        # the second communicator of the sharded kNN stage (long transfers beside the Gram kernels): same ranks, created
+        # once, and an asynchronous all-gather on it completes independently of collectives on the main group
+        side = plan.side_group()
+        assert side is plan.side_group() and dist.get_world_size(side) == world
+        mine = torch.full((4, 3), float(rank), dtype=torch.float64)
+        gathered = torch.empty((4 * world, 3), dtype=torch.float64)
+        work = dist.all_gather_into_tensor(gathered, mine, group=side, async_op=True)
+        small = plan.all_reduce_sum(torch.ones(1, dtype=torch.float64))          # main group, issued while `work` is in flight
+        work.wait()
+        assert float(small.item()) == world
+        assert all(bool((gathered[4 * r_: 4 * r_ + 4] == r_).all()) for r_ in range(world))
         assert stats.get("dense") or stats.get("operator") == ("sparse-fp64" if operator == "sparse" else "dense-fp32"), stats
         q.put((rank, out["S2_unmutated"].numpy(), out["N"].numpy(), out["Lambda"].numpy(), out["Ps"].numpy(),
                float(out["sigma_T"].item())))
